@@ -1,0 +1,227 @@
+"""Deterministic synthetic scenes and ray batches.
+
+Both arms (the CUDA path and the CPU oracle / reference) consume exactly the arrays produced here, so
+"identical bytes on both sides" holds by construction.  numpy only; nothing here touches the GPU.
+
+Mesh convention (the one `b200rt_upload_mesh` takes, include/b200rt.h):
+  xyz   float32 [n_verts, 3]
+  idx   uint32  [n_faces, 4]   idx[f, 3] == 0xFFFFFFFF marks a triangle, otherwise a quad
+  flags uint8   [n_faces]      bit0 Visible, bit1 CastsShadows, bit2 transparent material
+                               (the quad bit3 is derived from idx by the library)
+Ray convention: float32 [n, 8] = ox oy oz tmin dx dy dz tmax  (tmax < 0 means "unbounded", as
+`Ray::tmax_` does in the reference, include/accelerator/accelerator.h:91).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+TRI = np.uint32(0xFFFFFFFF)
+F_VISIBLE = 1
+F_SHADOW = 2
+F_TRANSPARENT = 4
+F_NORMAL = F_VISIBLE | F_SHADOW
+
+
+def _finish(xyz, idx, flags=None):
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    idx = np.ascontiguousarray(idx, dtype=np.uint32)
+    if flags is None:
+        flags = np.full(idx.shape[0], F_NORMAL, dtype=np.uint8)
+    return xyz, idx, np.ascontiguousarray(flags, dtype=np.uint8)
+
+
+def heightfield(cells: int = 707, seed: int = 12345, quads: bool = False):
+    """S1M-hf: `cells` x `cells` grid over [0,1]^2, two triangles per cell (707 -> 999 698 triangles).
+
+    z = 0.5 + 0.15 sin(17x) cos(13y) + 0.05 sin(71x + 3y) + 0.002 U(0,1)   
+    """
+    rng = np.random.RandomState(seed)
+    n = cells + 1
+    g = np.linspace(0.0, 1.0, n)
+    x, y = np.meshgrid(g, g, indexing="xy")
+    z = 0.5 + 0.15 * np.sin(17 * x) * np.cos(13 * y) + 0.05 * np.sin(71 * x + 3 * y) + 0.002 * rng.random_sample(x.shape)
+    xyz = np.stack([x, y, z], axis=-1).reshape(-1, 3)
+    j, i = np.meshgrid(np.arange(cells), np.arange(cells), indexing="xy")
+    v00 = (i * n + j).ravel()
+    v01 = v00 + 1
+    v10 = v00 + n
+    v11 = v10 + 1
+    if quads:
+        idx = np.stack([v00, v01, v11, v10], axis=1)
+    else:
+        t0 = np.stack([v00, v01, v11, np.full_like(v00, TRI)], axis=1)
+        t1 = np.stack([v00, v11, v10, np.full_like(v00, TRI)], axis=1)
+        idx = np.stack([t0, t1], axis=1).reshape(-1, 4)
+    return _finish(xyz, idx)
+
+
+def soup(n_tris: int = 1_000_000, seed: int = 12345, jitter_scale: float = 0.25):
+    """S1M-soup: random triangles, centres U[0,1]^3, vertex jitter +-jitter_scale/cbrt(N) (worst case)."""
+    rng = np.random.RandomState(seed)
+    c = rng.random_sample((n_tris, 1, 3))
+    r = jitter_scale / np.cbrt(n_tris)
+    v = c + (rng.random_sample((n_tris, 3, 3)) * 2.0 - 1.0) * r
+    xyz = v.reshape(-1, 3)
+    base = np.arange(n_tris, dtype=np.int64) * 3
+    idx = np.stack([base, base + 1, base + 2, np.full_like(base, TRI)], axis=1)
+    return _finish(xyz, idx)
+
+
+def _uv_sphere(center, radius, n_lat, n_lon):
+    th = np.linspace(0.0, np.pi, n_lat + 1)
+    ph = np.linspace(0.0, 2 * np.pi, n_lon, endpoint=False)
+    t, p = np.meshgrid(th, ph, indexing="ij")
+    xyz = np.stack([np.sin(t) * np.cos(p), np.sin(t) * np.sin(p), np.cos(t)], axis=-1).reshape(-1, 3) * radius + center
+    a = (np.arange(n_lat)[:, None] * n_lon + np.arange(n_lon)[None, :]).ravel()
+    b = (np.arange(n_lat)[:, None] * n_lon + (np.arange(n_lon)[None, :] + 1) % n_lon).ravel()
+    c = a + n_lon
+    d = b + n_lon
+    t0 = np.stack([a, c, d], axis=1)
+    t1 = np.stack([a, d, b], axis=1)
+    return xyz, np.concatenate([t0, t1], axis=0)
+
+
+def objects(n_tris_target: int = 1_000_000, seed: int = 12345, n_spheres: int = 64, mixed_quads: bool = True):
+    """S1M-obj: tessellated spheres over a tessellated ground plane inside [0,1]^3 (surface-like, occluding).
+
+    The ground is made of quads when `mixed_quads` (the reference's test01 mixes quads and triangles).
+    """
+    rng = np.random.RandomState(seed)
+    per = max(8, n_tris_target // (n_spheres + 1))
+    n_lat = max(2, int(np.sqrt(per / 4.0)))
+    n_lon = 2 * n_lat
+    vs, fs, off = [], [], 0
+    for _ in range(n_spheres):
+        c = np.array([rng.uniform(0.1, 0.9), rng.uniform(0.1, 0.9), rng.uniform(0.15, 0.8)])
+        r = rng.uniform(0.03, 0.09)
+        xyz, tri = _uv_sphere(c, r, n_lat, n_lon)
+        vs.append(xyz)
+        fs.append(np.concatenate([tri + off, np.full((tri.shape[0], 1), int(TRI), dtype=np.int64)], axis=1))
+        off += xyz.shape[0]
+    cells = max(1, int(np.sqrt(per / (1.0 if mixed_quads else 2.0))))
+    gx, gi, _ = heightfield(cells, seed + 1, quads=mixed_quads)
+    gx = gx.copy()
+    gx[:, 2] = 0.05 + 0.2 * (gx[:, 2] - 0.5)
+    vs.append(gx)
+    gi = gi.astype(np.int64)
+    tri_mask = gi[:, 3] == int(TRI)
+    gi[:, :3] += off
+    gi[~tri_mask, 3] += off
+    fs.append(gi)
+    return _finish(np.concatenate(vs, axis=0), np.concatenate(fs, axis=0))
+
+
+def cube_scene():
+    """A tiny mixed quad/triangle scene in the spirit of tests/test01 (boxes on a two-triangle plane)."""
+    vs, fs, off = [], [], 0
+    quad_faces = np.array([[2, 0, 1, 3], [3, 7, 6, 2], [7, 5, 4, 6], [0, 4, 5, 1], [0, 2, 6, 4], [5, 7, 3, 1]])
+    corners = np.array([[x, y, z] for x in (-1, 1) for y in (-1, 1) for z in (0, 2)], dtype=np.float64)
+    centers = [(-3.4, 2.4, 0.0), (4.27, 0.6, 0.0), (0.4, -1.2, 0.0), (-0.5, 3.0, 0.0), (2.0, 4.0, 0.5), (-4.0, -3.0, 0.25)]
+    for k, c in enumerate(centers):
+        v = corners * (0.5 + 0.15 * k) + np.array(c)
+        vs.append(v)
+        if k % 2 == 0:
+            fs.append(quad_faces + off)
+        else:
+            t0 = np.concatenate([quad_faces[:, [0, 1, 2]], np.full((6, 1), int(TRI))], axis=1)
+            t1 = np.concatenate([quad_faces[:, [0, 2, 3]], np.full((6, 1), int(TRI))], axis=1)
+            t = np.concatenate([t0, t1], axis=0)
+            t[:, :3] += off
+            fs.append(t)
+        off += 8
+    plane = np.array([[-10, -10, 0], [10, -10, 0], [10, 10, 0], [-10, 10, 0]], dtype=np.float64)
+    vs.append(plane)
+    fs.append(np.array([[off, off + 1, off + 2, int(TRI)], [off, off + 2, off + 3, int(TRI)]]))
+    return _finish(np.concatenate(vs, axis=0), np.concatenate(fs, axis=0))
+
+
+# ----------------------------------------------------------------------------------------------- rays
+
+def rays_incoherent(n: int, seed: int = 12345, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0), tmax: float = -1.0, tmin: float = 0.0):
+    """R-inc: origin uniform in the box [lo,hi], direction = normalised U[-.5,.5]^3."""
+    rng = np.random.RandomState(seed)
+    lo = np.asarray(lo, dtype=np.float64)
+    hi = np.asarray(hi, dtype=np.float64)
+    r = np.empty((n, 8), dtype=np.float32)
+    r[:, 0:3] = lo + rng.random_sample((n, 3)) * (hi - lo)
+    d = rng.random_sample((n, 3)) - 0.5
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-12)
+    r[:, 4:7] = d
+    r[:, 3] = tmin
+    r[:, 7] = tmax
+    return r
+
+
+def rays_shadow(n: int, seed: int = 12345, t_max: float = 0.25, **kw):
+    """R-shadow (first set): same distribution as R-inc with a finite `t_max` and the usual shadow bias
+    tmin = 0.0005 (Accelerator::shadowBias, include/accelerator/accelerator.h:86)."""
+    return rays_incoherent(n, seed, tmax=t_max, tmin=0.0005, **kw)
+
+
+def rays_camera(width: int, height: int, eye=(0.5, -1.2, 1.1), look=(0.5, 0.5, 0.45), up=(0, 0, 1), fov_deg: float = 50.0, seed: int | None = None):
+    """R-coh: one perspective camera ray per pixel (pin-hole; direction normalised), optional sub-pixel jitter."""
+    eye = np.asarray(eye, dtype=np.float64)
+    fwd = np.asarray(look, dtype=np.float64) - eye
+    fwd /= np.linalg.norm(fwd)
+    right = np.cross(fwd, np.asarray(up, dtype=np.float64))
+    right /= np.linalg.norm(right)
+    upv = np.cross(right, fwd)
+    px, py = np.meshgrid(np.arange(width, dtype=np.float64), np.arange(height, dtype=np.float64), indexing="xy")
+    if seed is not None:
+        rng = np.random.RandomState(seed)
+        px = px + rng.random_sample(px.shape)
+        py = py + rng.random_sample(py.shape)
+    else:
+        px, py = px + 0.5, py + 0.5
+    half = np.tan(np.radians(fov_deg) / 2)
+    sx = (2 * px / width - 1) * half
+    sy = (1 - 2 * py / height) * half * height / width
+    d = fwd[None, None, :] + sx[..., None] * right + sy[..., None] * upv
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    r = np.empty((width * height, 8), dtype=np.float32)
+    r[:, 0:3] = eye
+    r[:, 3] = 0.0
+    r[:, 4:7] = d.reshape(-1, 3)
+    r[:, 7] = -1.0
+    return r
+
+
+def rays_edge_cases(bound_lo, bound_hi, seed: int = 7):
+    """Hand-picked nasty rays: axis-parallel directions (zero components), origins on the bound, outside
+    pointing away, tmax = 0, tiny tmax, un-normalised and huge directions."""
+    rng = np.random.RandomState(seed)
+    lo = np.asarray(bound_lo, dtype=np.float64)
+    hi = np.asarray(bound_hi, dtype=np.float64)
+    c = 0.5 * (lo + hi)
+    ext = hi - lo
+    rows = []
+    for ax in range(3):
+        for s in (-1.0, 1.0):
+            d = np.zeros(3)
+            d[ax] = s
+            for _ in range(64):
+                o = lo + rng.random_sample(3) * ext
+                rows.append([*o, 0.0, *d, -1.0])
+                o2 = o.copy()
+                o2[ax] = c[ax] - s * ext[ax]
+                rows.append([*o2, 0.0, *d, -1.0])
+                rows.append([*o2, 0.0, *(-d), -1.0])            # outside, pointing away
+                rows.append([*o2, 0.0, *(d * 1e-3), -1.0])      # un-normalised, short
+                rows.append([*o2, 0.0, *(d * 1e4), -1.0])       # un-normalised, long
+            for a2 in range(3):
+                if a2 == ax:
+                    continue
+                d2 = d.copy()
+                d2[a2] = 0.37
+                for _ in range(32):
+                    o = lo + rng.random_sample(3) * ext
+                    rows.append([*o, 0.0, *d2, -1.0])
+    for _ in range(256):
+        o = lo + rng.random_sample(3) * ext
+        d = rng.random_sample(3) - 0.5
+        rows.append([*o, 0.0, *d, 0.0])                          # tmax == 0
+        rows.append([*o, 0.0, *d, 1e-6])
+        rows.append([*o, 0.01, *d, 0.05])
+        rows.append([*lo, 0.0, *d, -1.0])                        # origin on the bound corner
+        rows.append([*(hi + ext), 0.0, *(c - hi - ext), -1.0])   # from outside through the centre
+    return np.asarray(rows, dtype=np.float32)
