@@ -1,0 +1,179 @@
+/* include/b200rt.h -- C ABI of libb200rt: the B200 (sm_100a) ray-scene intersection path for libYafaRay.
+ *
+ * This is the drop-in boundary.  The entry points below are what a libYafaRay `Accelerator` subclass
+ * binds to replace the reference's CPU kd-tree (INTEGRATION.md shows that class and the two-file patch
+ * that registers it).  Paths cited are relative to the reference tree.
+ *
+ *   reference interface                                                    replaced by
+ *   -------------------------------------------------------------------    ---------------------------------
+ *   AcceleratorKdTree ctor / Accelerator::factory                          b200rt_create + b200rt_add_mesh
+ *     (src/accelerator/accelerator_kdtree_original.cc:57-141,               + b200rt_build
+ *      src/accelerator/accelerator.cc:44-55)
+ *   Accelerator::getBound()  (include/accelerator/accelerator.h:53)        b200rt_get_bound
+ *   Accelerator::intersect(ray,t_max) / intersect(ray,camera)              b200rt_trace_closest[_device]
+ *     (include/accelerator/accelerator.h:50,89-101;
+ *      include/accelerator/accelerator_kdtree_common.h:107-255 <Nearest>)
+ *   Accelerator::intersectShadow / isShadowed                              b200rt_trace_shadow[_device]
+ *     (accelerator.h:51,103-111; accelerator_kdtree_common.h <Shadow>)
+ *   Accelerator::intersectTransparentShadow / isShadowedTransparentShadow  b200rt_trace_tshadow[_device]
+ *     (accelerator.h:52,113-120,147-169; <TransparentShadow>)
+ *   Params depth / max_leaf_size_ / cost_ratio / empty_bonus               b200rt_build_params
+ *     (include/accelerator/accelerator_kdtree_original.h:56-59)
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a negative
+ * B200RT_E_* code on failure (b200rt_last_error() gives the text for the calling thread); no C++
+ * exception crosses this boundary; there is NO CPU fallback -- without a usable CUDA device
+ * b200rt_create fails.  Queries are thread-safe: any number of host threads may trace against one
+ * built scene concurrently (the reference's render workers do, integrator_tiled.cc:232-248).
+ */
+#ifndef B200RT_H
+#define B200RT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RT_VERSION 1
+#define B200RT_MISS 0xFFFFFFFFu
+
+enum
+{
+	B200RT_OK = 0,
+	B200RT_E_INVALID = -1,  /* bad argument / wrong call order */
+	B200RT_E_CUDA = -2,     /* CUDA runtime error (text in b200rt_last_error) */
+	B200RT_E_NO_DEVICE = -3,
+	B200RT_E_MEMORY = -4
+};
+
+/* per-face flag bits (b200rt_add_mesh).  Visible / CastsShadows must already be the AND of the object's
+ * and the material's visibility (include/accelerator/accelerator.h:126-127,138-139); TRANSPARENT is
+ * Material::isTransparent() (include/material/material.h:85). */
+enum
+{
+	B200RT_FACE_VISIBLE = 1,
+	B200RT_FACE_CASTS_SHADOWS = 2,
+	B200RT_FACE_TRANSPARENT = 4
+};
+
+/* Ray: the fields of yafaray::Ray the path reads (include/geometry/ray.h:46-50).  tmax < 0 means
+ * unbounded (accelerator.h:91).  dir need not be normalised.  32 bytes. */
+typedef struct b200rt_ray
+{
+	float ox, oy, oz, tmin;
+	float dx, dy, dz, tmax;
+} b200rt_ray;
+
+/* Closest hit: IntersectData's t_hit_/uv_/primitive_ (include/accelerator/intersect_data.h:30-39).
+ * prim = index of the face in upload order (B200RT_MISS and t = 0 on a miss).  16 bytes. */
+typedef struct b200rt_hit
+{
+	float t, u, v;
+	uint32_t prim;
+} b200rt_hit;
+
+/* Transparent shadow result.  The reference multiplies the ray colour by
+ * Material::getTransparency of every DISTINCT transparent shadow caster it meets and reports
+ * "shadowed" for an opaque caster or for more than max_depth distinct transparent ones
+ * (accelerator.h:147-169).  Material code stays on the host, so the kernel returns the casters:
+ * shadowed as in the reference; otherwise n_transparent (<= max_depth <= B200RT_TSHADOW_MAX) entries
+ * of prim/t/u/v to evaluate getSurface()/getTransparency() on.  144 bytes. */
+#define B200RT_TSHADOW_MAX 8
+typedef struct b200rt_tshadow
+{
+	uint32_t shadowed;
+	uint32_t n_transparent;
+	uint32_t occluder; /* last accepted caster (IntersectData::primitive_), B200RT_MISS if none */
+	uint32_t pad_;
+	b200rt_hit transparent[B200RT_TSHADOW_MAX];
+} b200rt_tshadow;
+
+/* Build parameters, named after the reference's (accelerator_kdtree_original.h:56-59).  Zero / negative
+ * values select the library default for that field. */
+typedef struct b200rt_build_params
+{
+	int max_depth;      /* "depth": 0 = automatic */
+	int max_leaf_size;  /* "max_leaf_size_" */
+	float cost_ratio;   /* "cost_ratio": node traversal cost / primitive test cost */
+	float empty_bonus;  /* "empty_bonus" */
+	int build_threads;  /* host threads for the build, 0 = all */
+	int reserved_[3];
+} b200rt_build_params;
+
+typedef struct b200rt_stats
+{
+	uint64_t n_faces, n_triangles, n_quads;
+	uint64_t n_nodes, n_interior, n_leaves, n_empty_leaves, n_leaf_refs;
+	uint32_t max_depth, max_leaf_prims;
+	double build_seconds, upload_seconds;
+	uint64_t device_bytes;
+} b200rt_stats;
+
+typedef struct b200rt_scene b200rt_scene;
+
+/* Number of CUDA devices (0 with an error code when there is no driver / device). */
+int b200rt_device_count(int *count);
+
+/* Create an empty scene bound to CUDA device `device`.  params may be NULL. */
+int b200rt_create(int device, const b200rt_build_params *params, b200rt_scene **out);
+void b200rt_destroy(b200rt_scene *scene);
+
+/* Append one mesh.  xyz: 3 floats per vertex.  idx: 4 uint32 per face, idx[4f+3] == 0xFFFFFFFF marks a
+ * triangle, anything else a quad (v0 v1 v2 v3; the reference tests (v0,v1,v2) then (v0,v2,v3),
+ * include/geometry/shape/shape_polygon.h:126-176).  flags: one byte per face (NULL = visible shadow
+ * caster).  Face ids continue across calls in upload order, like the primitive vector Scene::preprocess
+ * hands to the factory (src/scene/scene.cc:320-341). */
+int b200rt_add_mesh(b200rt_scene *scene, const float *xyz, size_t n_verts, const uint32_t *idx, size_t n_faces, const uint8_t *flags);
+
+/* Build the kd-tree on the host, flatten it and upload it.  Must precede any trace call; calling it
+ * again after more b200rt_add_mesh calls rebuilds. */
+int b200rt_build(b200rt_scene *scene);
+
+/* Tree bound after the reference's 0.1 % inflation (accelerator_kdtree_original.cc:88-103): lo xyz, hi xyz. */
+int b200rt_get_bound(const b200rt_scene *scene, float out6[6]);
+int b200rt_get_stats(const b200rt_scene *scene, b200rt_stats *out);
+
+/* Re-derive the per-face flag bytes without rebuilding (materials changed between renders). */
+int b200rt_update_face_flags(b200rt_scene *scene, const uint8_t *flags, size_t n_faces);
+
+/* ---- host-buffer queries: rays and results live in host memory; the call stages them through pinned
+ * buffers in chunks, overlapping H2D, kernel and D2H, and returns when `out` is complete.
+ * b200rt_trace_shadow writes the occluding face id or B200RT_MISS (not shadowed) per ray. */
+int b200rt_trace_closest(b200rt_scene *scene, const b200rt_ray *rays, size_t n, b200rt_hit *out);
+int b200rt_trace_shadow(b200rt_scene *scene, const b200rt_ray *rays, size_t n, uint32_t *out);
+int b200rt_trace_tshadow(b200rt_scene *scene, const b200rt_ray *rays, size_t n, int max_depth, b200rt_tshadow *out);
+
+/* ---- device-buffer queries: rays/out are device pointers on the scene's device; the kernel is
+ * enqueued on `stream` (a cudaStream_t passed as void*, NULL = legacy default stream) and the call
+ * returns without synchronising. */
+int b200rt_trace_closest_device(b200rt_scene *scene, const b200rt_ray *d_rays, size_t n, b200rt_hit *d_out, void *stream);
+int b200rt_trace_shadow_device(b200rt_scene *scene, const b200rt_ray *d_rays, size_t n, uint32_t *d_out, void *stream);
+int b200rt_trace_tshadow_device(b200rt_scene *scene, const b200rt_ray *d_rays, size_t n, int max_depth, b200rt_tshadow *d_out, void *stream);
+
+/* Pinned host memory for ray / result buffers (makes the host-buffer queries copy at full PCIe rate). */
+int b200rt_host_alloc(void **ptr, size_t bytes);
+int b200rt_host_free(void *ptr);
+
+/* ---- diagnostics: the host-side builder alone (no CUDA device needed).  Used by the CPU test-suite to
+ * validate the tree (every face reachable, same hits as the reference traversal run over it) and by tools.
+ * Export format: node i = (a[i], b[i]); interior: a = float bits of the split, b = (right child << 2) | axis,
+ * left child = i + 1; leaf: a = first index into refs, b = (count << 2) | 3; refs = face ids. */
+typedef struct b200rt_host_tree b200rt_host_tree;
+int b200rt_host_tree_build(const float *xyz, size_t n_verts, const uint32_t *idx, size_t n_faces, const b200rt_build_params *params, b200rt_host_tree **out);
+int b200rt_host_tree_sizes(const b200rt_host_tree *tree, size_t *n_nodes, size_t *n_refs);
+int b200rt_host_tree_export(const b200rt_host_tree *tree, uint32_t *node_a, uint32_t *node_b, uint32_t *refs, float bound6[6]);
+void b200rt_host_tree_destroy(b200rt_host_tree *tree);
+
+/* Kernels launched by this library in this process so far (all scenes); bench.py's gpu_launches. */
+uint64_t b200rt_launch_count(void);
+
+/* Text of the last error raised on the calling thread ("" if none). */
+const char *b200rt_last_error(void);
+int b200rt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

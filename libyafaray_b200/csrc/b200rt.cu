@@ -1,0 +1,561 @@
+// libyafaray_b200/csrc/b200rt.cu -- the C ABI of libb200rt (include/b200rt.h): scene ownership, host-side
+// flattening of the kd-tree into the HBM layout the kernels read, and the staged host-buffer queries.
+#include "../../include/b200rt.h"
+#include "kd_build.h"
+#include "kd_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const std::string &msg)
+{
+	g_last_error = msg;
+	return code;
+}
+
+#define CUDA_TRY(expr)                                                                                          \
+	do {                                                                                                        \
+		const cudaError_t e_ = (expr);                                                                          \
+		if(e_ != cudaSuccess)                                                                                   \
+			return fail(B200RT_E_CUDA, std::string(#expr) + ": " + cudaGetErrorName(e_) + " (" + cudaGetErrorString(e_) + ")"); \
+	} while(0)
+
+constexpr uint32_t kTriangle = 0xFFFFFFFFu;
+constexpr size_t kChunkBytes = size_t(32) << 20; // staging granularity of the host-buffer queries
+constexpr int kLanesPerCall = 3;
+
+// One staging lane: a stream with pinned host and device buffers for rays in / results out.
+struct Lane
+{
+	cudaStream_t stream = nullptr;
+	cudaEvent_t done = nullptr;
+	void *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
+	size_t in_cap = 0, out_cap = 0;
+	// pending copy-out of the previous chunk this lane carried
+	void *pending_dst = nullptr;
+	size_t pending_bytes = 0;
+	bool pending_direct = false;
+
+	~Lane()
+	{
+		if(h_in) cudaFreeHost(h_in);
+		if(h_out) cudaFreeHost(h_out);
+		if(d_in) cudaFree(d_in);
+		if(d_out) cudaFree(d_out);
+		if(done) cudaEventDestroy(done);
+		if(stream) cudaStreamDestroy(stream);
+	}
+};
+
+} // namespace
+
+struct b200rt_scene
+{
+	int device = 0;
+	b200rt::BuildConfig config;
+	// host mesh (all b200rt_add_mesh calls concatenated)
+	std::vector<float> xyz;
+	std::vector<uint32_t> idx;
+	std::vector<uint8_t> flags;
+	// built state
+	bool built = false;
+	b200rt::HostTree tree;
+	std::vector<uint32_t> record_of_ref; // float4 offset of every leaf reference's record (for flag updates)
+	uint2 *d_nodes = nullptr;
+	float4 *d_tris = nullptr;
+	size_t n_tri_vec4 = 0;
+	b200rt::SceneView view{};
+	b200rt_stats stats{};
+	std::mutex lane_mutex;
+	std::vector<std::unique_ptr<Lane>> free_lanes;
+
+	~b200rt_scene()
+	{
+		cudaSetDevice(device);
+		free_lanes.clear();
+		if(d_nodes) cudaFree(d_nodes);
+		if(d_tris) cudaFree(d_tris);
+	}
+};
+
+namespace {
+
+int ensureLane(Lane &l, size_t in_bytes, size_t out_bytes, bool need_h_in, bool need_h_out)
+{
+	if(!l.stream) CUDA_TRY(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+	if(!l.done) CUDA_TRY(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+	if(l.in_cap < in_bytes)
+	{
+		if(l.d_in) cudaFree(l.d_in);
+		if(l.h_in) cudaFreeHost(l.h_in);
+		l.d_in = l.h_in = nullptr;
+		l.in_cap = 0;
+		CUDA_TRY(cudaMalloc(&l.d_in, in_bytes));
+		l.in_cap = in_bytes;
+	}
+	if(need_h_in && !l.h_in) CUDA_TRY(cudaMallocHost(&l.h_in, l.in_cap));
+	if(l.out_cap < out_bytes)
+	{
+		if(l.d_out) cudaFree(l.d_out);
+		if(l.h_out) cudaFreeHost(l.h_out);
+		l.d_out = l.h_out = nullptr;
+		l.out_cap = 0;
+		CUDA_TRY(cudaMalloc(&l.d_out, out_bytes));
+		l.out_cap = out_bytes;
+	}
+	if(need_h_out && !l.h_out) CUDA_TRY(cudaMallocHost(&l.h_out, l.out_cap));
+	return B200RT_OK;
+}
+
+bool isPinned(const void *p)
+{
+	cudaPointerAttributes a;
+	if(cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return a.type == cudaMemoryTypeHost;
+}
+
+template <typename Out, typename LaunchFn>
+int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, LaunchFn launch)
+{
+	if(!s || (!rays && n) || (!out && n)) return fail(B200RT_E_INVALID, "null argument");
+	if(!s->built) return fail(B200RT_E_INVALID, "scene not built: call b200rt_build first");
+	if(n == 0) return B200RT_OK;
+	CUDA_TRY(cudaSetDevice(s->device));
+	const size_t per_ray = std::max(sizeof(b200rt_ray), sizeof(Out));
+	const size_t chunk = std::max<size_t>(1024, kChunkBytes / per_ray);
+	const size_t n_chunks = (n + chunk - 1) / chunk;
+	const int n_lanes = int(std::min<size_t>(kLanesPerCall, n_chunks));
+	const bool in_pinned = isPinned(rays), out_pinned = isPinned(out);
+
+	std::vector<std::unique_ptr<Lane>> lanes;
+	{
+		std::lock_guard<std::mutex> lock(s->lane_mutex);
+		while(int(lanes.size()) < n_lanes && !s->free_lanes.empty())
+		{
+			lanes.push_back(std::move(s->free_lanes.back()));
+			s->free_lanes.pop_back();
+		}
+	}
+	while(int(lanes.size()) < n_lanes) lanes.push_back(std::make_unique<Lane>());
+	auto give_back = [&]() {
+		std::lock_guard<std::mutex> lock(s->lane_mutex);
+		for(auto &l : lanes) s->free_lanes.push_back(std::move(l));
+	};
+	auto drain = [&](Lane &l) -> int {
+		if(!l.pending_dst) return B200RT_OK;
+		CUDA_TRY(cudaEventSynchronize(l.done));
+		if(!l.pending_direct) std::memcpy(l.pending_dst, l.h_out, l.pending_bytes);
+		l.pending_dst = nullptr;
+		return B200RT_OK;
+	};
+	const size_t rays_this = std::min(chunk, n);
+	int rc = B200RT_OK;
+	for(auto &l : lanes)
+	{
+		l->pending_dst = nullptr;
+		rc = ensureLane(*l, rays_this * sizeof(b200rt_ray), rays_this * sizeof(Out), !in_pinned, !out_pinned);
+		if(rc != B200RT_OK) { give_back(); return rc; }
+	}
+	for(size_t c = 0; c < n_chunks && rc == B200RT_OK; ++c)
+	{
+		Lane &l = *lanes[c % size_t(n_lanes)];
+		rc = drain(l);
+		if(rc != B200RT_OK) break;
+		const size_t begin = c * chunk, count = std::min(chunk, n - begin);
+		const void *src = rays + begin;
+		if(!in_pinned) { std::memcpy(l.h_in, src, count * sizeof(b200rt_ray)); src = l.h_in; }
+		cudaError_t e = cudaMemcpyAsync(l.d_in, src, count * sizeof(b200rt_ray), cudaMemcpyHostToDevice, l.stream);
+		if(e == cudaSuccess)
+		{
+			launch(static_cast<const b200rt_ray *>(l.d_in), count, static_cast<Out *>(l.d_out), l.stream);
+			e = cudaGetLastError();
+		}
+		if(e == cudaSuccess) e = cudaMemcpyAsync(out_pinned ? static_cast<void *>(out + begin) : l.h_out, l.d_out, count * sizeof(Out), cudaMemcpyDeviceToHost, l.stream);
+		if(e == cudaSuccess) e = cudaEventRecord(l.done, l.stream);
+		if(e != cudaSuccess) { rc = fail(B200RT_E_CUDA, std::string("staged trace: ") + cudaGetErrorString(e)); break; }
+		l.pending_dst = out + begin;
+		l.pending_bytes = count * sizeof(Out);
+		l.pending_direct = out_pinned;
+	}
+	for(auto &l : lanes)
+	{
+		const int r = drain(*l);
+		if(rc == B200RT_OK) rc = r;
+	}
+	if(rc != B200RT_OK) for(auto &l : lanes) cudaStreamSynchronize(l->stream);
+	give_back();
+	return rc;
+}
+
+inline unsigned gridFor(size_t n) { return unsigned((n + b200rt::kBlock - 1) / b200rt::kBlock); }
+
+int checkDeviceCall(const b200rt_scene *s, const void *rays, size_t n, const void *out)
+{
+	if(!s || (!rays && n) || (!out && n)) return fail(B200RT_E_INVALID, "null argument");
+	if(!s->built) return fail(B200RT_E_INVALID, "scene not built: call b200rt_build first");
+	if(n > (size_t(1) << 31) * b200rt::kBlock) return fail(B200RT_E_INVALID, "batch too large for one launch");
+	return B200RT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int b200rt_version(void) { return B200RT_VERSION; }
+const char *b200rt_last_error(void) { return g_last_error.c_str(); }
+uint64_t b200rt_launch_count(void) { return g_launches.load(); }
+
+int b200rt_device_count(int *count)
+{
+	if(!count) return fail(B200RT_E_INVALID, "null argument");
+	*count = 0;
+	int n = 0;
+	const cudaError_t e = cudaGetDeviceCount(&n);
+	if(e != cudaSuccess) { cudaGetLastError(); return fail(B200RT_E_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+	*count = n;
+	return B200RT_OK;
+}
+
+int b200rt_create(int device, const b200rt_build_params *params, b200rt_scene **out)
+{
+	if(!out) return fail(B200RT_E_INVALID, "null argument");
+	*out = nullptr;
+	int n = 0;
+	const int rc = b200rt_device_count(&n);
+	if(rc != B200RT_OK) return rc;
+	if(n == 0) return fail(B200RT_E_NO_DEVICE, "no CUDA device: libb200rt has no CPU fallback");
+	if(device < 0 || device >= n) return fail(B200RT_E_INVALID, "device index out of range");
+	CUDA_TRY(cudaSetDevice(device));
+	CUDA_TRY(cudaFree(nullptr));
+	b200rt_scene *s = new(std::nothrow) b200rt_scene;
+	if(!s) return fail(B200RT_E_MEMORY, "out of host memory");
+	s->device = device;
+	if(params)
+	{
+		s->config.max_depth = params->max_depth;
+		s->config.max_leaf_size = params->max_leaf_size;
+		s->config.cost_ratio = params->cost_ratio;
+		s->config.empty_bonus = params->empty_bonus > 0.f ? params->empty_bonus : -1.f;
+		s->config.threads = params->build_threads;
+	}
+	*out = s;
+	return B200RT_OK;
+}
+
+void b200rt_destroy(b200rt_scene *scene) { delete scene; }
+
+int b200rt_add_mesh(b200rt_scene *s, const float *xyz, size_t n_verts, const uint32_t *idx, size_t n_faces, const uint8_t *flags)
+{
+	if(!s || (!xyz && n_verts) || (!idx && n_faces)) return fail(B200RT_E_INVALID, "null argument");
+	const size_t base = s->xyz.size() / 3;
+	if(base + n_verts >= size_t(kTriangle)) return fail(B200RT_E_INVALID, "too many vertices");
+	if(s->idx.size() / 4 + n_faces >= (size_t(1) << 30)) return fail(B200RT_E_INVALID, "too many faces");
+	for(size_t f = 0; f < n_faces; ++f)
+		for(int k = 0; k < 4; ++k)
+		{
+			const uint32_t v = idx[4 * f + k];
+			if(k == 3 && v == kTriangle) continue;
+			if(v >= n_verts) return fail(B200RT_E_INVALID, "face " + std::to_string(f) + " references vertex " + std::to_string(v) + " >= n_verts");
+		}
+	try
+	{
+		s->xyz.insert(s->xyz.end(), xyz, xyz + 3 * n_verts);
+		s->idx.reserve(s->idx.size() + 4 * n_faces);
+		for(size_t f = 0; f < n_faces; ++f)
+			for(int k = 0; k < 4; ++k)
+			{
+				const uint32_t v = idx[4 * f + k];
+				s->idx.push_back((k == 3 && v == kTriangle) ? kTriangle : uint32_t(v + base));
+			}
+		if(flags) s->flags.insert(s->flags.end(), flags, flags + n_faces);
+		else s->flags.insert(s->flags.end(), n_faces, uint8_t(B200RT_FACE_VISIBLE | B200RT_FACE_CASTS_SHADOWS));
+	}
+	catch(const std::bad_alloc &) { return fail(B200RT_E_MEMORY, "out of host memory"); }
+	s->built = false;
+	return B200RT_OK;
+}
+
+int b200rt_build(b200rt_scene *s)
+{
+	if(!s) return fail(B200RT_E_INVALID, "null argument");
+	CUDA_TRY(cudaSetDevice(s->device));
+	s->built = false;
+	const size_t n_faces = s->idx.size() / 4;
+	const auto t0 = std::chrono::steady_clock::now();
+	std::vector<uint2> nodes;
+	std::vector<float4> tris;
+	try
+	{
+		const b200rt::MeshView mesh{s->xyz.data(), s->xyz.size() / 3, s->idx.data(), n_faces};
+		b200rt::buildKdTree(mesh, s->config, s->tree);
+		// flatten: one record per leaf reference, in leaf order
+		const auto &tree = s->tree;
+		s->record_of_ref.assign(tree.leaf_refs.size(), 0u);
+		tris.reserve(tree.leaf_refs.size() * 3 + 4);
+		nodes.resize(tree.nodes.size());
+		uint64_t n_tri = 0, n_quad = 0;
+		for(size_t f = 0; f < n_faces; ++f) (s->idx[4 * f + 3] == kTriangle ? n_tri : n_quad)++;
+		for(size_t i = 0; i < tree.nodes.size(); ++i)
+		{
+			const b200rt::HostNode hn = tree.nodes[i];
+			if((hn.b & 3u) != 3u) { nodes[i] = make_uint2(hn.a, hn.b); continue; }
+			const uint32_t count = hn.b >> 2;
+			nodes[i] = make_uint2(uint32_t(tris.size()), hn.b);
+			for(uint32_t k = 0; k < count; ++k)
+			{
+				const uint32_t face = tree.leaf_refs[hn.a + k];
+				const uint32_t *id = s->idx.data() + 4 * size_t(face);
+				const bool quad = id[3] != kTriangle;
+				const float *v0 = s->xyz.data() + 3 * size_t(id[0]);
+				s->record_of_ref[hn.a + k] = uint32_t(tris.size());
+				uint32_t fl = s->flags[face] & 7u;
+				if(quad) fl |= b200rt::kFlagQuad;
+				float4 q;
+				q.x = v0[0]; q.y = v0[1]; q.z = v0[2];
+				std::memcpy(&q.w, &face, 4);
+				tris.push_back(q);
+				for(int e = 1; e <= (quad ? 3 : 2); ++e)
+				{
+					const float *ve = s->xyz.data() + 3 * size_t(id[e]);
+					// edge_k = v_k - v_0, one float subtraction per component (shape_polygon.h:130-131,150)
+					volatile float ex = ve[0] - v0[0], ey = ve[1] - v0[1], ez = ve[2] - v0[2];
+					q.x = ex; q.y = ey; q.z = ez;
+					const uint32_t w = (e == 1) ? fl : 0u;
+					std::memcpy(&q.w, &w, 4);
+					tris.push_back(q);
+				}
+			}
+		}
+		if(tris.size() >= (size_t(1) << 32)) return fail(B200RT_E_INVALID, "leaf stream exceeds 2^32 records");
+		tris.push_back(make_float4(0.f, 0.f, 0.f, 0.f)); // a quad's 4th record may be prefetched one past a triangle
+		s->stats = b200rt_stats{};
+		s->stats.n_faces = n_faces;
+		s->stats.n_triangles = n_tri;
+		s->stats.n_quads = n_quad;
+		s->stats.n_nodes = tree.nodes.size();
+		s->stats.n_interior = tree.n_interior;
+		s->stats.n_leaves = tree.n_leaves;
+		s->stats.n_empty_leaves = tree.n_empty_leaves;
+		s->stats.n_leaf_refs = tree.leaf_refs.size();
+		s->stats.max_depth = tree.depth;
+		s->stats.max_leaf_prims = tree.max_leaf_prims;
+	}
+	catch(const std::bad_alloc &) { return fail(B200RT_E_MEMORY, "out of host memory during build"); }
+	catch(const std::exception &e) { return fail(B200RT_E_INVALID, std::string("build failed: ") + e.what()); }
+	const auto t1 = std::chrono::steady_clock::now();
+	s->stats.build_seconds = std::chrono::duration<double>(t1 - t0).count();
+
+	if(s->d_nodes) { cudaFree(s->d_nodes); s->d_nodes = nullptr; }
+	if(s->d_tris) { cudaFree(s->d_tris); s->d_tris = nullptr; }
+	CUDA_TRY(cudaMalloc(&s->d_nodes, nodes.size() * sizeof(uint2)));
+	CUDA_TRY(cudaMalloc(&s->d_tris, tris.size() * sizeof(float4)));
+	CUDA_TRY(cudaMemcpy(s->d_nodes, nodes.data(), nodes.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMemcpy(s->d_tris, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
+	s->n_tri_vec4 = tris.size();
+	s->view.nodes = s->d_nodes;
+	s->view.tris = s->d_tris;
+	std::memcpy(s->view.bound, s->tree.bound, sizeof(s->view.bound));
+	s->stats.device_bytes = nodes.size() * sizeof(uint2) + tris.size() * sizeof(float4);
+	s->stats.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+	s->built = true;
+	return B200RT_OK;
+}
+
+int b200rt_get_bound(const b200rt_scene *s, float out6[6])
+{
+	if(!s || !out6) return fail(B200RT_E_INVALID, "null argument");
+	if(!s->built) return fail(B200RT_E_INVALID, "scene not built");
+	std::memcpy(out6, s->tree.bound, 6 * sizeof(float));
+	return B200RT_OK;
+}
+
+int b200rt_get_stats(const b200rt_scene *s, b200rt_stats *out)
+{
+	if(!s || !out) return fail(B200RT_E_INVALID, "null argument");
+	if(!s->built) return fail(B200RT_E_INVALID, "scene not built");
+	*out = s->stats;
+	return B200RT_OK;
+}
+
+int b200rt_update_face_flags(b200rt_scene *s, const uint8_t *flags, size_t n_faces)
+{
+	if(!s || !flags) return fail(B200RT_E_INVALID, "null argument");
+	if(!s->built) return fail(B200RT_E_INVALID, "scene not built");
+	if(n_faces != s->idx.size() / 4) return fail(B200RT_E_INVALID, "n_faces does not match the scene");
+	CUDA_TRY(cudaSetDevice(s->device));
+	s->flags.assign(flags, flags + n_faces);
+	// patch the flag word (q1.w) of every record; small strided writes, done once per material change
+	std::vector<float4> tris(s->n_tri_vec4);
+	CUDA_TRY(cudaMemcpy(tris.data(), s->d_tris, tris.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+	for(size_t r = 0; r < s->record_of_ref.size(); ++r)
+	{
+		const uint32_t face = s->tree.leaf_refs[r];
+		uint32_t fl = s->flags[face] & 7u;
+		if(s->idx[4 * size_t(face) + 3] != kTriangle) fl |= b200rt::kFlagQuad;
+		std::memcpy(&tris[size_t(s->record_of_ref[r]) + 1].w, &fl, 4);
+	}
+	CUDA_TRY(cudaMemcpy(s->d_tris, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
+	return B200RT_OK;
+}
+
+// ---- device-buffer queries --------------------------------------------------------------------
+int b200rt_trace_closest_device(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, b200rt_hit *d_out, void *stream)
+{
+	const int rc = checkDeviceCall(s, d_rays, n, d_out);
+	if(rc != B200RT_OK || n == 0) return rc;
+	CUDA_TRY(cudaSetDevice(s->device));
+	b200rt::traceClosestKernel<<<gridFor(n), b200rt::kBlock, 0, static_cast<cudaStream_t>(stream)>>>(s->view, d_rays, n, d_out);
+	++g_launches;
+	CUDA_TRY(cudaGetLastError());
+	return B200RT_OK;
+}
+
+int b200rt_trace_shadow_device(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, uint32_t *d_out, void *stream)
+{
+	const int rc = checkDeviceCall(s, d_rays, n, d_out);
+	if(rc != B200RT_OK || n == 0) return rc;
+	CUDA_TRY(cudaSetDevice(s->device));
+	b200rt::traceShadowKernel<<<gridFor(n), b200rt::kBlock, 0, static_cast<cudaStream_t>(stream)>>>(s->view, d_rays, n, d_out);
+	++g_launches;
+	CUDA_TRY(cudaGetLastError());
+	return B200RT_OK;
+}
+
+int b200rt_trace_tshadow_device(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, int max_depth, b200rt_tshadow *d_out, void *stream)
+{
+	const int rc = checkDeviceCall(s, d_rays, n, d_out);
+	if(rc != B200RT_OK) return rc;
+	if(max_depth < 0 || max_depth > B200RT_TSHADOW_MAX) return fail(B200RT_E_INVALID, "max_depth must be in [0, B200RT_TSHADOW_MAX]");
+	if(n == 0) return B200RT_OK;
+	CUDA_TRY(cudaSetDevice(s->device));
+	b200rt::traceTShadowKernel<<<gridFor(n), b200rt::kBlock, 0, static_cast<cudaStream_t>(stream)>>>(s->view, d_rays, n, max_depth, d_out);
+	++g_launches;
+	CUDA_TRY(cudaGetLastError());
+	return B200RT_OK;
+}
+
+// ---- host-buffer queries ----------------------------------------------------------------------
+int b200rt_trace_closest(b200rt_scene *s, const b200rt_ray *rays, size_t n, b200rt_hit *out)
+{
+	return tracedStaged(s, rays, n, out, [&](const b200rt_ray *d_rays, size_t count, b200rt_hit *d_out, cudaStream_t st) {
+		b200rt::traceClosestKernel<<<gridFor(count), b200rt::kBlock, 0, st>>>(s->view, d_rays, count, d_out);
+		++g_launches;
+	});
+}
+
+int b200rt_trace_shadow(b200rt_scene *s, const b200rt_ray *rays, size_t n, uint32_t *out)
+{
+	return tracedStaged(s, rays, n, out, [&](const b200rt_ray *d_rays, size_t count, uint32_t *d_out, cudaStream_t st) {
+		b200rt::traceShadowKernel<<<gridFor(count), b200rt::kBlock, 0, st>>>(s->view, d_rays, count, d_out);
+		++g_launches;
+	});
+}
+
+int b200rt_trace_tshadow(b200rt_scene *s, const b200rt_ray *rays, size_t n, int max_depth, b200rt_tshadow *out)
+{
+	if(max_depth < 0 || max_depth > B200RT_TSHADOW_MAX) return fail(B200RT_E_INVALID, "max_depth must be in [0, B200RT_TSHADOW_MAX]");
+	return tracedStaged(s, rays, n, out, [&](const b200rt_ray *d_rays, size_t count, b200rt_tshadow *d_out, cudaStream_t st) {
+		b200rt::traceTShadowKernel<<<gridFor(count), b200rt::kBlock, 0, st>>>(s->view, d_rays, count, max_depth, d_out);
+		++g_launches;
+	});
+}
+
+int b200rt_host_alloc(void **ptr, size_t bytes)
+{
+	if(!ptr) return fail(B200RT_E_INVALID, "null argument");
+	*ptr = nullptr;
+	CUDA_TRY(cudaMallocHost(ptr, bytes ? bytes : 1));
+	return B200RT_OK;
+}
+
+int b200rt_host_free(void *ptr)
+{
+	if(!ptr) return B200RT_OK;
+	CUDA_TRY(cudaFreeHost(ptr));
+	return B200RT_OK;
+}
+
+} // extern "C"
+
+// ---- diagnostics: host builder only -----------------------------------------------------------
+struct b200rt_host_tree
+{
+	b200rt::HostTree tree;
+};
+
+namespace {
+b200rt::BuildConfig configFrom(const b200rt_build_params *params)
+{
+	b200rt::BuildConfig c;
+	if(params)
+	{
+		c.max_depth = params->max_depth;
+		c.max_leaf_size = params->max_leaf_size;
+		c.cost_ratio = params->cost_ratio;
+		c.empty_bonus = params->empty_bonus > 0.f ? params->empty_bonus : -1.f;
+		c.threads = params->build_threads;
+	}
+	return c;
+}
+} // namespace
+
+extern "C" {
+
+int b200rt_host_tree_build(const float *xyz, size_t n_verts, const uint32_t *idx, size_t n_faces, const b200rt_build_params *params, b200rt_host_tree **out)
+{
+	if(!out || (!xyz && n_verts) || (!idx && n_faces)) return fail(B200RT_E_INVALID, "null argument");
+	*out = nullptr;
+	for(size_t f = 0; f < n_faces; ++f)
+		for(int k = 0; k < 4; ++k)
+		{
+			const uint32_t v = idx[4 * f + k];
+			if(k == 3 && v == kTriangle) continue;
+			if(v >= n_verts) return fail(B200RT_E_INVALID, "face references a vertex >= n_verts");
+		}
+	try
+	{
+		auto t = std::make_unique<b200rt_host_tree>();
+		b200rt::buildKdTree(b200rt::MeshView{xyz, n_verts, idx, n_faces}, configFrom(params), t->tree);
+		*out = t.release();
+	}
+	catch(const std::exception &e) { return fail(B200RT_E_MEMORY, std::string("host build failed: ") + e.what()); }
+	return B200RT_OK;
+}
+
+int b200rt_host_tree_sizes(const b200rt_host_tree *t, size_t *n_nodes, size_t *n_refs)
+{
+	if(!t) return fail(B200RT_E_INVALID, "null argument");
+	if(n_nodes) *n_nodes = t->tree.nodes.size();
+	if(n_refs) *n_refs = t->tree.leaf_refs.size();
+	return B200RT_OK;
+}
+
+int b200rt_host_tree_export(const b200rt_host_tree *t, uint32_t *node_a, uint32_t *node_b, uint32_t *refs, float bound6[6])
+{
+	if(!t) return fail(B200RT_E_INVALID, "null argument");
+	for(size_t i = 0; i < t->tree.nodes.size(); ++i)
+	{
+		if(node_a) node_a[i] = t->tree.nodes[i].a;
+		if(node_b) node_b[i] = t->tree.nodes[i].b;
+	}
+	if(refs && !t->tree.leaf_refs.empty()) std::memcpy(refs, t->tree.leaf_refs.data(), t->tree.leaf_refs.size() * sizeof(uint32_t));
+	if(bound6) std::memcpy(bound6, t->tree.bound, 6 * sizeof(float));
+	return B200RT_OK;
+}
+
+void b200rt_host_tree_destroy(b200rt_host_tree *t) { delete t; }
+
+} // extern "C"

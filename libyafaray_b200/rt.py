@@ -1,0 +1,250 @@
+"""ctypes binding of libyafaray_b200/libb200rt.so (C ABI: include/b200rt.h).
+
+The shared library is the product; this module only marshals pointers.  There is no CPU fallback: if the
+library has not been built, or no CUDA device is usable, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200rt.so")
+MISS = 0xFFFFFFFF
+TSHADOW_MAX = 8
+
+RAY_DTYPE = np.dtype([("o", np.float32, 3), ("tmin", np.float32), ("d", np.float32, 3), ("tmax", np.float32)])
+HIT_DTYPE = np.dtype([("t", np.float32), ("u", np.float32), ("v", np.float32), ("prim", np.uint32)])
+TSHADOW_DTYPE = np.dtype([("shadowed", np.uint32), ("n_transparent", np.uint32), ("occluder", np.uint32), ("pad_", np.uint32),
+                          ("transparent", HIT_DTYPE, TSHADOW_MAX)])
+assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 16 and TSHADOW_DTYPE.itemsize == 144
+
+
+class BuildParams(C.Structure):
+    _fields_ = [("max_depth", C.c_int), ("max_leaf_size", C.c_int), ("cost_ratio", C.c_float), ("empty_bonus", C.c_float),
+                ("build_threads", C.c_int), ("reserved_", C.c_int * 3)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_faces", C.c_uint64), ("n_triangles", C.c_uint64), ("n_quads", C.c_uint64),
+                ("n_nodes", C.c_uint64), ("n_interior", C.c_uint64), ("n_leaves", C.c_uint64), ("n_empty_leaves", C.c_uint64),
+                ("n_leaf_refs", C.c_uint64), ("max_depth", C.c_uint32), ("max_leaf_prims", C.c_uint32),
+                ("build_seconds", C.c_double), ("upload_seconds", C.c_double), ("device_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class B200RTError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__(f"libb200rt error {code}: {text}")
+        self.code = code
+
+
+#: every symbol include/b200rt.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "b200rt_device_count", "b200rt_create", "b200rt_destroy", "b200rt_add_mesh", "b200rt_build", "b200rt_get_bound",
+    "b200rt_get_stats", "b200rt_update_face_flags", "b200rt_trace_closest", "b200rt_trace_shadow", "b200rt_trace_tshadow",
+    "b200rt_trace_closest_device", "b200rt_trace_shadow_device", "b200rt_trace_tshadow_device", "b200rt_host_alloc",
+    "b200rt_host_free", "b200rt_host_tree_build", "b200rt_host_tree_sizes", "b200rt_host_tree_export",
+    "b200rt_host_tree_destroy", "b200rt_launch_count", "b200rt_last_error", "b200rt_version",
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C libyafaray_b200/csrc); there is no fallback path")
+        L = C.CDLL(LIB_PATH)
+        P, Z = C.c_void_p, C.c_size_t
+        L.b200rt_device_count.argtypes = [P]
+        L.b200rt_create.argtypes = [C.c_int, P, P]
+        L.b200rt_destroy.argtypes = [P]
+        L.b200rt_destroy.restype = None
+        L.b200rt_add_mesh.argtypes = [P, P, Z, P, Z, P]
+        L.b200rt_build.argtypes = [P]
+        L.b200rt_get_bound.argtypes = [P, P]
+        L.b200rt_get_stats.argtypes = [P, P]
+        L.b200rt_update_face_flags.argtypes = [P, P, Z]
+        L.b200rt_trace_closest.argtypes = [P, P, Z, P]
+        L.b200rt_trace_shadow.argtypes = [P, P, Z, P]
+        L.b200rt_trace_tshadow.argtypes = [P, P, Z, C.c_int, P]
+        L.b200rt_trace_closest_device.argtypes = [P, P, Z, P, P]
+        L.b200rt_trace_shadow_device.argtypes = [P, P, Z, P, P]
+        L.b200rt_trace_tshadow_device.argtypes = [P, P, Z, C.c_int, P, P]
+        L.b200rt_host_alloc.argtypes = [P, Z]
+        L.b200rt_host_free.argtypes = [P]
+        L.b200rt_host_tree_build.argtypes = [P, Z, P, Z, P, P]
+        L.b200rt_host_tree_sizes.argtypes = [P, P, P]
+        L.b200rt_host_tree_export.argtypes = [P, P, P, P, P]
+        L.b200rt_host_tree_destroy.argtypes = [P]
+        L.b200rt_host_tree_destroy.restype = None
+        L.b200rt_launch_count.restype = C.c_uint64
+        L.b200rt_last_error.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise B200RTError(rc, lib().b200rt_last_error().decode(errors="replace"))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    rc = lib().b200rt_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def launch_count() -> int:
+    return int(lib().b200rt_launch_count())
+
+
+def make_params(depth=0, max_leaf_size=0, cost_ratio=0.0, empty_bonus=0.0, build_threads=0) -> BuildParams:
+    p = BuildParams()
+    p.max_depth, p.max_leaf_size, p.cost_ratio, p.empty_bonus, p.build_threads = int(depth), int(max_leaf_size), float(cost_ratio), float(empty_bonus), int(build_threads)
+    return p
+
+
+def as_rays(rays) -> np.ndarray:
+    """Accept float32 [n, 8] (ox oy oz tmin dx dy dz tmax) or a RAY_DTYPE array; return contiguous float32 [n, 8]."""
+    r = np.asarray(rays)
+    if r.dtype == RAY_DTYPE:
+        r = r.view(np.float32).reshape(-1, 8)
+    r = np.ascontiguousarray(r, dtype=np.float32)
+    if r.ndim != 2 or r.shape[1] != 8:
+        raise ValueError("rays must have shape [n, 8]")
+    return r
+
+
+class PinnedBuffer:
+    """Page-locked host memory from b200rt_host_alloc, viewed as a numpy array."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(np.atleast_1d(shape))
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._ptr = C.c_void_p(0)
+        _check(lib().b200rt_host_alloc(C.byref(self._ptr), nbytes))
+        buf = (C.c_char * max(1, nbytes)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self._ptr and self._ptr.value:
+            self.array = None
+            lib().b200rt_host_free(self._ptr)
+            self._ptr = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Scene:
+    """Owns one b200rt_scene: add meshes, build, trace."""
+
+    def __init__(self, device: int = 0, params: BuildParams | None = None):
+        self._h = C.c_void_p(0)
+        _check(lib().b200rt_create(int(device), C.byref(params) if params is not None else None, C.byref(self._h)))
+        self.device = device
+        self.n_faces = 0
+
+    def close(self):
+        if self._h and self._h.value:
+            lib().b200rt_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_mesh(self, xyz, idx, flags=None):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1, 4)
+        if flags is not None:
+            flags = np.ascontiguousarray(flags, dtype=np.uint8)
+            if flags.shape[0] != idx.shape[0]:
+                raise ValueError("one flag byte per face")
+        _check(lib().b200rt_add_mesh(self._h, _p(xyz), xyz.shape[0], _p(idx), idx.shape[0], _p(flags)))
+        self.n_faces += idx.shape[0]
+
+    def build(self):
+        _check(lib().b200rt_build(self._h))
+
+    def bound(self) -> np.ndarray:
+        b = np.zeros(6, np.float32)
+        _check(lib().b200rt_get_bound(self._h, _p(b)))
+        return b
+
+    def stats(self) -> dict:
+        s = Stats()
+        _check(lib().b200rt_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def update_face_flags(self, flags):
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        _check(lib().b200rt_update_face_flags(self._h, _p(flags), flags.shape[0]))
+
+    # ---- host-buffer queries (numpy in, numpy out) ----
+    def trace_closest(self, rays, out=None) -> np.ndarray:
+        r = as_rays(rays)
+        if out is None:
+            out = np.empty(r.shape[0], HIT_DTYPE)
+        _check(lib().b200rt_trace_closest(self._h, _p(r), r.shape[0], _p(out)))
+        return out
+
+    def trace_shadow(self, rays, out=None) -> np.ndarray:
+        r = as_rays(rays)
+        if out is None:
+            out = np.empty(r.shape[0], np.uint32)
+        _check(lib().b200rt_trace_shadow(self._h, _p(r), r.shape[0], _p(out)))
+        return out
+
+    def trace_tshadow(self, rays, max_depth, out=None) -> np.ndarray:
+        r = as_rays(rays)
+        if out is None:
+            out = np.empty(r.shape[0], TSHADOW_DTYPE)
+        _check(lib().b200rt_trace_tshadow(self._h, _p(r), r.shape[0], int(max_depth), _p(out)))
+        return out
+
+    # ---- device-buffer queries (raw device pointers, e.g. torch.Tensor.data_ptr()) ----
+    def trace_closest_device(self, d_rays: int, n: int, d_out: int, stream: int = 0):
+        _check(lib().b200rt_trace_closest_device(self._h, C.c_void_p(d_rays), n, C.c_void_p(d_out), C.c_void_p(stream)))
+
+    def trace_shadow_device(self, d_rays: int, n: int, d_out: int, stream: int = 0):
+        _check(lib().b200rt_trace_shadow_device(self._h, C.c_void_p(d_rays), n, C.c_void_p(d_out), C.c_void_p(stream)))
+
+    def trace_tshadow_device(self, d_rays: int, n: int, max_depth: int, d_out: int, stream: int = 0):
+        _check(lib().b200rt_trace_tshadow_device(self._h, C.c_void_p(d_rays), n, int(max_depth), C.c_void_p(d_out), C.c_void_p(stream)))
+
+
+def host_tree(xyz, idx, params: BuildParams | None = None) -> dict:
+    """Run only the host-side builder (no GPU needed) and return the tree in the export format of b200rt.h."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1, 4)
+    h = C.c_void_p(0)
+    L = lib()
+    _check(L.b200rt_host_tree_build(_p(xyz), xyz.shape[0], _p(idx), idx.shape[0], C.byref(params) if params is not None else None, C.byref(h)))
+    try:
+        nn, nr = C.c_size_t(0), C.c_size_t(0)
+        _check(L.b200rt_host_tree_sizes(h, C.byref(nn), C.byref(nr)))
+        a = np.zeros(nn.value, np.uint32); b = np.zeros(nn.value, np.uint32)
+        refs = np.zeros(max(1, nr.value), np.uint32); bound = np.zeros(6, np.float32)
+        _check(L.b200rt_host_tree_export(h, _p(a), _p(b), _p(refs), _p(bound)))
+    finally:
+        L.b200rt_host_tree_destroy(h)
+    return dict(a=a, b=b, refs=refs[: nr.value], bound=bound)

@@ -1,0 +1,83 @@
+"""Shared helpers of the test-suite (scene zoo, conversions)."""
+import numpy as np
+
+from libyafaray_b200 import scenes
+
+
+def flag_mix(n_faces, seed=1):
+    """Per-face flags exercising every visibility combination and the transparent bit."""
+    rng = np.random.RandomState(seed)
+    fl = np.full(n_faces, scenes.F_NORMAL, np.uint8)
+    r = rng.random_sample(n_faces)
+    fl[r < 0.1] = 0
+    fl[(r >= 0.1) & (r < 0.2)] = scenes.F_VISIBLE
+    fl[(r >= 0.2) & (r < 0.3)] = scenes.F_SHADOW
+    fl[(r >= 0.3) & (r < 0.5)] |= scenes.F_TRANSPARENT
+    return fl
+
+
+def scene_zoo(small=True):
+    """name -> (xyz, idx, flags): triangles, quads, mixed, random soup, axis-aligned boxes with coplanar faces."""
+    k = 1 if small else 4
+    zoo = {
+        "hf": scenes.heightfield(40 * k),
+        "hf_quads": scenes.heightfield(30 * k, quads=True),
+        "cubes": scenes.cube_scene(),
+        "soup": scenes.soup(3000 * k * k),
+        "objects": scenes.objects(6000 * k * k, n_spheres=12),
+    }
+    out = {}
+    for i, (name, (xyz, idx, fl)) in enumerate(zoo.items()):
+        out[name] = (xyz, idx, fl)
+        out[name + "_flags"] = (xyz, idx, flag_mix(idx.shape[0], seed=10 + i))
+    return out
+
+
+def ray_zoo(bound, n=20000, seed=3):
+    lo, hi = bound[:3].astype(np.float64), bound[3:].astype(np.float64)
+    ext = hi - lo
+    diag = float(np.linalg.norm(ext))
+    closest = np.concatenate([
+        scenes.rays_incoherent(n, seed=seed, lo=lo - 0.1 * ext, hi=hi + 0.1 * ext),
+        scenes.rays_incoherent(n // 4, seed=seed + 1, lo=lo, hi=hi, tmax=0.3 * diag, tmin=0.01 * diag),
+        scenes.rays_edge_cases(lo, hi, seed=seed + 2),
+    ])
+    shadow = np.concatenate([
+        scenes.rays_shadow(n, seed=seed + 3, lo=lo, hi=hi, t_max=0.25 * diag),
+        scenes.rays_incoherent(n // 4, seed=seed + 4, lo=lo, hi=hi, tmax=-1.0, tmin=0.0005),
+        scenes.rays_edge_cases(lo, hi, seed=seed + 5),
+    ])
+    return closest, shadow
+
+
+def host_tree_as_oracle_tree(t):
+    """libb200rt's exported host tree (include/b200rt.h) -> the oracle's kdo_tree arrays."""
+    a, b = t["a"], t["b"]
+    leaf = (b & 3) == 3
+    split = np.where(leaf, 0, a).astype(np.uint32).view(np.float32)
+    first = np.where(leaf, a, 0).astype(np.uint32)
+    refs = t["refs"] if len(t["refs"]) else np.zeros(1, np.uint32)
+    return dict(split=split, flags=b.astype(np.uint32), first_ref=first, refs=refs.astype(np.uint32))
+
+
+def prim_signed(prim_u32):
+    p = prim_u32.astype(np.int64)
+    p[p == 0xFFFFFFFF] = -1
+    return p
+
+
+def check_closest_parity(got_prim, got_t, got_u, got_v, ref, min_agree=0.9999, rtol=1e-5):
+    """North-star bar: same face id on >= 99.99 % of rays, t within 1e-5 relative; where ids agree the
+    arithmetic is the reference's, so t/u/v must be BIT-identical; where they differ it must be a tie."""
+    same = got_prim == ref["prim"]
+    agree = float(np.mean(same)) if len(same) else 1.0
+    assert agree >= min_agree, f"id agreement {agree:.6f} < {min_agree}"
+    assert np.array_equal(got_t[same], ref["t"][same]), "t differs bitwise on rays with equal ids"
+    assert np.array_equal(got_u[same], ref["u"][same]) and np.array_equal(got_v[same], ref["v"][same]), "uv differs bitwise"
+    diff = ~same
+    if diff.any():
+        # a documented tie: both sides hit, and the two t agree to 1e-5 relative
+        assert np.all(got_prim[diff] >= 0) and np.all(ref["prim"][diff] >= 0), "hit/miss disagreement"
+        rel = np.abs(got_t[diff] - ref["t"][diff]) / np.maximum(np.abs(ref["t"][diff]), 1e-30)
+        assert np.all(rel <= rtol), f"non-tie id mismatch, max rel t diff {rel.max()}"
+    return agree

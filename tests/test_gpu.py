@@ -1,0 +1,265 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of libb200rt.so
+and is checked against (a) the golden vectors generated from the unmodified reference, (b) the oracle's C
+restatement on the same seeded inputs, (c) the live reference when oracle/_ref travelled with the repo, and
+(d) size-independent properties at the full BASELINE.json size (1 M triangles, 16 M rays)."""
+import glob
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from libyafaray_b200 import rt, scenes
+from oracle import kdo, yref
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+NCPU = os.cpu_count() or 1
+
+
+def make_scene(xyz, idx, flags=None, params=None):
+    s = rt.Scene(0, params)
+    s.add_mesh(xyz, idx, flags)
+    s.build()
+    return s
+
+
+def tie_floor(name):
+    return 0.98 if "cubes" in name else 0.9999  # coplanar cube/floor faces are genuine exact-t ties
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_vectors(built, path):
+    g = np.load(path)
+    s = make_scene(g["xyz"], g["idx"], g["flags"])
+    assert np.array_equal(s.bound(), g["bound"])
+    h = s.trace_closest(g["closest_rays"])
+    ref = dict(prim=g["closest_prim"], t=g["closest_t"], u=g["closest_u"], v=g["closest_v"])
+    helpers.check_closest_parity(helpers.prim_signed(h["prim"]), h["t"], h["u"], h["v"], ref, min_agree=tie_floor(path))
+    sh = s.trace_shadow(g["shadow_rays"])
+    assert np.array_equal((sh != rt.MISS).astype(np.uint8), g["shadow_shadowed"])
+    depth = int(g["tshadow_depth"])
+    ts = s.trace_tshadow(g["shadow_rays"], depth)
+    assert np.array_equal(ts["shadowed"].astype(np.uint8), g["tshadow_shadowed"])
+    lit = g["tshadow_shadowed"] == 0
+    assert np.allclose(g["tshadow_rgb"][lit, 0], np.power(0.4, ts["n_transparent"][lit].astype(np.float64)), rtol=1e-5)
+    assert np.all(ts["occluder"][lit] == rt.MISS)
+    s.close()
+
+
+ZOO = helpers.scene_zoo(small=False)
+
+
+@pytest.mark.parametrize("name", sorted(ZOO))
+def test_zoo_against_oracle(built, name):
+    xyz, idx, flags = ZOO[name]
+    s = make_scene(xyz, idx, flags)
+    o = kdo.Oracle(xyz, idx, flags)
+    assert np.array_equal(s.bound(), o.bound())
+    closest, shadow = helpers.ray_zoo(s.bound(), n=200000, seed=11)
+    h = s.trace_closest(closest)
+    ref = o.trace_closest(closest, threads=NCPU)
+    helpers.check_closest_parity(helpers.prim_signed(h["prim"]), h["t"], h["u"], h["v"], ref, min_agree=tie_floor(name))
+    sh = s.trace_shadow(shadow)
+    rs = o.trace_shadow(shadow, threads=NCPU)
+    assert np.array_equal((sh != rt.MISS).astype(np.uint8), rs["shadowed"])
+    # the occluder is any-hit: it may differ from the oracle's, but it must be a real shadow caster
+    occ = sh[sh != rt.MISS]
+    assert np.all(occ < idx.shape[0]) and np.all(flags[occ] & scenes.F_SHADOW)
+    for depth in (0, 2, 8):
+        ts = s.trace_tshadow(shadow, depth)
+        rts = o.trace_tshadow(shadow, depth, threads=NCPU, max_list=8)
+        assert np.array_equal(ts["shadowed"].astype(np.uint8), rts["shadowed"]), depth
+        lit = rts["shadowed"] == 0
+        assert np.array_equal(ts["n_transparent"][lit].astype(np.int32), rts["n_transparent"][lit]), depth
+        # same SET of distinct transparent casters (order follows the traversal, which is ours)
+        got = np.sort(helpers.prim_signed(ts["transparent"]["prim"][lit]), axis=1)
+        exp = np.sort(rts["list"][lit].astype(np.int64), axis=1)
+        assert np.array_equal(got, exp), depth
+    s.close()
+
+
+@pytest.mark.skipif(not yref.available(), reason="oracle/_ref/libyafref.so did not travel")
+@pytest.mark.parametrize("name", ["hf_flags", "objects_flags", "soup", "hf_quads"])
+def test_zoo_against_live_reference(built, name):
+    xyz, idx, flags = ZOO[name]
+    s = make_scene(xyz, idx, flags)
+    ref = yref.RefScene(xyz, idx, flags)
+    assert np.array_equal(s.bound(), ref.bound())
+    closest, shadow = helpers.ray_zoo(s.bound(), n=200000, seed=13)
+    h = s.trace_closest(closest)
+    r = ref.trace_closest(closest, threads=NCPU)
+    helpers.check_closest_parity(helpers.prim_signed(h["prim"]), h["t"], h["u"], h["v"], r)
+    sh = s.trace_shadow(shadow)
+    assert np.array_equal((sh != rt.MISS).astype(np.uint8), ref.trace_shadow(shadow, threads=NCPU)["shadowed"])
+    ts = s.trace_tshadow(shadow, 3)
+    assert np.array_equal(ts["shadowed"].astype(np.uint8), ref.trace_tshadow(shadow, 3, threads=NCPU)["shadowed"])
+    ref.close(); s.close()
+
+
+@pytest.fixture(scope="module")
+def big():
+    xyz, idx, flags = scenes.heightfield(707)  # S1M-hf: 999 698 triangles (BASELINE.json configs[1])
+    s = make_scene(xyz, idx, flags)
+    yield s, xyz, idx, flags
+    s.close()
+
+
+def test_full_size_sample_against_oracle(built, big):
+    s, xyz, idx, flags = big
+    assert s.stats()["n_faces"] == 999698
+    o = kdo.Oracle(xyz, idx, flags)
+    rays = scenes.rays_incoherent(400000, seed=99)
+    h = s.trace_closest(rays)
+    ref = o.trace_closest(rays, threads=NCPU)
+    helpers.check_closest_parity(helpers.prim_signed(h["prim"]), h["t"], h["u"], h["v"], ref)
+    srays = scenes.rays_shadow(400000, seed=98)
+    sh = s.trace_shadow(srays)
+    assert np.array_equal((sh != rt.MISS).astype(np.uint8), o.trace_shadow(srays, threads=NCPU)["shadowed"])
+
+
+def test_full_size_properties(built, big):
+    """16 M incoherent rays on 1 M triangles: determinism, shard invariance, closest/shadow consistency."""
+    s, xyz, idx, flags = big
+    n = 1 << 24
+    rays = scenes.rays_incoherent(n, seed=12345)
+    h = s.trace_closest(rays)
+    prim = helpers.prim_signed(h["prim"])
+    hit = prim >= 0
+    assert 0.25 < hit.mean() < 0.45
+    assert np.all(h["t"][~hit] == 0) and np.all(h["t"][hit] > 0)
+    # every hit point lies inside the tree bound
+    b = s.bound().astype(np.float64)
+    p = rays[hit, 0:3].astype(np.float64) + h["t"][hit, None].astype(np.float64) * rays[hit, 4:7].astype(np.float64)
+    assert np.all(p >= b[:3] - 1e-4) and np.all(p <= b[3:] + 1e-4)
+    # determinism: a second pass is byte-identical
+    h2 = s.trace_closest(rays)
+    assert h.tobytes() == h2.tobytes()
+    # shard invariance: ragged shards traced separately give the same bytes as the whole batch
+    cuts = [0, 1, 777, 5_000_001, n // 2 + 3, n]
+    parts = [s.trace_closest(rays[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert np.concatenate(parts).tobytes() == h.tobytes()
+    # closest/shadow consistency (all faces are visible shadow casters here, tmin = 0):
+    # shadowed within T  <=>  the closest hit is nearer than T
+    T = 0.25
+    srays = rays.copy()
+    srays[:, 7] = T
+    sh = s.trace_shadow(srays) != rt.MISS
+    assert np.array_equal(sh, hit & (h["t"] < T))
+
+
+def test_host_and_device_entry_points_agree(built, big):
+    import torch
+    s = big[0]
+    rays = scenes.rays_incoherent(1 << 20, seed=4)
+    h = s.trace_closest(rays)
+    d_rays = torch.from_numpy(rays).cuda()
+    d_out = torch.empty((rays.shape[0], 4), dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    s.trace_closest_device(d_rays.data_ptr(), rays.shape[0], d_out.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert d_out.cpu().numpy().tobytes() == h.tobytes()
+    srays = scenes.rays_shadow(1 << 20, seed=5)
+    sh = s.trace_shadow(srays)
+    d_s = torch.from_numpy(srays).cuda()
+    d_o = torch.empty(srays.shape[0], dtype=torch.int32, device="cuda")
+    s.trace_shadow_device(d_s.data_ptr(), srays.shape[0], d_o.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert d_o.cpu().numpy().view(np.uint32).tobytes() == sh.tobytes()
+    # pinned host buffers take the direct-copy path and must give the same bytes
+    pin_in = rt.PinnedBuffer((rays.shape[0], 8), np.float32)
+    pin_out = rt.PinnedBuffer((rays.shape[0],), rt.HIT_DTYPE)
+    pin_in.array[:] = rays
+    s.trace_closest(pin_in.array, out=pin_out.array)
+    assert pin_out.array.tobytes() == h.tobytes()
+    pin_in.free(); pin_out.free()
+
+
+def test_concurrent_host_threads(built, big):
+    """Render workers call the accelerator concurrently (integrator_tiled.cc:232-248)."""
+    s = big[0]
+    batches = [scenes.rays_incoherent(300000 + 1000 * k, seed=50 + k) for k in range(6)]
+    expect = [s.trace_closest(b) for b in batches]
+    got = [None] * len(batches)
+    errors = []
+
+    def work(k):
+        try:
+            for _ in range(3):
+                got[k] = s.trace_closest(batches[k])
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(len(batches))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors
+    for a, b in zip(expect, got):
+        assert a.tobytes() == b.tobytes()
+
+
+def test_single_ray_calls(built):
+    """The per-ray compatibility path: batches of one."""
+    xyz, idx, flags = scenes.cube_scene()
+    s = make_scene(xyz, idx, flags)
+    o = kdo.Oracle(xyz, idx, flags)
+    rays = scenes.rays_camera(16, 9, eye=(8, -9, 6), look=(0, 0, 0.5))
+    ref = o.brute_closest(rays)
+    for i in range(rays.shape[0]):
+        h = s.trace_closest(rays[i:i + 1])
+        assert h["t"][0] == ref["t"][i] or abs(h["t"][0] - ref["t"][i]) <= 1e-5 * abs(ref["t"][i])
+    assert s.trace_closest(rays[:0]).shape == (0,)
+    s.close()
+
+
+def test_update_face_flags_and_multi_mesh(built):
+    xyz, idx, flags = scenes.objects(20000, n_spheres=8)
+    new_flags = helpers.flag_mix(idx.shape[0], seed=5)
+    a = make_scene(xyz, idx, flags)
+    a.update_face_flags(new_flags)
+    b = make_scene(xyz, idx, new_flags)
+    closest, shadow = helpers.ray_zoo(a.bound(), n=100000, seed=8)
+    assert a.trace_closest(closest).tobytes() == b.trace_closest(closest).tobytes()
+    assert np.array_equal(a.trace_shadow(shadow) != rt.MISS, b.trace_shadow(shadow) != rt.MISS)
+    # two uploads == one upload of the concatenation; face ids continue across meshes
+    half = idx.shape[0] // 2
+    c = rt.Scene(0)
+    c.add_mesh(xyz, idx[:half], new_flags[:half])
+    c.add_mesh(xyz, idx[half:], new_flags[half:])
+    c.build()
+    assert c.trace_closest(closest).tobytes() == b.trace_closest(closest).tobytes()
+    a.close(); b.close(); c.close()
+
+
+def test_empty_scene_and_errors(built):
+    s = rt.Scene(0)
+    with pytest.raises(rt.B200RTError):
+        s.trace_closest(scenes.rays_incoherent(10))  # not built yet
+    s.build()  # empty scene: zero bound, every ray misses (accelerator_kdtree_original.cc:96)
+    assert np.array_equal(s.bound(), np.zeros(6, np.float32))
+    h = s.trace_closest(scenes.rays_incoherent(1000))
+    assert np.all(h["prim"] == rt.MISS) and np.all(h["t"] == 0)
+    assert np.all(s.trace_shadow(scenes.rays_shadow(1000)) == rt.MISS)
+    with pytest.raises(rt.B200RTError):
+        s.trace_tshadow(scenes.rays_shadow(10), rt.TSHADOW_MAX + 1)
+    with pytest.raises(rt.B200RTError):
+        rt.Scene(99)
+    s.close()
+
+
+def test_build_parameters_do_not_change_hits(built):
+    """Different trees, same answers (up to ties): the SURVEY 8a argument, checked on the GPU path."""
+    xyz, idx, flags = scenes.objects(60000, n_spheres=16)
+    rays = scenes.rays_incoherent(300000, seed=21)
+    base = None
+    for p in (None, rt.make_params(max_leaf_size=1), rt.make_params(max_leaf_size=8, cost_ratio=2.5, empty_bonus=0.1), rt.make_params(depth=12)):
+        s = make_scene(xyz, idx, flags, p)
+        h = s.trace_closest(rays)
+        if base is None:
+            base = h
+        else:
+            ref = dict(prim=helpers.prim_signed(base["prim"]), t=base["t"], u=base["u"], v=base["v"])
+            helpers.check_closest_parity(helpers.prim_signed(h["prim"]), h["t"], h["u"], h["v"], ref)
+        s.close()
