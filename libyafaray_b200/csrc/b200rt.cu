@@ -79,6 +79,10 @@ struct b200rt_scene
 	size_t n_tri_vec4 = 0;
 	b200rt::SceneView view{};
 	b200rt_stats stats{};
+	// persistent-kernel launch state
+	uint32_t *d_cursors = nullptr;          // ring of ray cursors, one per launch in flight
+	std::atomic<uint32_t> next_cursor{0};
+	int resident_blocks[3] = {0, 0, 0};     // blocks of traceKernel<Q> that fit the whole device
 	std::mutex lane_mutex;
 	std::vector<std::unique_ptr<Lane>> free_lanes;
 
@@ -88,6 +92,7 @@ struct b200rt_scene
 		free_lanes.clear();
 		if(d_nodes) cudaFree(d_nodes);
 		if(d_tris) cudaFree(d_tris);
+		if(d_cursors) cudaFree(d_cursors);
 	}
 };
 
@@ -180,8 +185,8 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, La
 		cudaError_t e = cudaMemcpyAsync(l.d_in, src, count * sizeof(b200rt_ray), cudaMemcpyHostToDevice, l.stream);
 		if(e == cudaSuccess)
 		{
-			launch(static_cast<const b200rt_ray *>(l.d_in), count, static_cast<Out *>(l.d_out), l.stream);
-			e = cudaGetLastError();
+			rc = launch(static_cast<const b200rt_ray *>(l.d_in), count, static_cast<Out *>(l.d_out), l.stream);
+			if(rc != B200RT_OK) break;
 		}
 		if(e == cudaSuccess) e = cudaMemcpyAsync(out_pinned ? static_cast<void *>(out + begin) : l.h_out, l.d_out, count * sizeof(Out), cudaMemcpyDeviceToHost, l.stream);
 		if(e == cudaSuccess) e = cudaEventRecord(l.done, l.stream);
@@ -200,13 +205,42 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, La
 	return rc;
 }
 
-inline unsigned gridFor(size_t n) { return unsigned((n + b200rt::kBlock - 1) / b200rt::kBlock); }
+constexpr uint32_t kCursorRing = 4096;
+constexpr size_t kMaxRaysPerLaunch = size_t(1) << 30;
 
 int checkDeviceCall(const b200rt_scene *s, const void *rays, size_t n, const void *out)
 {
 	if(!s || (!rays && n) || (!out && n)) return fail(B200RT_E_INVALID, "null argument");
 	if(!s->built) return fail(B200RT_E_INVALID, "scene not built: call b200rt_build first");
-	if(n > (size_t(1) << 31) * b200rt::kBlock) return fail(B200RT_E_INVALID, "batch too large for one launch");
+	return B200RT_OK;
+}
+
+// Enqueue traceKernel<Q> over n rays on `stream`: a persistent grid (at most one resident wave) whose warps
+// pull rays from a cursor that is zeroed on the same stream just before the launch.
+template <int Q>
+int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b200rt::OutType<Q>::type *d_out, cudaStream_t stream, int max_depth)
+{
+	for(size_t begin = 0; begin < n; begin += kMaxRaysPerLaunch)
+	{
+		const uint32_t count = uint32_t(std::min(kMaxRaysPerLaunch, n - begin));
+		uint32_t *cursor = s->d_cursors + (s->next_cursor.fetch_add(1) % kCursorRing);
+		CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), stream));
+		const unsigned wanted = unsigned((size_t(count) + b200rt::kBlock - 1) / b200rt::kBlock);
+		const unsigned grid = std::max(1u, std::min(wanted, unsigned(s->resident_blocks[Q])));
+		b200rt::traceKernel<Q><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, cursor, max_depth);
+		++g_launches;
+		CUDA_TRY(cudaGetLastError());
+	}
+	return B200RT_OK;
+}
+
+template <int Q>
+int queryResidency(b200rt_scene *s)
+{
+	int per_sm = 0, sms = 0;
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b200rt::traceKernel<Q>, b200rt::kBlock, 0));
+	CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+	s->resident_blocks[Q] = std::max(1, per_sm) * std::max(1, sms);
 	return B200RT_OK;
 }
 
@@ -364,6 +398,14 @@ int b200rt_build(b200rt_scene *s)
 	CUDA_TRY(cudaMalloc(&s->d_tris, tris.size() * sizeof(float4)));
 	CUDA_TRY(cudaMemcpy(s->d_nodes, nodes.data(), nodes.size() * sizeof(uint2), cudaMemcpyHostToDevice));
 	CUDA_TRY(cudaMemcpy(s->d_tris, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
+	if(!s->d_cursors)
+	{
+		CUDA_TRY(cudaMalloc(&s->d_cursors, kCursorRing * sizeof(uint32_t)));
+		int rc = queryResidency<b200rt::kClosest>(s);
+		if(rc == B200RT_OK) rc = queryResidency<b200rt::kShadow>(s);
+		if(rc == B200RT_OK) rc = queryResidency<b200rt::kTShadow>(s);
+		if(rc != B200RT_OK) return rc;
+	}
 	s->n_tri_vec4 = tris.size();
 	s->view.nodes = s->d_nodes;
 	s->view.tris = s->d_tris;
@@ -417,10 +459,7 @@ int b200rt_trace_closest_device(b200rt_scene *s, const b200rt_ray *d_rays, size_
 	const int rc = checkDeviceCall(s, d_rays, n, d_out);
 	if(rc != B200RT_OK || n == 0) return rc;
 	CUDA_TRY(cudaSetDevice(s->device));
-	b200rt::traceClosestKernel<<<gridFor(n), b200rt::kBlock, 0, static_cast<cudaStream_t>(stream)>>>(s->view, d_rays, n, d_out);
-	++g_launches;
-	CUDA_TRY(cudaGetLastError());
-	return B200RT_OK;
+	return launchTrace<b200rt::kClosest>(s, d_rays, n, d_out, static_cast<cudaStream_t>(stream), 0);
 }
 
 int b200rt_trace_shadow_device(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, uint32_t *d_out, void *stream)
@@ -428,10 +467,7 @@ int b200rt_trace_shadow_device(b200rt_scene *s, const b200rt_ray *d_rays, size_t
 	const int rc = checkDeviceCall(s, d_rays, n, d_out);
 	if(rc != B200RT_OK || n == 0) return rc;
 	CUDA_TRY(cudaSetDevice(s->device));
-	b200rt::traceShadowKernel<<<gridFor(n), b200rt::kBlock, 0, static_cast<cudaStream_t>(stream)>>>(s->view, d_rays, n, d_out);
-	++g_launches;
-	CUDA_TRY(cudaGetLastError());
-	return B200RT_OK;
+	return launchTrace<b200rt::kShadow>(s, d_rays, n, d_out, static_cast<cudaStream_t>(stream), 0);
 }
 
 int b200rt_trace_tshadow_device(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, int max_depth, b200rt_tshadow *d_out, void *stream)
@@ -441,26 +477,21 @@ int b200rt_trace_tshadow_device(b200rt_scene *s, const b200rt_ray *d_rays, size_
 	if(max_depth < 0 || max_depth > B200RT_TSHADOW_MAX) return fail(B200RT_E_INVALID, "max_depth must be in [0, B200RT_TSHADOW_MAX]");
 	if(n == 0) return B200RT_OK;
 	CUDA_TRY(cudaSetDevice(s->device));
-	b200rt::traceTShadowKernel<<<gridFor(n), b200rt::kBlock, 0, static_cast<cudaStream_t>(stream)>>>(s->view, d_rays, n, max_depth, d_out);
-	++g_launches;
-	CUDA_TRY(cudaGetLastError());
-	return B200RT_OK;
+	return launchTrace<b200rt::kTShadow>(s, d_rays, n, d_out, static_cast<cudaStream_t>(stream), max_depth);
 }
 
 // ---- host-buffer queries ----------------------------------------------------------------------
 int b200rt_trace_closest(b200rt_scene *s, const b200rt_ray *rays, size_t n, b200rt_hit *out)
 {
 	return tracedStaged(s, rays, n, out, [&](const b200rt_ray *d_rays, size_t count, b200rt_hit *d_out, cudaStream_t st) {
-		b200rt::traceClosestKernel<<<gridFor(count), b200rt::kBlock, 0, st>>>(s->view, d_rays, count, d_out);
-		++g_launches;
+		return launchTrace<b200rt::kClosest>(s, d_rays, count, d_out, st, 0);
 	});
 }
 
 int b200rt_trace_shadow(b200rt_scene *s, const b200rt_ray *rays, size_t n, uint32_t *out)
 {
 	return tracedStaged(s, rays, n, out, [&](const b200rt_ray *d_rays, size_t count, uint32_t *d_out, cudaStream_t st) {
-		b200rt::traceShadowKernel<<<gridFor(count), b200rt::kBlock, 0, st>>>(s->view, d_rays, count, d_out);
-		++g_launches;
+		return launchTrace<b200rt::kShadow>(s, d_rays, count, d_out, st, 0);
 	});
 }
 
@@ -468,8 +499,7 @@ int b200rt_trace_tshadow(b200rt_scene *s, const b200rt_ray *rays, size_t n, int 
 {
 	if(max_depth < 0 || max_depth > B200RT_TSHADOW_MAX) return fail(B200RT_E_INVALID, "max_depth must be in [0, B200RT_TSHADOW_MAX]");
 	return tracedStaged(s, rays, n, out, [&](const b200rt_ray *d_rays, size_t count, b200rt_tshadow *d_out, cudaStream_t st) {
-		b200rt::traceTShadowKernel<<<gridFor(count), b200rt::kBlock, 0, st>>>(s->view, d_rays, count, max_depth, d_out);
-		++g_launches;
+		return launchTrace<b200rt::kTShadow>(s, d_rays, count, d_out, st, max_depth);
 	});
 }
 

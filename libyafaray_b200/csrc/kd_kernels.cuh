@@ -145,172 +145,300 @@ __device__ __forceinline__ float polyIntersect(const float4 q0, const float4 q1,
 	return 0.f;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Persistent-warp traversal ("while-while" with ray replacement).
+//
+// A warp owns 32 ray slots.  Whenever at least kRefill slots are idle, the idle lanes take the next rays of
+// the warp's pool (the pool is refilled kPoolRays at a time with one atomicAdd on a global cursor), so a warp's
+// lifetime is no longer the maximum over its 32 first rays: measured with the one-thread-per-ray kernel, only
+// 3.3 of 32 lanes were active per issued instruction (profiles/r1a_*), here they are kept busy.
+// Every lane then alternates between
+//   (1) descending the tree -- interior nodes AND empty leaves (two thirds of all leaves) are consumed here,
+//   (2) testing the primitives of one non-empty leaf,
+// and the two phases are warp-converged: the control flow below has one exit per loop (flags, no return
+// from inside), so that the compiler's reconvergence points sit right after each phase.
+//
+// The traversal is t-interval based: [seg_lo, seg_hi] is the ray parameter range inside the current node.
+//   t_plane >= min(seg_hi, closest so far)  -> near child only
+//   t_plane <= seg_lo                       -> far child only
+//   otherwise near first, far child pushed with the current seg_hi
+// "near" is decided by the sign of the direction component (of its inverse, so that a zero component, whose
+// inverse is +FLT_MAX as in math::inverse, math.h:71-77, behaves as "positive").
+// -------------------------------------------------------------------------------------------------
+static constexpr int kBlock = 128;
+static constexpr int kPoolRays = 256;  // rays taken from the global cursor per atomicAdd
+static constexpr int kRefill = 8;      // idle lanes that trigger a refill
+static constexpr unsigned kFullMask = 0xFFFFFFFFu;
+
+struct RayState
+{
+	float ox, oy, oz, dx, dy, dz; // the ray the tree sees
+	float ix, iy, iz;             // traversal inverse direction
+	float t_min;                  // ray bias
+	float t_max;                  // closest: shrinking; shadow: fixed
+	float seg_lo, seg_hi;
+	float best_u, best_v;
+	uint32_t best_prim;
+	uint32_t node;
+	uint32_t index;               // ray index in the batch
+	uint32_t neg;                 // bit k set: direction component k is negative
+	int sp;
+};
+
+// Ray setup: root slab test (bound.h:156-198), bias (accelerator.h:64), traversal interval.  Returns false when
+// the ray misses the tree bound.
+template <int QUERY>
+__device__ __forceinline__ bool setupRay(const SceneView &s, const float4 a, const float4 b, RayState &r)
+{
+	float t_max;
+	if(QUERY == kClosest)
+	{
+		r.ox = a.x; r.oy = a.y; r.oz = a.z;
+		t_max = (b.w >= 0.f) ? b.w : FLT_MAX; // accelerator.h:91
+	}
+	else
+	{
+		// accelerator.h:103-111: origin moved by dir * tmin, t_max = tmax - 2 tmin (unbounded if tmax < 0)
+		r.ox = __fadd_rn(a.x, __fmul_rn(b.x, a.w));
+		r.oy = __fadd_rn(a.y, __fmul_rn(b.y, a.w));
+		r.oz = __fadd_rn(a.z, __fmul_rn(b.z, a.w));
+		t_max = (b.w >= 0.f) ? __fsub_rn(b.w, __fmul_rn(2.f, a.w)) : FLT_MAX;
+	}
+	r.dx = b.x; r.dy = b.y; r.dz = b.z;
+	// math::inverse (math.h:71-77); the same quotient is what Bound::cross computes for a non-zero component
+	const float ix = (r.dx == 0.f) ? FLT_MAX : __fdiv_rn(1.f, r.dx);
+	const float iy = (r.dy == 0.f) ? FLT_MAX : __fdiv_rn(1.f, r.dy);
+	const float iz = (r.dz == 0.f) ? FLT_MAX : __fdiv_rn(1.f, r.dz);
+	float lmin = -FLT_MAX, lmax = FLT_MAX;
+	bool crossed = true;
+	const float o[3] = {r.ox, r.oy, r.oz}, d[3] = {r.dx, r.dy, r.dz}, inv[3] = {ix, iy, iz};
+#pragma unroll
+	for(int axis = 0; axis < 3; ++axis)
+	{
+		if(d[axis] != 0.f && crossed)
+		{
+			const float p = __fsub_rn(o[axis], s.bound[axis]);
+			const float near_t = __fmul_rn(-p, inv[axis]);
+			const float far_t = __fmul_rn(__fsub_rn(__fsub_rn(s.bound[3 + axis], s.bound[axis]), p), inv[axis]);
+			const float ltmin = (inv[axis] > 0.f) ? near_t : far_t;
+			const float ltmax = (inv[axis] > 0.f) ? far_t : near_t;
+			if(axis == 0) { lmin = ltmin; lmax = ltmax; }
+			else
+			{
+				lmin = (ltmin < lmin) ? lmin : ltmin; // std::max(ltmin, lmin)
+				lmax = (lmax < ltmax) ? lmax : ltmax; // std::min(ltmax, lmax)
+			}
+			if((lmax < 0.f) || (lmin > t_max)) crossed = false;
+		}
+	}
+	crossed = crossed && (lmin <= lmax) && (lmax >= 0.f) && (lmin <= t_max);
+	const float bias = __fmul_rn(__fmul_rn(0.1f, 0.00005f), fabsf(__fsub_rn(lmax, lmin)));
+	r.t_min = (QUERY == kShadow) ? bias : ((a.w < bias) ? bias : a.w); // accelerator_kdtree_common.h:139
+	r.t_max = t_max;
+	// traversal-only quantities (not part of the reference arithmetic)
+	r.ix = isinf(ix) ? copysignf(FLT_MAX, ix) : ix;
+	r.iy = isinf(iy) ? copysignf(FLT_MAX, iy) : iy;
+	r.iz = isinf(iz) ? copysignf(FLT_MAX, iz) : iz;
+	r.neg = (r.ix < 0.f ? 1u : 0u) | (r.iy < 0.f ? 2u : 0u) | (r.iz < 0.f ? 4u : 0u);
+	r.seg_lo = fmaxf(lmin, 0.f);
+	r.seg_hi = fminf(lmax, t_max);
+	r.best_u = 0.f; r.best_v = 0.f; r.best_prim = B200RT_MISS;
+	r.node = 0u;
+	r.sp = 0;
+	return crossed;
+}
+
 struct TShadowState
 {
-	int depth, max_depth;
+	int depth;
 	b200rt_hit list[B200RT_TSHADOW_MAX];
 };
 
-// One ray through the tree.  (ox..dz) is the ray the TREE sees (shadow wrappers have already moved the
-// origin); ray_tmin is Ray::tmin_.  Closest: returns hit in best_*.  Shadow/TShadow: returns true when
-// "shadowed" with the occluder in best_prim.
-template <int QUERY>
-__device__ __forceinline__ bool traverse(const SceneView &s, float ox, float oy, float oz, float dx, float dy, float dz,
-                                         float ray_tmin, const float t_max,
-                                         float &best_t, float &best_u, float &best_v, uint32_t &best_prim, TShadowState *ts)
-{
-	best_t = 0.f;
-	best_u = 0.f;
-	best_v = 0.f;
-	best_prim = B200RT_MISS;
-	float enter, leave;
-	if(!boundCross(s.bound, ox, oy, oz, dx, dy, dz, t_max, enter, leave)) return false;
-	// math::inverse (math.h:71-77): FLT_MAX for a zero component, so that no NaN can appear below
-	const float ix = (dx == 0.f) ? FLT_MAX : __fdiv_rn(1.f, dx);
-	const float iy = (dy == 0.f) ? FLT_MAX : __fdiv_rn(1.f, dy);
-	const float iz = (dz == 0.f) ? FLT_MAX : __fdiv_rn(1.f, dz);
-	const float bias = __fmul_rn(__fmul_rn(0.1f, 0.00005f), fabsf(__fsub_rn(leave, enter)));
-	const float t_min = (QUERY == kShadow) ? bias : ((ray_tmin < bias) ? bias : ray_tmin);
-	float cur_t_max = t_max; // closest: shrinks with every accepted hit
+template <int QUERY> struct OutType;
+template <> struct OutType<kClosest> { using type = b200rt_hit; };
+template <> struct OutType<kShadow> { using type = uint32_t; };
+template <> struct OutType<kTShadow> { using type = b200rt_tshadow; };
 
+template <int QUERY>
+__device__ __forceinline__ void writeResult(typename OutType<QUERY>::type *out, const RayState &r, bool hit, const TShadowState &ts)
+{
+	if(QUERY == kClosest)
+	{
+		float4 v;
+		v.x = hit ? r.t_max : 0.f; v.y = r.best_u; v.z = r.best_v; v.w = __uint_as_float(r.best_prim);
+		reinterpret_cast<float4 *>(out)[r.index] = v;
+	}
+	else if(QUERY == kShadow) reinterpret_cast<uint32_t *>(out)[r.index] = hit ? r.best_prim : B200RT_MISS;
+	else
+	{
+		uint4 *o = reinterpret_cast<uint4 *>(reinterpret_cast<b200rt_tshadow *>(out) + r.index);
+		o[0] = make_uint4(hit ? 1u : 0u, uint32_t(ts.depth), hit ? r.best_prim : B200RT_MISS, 0u); // setNoHit() clears primitive_
+#pragma unroll
+		for(int k = 0; k < B200RT_TSHADOW_MAX; ++k)
+		{
+			uint4 e = make_uint4(0u, 0u, 0u, B200RT_MISS);
+			if(k < ts.depth) e = make_uint4(__float_as_uint(ts.list[k].t), __float_as_uint(ts.list[k].u), __float_as_uint(ts.list[k].v), ts.list[k].prim);
+			o[1 + k] = e;
+		}
+	}
+}
+
+template <int QUERY>
+__global__ void __launch_bounds__(kBlock) traceKernel(SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
+                                                     typename OutType<QUERY>::type *__restrict__ out, uint32_t *__restrict__ cursor, int max_depth)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned lanes_below = (1u << lane) - 1u;
 	uint32_t st_node[kStackSize];
 	float st_far[kStackSize];
-	int sp = 0;
-	uint32_t node = 0;
-	float seg_lo = enter, seg_hi = fminf(leave, t_max);
+	RayState r;
+	TShadowState ts;
+	ts.depth = 0;
+	bool alive = false;
+	uint32_t pool_next = 0u, pool_end = 0u; // warp-uniform
+	bool exhausted = false;                 // warp-uniform
+
 	for(;;)
 	{
-		uint2 nd = __ldg(&s.nodes[node]);
-		while((nd.y & 3u) != 3u)
+		// ---------------- refill idle lanes ----------------
+		unsigned idle = __ballot_sync(kFullMask, !alive);
+		if(!exhausted && (__popc(idle) >= kRefill))
 		{
-			const uint32_t axis = nd.y & 3u;
-			const float split = __uint_as_float(nd.x);
-			const float o = (axis == 0u) ? ox : ((axis == 1u) ? oy : oz);
-			const float d = (axis == 0u) ? dx : ((axis == 1u) ? dy : dz);
-			const float inv = (axis == 0u) ? ix : ((axis == 1u) ? iy : iz);
-			const float t_plane = (split - o) * inv;
-			const bool left_first = (o < split) || (o == split && d <= 0.f);
-			const uint32_t left = node + 1u, right = nd.y >> 2;
-			const uint32_t first = left_first ? left : right, second = left_first ? right : left;
-			if(t_plane > seg_hi || t_plane <= 0.f) node = first;
-			else if(t_plane < seg_lo) node = second;
-			else
+			while(idle != 0u)
 			{
-				st_node[sp] = second;
-				st_far[sp] = seg_hi;
-				++sp;
-				node = first;
-				seg_hi = t_plane;
-			}
-			nd = __ldg(&s.nodes[node]);
-		}
-		// leaf
-		uint32_t count = nd.y >> 2;
-		const float4 *rec = s.tris + nd.x;
-		for(; count != 0u; --count)
-		{
-			const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
-			const uint32_t flags = __float_as_uint(q1.w);
-			const bool quad = (flags & kFlagQuad) != 0u;
-			float u, v;
-			const float t = polyIntersect(q0, q1, q2, rec + 3, quad, ox, oy, oz, dx, dy, dz, u, v);
-			rec += quad ? 4 : 3;
-			// accelerator.h:125 / :137 / :150
-			if(t <= 0.f || t < t_min || t >= cur_t_max) continue;
-			if(QUERY == kClosest)
-			{
-				if(!(flags & B200RT_FACE_VISIBLE)) continue;
-				best_t = t; best_u = u; best_v = v; best_prim = __float_as_uint(q0.w);
-				cur_t_max = t;
-			}
-			else
-			{
-				if(!(flags & B200RT_FACE_CASTS_SHADOWS)) continue;
-				best_t = t; best_u = u; best_v = v; best_prim = __float_as_uint(q0.w);
-				if(QUERY == kShadow) return true;
-				if(!(flags & B200RT_FACE_TRANSPARENT)) return true; // opaque caster
-				bool seen = false;
-				for(int k = 0; k < ts->depth; ++k) seen = seen || (ts->list[k].prim == best_prim);
-				if(!seen)
+				if(pool_next == pool_end)
 				{
-					if(ts->depth >= ts->max_depth) return true;
-					ts->list[ts->depth].t = t; ts->list[ts->depth].u = u; ts->list[ts->depth].v = v; ts->list[ts->depth].prim = best_prim;
-					++ts->depth;
+					uint32_t base = 0u;
+					if(lane == 0u) base = atomicAdd(cursor, uint32_t(kPoolRays));
+					base = __shfl_sync(kFullMask, base, 0);
+					if(base >= n) { exhausted = true; break; }
+					pool_next = base;
+					pool_end = (n - base < uint32_t(kPoolRays)) ? n : base + uint32_t(kPoolRays);
+				}
+				const uint32_t avail = pool_end - pool_next;
+				const uint32_t rank = __popc(idle & lanes_below);
+				if(!alive && rank < avail)
+				{
+					r.index = pool_next + rank;
+					const float4 a = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * size_t(r.index));
+					const float4 b = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * size_t(r.index) + 1);
+					ts.depth = 0;
+					alive = setupRay<QUERY>(s, a, b, r);
+					if(!alive) writeResult<QUERY>(out, r, false, ts); // missed the tree bound
+				}
+				pool_next += min(avail, uint32_t(__popc(idle)));
+				idle = __ballot_sync(kFullMask, !alive);
+			}
+		}
+		if(__ballot_sync(kFullMask, alive) == 0u)
+		{
+			if(exhausted) break;
+			continue;
+		}
+
+		// ---------------- phase 1: descend until a non-empty leaf (or the ray ends) ----------------
+		uint32_t leaf_count = 0u, leaf_first = 0u;
+		bool finished = false; // ray ended in this round (result to be written)
+		bool hit = false;      // shadow queries: occluded
+		if(alive)
+		{
+			for(;;)
+			{
+				const uint2 nd = __ldg(&s.nodes[r.node]);
+				const uint32_t axis = nd.y & 3u;
+				if(axis != 3u)
+				{
+					const float split = __uint_as_float(nd.x);
+					const float o = (axis == 0u) ? r.ox : ((axis == 1u) ? r.oy : r.oz);
+					const float inv = (axis == 0u) ? r.ix : ((axis == 1u) ? r.iy : r.iz);
+					const float t_plane = (split - o) * inv;
+					const bool neg = ((r.neg >> axis) & 1u) != 0u;
+					const uint32_t left = r.node + 1u, right = nd.y >> 2;
+					const uint32_t near = neg ? right : left, far = neg ? left : right;
+					const float limit = (QUERY == kClosest) ? fminf(r.seg_hi, r.t_max) : r.seg_hi;
+					if(t_plane >= limit) r.node = near;
+					else if(t_plane <= r.seg_lo) r.node = far;
+					else
+					{
+						st_node[r.sp] = far;
+						st_far[r.sp] = r.seg_hi;
+						++r.sp;
+						r.node = near;
+						r.seg_hi = t_plane;
+					}
+				}
+				else
+				{
+					leaf_count = nd.y >> 2;
+					if(leaf_count != 0u) { leaf_first = nd.x; break; }
+					// empty leaf: next node from the stack.  Closest: once the best hit is not beyond the end of
+					// this leaf nothing nearer can follow (accelerator_kdtree_common.h:232).
+					if(r.sp == 0 || (QUERY == kClosest && r.best_prim != B200RT_MISS && r.t_max <= r.seg_hi)) { finished = true; break; }
+					--r.sp;
+					r.node = st_node[r.sp];
+					r.seg_lo = r.seg_hi;
+					r.seg_hi = st_far[r.sp];
 				}
 			}
 		}
-		if(QUERY == kClosest && best_prim != B200RT_MISS && best_t <= seg_hi) return true; // accelerator_kdtree_common.h:232
-		if(sp == 0) break;
-		--sp;
-		node = st_node[sp];
-		seg_lo = seg_hi;
-		seg_hi = st_far[sp];
-		if(QUERY == kClosest && best_prim != B200RT_MISS && best_t <= seg_lo) return true;
-	}
-	return QUERY == kClosest ? (best_prim != B200RT_MISS) : false;
-}
 
-// ---- kernels: one ray per thread ----------------------------------------------------------------
-static constexpr int kBlock = 128;
+		// ---------------- phase 2: the primitives of one leaf ----------------
+		if(leaf_count != 0u)
+		{
+			const float4 *rec = s.tris + leaf_first;
+			do
+			{
+				const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+				const uint32_t flags = __float_as_uint(q1.w);
+				const bool quad = (flags & kFlagQuad) != 0u;
+				float u, v;
+				const float t = polyIntersect(q0, q1, q2, rec + 3, quad, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, u, v);
+				rec += quad ? 4 : 3;
+				--leaf_count;
+				// accept rules, accelerator.h:125-127 / :137-139 / :150-154
+				const uint32_t need = (QUERY == kClosest) ? uint32_t(B200RT_FACE_VISIBLE) : uint32_t(B200RT_FACE_CASTS_SHADOWS);
+				if(!(t <= 0.f || t < r.t_min || t >= r.t_max) && (flags & need))
+				{
+					const uint32_t prim = __float_as_uint(q0.w);
+					r.best_u = u; r.best_v = v; r.best_prim = prim;
+					if(QUERY == kClosest) r.t_max = t;
+					else if(QUERY == kShadow) { hit = true; leaf_count = 0u; }
+					else
+					{
+						if(!(flags & B200RT_FACE_TRANSPARENT)) { hit = true; leaf_count = 0u; } // opaque caster
+						else
+						{
+							bool seen = false;
+							for(int k = 0; k < ts.depth; ++k) seen = seen || (ts.list[k].prim == prim);
+							if(!seen)
+							{
+								if(ts.depth >= max_depth) { hit = true; leaf_count = 0u; }
+								else
+								{
+									ts.list[ts.depth].t = t; ts.list[ts.depth].u = u; ts.list[ts.depth].v = v; ts.list[ts.depth].prim = prim;
+									++ts.depth;
+								}
+							}
+						}
+					}
+				}
+			} while(leaf_count != 0u);
+			// leave the leaf
+			if(hit || r.sp == 0 || (QUERY == kClosest && r.best_prim != B200RT_MISS && r.t_max <= r.seg_hi)) finished = true;
+			else
+			{
+				--r.sp;
+				r.node = st_node[r.sp];
+				r.seg_lo = r.seg_hi;
+				r.seg_hi = st_far[r.sp];
+			}
+		}
 
-__global__ void __launch_bounds__(kBlock) traceClosestKernel(SceneView s, const b200rt_ray *__restrict__ rays, size_t n, b200rt_hit *__restrict__ out)
-{
-	const size_t i = size_t(blockIdx.x) * kBlock + threadIdx.x;
-	if(i >= n) return;
-	const float4 a = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * i);
-	const float4 b = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * i + 1);
-	const float t_max = (b.w >= 0.f) ? b.w : FLT_MAX; // accelerator.h:91
-	float t, u, v;
-	uint32_t prim;
-	traverse<kClosest>(s, a.x, a.y, a.z, b.x, b.y, b.z, a.w, t_max, t, u, v, prim, nullptr);
-	float4 r;
-	r.x = t; r.y = u; r.z = v; r.w = __uint_as_float(prim);
-	reinterpret_cast<float4 *>(out)[i] = r;
-}
-
-// accelerator.h:103-111: origin moved by dir * tmin, t_max = tmax - 2 tmin (unbounded if tmax < 0)
-__device__ __forceinline__ void shadowRay(const float4 a, const float4 b, float &ox, float &oy, float &oz, float &t_max)
-{
-	ox = __fadd_rn(a.x, __fmul_rn(b.x, a.w));
-	oy = __fadd_rn(a.y, __fmul_rn(b.y, a.w));
-	oz = __fadd_rn(a.z, __fmul_rn(b.z, a.w));
-	t_max = (b.w >= 0.f) ? __fsub_rn(b.w, __fmul_rn(2.f, a.w)) : FLT_MAX;
-}
-
-__global__ void __launch_bounds__(kBlock) traceShadowKernel(SceneView s, const b200rt_ray *__restrict__ rays, size_t n, uint32_t *__restrict__ out)
-{
-	const size_t i = size_t(blockIdx.x) * kBlock + threadIdx.x;
-	if(i >= n) return;
-	const float4 a = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * i);
-	const float4 b = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * i + 1);
-	float ox, oy, oz, t_max, t, u, v;
-	shadowRay(a, b, ox, oy, oz, t_max);
-	uint32_t prim;
-	const bool shadowed = traverse<kShadow>(s, ox, oy, oz, b.x, b.y, b.z, a.w, t_max, t, u, v, prim, nullptr);
-	out[i] = shadowed ? prim : B200RT_MISS;
-}
-
-__global__ void __launch_bounds__(kBlock) traceTShadowKernel(SceneView s, const b200rt_ray *__restrict__ rays, size_t n, int max_depth, b200rt_tshadow *__restrict__ out)
-{
-	const size_t i = size_t(blockIdx.x) * kBlock + threadIdx.x;
-	if(i >= n) return;
-	const float4 a = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * i);
-	const float4 b = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * i + 1);
-	float ox, oy, oz, t_max, t, u, v;
-	shadowRay(a, b, ox, oy, oz, t_max);
-	TShadowState ts;
-	ts.depth = 0;
-	ts.max_depth = max_depth;
-	uint32_t prim;
-	const bool shadowed = traverse<kTShadow>(s, ox, oy, oz, b.x, b.y, b.z, a.w, t_max, t, u, v, prim, &ts);
-	uint4 *o = reinterpret_cast<uint4 *>(out + i);
-	o[0] = make_uint4(shadowed ? 1u : 0u, uint32_t(ts.depth), shadowed ? prim : B200RT_MISS, 0u); // setNoHit() clears primitive_
-#pragma unroll
-	for(int k = 0; k < B200RT_TSHADOW_MAX; ++k)
-	{
-		uint4 e = make_uint4(0u, 0u, 0u, B200RT_MISS);
-		if(k < ts.depth) e = make_uint4(__float_as_uint(ts.list[k].t), __float_as_uint(ts.list[k].u), __float_as_uint(ts.list[k].v), ts.list[k].prim);
-		o[1 + k] = e;
+		if(finished)
+		{
+			writeResult<QUERY>(out, r, (QUERY == kClosest) ? (r.best_prim != B200RT_MISS) : hit, ts);
+			alive = false;
+		}
 	}
 }
 
