@@ -165,9 +165,28 @@ __device__ __forceinline__ float polyIntersect(const float4 q0, const float4 q1,
 // "near" is decided by the sign of the direction component (of its inverse, so that a zero component, whose
 // inverse is +FLT_MAX as in math::inverse, math.h:71-77, behaves as "positive").
 // -------------------------------------------------------------------------------------------------
-static constexpr int kBlock = 128;
-static constexpr int kPoolRays = 256;  // rays taken from the global cursor per atomicAdd
-static constexpr int kRefill = 8;      // idle lanes that trigger a refill
+// tuning knobs (overridable with -D for the sweeps under tools/; the defaults are the measured best)
+#ifndef B200RT_BLOCK
+#define B200RT_BLOCK 128
+#endif
+#ifndef B200RT_MIN_BLOCKS
+#define B200RT_MIN_BLOCKS 8
+#endif
+#ifndef B200RT_REFILL
+#define B200RT_REFILL 8
+#endif
+#ifndef B200RT_LEAF_BATCH
+#define B200RT_LEAF_BATCH 8
+#endif
+#ifndef B200RT_STEPS
+#define B200RT_STEPS 4
+#endif
+static constexpr int kBlock = B200RT_BLOCK;
+static constexpr int kPoolRays = 256;               // rays taken from the global cursor per atomicAdd
+static constexpr int kRefill = B200RT_REFILL;       // idle lanes that trigger a refill
+static constexpr int kLeafBatch = B200RT_LEAF_BATCH; // lanes holding a leaf that trigger the leaf phase
+static constexpr int kSteps = B200RT_STEPS;         // node steps per lane between two warp votes
+static constexpr int kMinBlocks = B200RT_MIN_BLOCKS; // blocks per SM the register allocation is held to
 static constexpr unsigned kFullMask = 0xFFFFFFFFu;
 
 struct RayState
@@ -283,9 +302,23 @@ __device__ __forceinline__ void writeResult(typename OutType<QUERY>::type *out, 
 	}
 }
 
+// Leave the current leaf: closest queries stop once the best hit is not beyond the end of this leaf
+// (accelerator_kdtree_common.h:232); otherwise continue with the nearest postponed subtree, if any.
+// Returns true when the ray has ended.
 template <int QUERY>
-__global__ void __launch_bounds__(kBlock) traceKernel(SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
-                                                     typename OutType<QUERY>::type *__restrict__ out, uint32_t *__restrict__ cursor, int max_depth)
+__device__ __forceinline__ bool popNode(RayState &r, const uint32_t *st_node, const float *st_far)
+{
+	if(r.sp == 0 || (QUERY == kClosest && r.best_prim != B200RT_MISS && r.t_max <= r.seg_hi)) return true;
+	--r.sp;
+	r.node = st_node[r.sp];
+	r.seg_lo = r.seg_hi;
+	r.seg_hi = st_far[r.sp];
+	return false;
+}
+
+template <int QUERY>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
+                                                                 typename OutType<QUERY>::type *__restrict__ out, uint32_t *__restrict__ cursor, int max_depth)
 {
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned lanes_below = (1u << lane) - 1u;
@@ -294,7 +327,9 @@ __global__ void __launch_bounds__(kBlock) traceKernel(SceneView s, const b200rt_
 	RayState r;
 	TShadowState ts;
 	ts.depth = 0;
-	bool alive = false;
+	// lane state: !alive = idle slot; alive && !pending = descending; alive && pending = holds a non-empty leaf
+	bool alive = false, pending = false;
+	uint32_t leaf_count = 0u, leaf_first = 0u;
 	uint32_t pool_next = 0u, pool_end = 0u; // warp-uniform
 	bool exhausted = false;                 // warp-uniform
 
@@ -330,107 +365,102 @@ __global__ void __launch_bounds__(kBlock) traceKernel(SceneView s, const b200rt_
 				idle = __ballot_sync(kFullMask, !alive);
 			}
 		}
-		if(__ballot_sync(kFullMask, alive) == 0u)
+		const unsigned m_alive = __ballot_sync(kFullMask, alive);
+		if(m_alive == 0u)
 		{
 			if(exhausted) break;
 			continue;
 		}
-
-		// ---------------- phase 1: descend until a non-empty leaf (or the ray ends) ----------------
-		uint32_t leaf_count = 0u, leaf_first = 0u;
+		const unsigned m_pending = __ballot_sync(kFullMask, pending);
 		bool finished = false; // ray ended in this round (result to be written)
 		bool hit = false;      // shadow queries: occluded
-		if(alive)
-		{
-			for(;;)
-			{
-				const uint2 nd = __ldg(&s.nodes[r.node]);
-				const uint32_t axis = nd.y & 3u;
-				if(axis != 3u)
-				{
-					const float split = __uint_as_float(nd.x);
-					const float o = (axis == 0u) ? r.ox : ((axis == 1u) ? r.oy : r.oz);
-					const float inv = (axis == 0u) ? r.ix : ((axis == 1u) ? r.iy : r.iz);
-					const float t_plane = (split - o) * inv;
-					const bool neg = ((r.neg >> axis) & 1u) != 0u;
-					const uint32_t left = r.node + 1u, right = nd.y >> 2;
-					const uint32_t near = neg ? right : left, far = neg ? left : right;
-					const float limit = (QUERY == kClosest) ? fminf(r.seg_hi, r.t_max) : r.seg_hi;
-					if(t_plane >= limit) r.node = near;
-					else if(t_plane <= r.seg_lo) r.node = far;
-					else
-					{
-						st_node[r.sp] = far;
-						st_far[r.sp] = r.seg_hi;
-						++r.sp;
-						r.node = near;
-						r.seg_hi = t_plane;
-					}
-				}
-				else
-				{
-					leaf_count = nd.y >> 2;
-					if(leaf_count != 0u) { leaf_first = nd.x; break; }
-					// empty leaf: next node from the stack.  Closest: once the best hit is not beyond the end of
-					// this leaf nothing nearer can follow (accelerator_kdtree_common.h:232).
-					if(r.sp == 0 || (QUERY == kClosest && r.best_prim != B200RT_MISS && r.t_max <= r.seg_hi)) { finished = true; break; }
-					--r.sp;
-					r.node = st_node[r.sp];
-					r.seg_lo = r.seg_hi;
-					r.seg_hi = st_far[r.sp];
-				}
-			}
-		}
 
-		// ---------------- phase 2: the primitives of one leaf ----------------
-		if(leaf_count != 0u)
+		if(__popc(m_pending) >= kLeafBatch || m_pending == m_alive)
 		{
-			const float4 *rec = s.tris + leaf_first;
-			do
+			// ---------------- leaf phase: every lane holding a leaf tests its primitives ----------------
+			if(pending)
 			{
-				const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
-				const uint32_t flags = __float_as_uint(q1.w);
-				const bool quad = (flags & kFlagQuad) != 0u;
-				float u, v;
-				const float t = polyIntersect(q0, q1, q2, rec + 3, quad, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, u, v);
-				rec += quad ? 4 : 3;
-				--leaf_count;
-				// accept rules, accelerator.h:125-127 / :137-139 / :150-154
-				const uint32_t need = (QUERY == kClosest) ? uint32_t(B200RT_FACE_VISIBLE) : uint32_t(B200RT_FACE_CASTS_SHADOWS);
-				if(!(t <= 0.f || t < r.t_min || t >= r.t_max) && (flags & need))
+				const float4 *rec = s.tris + leaf_first;
+				do
 				{
-					const uint32_t prim = __float_as_uint(q0.w);
-					r.best_u = u; r.best_v = v; r.best_prim = prim;
-					if(QUERY == kClosest) r.t_max = t;
-					else if(QUERY == kShadow) { hit = true; leaf_count = 0u; }
-					else
+					const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+					const uint32_t flags = __float_as_uint(q1.w);
+					const bool quad = (flags & kFlagQuad) != 0u;
+					float u, v;
+					const float t = polyIntersect(q0, q1, q2, rec + 3, quad, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, u, v);
+					rec += quad ? 4 : 3;
+					--leaf_count;
+					// accept rules, accelerator.h:125-127 / :137-139 / :150-154
+					const uint32_t need = (QUERY == kClosest) ? uint32_t(B200RT_FACE_VISIBLE) : uint32_t(B200RT_FACE_CASTS_SHADOWS);
+					if(!(t <= 0.f || t < r.t_min || t >= r.t_max) && (flags & need))
 					{
-						if(!(flags & B200RT_FACE_TRANSPARENT)) { hit = true; leaf_count = 0u; } // opaque caster
+						const uint32_t prim = __float_as_uint(q0.w);
+						r.best_u = u; r.best_v = v; r.best_prim = prim;
+						if(QUERY == kClosest) r.t_max = t;
+						else if(QUERY == kShadow) { hit = true; leaf_count = 0u; }
 						else
 						{
-							bool seen = false;
-							for(int k = 0; k < ts.depth; ++k) seen = seen || (ts.list[k].prim == prim);
-							if(!seen)
+							if(!(flags & B200RT_FACE_TRANSPARENT)) { hit = true; leaf_count = 0u; } // opaque caster
+							else
 							{
-								if(ts.depth >= max_depth) { hit = true; leaf_count = 0u; }
-								else
+								bool seen = false;
+								for(int k = 0; k < ts.depth; ++k) seen = seen || (ts.list[k].prim == prim);
+								if(!seen)
 								{
-									ts.list[ts.depth].t = t; ts.list[ts.depth].u = u; ts.list[ts.depth].v = v; ts.list[ts.depth].prim = prim;
-									++ts.depth;
+									if(ts.depth >= max_depth) { hit = true; leaf_count = 0u; }
+									else
+									{
+										ts.list[ts.depth].t = t; ts.list[ts.depth].u = u; ts.list[ts.depth].v = v; ts.list[ts.depth].prim = prim;
+										++ts.depth;
+									}
 								}
 							}
 						}
 					}
-				}
-			} while(leaf_count != 0u);
-			// leave the leaf
-			if(hit || r.sp == 0 || (QUERY == kClosest && r.best_prim != B200RT_MISS && r.t_max <= r.seg_hi)) finished = true;
-			else
+				} while(leaf_count != 0u);
+				pending = false;
+				finished = hit || popNode<QUERY>(r, st_node, st_far);
+			}
+		}
+		else
+		{
+			// ---------------- descend: up to kSteps nodes per lane; empty leaves are consumed here ----------------
+#pragma unroll 1
+			for(int step = 0; step < kSteps; ++step)
 			{
-				--r.sp;
-				r.node = st_node[r.sp];
-				r.seg_lo = r.seg_hi;
-				r.seg_hi = st_far[r.sp];
+				if(alive && !pending && !finished)
+				{
+					const uint2 nd = __ldg(&s.nodes[r.node]);
+					const uint32_t axis = nd.y & 3u;
+					if(axis != 3u)
+					{
+						const float split = __uint_as_float(nd.x);
+						const float o = (axis == 0u) ? r.ox : ((axis == 1u) ? r.oy : r.oz);
+						const float inv = (axis == 0u) ? r.ix : ((axis == 1u) ? r.iy : r.iz);
+						const float t_plane = (split - o) * inv;
+						const bool neg = ((r.neg >> axis) & 1u) != 0u;
+						const uint32_t left = r.node + 1u, right = nd.y >> 2;
+						const uint32_t near = neg ? right : left, far = neg ? left : right;
+						const float limit = (QUERY == kClosest) ? fminf(r.seg_hi, r.t_max) : r.seg_hi;
+						if(t_plane >= limit) r.node = near;
+						else if(t_plane <= r.seg_lo) r.node = far;
+						else
+						{
+							st_node[r.sp] = far;
+							st_far[r.sp] = r.seg_hi;
+							++r.sp;
+							r.node = near;
+							r.seg_hi = t_plane;
+						}
+					}
+					else
+					{
+						leaf_count = nd.y >> 2;
+						leaf_first = nd.x;
+						if(leaf_count != 0u) pending = true;
+						else finished = popNode<QUERY>(r, st_node, st_far);
+					}
+				}
 			}
 		}
 

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200rt.so")
+LIB_PATH = os.environ.get("B200RT_LIB") or os.path.join(_HERE, "libb200rt.so")  # B200RT_LIB: tuning builds (tools/sweep.sh)
 MISS = 0xFFFFFFFF
 TSHADOW_MAX = 8
 
