@@ -179,7 +179,7 @@ __device__ __forceinline__ float polyIntersect(const float4 q0, const float4 q1,
 #define B200RT_LEAF_BATCH 8
 #endif
 #ifndef B200RT_STEPS
-#define B200RT_STEPS 4
+#define B200RT_STEPS 8
 #endif
 static constexpr int kBlock = B200RT_BLOCK;
 static constexpr int kPoolRays = 256;               // rays taken from the global cursor per atomicAdd
@@ -302,36 +302,74 @@ __device__ __forceinline__ void writeResult(typename OutType<QUERY>::type *out, 
 	}
 }
 
-// Leave the current leaf: closest queries stop once the best hit is not beyond the end of this leaf
-// (accelerator_kdtree_common.h:232); otherwise continue with the nearest postponed subtree, if any.
-// Returns true when the ray has ended.
-template <int QUERY>
-__device__ __forceinline__ bool popNode(RayState &r, const uint32_t *st_node, const float *st_far)
+// ---- per-thread short stack in shared memory -----------------------------------------------------
+// kShortStack entries per thread, laid out [entry][thread] so that a warp's accesses are conflict-free
+// whatever the lanes' stack depths are (bank = thread % 32).  It is a ring: a push onto a full ring
+// overwrites the OLDEST entry and raises `floor`; popping down to a raised floor means entries were lost,
+// and the ray then restarts from the root with seg_lo advanced to the end of the leaf it just left
+// (kd-restart).  Pushes are unconditional stores (the slot is simply not committed when the ray visits
+// one child only), which keeps the node step free of divergent branches; the price is that the ring
+// effectively holds kShortStack - 1 entries.
+#ifndef B200RT_SHORT_STACK
+#define B200RT_SHORT_STACK 8
+#endif
+static constexpr int kShortStack = B200RT_SHORT_STACK;
+static_assert((kShortStack & (kShortStack - 1)) == 0, "ring size must be a power of two");
+
+__device__ __forceinline__ float selectf(bool p, float a, float b)
 {
-	if(r.sp == 0 || (QUERY == kClosest && r.best_prim != B200RT_MISS && r.t_max <= r.seg_hi)) return true;
-	--r.sp;
-	r.node = st_node[r.sp];
-	r.seg_lo = r.seg_hi;
-	r.seg_hi = st_far[r.sp];
-	return false;
+	float r;
+	asm("{ .reg .pred q; setp.ne.s32 q, %3, 0; selp.f32 %0, %1, %2, q; }" : "=f"(r) : "f"(a), "f"(b), "r"(int(p)));
+	return r;
+}
+__device__ __forceinline__ uint32_t selectu(bool p, uint32_t a, uint32_t b)
+{
+	uint32_t r;
+	asm("{ .reg .pred q; setp.ne.s32 q, %3, 0; selp.u32 %0, %1, %2, q; }" : "=r"(r) : "r"(a), "r"(b), "r"(int(p)));
+	return r;
 }
 
 template <int QUERY>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
                                                                  typename OutType<QUERY>::type *__restrict__ out, uint32_t *__restrict__ cursor, int max_depth)
 {
-	const unsigned lane = threadIdx.x & 31u;
+	__shared__ uint32_t sh_node[kShortStack][kBlock];
+	__shared__ float sh_far[kShortStack][kBlock];
+	const unsigned tid = threadIdx.x;
+	const unsigned lane = tid & 31u;
 	const unsigned lanes_below = (1u << lane) - 1u;
-	uint32_t st_node[kStackSize];
-	float st_far[kStackSize];
 	RayState r;
 	TShadowState ts;
 	ts.depth = 0;
 	// lane state: !alive = idle slot; alive && !pending = descending; alive && pending = holds a non-empty leaf
 	bool alive = false, pending = false;
 	uint32_t leaf_count = 0u, leaf_first = 0u;
+	int floor = 0;          // ring entries below this index were overwritten
+	float t_exit = 0.f;     // where the ray leaves the tree bound (or its t_max)
 	uint32_t pool_next = 0u, pool_end = 0u; // warp-uniform
 	bool exhausted = false;                 // warp-uniform
+
+	// Leave the current leaf.  Closest queries stop once the best hit is not beyond the end of this leaf
+	// (accelerator_kdtree_common.h:232); otherwise continue with the nearest postponed subtree, or restart
+	// from the root behind this leaf when ring entries were lost.  Returns true when the ray has ended.
+	auto popNode = [&]() -> bool {
+		if(QUERY == kClosest && r.best_prim != B200RT_MISS && r.t_max <= r.seg_hi) return true;
+		if(r.sp > floor)
+		{
+			--r.sp;
+			r.node = sh_node[r.sp & (kShortStack - 1)][tid];
+			r.seg_lo = r.seg_hi;
+			r.seg_hi = sh_far[r.sp & (kShortStack - 1)][tid];
+			return false;
+		}
+		if(floor == 0) return true;
+		r.sp = 0;
+		floor = 0;
+		r.node = 0u;
+		r.seg_lo = r.seg_hi;
+		r.seg_hi = t_exit;
+		return !(r.seg_lo < t_exit);
+	};
 
 	for(;;)
 	{
@@ -358,7 +396,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 					const float4 a = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * size_t(r.index));
 					const float4 b = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * size_t(r.index) + 1);
 					ts.depth = 0;
+					floor = 0;
 					alive = setupRay<QUERY>(s, a, b, r);
+					t_exit = r.seg_hi;
 					if(!alive) writeResult<QUERY>(out, r, false, ts); // missed the tree bound
 				}
 				pool_next += min(avail, uint32_t(__popc(idle)));
@@ -419,7 +459,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 					}
 				} while(leaf_count != 0u);
 				pending = false;
-				finished = hit || popNode<QUERY>(r, st_node, st_far);
+				finished = hit || popNode();
 			}
 		}
 		else
@@ -434,31 +474,32 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 					const uint32_t axis = nd.y & 3u;
 					if(axis != 3u)
 					{
+						// branch-free node step
 						const float split = __uint_as_float(nd.x);
-						const float o = (axis == 0u) ? r.ox : ((axis == 1u) ? r.oy : r.oz);
-						const float inv = (axis == 0u) ? r.ix : ((axis == 1u) ? r.iy : r.iz);
+						const bool a1 = (axis == 1u), a2 = (axis == 2u);
+						const float o = selectf(a2, r.oz, selectf(a1, r.oy, r.ox));
+						const float inv = selectf(a2, r.iz, selectf(a1, r.iy, r.ix));
 						const float t_plane = (split - o) * inv;
-						const bool neg = ((r.neg >> axis) & 1u) != 0u;
+						const bool neg = inv < 0.f;
 						const uint32_t left = r.node + 1u, right = nd.y >> 2;
-						const uint32_t near = neg ? right : left, far = neg ? left : right;
+						const uint32_t near = selectu(neg, right, left), far = selectu(neg, left, right);
 						const float limit = (QUERY == kClosest) ? fminf(r.seg_hi, r.t_max) : r.seg_hi;
-						if(t_plane >= limit) r.node = near;
-						else if(t_plane <= r.seg_lo) r.node = far;
-						else
-						{
-							st_node[r.sp] = far;
-							st_far[r.sp] = r.seg_hi;
-							++r.sp;
-							r.node = near;
-							r.seg_hi = t_plane;
-						}
+						const bool far_only = t_plane <= r.seg_lo;
+						const bool both = !(t_plane >= limit) && !far_only;
+						const int slot = r.sp & (kShortStack - 1);
+						sh_node[slot][tid] = far;
+						sh_far[slot][tid] = r.seg_hi;
+						floor = max(floor, r.sp + 1 - kShortStack); // the store above has clobbered the oldest slot of a full ring, pushed or not
+						r.sp += both ? 1 : 0;
+						r.node = selectu(far_only, far, near);
+						r.seg_hi = selectf(both, t_plane, r.seg_hi);
 					}
 					else
 					{
 						leaf_count = nd.y >> 2;
 						leaf_first = nd.x;
 						if(leaf_count != 0u) pending = true;
-						else finished = popNode<QUERY>(r, st_node, st_far);
+						else finished = popNode();
 					}
 				}
 			}

@@ -263,3 +263,33 @@ def test_build_parameters_do_not_change_hits(built):
             ref = dict(prim=helpers.prim_signed(base["prim"]), t=base["t"], u=base["u"], v=base["v"])
             helpers.check_closest_parity(helpers.prim_signed(h["prim"]), h["t"], h["u"], h["v"], ref)
         s.close()
+
+
+def test_restart_path_with_tiny_stack(built):
+    """libb200rt_stack2.so is the same source built with a 2-entry short stack: nearly every ray overflows the ring
+    and takes the kd-restart path.  Results must be byte-identical to the regular build's."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    stress = os.path.join(root, "libyafaray_b200", "libb200rt_stack2.so")
+    assert os.path.exists(stress), "build() must produce libb200rt_stack2.so"
+    code = (
+        "import sys, hashlib, numpy as np; sys.path.insert(0, %r)\n"
+        "from libyafaray_b200 import rt, scenes\n"
+        "from tests import helpers\n"
+        "xyz, idx, fl = scenes.objects(150000, n_spheres=24); fl = helpers.flag_mix(idx.shape[0], 3)\n"
+        "s = rt.Scene(0); s.add_mesh(xyz, idx, fl); s.build()\n"
+        "c, sh = helpers.ray_zoo(s.bound(), n=300000, seed=17)\n"
+        "h = hashlib.md5()\n"
+        "h.update(s.trace_closest(c).tobytes()); h.update((s.trace_shadow(sh) != rt.MISS).tobytes())\n"
+        "h.update(s.trace_tshadow(sh, 2)['shadowed'].tobytes()); print(h.hexdigest())\n" % root)
+    digests = []
+    for lib in ("", stress):
+        env = dict(os.environ)
+        env.pop("B200RT_LIB", None)
+        if lib:
+            env["B200RT_LIB"] = lib
+        out = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests.append(out.stdout.strip().splitlines()[-1])
+    assert digests[0] == digests[1]
