@@ -178,6 +178,9 @@ __device__ __forceinline__ float polyIntersect(const float4 q0, const float4 q1,
 #ifndef B200RT_LEAF_BATCH
 #define B200RT_LEAF_BATCH 8
 #endif
+#ifndef B200RT_POP_IN_LEAF_PHASE
+#define B200RT_POP_IN_LEAF_PHASE 0
+#endif
 #ifndef B200RT_STEPS
 #define B200RT_STEPS 8
 #endif
@@ -374,20 +377,26 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 	for(;;)
 	{
 		// ---------------- refill idle lanes ----------------
-		unsigned idle = __ballot_sync(kFullMask, !alive);
+		// One pass per round: every idle lane takes the next ray of the warp's pool.  Rays that miss the tree bound
+		// are answered on the spot and leave their lane idle until the next round (looping here until every lane
+		// holds a live ray ran the ~160-instruction setup with only a few lanes active).
+		const unsigned idle = __ballot_sync(kFullMask, !alive);
 		if(!exhausted && (__popc(idle) >= kRefill))
 		{
-			while(idle != 0u)
+			if(pool_next == pool_end)
 			{
-				if(pool_next == pool_end)
+				uint32_t base = 0u;
+				if(lane == 0u) base = atomicAdd(cursor, uint32_t(kPoolRays));
+				base = __shfl_sync(kFullMask, base, 0);
+				if(base >= n) exhausted = true;
+				else
 				{
-					uint32_t base = 0u;
-					if(lane == 0u) base = atomicAdd(cursor, uint32_t(kPoolRays));
-					base = __shfl_sync(kFullMask, base, 0);
-					if(base >= n) { exhausted = true; break; }
 					pool_next = base;
 					pool_end = (n - base < uint32_t(kPoolRays)) ? n : base + uint32_t(kPoolRays);
 				}
+			}
+			if(!exhausted)
+			{
 				const uint32_t avail = pool_end - pool_next;
 				const uint32_t rank = __popc(idle & lanes_below);
 				if(!alive && rank < avail)
@@ -402,7 +411,6 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 					if(!alive) writeResult<QUERY>(out, r, false, ts); // missed the tree bound
 				}
 				pool_next += min(avail, uint32_t(__popc(idle)));
-				idle = __ballot_sync(kFullMask, !alive);
 			}
 		}
 		const unsigned m_alive = __ballot_sync(kFullMask, alive);
@@ -421,7 +429,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 			if(pending)
 			{
 				const float4 *rec = s.tris + leaf_first;
-				do
+				while(leaf_count != 0u)
 				{
 					const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
 					const uint32_t flags = __float_as_uint(q1.w);
@@ -457,7 +465,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 							}
 						}
 					}
-				} while(leaf_count != 0u);
+				}
 				pending = false;
 				finished = hit || popNode();
 			}
@@ -498,8 +506,12 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 					{
 						leaf_count = nd.y >> 2;
 						leaf_first = nd.x;
+#if B200RT_POP_IN_LEAF_PHASE
+						pending = true;
+#else
 						if(leaf_count != 0u) pending = true;
 						else finished = popNode();
+#endif
 					}
 				}
 			}
