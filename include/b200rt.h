@@ -152,6 +152,27 @@ int b200rt_trace_closest_device(b200rt_scene *scene, const b200rt_ray *d_rays, s
 int b200rt_trace_shadow_device(b200rt_scene *scene, const b200rt_ray *d_rays, size_t n, uint32_t *d_out, void *stream);
 int b200rt_trace_tshadow_device(b200rt_scene *scene, const b200rt_ray *d_rays, size_t n, int max_depth, b200rt_tshadow *d_out, void *stream);
 
+/* ---- generic entry points: query kind + flags.  The functions above are b200rt_trace[_device] with flags = 0.
+ *
+ * B200RT_RAYS_TREE_SPACE: the rays are what the reference's VIRTUAL queries receive -- Accelerator::intersect(ray,
+ * t_max), intersectShadow(ray, t_max), intersectTransparentShadow(ray, max_depth, t_max, camera)
+ * (include/accelerator/accelerator.h:50-52) -- i.e. the public wrappers (accelerator.h:89-120) have already run:
+ * the origin is used as is and the `tmax` field IS the t_max argument (negative = unbounded); `tmin` is
+ * Ray::tmin_ (closest and transparent shadow use max(tmin, bias); shadow ignores it,
+ * accelerator_kdtree_common.h:139).  Without the flag the library applies the wrappers itself. */
+enum
+{
+	B200RT_QUERY_CLOSEST = 0, /* out: b200rt_hit[n] */
+	B200RT_QUERY_SHADOW = 1,  /* out: uint32_t[n] */
+	B200RT_QUERY_TSHADOW = 2  /* out: b200rt_tshadow[n] */
+};
+enum
+{
+	B200RT_RAYS_TREE_SPACE = 1
+};
+int b200rt_trace(b200rt_scene *scene, int query, unsigned flags, const b200rt_ray *rays, size_t n, void *out, int max_depth);
+int b200rt_trace_device(b200rt_scene *scene, int query, unsigned flags, const b200rt_ray *d_rays, size_t n, void *d_out, int max_depth, void *stream);
+
 /* Pinned host memory for ray / result buffers (makes the host-buffer queries copy at full PCIe rate). */
 int b200rt_host_alloc(void **ptr, size_t bytes);
 int b200rt_host_free(void *ptr);

@@ -218,7 +218,7 @@ int checkDeviceCall(const b200rt_scene *s, const void *rays, size_t n, const voi
 // Enqueue traceKernel<Q> over n rays on `stream`: a persistent grid (at most one resident wave) whose warps
 // pull rays from a cursor that is zeroed on the same stream just before the launch.
 template <int Q>
-int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b200rt::OutType<Q>::type *d_out, cudaStream_t stream, int max_depth)
+int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b200rt::OutType<Q>::type *d_out, cudaStream_t stream, int max_depth, unsigned flags = 0u)
 {
 	for(size_t begin = 0; begin < n; begin += kMaxRaysPerLaunch)
 	{
@@ -227,7 +227,7 @@ int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b2
 		CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), stream));
 		const unsigned wanted = unsigned((size_t(count) + b200rt::kBlock - 1) / b200rt::kBlock);
 		const unsigned grid = std::max(1u, std::min(wanted, unsigned(s->resident_blocks[Q])));
-		b200rt::traceKernel<Q><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, cursor, max_depth);
+		b200rt::traceKernel<Q><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, cursor, max_depth, (flags & B200RT_RAYS_TREE_SPACE) != 0u);
 		++g_launches;
 		CUDA_TRY(cudaGetLastError());
 	}
@@ -501,6 +501,45 @@ int b200rt_trace_tshadow(b200rt_scene *s, const b200rt_ray *rays, size_t n, int 
 	return tracedStaged(s, rays, n, out, [&](const b200rt_ray *d_rays, size_t count, b200rt_tshadow *d_out, cudaStream_t st) {
 		return launchTrace<b200rt::kTShadow>(s, d_rays, count, d_out, st, max_depth);
 	});
+}
+
+// ---- generic entry points (query kind + flags) ------------------------------------------------
+int b200rt_trace_device(b200rt_scene *s, int query, unsigned flags, const b200rt_ray *d_rays, size_t n, void *d_out, int max_depth, void *stream)
+{
+	const int rc = checkDeviceCall(s, d_rays, n, d_out);
+	if(rc != B200RT_OK) return rc;
+	if(query == B200RT_QUERY_TSHADOW && (max_depth < 0 || max_depth > B200RT_TSHADOW_MAX)) return fail(B200RT_E_INVALID, "max_depth must be in [0, B200RT_TSHADOW_MAX]");
+	if(n == 0) return B200RT_OK;
+	CUDA_TRY(cudaSetDevice(s->device));
+	cudaStream_t st = static_cast<cudaStream_t>(stream);
+	switch(query)
+	{
+		case B200RT_QUERY_CLOSEST: return launchTrace<b200rt::kClosest>(s, d_rays, n, static_cast<b200rt_hit *>(d_out), st, 0, flags);
+		case B200RT_QUERY_SHADOW: return launchTrace<b200rt::kShadow>(s, d_rays, n, static_cast<uint32_t *>(d_out), st, 0, flags);
+		case B200RT_QUERY_TSHADOW: return launchTrace<b200rt::kTShadow>(s, d_rays, n, static_cast<b200rt_tshadow *>(d_out), st, max_depth, flags);
+		default: return fail(B200RT_E_INVALID, "unknown query kind");
+	}
+}
+
+int b200rt_trace(b200rt_scene *s, int query, unsigned flags, const b200rt_ray *rays, size_t n, void *out, int max_depth)
+{
+	switch(query)
+	{
+		case B200RT_QUERY_CLOSEST:
+			return tracedStaged(s, rays, n, static_cast<b200rt_hit *>(out), [&](const b200rt_ray *d_rays, size_t count, b200rt_hit *d_out, cudaStream_t st) {
+				return launchTrace<b200rt::kClosest>(s, d_rays, count, d_out, st, 0, flags);
+			});
+		case B200RT_QUERY_SHADOW:
+			return tracedStaged(s, rays, n, static_cast<uint32_t *>(out), [&](const b200rt_ray *d_rays, size_t count, uint32_t *d_out, cudaStream_t st) {
+				return launchTrace<b200rt::kShadow>(s, d_rays, count, d_out, st, 0, flags);
+			});
+		case B200RT_QUERY_TSHADOW:
+			if(max_depth < 0 || max_depth > B200RT_TSHADOW_MAX) return fail(B200RT_E_INVALID, "max_depth must be in [0, B200RT_TSHADOW_MAX]");
+			return tracedStaged(s, rays, n, static_cast<b200rt_tshadow *>(out), [&](const b200rt_ray *d_rays, size_t count, b200rt_tshadow *d_out, cudaStream_t st) {
+				return launchTrace<b200rt::kTShadow>(s, d_rays, count, d_out, st, max_depth, flags);
+			});
+		default: return fail(B200RT_E_INVALID, "unknown query kind");
+	}
 }
 
 int b200rt_host_alloc(void **ptr, size_t bytes)

@@ -210,13 +210,14 @@ struct RayState
 // Ray setup: root slab test (bound.h:156-198), bias (accelerator.h:64), traversal interval.  Returns false when
 // the ray misses the tree bound.
 template <int QUERY>
-__device__ __forceinline__ bool setupRay(const SceneView &s, const float4 a, const float4 b, RayState &r)
+__device__ __forceinline__ bool setupRay(const SceneView &s, const float4 a, const float4 b, RayState &r, bool tree_space)
 {
 	float t_max;
-	if(QUERY == kClosest)
+	if(QUERY == kClosest || tree_space)
 	{
+		// closest (accelerator.h:91), or a shadow ray its caller has already wrapped (B200RT_RAYS_TREE_SPACE)
 		r.ox = a.x; r.oy = a.y; r.oz = a.z;
-		t_max = (b.w >= 0.f) ? b.w : FLT_MAX; // accelerator.h:91
+		t_max = (b.w >= 0.f) ? b.w : FLT_MAX;
 	}
 	else
 	{
@@ -334,7 +335,7 @@ __device__ __forceinline__ uint32_t selectu(bool p, uint32_t a, uint32_t b)
 
 template <int QUERY>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
-                                                                 typename OutType<QUERY>::type *__restrict__ out, uint32_t *__restrict__ cursor, int max_depth)
+                                                                 typename OutType<QUERY>::type *__restrict__ out, uint32_t *__restrict__ cursor, int max_depth, bool tree_space)
 {
 	__shared__ uint32_t sh_node[kShortStack][kBlock];
 	__shared__ float sh_far[kShortStack][kBlock];
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 					const float4 b = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * size_t(r.index) + 1);
 					ts.depth = 0;
 					floor = 0;
-					alive = setupRay<QUERY>(s, a, b, r);
+					alive = setupRay<QUERY>(s, a, b, r, tree_space);
 					t_exit = r.seg_hi;
 					if(!alive) writeResult<QUERY>(out, r, false, ts); // missed the tree bound
 				}

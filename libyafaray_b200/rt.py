@@ -13,6 +13,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200RT_LIB") or os.path.join(_HERE, "libb200rt.so")  # B200RT_LIB: tuning builds (tools/sweep.sh)
 MISS = 0xFFFFFFFF
+QUERY_CLOSEST, QUERY_SHADOW, QUERY_TSHADOW = 0, 1, 2
+RAYS_TREE_SPACE = 1
 TSHADOW_MAX = 8
 
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("tmin", np.float32), ("d", np.float32, 3), ("tmax", np.float32)])
@@ -47,7 +49,8 @@ class B200RTError(RuntimeError):
 SYMBOLS = [
     "b200rt_device_count", "b200rt_create", "b200rt_destroy", "b200rt_add_mesh", "b200rt_build", "b200rt_get_bound",
     "b200rt_get_stats", "b200rt_update_face_flags", "b200rt_trace_closest", "b200rt_trace_shadow", "b200rt_trace_tshadow",
-    "b200rt_trace_closest_device", "b200rt_trace_shadow_device", "b200rt_trace_tshadow_device", "b200rt_host_alloc",
+    "b200rt_trace_closest_device", "b200rt_trace_shadow_device", "b200rt_trace_tshadow_device", "b200rt_trace",
+    "b200rt_trace_device", "b200rt_host_alloc",
     "b200rt_host_free", "b200rt_host_tree_build", "b200rt_host_tree_sizes", "b200rt_host_tree_export",
     "b200rt_host_tree_destroy", "b200rt_launch_count", "b200rt_last_error", "b200rt_version",
 ]
@@ -78,6 +81,8 @@ def lib():
         L.b200rt_trace_closest_device.argtypes = [P, P, Z, P, P]
         L.b200rt_trace_shadow_device.argtypes = [P, P, Z, P, P]
         L.b200rt_trace_tshadow_device.argtypes = [P, P, Z, C.c_int, P, P]
+        L.b200rt_trace.argtypes = [P, C.c_int, C.c_uint, P, Z, P, C.c_int]
+        L.b200rt_trace_device.argtypes = [P, C.c_int, C.c_uint, P, Z, P, C.c_int, P]
         L.b200rt_host_alloc.argtypes = [P, Z]
         L.b200rt_host_free.argtypes = [P]
         L.b200rt_host_tree_build.argtypes = [P, Z, P, Z, P, P]
@@ -219,6 +224,14 @@ class Scene:
         if out is None:
             out = np.empty(r.shape[0], TSHADOW_DTYPE)
         _check(lib().b200rt_trace_tshadow(self._h, _p(r), r.shape[0], int(max_depth), _p(out)))
+        return out
+
+    def trace(self, query, rays, flags=0, max_depth=0, out=None) -> np.ndarray:
+        """Generic entry point: query = QUERY_CLOSEST / QUERY_SHADOW / QUERY_TSHADOW, flags = RAYS_TREE_SPACE or 0."""
+        r = as_rays(rays)
+        if out is None:
+            out = np.empty(r.shape[0], (HIT_DTYPE, np.uint32, TSHADOW_DTYPE)[query])
+        _check(lib().b200rt_trace(self._h, int(query), int(flags), _p(r), r.shape[0], _p(out), int(max_depth)))
         return out
 
     # ---- device-buffer queries (raw device pointers, e.g. torch.Tensor.data_ptr()) ----

@@ -293,3 +293,28 @@ def test_restart_path_with_tiny_stack(built):
         assert out.returncode == 0, out.stderr[-2000:]
         digests.append(out.stdout.strip().splitlines()[-1])
     assert digests[0] == digests[1]
+
+
+def test_tree_space_rays_equal_wrapped_rays(built):
+    """B200RT_RAYS_TREE_SPACE: feeding the rays the reference's wrappers would hand to the virtual queries
+    (accelerator.h:103-120: origin += dir * tmin, t_max = tmax - 2 tmin) gives the same answers as letting the
+    library apply the wrappers."""
+    xyz, idx, _ = scenes.objects(40000, n_spheres=12)
+    flags = helpers.flag_mix(idx.shape[0], seed=9)
+    s = make_scene(xyz, idx, flags)
+    closest, shadow = helpers.ray_zoo(s.bound(), n=100000, seed=31)
+    pre = shadow.copy()
+    tmin = shadow[:, 3:4]
+    pre[:, 0:3] = shadow[:, 0:3] + shadow[:, 4:7] * tmin            # float32 multiply then add, as the wrapper does
+    bounded = shadow[:, 7] >= 0
+    pre[bounded, 7] = shadow[bounded, 7] - np.float32(2) * shadow[bounded, 3]
+    a = s.trace_shadow(shadow)
+    b = s.trace(rt.QUERY_SHADOW, pre, flags=rt.RAYS_TREE_SPACE)
+    assert np.array_equal(a != rt.MISS, b != rt.MISS)
+    ta = s.trace_tshadow(shadow, 3)
+    tb = s.trace(rt.QUERY_TSHADOW, pre, flags=rt.RAYS_TREE_SPACE, max_depth=3)
+    assert np.array_equal(ta["shadowed"], tb["shadowed"]) and np.array_equal(ta["n_transparent"], tb["n_transparent"])
+    assert s.trace(rt.QUERY_CLOSEST, closest, flags=rt.RAYS_TREE_SPACE).tobytes() == s.trace_closest(closest).tobytes()
+    with pytest.raises(rt.B200RTError):
+        s.trace(7, closest)
+    s.close()
