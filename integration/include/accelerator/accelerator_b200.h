@@ -1,0 +1,69 @@
+/* integration/accelerator_b200.h -- the libYafaRay `Accelerator` that puts libb200rt behind the reference's own
+ * accelerator factory (type "b200-kdtree").  This file is compiled INSIDE a libYafaRay source tree (it includes the
+ * reference's headers); INTEGRATION.md and integration/b200-kdtree.patch show the registration.
+ *
+ * It mirrors the interface of the reference's kd-tree accelerators
+ * (include/accelerator/accelerator_kdtree_original.h:37-104): same factory signature, same ParamMap keys
+ * ("depth", "max_leaf_size_", "cost_ratio", "empty_bonus"), same virtual queries, plus batched entry points.
+ * All ray work is done by the CUDA kernels of libb200rt; there is no CPU traversal in this class.
+ */
+#ifndef LIBYAFARAY_ACCELERATOR_B200_H
+#define LIBYAFARAY_ACCELERATOR_B200_H
+
+#include "accelerator/accelerator.h"
+#include <vector>
+
+struct b200rt_scene;
+
+namespace yafaray {
+
+class AcceleratorB200 final : public Accelerator
+{
+		using ThisClassType_t = AcceleratorB200; using ParentClassType_t = Accelerator;
+
+	public:
+		inline static std::string getClassName() { return "AcceleratorB200"; }
+		static std::pair<std::unique_ptr<Accelerator>, ParamResult> factory(Logger &logger, const RenderControl *render_control, const std::vector<const Primitive *> &primitives, const ParamMap &params);
+		[[nodiscard]] std::map<std::string, const ParamMeta *> getParamMetaMap() const override { return params_.getParamMetaMap(); }
+		static std::string printMeta(const std::vector<std::string> &excluded_params) { return class_meta::print<Params>(excluded_params); }
+		AcceleratorB200(Logger &logger, ParamResult &param_result, const RenderControl *render_control, const std::vector<const Primitive *> &primitives, const ParamMap &param_map);
+		~AcceleratorB200() override;
+		bool ok() const { return scene_ != nullptr; }
+
+		/* Batched entry points (north-star (c)): n rays per call, one kernel launch per chunk.
+		 * intersectBatch is Accelerator::intersect(ray, camera) without the getSurface() step: out[i].isHit(),
+		 * t_hit_/t_max_, uv_ and primitive_ are filled exactly as the per-ray query fills them. */
+		bool intersectBatch(const Ray *rays, size_t n, IntersectData *out) const;
+		/* isShadowedBatch is Accelerator::isShadowed(ray): shadowed[i] and (optionally) the occluder. */
+		bool isShadowedBatch(const Ray *rays, size_t n, bool *shadowed, const Primitive **occluders) const;
+		/* isShadowedTransparentShadowBatch is Accelerator::isShadowedTransparentShadow(ray, max_depth, camera). */
+		bool isShadowedTransparentShadowBatch(const Ray *rays, size_t n, int max_depth, const Camera *camera, bool *shadowed, Rgb *colors, const Primitive **occluders) const;
+
+	private:
+		[[nodiscard]] Type type() const override { return Type::B200KdTree; }
+		const struct Params
+		{
+			Params(ParamResult &param_result, const ParamMap &param_map);
+			static std::map<std::string, const ParamMeta *> getParamMetaMap();
+			PARAM_DECL(int, max_depth_, 0, "depth", "0 = automatic");
+			PARAM_DECL(int, max_leaf_size_, 0, "max_leaf_size_", "0 = library default");
+			PARAM_DECL(float, cost_ratio_, 0.f, "cost_ratio", "node traversal cost divided by primitive intersection cost; 0 = library default");
+			PARAM_DECL(float, empty_bonus_, 0.f, "empty_bonus", "0 = library default");
+			PARAM_DECL(int, device_, 0, "device", "CUDA device index");
+			PARAM_DECL(int, num_threads_, 0, "accelerator_threads", "host threads for the tree build; 0 = all");
+		} params_;
+		[[nodiscard]] ParamMap getAsParamMap(bool only_non_default) const override;
+
+		IntersectData intersect(const Ray &ray, float t_max) const override;
+		IntersectData intersectShadow(const Ray &ray, float t_max) const override;
+		IntersectData intersectTransparentShadow(const Ray &ray, int max_depth, float dist, const Camera *camera) const override;
+		Bound<float> getBound() const override { return bound_; }
+
+		std::vector<const Primitive *> primitives_; //!< face id (upload order) -> primitive; copies the factory's temporary vector
+		b200rt_scene *scene_ = nullptr;             //!< owned; device memory lives behind this handle
+		Bound<float> bound_{{{0.f, 0.f, 0.f}}, {{0.f, 0.f, 0.f}}};
+};
+
+} //namespace yafaray
+
+#endif //LIBYAFARAY_ACCELERATOR_B200_H

@@ -1,0 +1,283 @@
+/* integration/accelerator_b200.cc -- see accelerator_b200.h.  Compiled inside a libYafaRay tree and linked with
+ * libb200rt (include/b200rt.h).  Follows the conventions of the reference's accelerators
+ * (src/accelerator/accelerator_kdtree_original.cc:28-63 for params/factory; error handling per SURVEY.md 8b:
+ * no exception leaves this class, a CUDA failure is logged and the factory returns no accelerator, so that
+ * SurfaceIntegrator::preprocess fails instead of silently rendering on a CPU path). */
+#include "accelerator/accelerator_b200.h"
+#include "b200rt.h"
+#include "common/logger.h"
+#include "geometry/primitive/primitive_face.h"
+#include "material/material.h"
+#include "param/param.h"
+#include "render/render_control.h"
+#include <limits>
+
+namespace yafaray {
+
+std::map<std::string, const ParamMeta *> AcceleratorB200::Params::getParamMetaMap()
+{
+	auto param_meta_map{ParentClassType_t::Params::getParamMetaMap()};
+	PARAM_META(max_depth_);
+	PARAM_META(max_leaf_size_);
+	PARAM_META(cost_ratio_);
+	PARAM_META(empty_bonus_);
+	PARAM_META(device_);
+	PARAM_META(num_threads_);
+	return param_meta_map;
+}
+
+AcceleratorB200::Params::Params(ParamResult &param_result, const ParamMap &param_map)
+{
+	PARAM_LOAD(max_depth_);
+	PARAM_LOAD(max_leaf_size_);
+	PARAM_LOAD(cost_ratio_);
+	PARAM_LOAD(empty_bonus_);
+	PARAM_LOAD(device_);
+	PARAM_LOAD(num_threads_);
+}
+
+ParamMap AcceleratorB200::getAsParamMap(bool only_non_default) const
+{
+	auto param_map{ParentClassType_t::getAsParamMap(only_non_default)};
+	param_map.setParam("type", type().print());
+	PARAM_SAVE(max_depth_);
+	PARAM_SAVE(max_leaf_size_);
+	PARAM_SAVE(cost_ratio_);
+	PARAM_SAVE(empty_bonus_);
+	PARAM_SAVE(device_);
+	PARAM_SAVE(num_threads_);
+	return param_map;
+}
+
+std::pair<std::unique_ptr<Accelerator>, ParamResult> AcceleratorB200::factory(Logger &logger, const RenderControl *render_control, const std::vector<const Primitive *> &primitives, const ParamMap &param_map)
+{
+	auto param_result{class_meta::check<Params>(param_map, {"type"}, {})};
+	auto accelerator{std::make_unique<AcceleratorB200>(logger, param_result, render_control, primitives, param_map)};
+	if(param_result.notOk()) logger.logWarning(param_result.print<ThisClassType_t>("", {"type"}));
+	if(!accelerator->ok())
+	{
+		// Scene::preprocess dereferences the returned accelerator unconditionally (src/scene/scene.cc:352-353) and the C API
+		// ignores the result of the preprocess calls, so returning nullptr would crash the host application.  The failed
+		// accelerator is returned instead: it has a zero bound, every query misses, the error has been logged at ERROR level
+		// and the result carries YAFARAY_RESULT_ERROR_WHILE_CREATING.  No CPU traversal path exists in this class.
+		param_result.flags_ |= ResultFlags{YAFARAY_RESULT_ERROR_WHILE_CREATING};
+		logger.logError(getClassName(), ": no usable accelerator was built; every ray will miss");
+	}
+	return {std::move(accelerator), param_result};
+}
+
+namespace {
+
+// per-face flag byte: the visibility tests of accelerator.h:126-127,138-139,152-154 and Material::isTransparent()
+uint8_t faceFlags(const Primitive *primitive)
+{
+	const Visibility prim_visibility{primitive->getVisibility()};
+	const Material *material{primitive->getMaterial()};
+	const Visibility mat_visibility{material ? material->getVisibility() : Visibility{Visibility::Normal}};
+	uint8_t flags = 0;
+	if(prim_visibility.has(Visibility::Visible) && mat_visibility.has(Visibility::Visible)) flags |= B200RT_FACE_VISIBLE;
+	if(prim_visibility.has(Visibility::CastsShadows) && mat_visibility.has(Visibility::CastsShadows)) flags |= B200RT_FACE_CASTS_SHADOWS;
+	if(material && material->isTransparent()) flags |= B200RT_FACE_TRANSPARENT;
+	return flags;
+}
+
+inline b200rt_ray toRay(const Ray &ray, float t_max)
+{
+	return {ray.from_[Axis::X], ray.from_[Axis::Y], ray.from_[Axis::Z], ray.tmin_, ray.dir_[Axis::X], ray.dir_[Axis::Y], ray.dir_[Axis::Z], t_max};
+}
+
+} //namespace
+
+AcceleratorB200::AcceleratorB200(Logger &logger, ParamResult &param_result, const RenderControl *render_control, const std::vector<const Primitive *> &primitives, const ParamMap &param_map) : ParentClassType_t{logger, param_result, render_control, param_map}, params_{param_result, param_map}, primitives_{primitives}
+{
+	if(logger.isDebug()) logger.logDebug("**" + getClassName() + " params_:\n" + getAsParamMap(true).print());
+	logger_.logInfo(getClassName(), ": Starting build (", primitives_.size(), " prims) on CUDA device ", params_.device_);
+	// flatten the primitives: only static triangle / quad faces live in the GPU tree (SURVEY.md 8f N3 lists the rest)
+	std::vector<float> xyz;
+	std::vector<uint32_t> idx;
+	std::vector<uint8_t> flags;
+	xyz.reserve(primitives_.size() * 12);
+	idx.reserve(primitives_.size() * 4);
+	flags.reserve(primitives_.size());
+	for(const Primitive *primitive : primitives_)
+	{
+		if(render_control_ && render_control_->canceled()) return;
+		const auto *face{dynamic_cast<const FacePrimitive *>(primitive)};
+		const int n_vertices{face ? face->numVertices() : 0};
+		if(!face || face->hasMotionBlur() || (n_vertices != 3 && n_vertices != 4))
+		{
+			logger_.logError(getClassName(), ": primitive kind not supported by the b200-kdtree accelerator (only static triangle and quad mesh faces are); no accelerator created");
+			return;
+		}
+		const uint32_t first_vertex{static_cast<uint32_t>(xyz.size() / 3)};
+		for(int v = 0; v < n_vertices; ++v)
+		{
+			const Point3f p{face->getVertex(v, 0)};
+			xyz.push_back(p[Axis::X]); xyz.push_back(p[Axis::Y]); xyz.push_back(p[Axis::Z]);
+		}
+		for(int v = 0; v < 4; ++v) idx.push_back(v < n_vertices ? first_vertex + static_cast<uint32_t>(v) : 0xFFFFFFFFu);
+		flags.push_back(faceFlags(primitive));
+	}
+	b200rt_build_params build_params{};
+	build_params.max_depth = params_.max_depth_;
+	build_params.max_leaf_size = params_.max_leaf_size_;
+	build_params.cost_ratio = params_.cost_ratio_;
+	build_params.empty_bonus = params_.empty_bonus_;
+	build_params.build_threads = params_.num_threads_;
+	b200rt_scene *scene = nullptr;
+	int rc = b200rt_create(params_.device_, &build_params, &scene);
+	if(rc == B200RT_OK) rc = b200rt_add_mesh(scene, xyz.data(), xyz.size() / 3, idx.data(), idx.size() / 4, flags.data());
+	if(rc == B200RT_OK) rc = b200rt_build(scene);
+	float bound[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+	if(rc == B200RT_OK) rc = b200rt_get_bound(scene, bound);
+	if(rc != B200RT_OK)
+	{
+		logger_.logError(getClassName(), ": libb200rt failed (", rc, "): ", b200rt_last_error());
+		if(scene) b200rt_destroy(scene);
+		return;
+	}
+	scene_ = scene;
+	bound_ = Bound<float>{{{bound[0], bound[1], bound[2]}}, {{bound[3], bound[4], bound[5]}}};
+	b200rt_stats stats{};
+	if(b200rt_get_stats(scene_, &stats) == B200RT_OK && logger_.isVerbose())
+	{
+		logger_.logVerbose(getClassName(), ": Stats (build ", stats.build_seconds, "s, upload ", stats.upload_seconds, "s)");
+		logger_.logVerbose(getClassName(), ": Primitives in tree: ", stats.n_faces, " (", stats.n_triangles, " triangles, ", stats.n_quads, " quads)");
+		logger_.logVerbose(getClassName(), ": Interior nodes: ", stats.n_interior, " / leaf nodes: ", stats.n_leaves, " (empty: ", stats.n_empty_leaves, ")");
+		logger_.logVerbose(getClassName(), ": Leaf prims: ", stats.n_leaf_refs, ", depth: ", stats.max_depth, ", device bytes: ", stats.device_bytes);
+	}
+}
+
+AcceleratorB200::~AcceleratorB200()
+{
+	if(scene_) b200rt_destroy(scene_);
+}
+
+// ---- the three virtual per-ray queries: batches of one, rays already wrapped by the caller ------------------
+IntersectData AcceleratorB200::intersect(const Ray &ray, float t_max) const
+{
+	const b200rt_ray r{toRay(ray, t_max)};
+	b200rt_hit hit{};
+	IntersectData data;
+	data.t_max_ = t_max;
+	if(!scene_) return data;
+	if(b200rt_trace(scene_, B200RT_QUERY_CLOSEST, B200RT_RAYS_TREE_SPACE, &r, 1, &hit, 0) != B200RT_OK || hit.prim == B200RT_MISS) return data;
+	data.t_hit_ = hit.t;
+	data.t_max_ = hit.t;
+	data.uv_ = {hit.u, hit.v};
+	data.primitive_ = primitives_[hit.prim];
+	return data;
+}
+
+IntersectData AcceleratorB200::intersectShadow(const Ray &ray, float t_max) const
+{
+	const b200rt_ray r{toRay(ray, t_max)};
+	uint32_t occluder = B200RT_MISS;
+	IntersectData data;
+	if(!scene_) return data;
+	if(b200rt_trace(scene_, B200RT_QUERY_SHADOW, B200RT_RAYS_TREE_SPACE, &r, 1, &occluder, 0) != B200RT_OK || occluder == B200RT_MISS) return data;
+	data.t_hit_ = 1.f; //any value > 0: callers only use isHit() and primitive_ (accelerator.h:110)
+	data.primitive_ = primitives_[occluder];
+	return data;
+}
+
+IntersectData AcceleratorB200::intersectTransparentShadow(const Ray &ray, int max_depth, float dist, const Camera *camera) const
+{
+	const b200rt_ray r{toRay(ray, dist)};
+	b200rt_tshadow res{};
+	IntersectData data;
+	if(max_depth > B200RT_TSHADOW_MAX) max_depth = B200RT_TSHADOW_MAX; //documented limit of the result record
+	if(!scene_) return data;
+	if(b200rt_trace(scene_, B200RT_QUERY_TSHADOW, B200RT_RAYS_TREE_SPACE, &r, 1, &res, max_depth) != B200RT_OK) return data;
+	if(res.shadowed)
+	{
+		data.t_hit_ = 1.f;
+		data.primitive_ = primitives_[res.occluder];
+		return data;
+	}
+	// material evaluation stays on the host: colour = product of the transparencies of the distinct casters (accelerator.h:163-166)
+	for(uint32_t k = 0; k < res.n_transparent; ++k)
+	{
+		const b200rt_hit &h{res.transparent[k]};
+		const Primitive *primitive{primitives_[h.prim]};
+		const Point3f hit_point{ray.from_ + h.t * ray.dir_};
+		const auto sp{primitive->getSurface(nullptr, hit_point, ray.time_, {h.u, h.v}, camera)};
+		if(sp) data.color_ *= sp->getTransparency(ray.dir_, camera);
+	}
+	return data; //setNoHit(): t_hit_ = 0, primitive_ = nullptr, colour kept (accelerator_kdtree_common.h:246-250)
+}
+
+// ---- batched entry points ---------------------------------------------------------------------------------
+bool AcceleratorB200::intersectBatch(const Ray *rays, size_t n, IntersectData *out) const
+{
+	if(!scene_) return false;
+	std::vector<b200rt_ray> r(n);
+	std::vector<b200rt_hit> hits(n);
+	for(size_t i = 0; i < n; ++i) r[i] = toRay(rays[i], rays[i].tmax_); //tmax_ < 0 means unbounded, as accelerator.h:91
+	if(b200rt_trace_closest(scene_, r.data(), n, hits.data()) != B200RT_OK)
+	{
+		logger_.logError(getClassName(), ": intersectBatch failed: ", b200rt_last_error());
+		return false;
+	}
+	for(size_t i = 0; i < n; ++i)
+	{
+		out[i] = IntersectData{};
+		if(hits[i].prim == B200RT_MISS) continue;
+		out[i].t_hit_ = hits[i].t;
+		out[i].t_max_ = hits[i].t;
+		out[i].uv_ = {hits[i].u, hits[i].v};
+		out[i].primitive_ = primitives_[hits[i].prim];
+	}
+	return true;
+}
+
+bool AcceleratorB200::isShadowedBatch(const Ray *rays, size_t n, bool *shadowed, const Primitive **occluders) const
+{
+	if(!scene_) return false;
+	std::vector<b200rt_ray> r(n);
+	std::vector<uint32_t> occ(n);
+	for(size_t i = 0; i < n; ++i) r[i] = toRay(rays[i], rays[i].tmax_);
+	if(b200rt_trace_shadow(scene_, r.data(), n, occ.data()) != B200RT_OK)
+	{
+		logger_.logError(getClassName(), ": isShadowedBatch failed: ", b200rt_last_error());
+		return false;
+	}
+	for(size_t i = 0; i < n; ++i)
+	{
+		shadowed[i] = occ[i] != B200RT_MISS;
+		if(occluders) occluders[i] = shadowed[i] ? primitives_[occ[i]] : nullptr;
+	}
+	return true;
+}
+
+bool AcceleratorB200::isShadowedTransparentShadowBatch(const Ray *rays, size_t n, int max_depth, const Camera *camera, bool *shadowed, Rgb *colors, const Primitive **occluders) const
+{
+	if(!scene_) return false;
+	std::vector<b200rt_ray> r(n);
+	std::vector<b200rt_tshadow> res(n);
+	for(size_t i = 0; i < n; ++i) r[i] = toRay(rays[i], rays[i].tmax_);
+	if(max_depth > B200RT_TSHADOW_MAX) max_depth = B200RT_TSHADOW_MAX;
+	if(b200rt_trace_tshadow(scene_, r.data(), n, max_depth, res.data()) != B200RT_OK)
+	{
+		logger_.logError(getClassName(), ": isShadowedTransparentShadowBatch failed: ", b200rt_last_error());
+		return false;
+	}
+	for(size_t i = 0; i < n; ++i)
+	{
+		shadowed[i] = res[i].shadowed != 0;
+		colors[i] = Rgb{1.f};
+		if(occluders) occluders[i] = shadowed[i] ? primitives_[res[i].occluder] : nullptr;
+		if(shadowed[i]) continue;
+		const Point3f from{rays[i].from_ + rays[i].dir_ * rays[i].tmin_}; //the wrapper's moved origin (accelerator.h:116)
+		for(uint32_t k = 0; k < res[i].n_transparent; ++k)
+		{
+			const b200rt_hit &h{res[i].transparent[k]};
+			const Primitive *primitive{primitives_[h.prim]};
+			const auto sp{primitive->getSurface(nullptr, from + h.t * rays[i].dir_, rays[i].time_, {h.u, h.v}, camera)};
+			if(sp) colors[i] *= sp->getTransparency(rays[i].dir_, camera);
+		}
+	}
+	return true;
+}
+
+} //namespace yafaray

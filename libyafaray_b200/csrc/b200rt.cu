@@ -139,6 +139,33 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, La
 	if(!s->built) return fail(B200RT_E_INVALID, "scene not built: call b200rt_build first");
 	if(n == 0) return B200RT_OK;
 	CUDA_TRY(cudaSetDevice(s->device));
+	if(n <= size_t(b200rt::kPoolRays))
+	{
+		// Small batches (the per-ray compatibility path of the Accelerator virtuals): no staging copies at all.  The
+		// kernel reads the rays from, and writes the results to, pinned host memory (device-addressable under UVA), as
+		// one warp without a ray cursor: one launch and one stream synchronisation per call.
+		std::unique_ptr<Lane> lane;
+		{
+			std::lock_guard<std::mutex> lock(s->lane_mutex);
+			if(!s->free_lanes.empty()) { lane = std::move(s->free_lanes.back()); s->free_lanes.pop_back(); }
+		}
+		if(!lane) lane = std::make_unique<Lane>();
+		int rc = ensureLane(*lane, b200rt::kPoolRays * sizeof(b200rt_ray), b200rt::kPoolRays * sizeof(Out), true, true);
+		if(rc == B200RT_OK)
+		{
+			std::memcpy(lane->h_in, rays, n * sizeof(b200rt_ray));
+			rc = launch(static_cast<const b200rt_ray *>(lane->h_in), n, static_cast<Out *>(lane->h_out), lane->stream, /*cursorless*/ true);
+			if(rc == B200RT_OK)
+			{
+				const cudaError_t e = cudaStreamSynchronize(lane->stream);
+				if(e != cudaSuccess) rc = fail(B200RT_E_CUDA, std::string("small-batch trace: ") + cudaGetErrorString(e));
+				else std::memcpy(out, lane->h_out, n * sizeof(Out));
+			}
+		}
+		std::lock_guard<std::mutex> lock(s->lane_mutex);
+		s->free_lanes.push_back(std::move(lane));
+		return rc;
+	}
 	const size_t per_ray = std::max(sizeof(b200rt_ray), sizeof(Out));
 	const size_t chunk = std::max<size_t>(1024, kChunkBytes / per_ray);
 	const size_t n_chunks = (n + chunk - 1) / chunk;
@@ -185,7 +212,7 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, La
 		cudaError_t e = cudaMemcpyAsync(l.d_in, src, count * sizeof(b200rt_ray), cudaMemcpyHostToDevice, l.stream);
 		if(e == cudaSuccess)
 		{
-			rc = launch(static_cast<const b200rt_ray *>(l.d_in), count, static_cast<Out *>(l.d_out), l.stream);
+			rc = launch(static_cast<const b200rt_ray *>(l.d_in), count, static_cast<Out *>(l.d_out), l.stream, false);
 			if(rc != B200RT_OK) break;
 		}
 		if(e == cudaSuccess) e = cudaMemcpyAsync(out_pinned ? static_cast<void *>(out + begin) : l.h_out, l.d_out, count * sizeof(Out), cudaMemcpyDeviceToHost, l.stream);
@@ -218,8 +245,15 @@ int checkDeviceCall(const b200rt_scene *s, const void *rays, size_t n, const voi
 // Enqueue traceKernel<Q> over n rays on `stream`: a persistent grid (at most one resident wave) whose warps
 // pull rays from a cursor that is zeroed on the same stream just before the launch.
 template <int Q>
-int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b200rt::OutType<Q>::type *d_out, cudaStream_t stream, int max_depth, unsigned flags = 0u)
+int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b200rt::OutType<Q>::type *d_out, cudaStream_t stream, int max_depth, unsigned flags = 0u, bool cursorless = false)
 {
+	if(cursorless)
+	{
+		b200rt::traceKernel<Q><<<1, b200rt::kBlock, 0, stream>>>(s->view, d_rays, uint32_t(n), d_out, nullptr, max_depth, (flags & B200RT_RAYS_TREE_SPACE) != 0u);
+		++g_launches;
+		CUDA_TRY(cudaGetLastError());
+		return B200RT_OK;
+	}
 	for(size_t begin = 0; begin < n; begin += kMaxRaysPerLaunch)
 	{
 		const uint32_t count = uint32_t(std::min(kMaxRaysPerLaunch, n - begin));
@@ -483,23 +517,23 @@ int b200rt_trace_tshadow_device(b200rt_scene *s, const b200rt_ray *d_rays, size_
 // ---- host-buffer queries ----------------------------------------------------------------------
 int b200rt_trace_closest(b200rt_scene *s, const b200rt_ray *rays, size_t n, b200rt_hit *out)
 {
-	return tracedStaged(s, rays, n, out, [&](const b200rt_ray *d_rays, size_t count, b200rt_hit *d_out, cudaStream_t st) {
-		return launchTrace<b200rt::kClosest>(s, d_rays, count, d_out, st, 0);
+	return tracedStaged(s, rays, n, out, [&](const b200rt_ray *d_rays, size_t count, b200rt_hit *d_out, cudaStream_t st, bool small) {
+		return launchTrace<b200rt::kClosest>(s, d_rays, count, d_out, st, 0, 0u, small);
 	});
 }
 
 int b200rt_trace_shadow(b200rt_scene *s, const b200rt_ray *rays, size_t n, uint32_t *out)
 {
-	return tracedStaged(s, rays, n, out, [&](const b200rt_ray *d_rays, size_t count, uint32_t *d_out, cudaStream_t st) {
-		return launchTrace<b200rt::kShadow>(s, d_rays, count, d_out, st, 0);
+	return tracedStaged(s, rays, n, out, [&](const b200rt_ray *d_rays, size_t count, uint32_t *d_out, cudaStream_t st, bool small) {
+		return launchTrace<b200rt::kShadow>(s, d_rays, count, d_out, st, 0, 0u, small);
 	});
 }
 
 int b200rt_trace_tshadow(b200rt_scene *s, const b200rt_ray *rays, size_t n, int max_depth, b200rt_tshadow *out)
 {
 	if(max_depth < 0 || max_depth > B200RT_TSHADOW_MAX) return fail(B200RT_E_INVALID, "max_depth must be in [0, B200RT_TSHADOW_MAX]");
-	return tracedStaged(s, rays, n, out, [&](const b200rt_ray *d_rays, size_t count, b200rt_tshadow *d_out, cudaStream_t st) {
-		return launchTrace<b200rt::kTShadow>(s, d_rays, count, d_out, st, max_depth);
+	return tracedStaged(s, rays, n, out, [&](const b200rt_ray *d_rays, size_t count, b200rt_tshadow *d_out, cudaStream_t st, bool small) {
+		return launchTrace<b200rt::kTShadow>(s, d_rays, count, d_out, st, max_depth, 0u, small);
 	});
 }
 
@@ -526,17 +560,17 @@ int b200rt_trace(b200rt_scene *s, int query, unsigned flags, const b200rt_ray *r
 	switch(query)
 	{
 		case B200RT_QUERY_CLOSEST:
-			return tracedStaged(s, rays, n, static_cast<b200rt_hit *>(out), [&](const b200rt_ray *d_rays, size_t count, b200rt_hit *d_out, cudaStream_t st) {
-				return launchTrace<b200rt::kClosest>(s, d_rays, count, d_out, st, 0, flags);
+			return tracedStaged(s, rays, n, static_cast<b200rt_hit *>(out), [&](const b200rt_ray *d_rays, size_t count, b200rt_hit *d_out, cudaStream_t st, bool small) {
+				return launchTrace<b200rt::kClosest>(s, d_rays, count, d_out, st, 0, flags, small);
 			});
 		case B200RT_QUERY_SHADOW:
-			return tracedStaged(s, rays, n, static_cast<uint32_t *>(out), [&](const b200rt_ray *d_rays, size_t count, uint32_t *d_out, cudaStream_t st) {
-				return launchTrace<b200rt::kShadow>(s, d_rays, count, d_out, st, 0, flags);
+			return tracedStaged(s, rays, n, static_cast<uint32_t *>(out), [&](const b200rt_ray *d_rays, size_t count, uint32_t *d_out, cudaStream_t st, bool small) {
+				return launchTrace<b200rt::kShadow>(s, d_rays, count, d_out, st, 0, flags, small);
 			});
 		case B200RT_QUERY_TSHADOW:
 			if(max_depth < 0 || max_depth > B200RT_TSHADOW_MAX) return fail(B200RT_E_INVALID, "max_depth must be in [0, B200RT_TSHADOW_MAX]");
-			return tracedStaged(s, rays, n, static_cast<b200rt_tshadow *>(out), [&](const b200rt_ray *d_rays, size_t count, b200rt_tshadow *d_out, cudaStream_t st) {
-				return launchTrace<b200rt::kTShadow>(s, d_rays, count, d_out, st, max_depth, flags);
+			return tracedStaged(s, rays, n, static_cast<b200rt_tshadow *>(out), [&](const b200rt_ray *d_rays, size_t count, b200rt_tshadow *d_out, cudaStream_t st, bool small) {
+				return launchTrace<b200rt::kTShadow>(s, d_rays, count, d_out, st, max_depth, flags, small);
 			});
 		default: return fail(B200RT_E_INVALID, "unknown query kind");
 	}

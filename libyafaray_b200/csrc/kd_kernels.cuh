@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 	float t_exit = 0.f;     // where the ray leaves the tree bound (or its t_max)
 	uint32_t pool_next = 0u, pool_end = 0u; // warp-uniform
 	bool exhausted = false;                 // warp-uniform
+	bool first_pool = true;                 // warp-uniform
 
 	// Leave the current leaf.  Closest queries stop once the best hit is not beyond the end of this leaf
 	// (accelerator_kdtree_common.h:232); otherwise continue with the nearest postponed subtree, or restart
@@ -386,9 +387,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 		{
 			if(pool_next == pool_end)
 			{
-				uint32_t base = 0u;
-				if(lane == 0u) base = atomicAdd(cursor, uint32_t(kPoolRays));
-				base = __shfl_sync(kFullMask, base, 0);
+				uint32_t base = n;
+				if(cursor != nullptr)
+				{
+					if(lane == 0u) base = atomicAdd(cursor, uint32_t(kPoolRays));
+					base = __shfl_sync(kFullMask, base, 0);
+				}
+				else if(first_pool && blockIdx.x == 0 && tid < 32u) base = 0u; // cursor-less launch: one warp, one pool (n <= kPoolRays)
+				first_pool = false;
 				if(base >= n) exhausted = true;
 				else
 				{

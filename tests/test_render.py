@@ -1,0 +1,104 @@
+"""BASELINE.json configs[0]: the reference's own tests/test01 scene (56 quads+triangles, DirectLight) rendered by the
+UNMODIFIED reference client through a libYafaRay patched with integration/b200-kdtree.patch, once with the default
+CPU accelerator ("yafaray-kdtree-original") and once with type "b200-kdtree" (AcceleratorB200 -> libb200rt -> CUDA),
+and compared by PSNR.  The binaries are prebuilt by integration/Makefile where /root/reference exists."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "integration", "_build")
+PSNR_FLOOR_DB = 50.0  # stated bar; two runs of the stock reference itself differ in a few bytes
+
+
+def read_tga(path):
+    raw = np.fromfile(path, dtype=np.uint8)
+    id_len, cmap_type, img_type = int(raw[0]), int(raw[1]), int(raw[2])
+    w, h, bpp = int(raw[12]) | int(raw[13]) << 8, int(raw[14]) | int(raw[15]) << 8, int(raw[16])
+    assert cmap_type == 0 and bpp in (24, 32)
+    px = bpp // 8
+    off = 18 + id_len
+    if img_type == 2:
+        data = raw[off:off + w * h * px]
+    else:
+        assert img_type == 10, f"unsupported TGA type {img_type}"
+        out = np.empty(w * h * px, np.uint8)
+        i, o = off, 0
+        while o < out.size:
+            c = int(raw[i]); i += 1
+            n = (c & 0x7F) + 1
+            if c & 0x80:
+                out[o:o + n * px] = np.tile(raw[i:i + px], n); i += px
+            else:
+                out[o:o + n * px] = raw[i:i + n * px]; i += n * px
+            o += n * px
+        data = out
+    return data.reshape(h, w, px).astype(np.float64)
+
+
+def psnr(a, b):
+    mse = np.mean((a - b) ** 2)
+    return float("inf") if mse == 0 else 10.0 * np.log10(255.0 ** 2 / mse)
+
+
+def render(binary, workdir, accel, extra_env):
+    env = dict(os.environ)
+    env.update(extra_env)
+    env.pop("B200_ACCEL_TYPE", None)
+    if accel:
+        env["B200_ACCEL_TYPE"] = accel
+    log = subprocess.run([binary], cwd=workdir, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, errors="replace", timeout=1500)
+    assert log.returncode == 0, log.stdout[-3000:]
+    return log.stdout
+
+
+def needs_build(name):
+    return pytest.mark.skipif(not os.path.exists(os.path.join(BUILD, name)), reason=f"integration/_build/{name} not prebuilt")
+
+
+@pytest.mark.gpu
+@needs_build("yafaray_test01")
+@pytest.mark.parametrize("test,deterministic", [("test01", True), ("test01", False), ("test09", True)])
+def test_reference_scene_renders_through_b200_accelerator(built, test, deterministic):
+    binary = os.path.join(BUILD, "yafaray_" + test)
+    if not os.path.exists(binary):
+        pytest.skip(binary + " not prebuilt")
+    extra = {"B200_AA_PASSES": "1"}
+    if deterministic:
+        extra["B200_DETERMINISTIC"] = "1"
+    images = {}
+    for accel in ("", "b200-kdtree"):
+        with tempfile.TemporaryDirectory() as d:
+            log = render(binary, d, accel, extra)
+            if accel:
+                assert "Added AcceleratorB200 (b200-kdtree)" in log or "(b200-kdtree)" in log, "the b200 accelerator was not selected"
+                assert "no usable accelerator" not in log, "libb200rt failed to build the scene on this box"
+            else:
+                assert "(yafaray-kdtree-original)" in log
+            out = [f for f in os.listdir(d) if f.endswith(".tga")]
+            assert out, "no image written"
+            images[accel] = read_tga(os.path.join(d, out[0]))
+    a, b = images[""], images["b200-kdtree"]
+    assert a.shape == b.shape
+    # the badge strip carries no text in this build (FreeType is off), so the whole image is compared; PSNR is taken over
+    # the film rows only (the badge is 78 identical black rows at the top of test01's 480x348 output)
+    badge = a.shape[0] - 270 if a.shape[0] > 270 else 0
+    value = psnr(a[badge:], b[badge:])
+    print(f"{test} deterministic={deterministic}: PSNR {value:.2f} dB, differing bytes {(a[badge:] != b[badge:]).sum()} of {a[badge:].size}")
+    assert value >= PSNR_FLOOR_DB
+    assert a[badge:].std() > 5.0, "reference image is flat: nothing was rendered"
+
+
+@needs_build("yafaray_test01")
+def test_b200_accelerator_fails_loudly_without_a_device(built):
+    """CPU box: the patched reference selects b200-kdtree, libb200rt reports the missing device, the error is logged and
+    the scene renders no geometry -- there is no hidden CPU traversal."""
+    from libyafaray_b200 import rt
+    if rt.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with tempfile.TemporaryDirectory() as d:
+        log = render(os.path.join(BUILD, "yafaray_test01"), d, "b200-kdtree", {"B200_AA_PASSES": "1", "B200_DETERMINISTIC": "1"})
+        assert "libb200rt failed" in log and "no usable accelerator" in log
