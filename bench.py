@@ -51,46 +51,54 @@ def parse():
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md), through NVML
+    (nvidia_ml_py) every few milliseconds -- a timed region of a few tens of ms is too short for `nvidia-smi -lms`."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80}
 
-    def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index: int, period_s: float = 0.004):
+        self.rows, self.ok, self.stop_flag, self.period = [], False, False, period_s
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(index), "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+            self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.perf_counter(), sm, mask))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def window(self, t0, t1):
-        sm, mx, reasons = [], [], set()
-        for t, line in self.rows:
-            if t < t0 or t > t1 + 0.15:
-                continue
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "error": getattr(self, "err", "nvml unavailable")}
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        if len(rows) < 2:  # region shorter than two periods: take the nearest samples around it
+            rows = sorted(self.rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))[:4]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": [], "samples": 0}
+        mask = 0
+        for r in rows:
+            mask |= r[2]
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": self.max_sm,
+                "reasons": sorted(k for k, bit in self.REASONS.items() if mask & bit), "samples": len(rows)}
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
+        self.stop_flag = True
 
 
 # ------------------------------------------------------------------------------------------ workload
@@ -241,7 +249,6 @@ def run_b200(args):
         step()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    time.sleep(0.25 if sampler else 0)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     launches0 = rt.launch_count()
     barrier()

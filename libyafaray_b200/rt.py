@@ -230,7 +230,7 @@ class Scene:
         """Generic entry point: query = QUERY_CLOSEST / QUERY_SHADOW / QUERY_TSHADOW, flags = RAYS_TREE_SPACE or 0."""
         r = as_rays(rays)
         if out is None:
-            out = np.empty(r.shape[0], (HIT_DTYPE, np.uint32, TSHADOW_DTYPE)[query])
+            out = np.empty(r.shape[0], {QUERY_CLOSEST: HIT_DTYPE, QUERY_SHADOW: np.uint32, QUERY_TSHADOW: TSHADOW_DTYPE}.get(int(query), TSHADOW_DTYPE))
         _check(lib().b200rt_trace(self._h, int(query), int(flags), _p(r), r.shape[0], _p(out), int(max_depth)))
         return out
 
