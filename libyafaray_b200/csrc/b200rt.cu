@@ -272,6 +272,9 @@ template <int Q>
 int queryResidency(b200rt_scene *s)
 {
 	int per_sm = 0, sms = 0;
+#ifdef B200RT_CARVEOUT
+	CUDA_TRY(cudaFuncSetAttribute(b200rt::traceKernel<Q>, cudaFuncAttributePreferredSharedMemoryCarveout, B200RT_CARVEOUT));
+#endif
 	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b200rt::traceKernel<Q>, b200rt::kBlock, 0));
 	CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
 	s->resident_blocks[Q] = std::max(1, per_sm) * std::max(1, sms);

@@ -181,6 +181,9 @@ __device__ __forceinline__ float polyIntersect(const float4 q0, const float4 q1,
 #ifndef B200RT_POP_IN_LEAF_PHASE
 #define B200RT_POP_IN_LEAF_PHASE 0
 #endif
+#ifndef B200RT_STREAM_IO
+#define B200RT_STREAM_IO 1
+#endif
 #ifndef B200RT_STEPS
 #define B200RT_STEPS 8
 #endif
@@ -289,9 +292,20 @@ __device__ __forceinline__ void writeResult(typename OutType<QUERY>::type *out, 
 	{
 		float4 v;
 		v.x = hit ? r.t_max : 0.f; v.y = r.best_u; v.z = r.best_v; v.w = __uint_as_float(r.best_prim);
+#if B200RT_STREAM_IO
+		__stcs(reinterpret_cast<float4 *>(out) + r.index, v);
+#else
 		reinterpret_cast<float4 *>(out)[r.index] = v;
+#endif
 	}
-	else if(QUERY == kShadow) reinterpret_cast<uint32_t *>(out)[r.index] = hit ? r.best_prim : B200RT_MISS;
+	else if(QUERY == kShadow)
+	{
+#if B200RT_STREAM_IO
+		__stcs(reinterpret_cast<uint32_t *>(out) + r.index, hit ? r.best_prim : B200RT_MISS);
+#else
+		reinterpret_cast<uint32_t *>(out)[r.index] = hit ? r.best_prim : B200RT_MISS;
+#endif
+	}
 	else
 	{
 		uint4 *o = reinterpret_cast<uint4 *>(reinterpret_cast<b200rt_tshadow *>(out) + r.index);
@@ -409,8 +423,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 				if(!alive && rank < avail)
 				{
 					r.index = pool_next + rank;
+#if B200RT_STREAM_IO
+					// rays are read once: do not let them displace tree nodes from L1/L2
+					const float4 a = __ldcs(reinterpret_cast<const float4 *>(rays) + 2 * size_t(r.index));
+					const float4 b = __ldcs(reinterpret_cast<const float4 *>(rays) + 2 * size_t(r.index) + 1);
+#else
 					const float4 a = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * size_t(r.index));
 					const float4 b = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * size_t(r.index) + 1);
+#endif
 					ts.depth = 0;
 					floor = 0;
 					alive = setupRay<QUERY>(s, a, b, r, tree_space);
@@ -485,40 +505,57 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 			{
 				if(alive && !pending && !finished)
 				{
+					// One node per step, interior or leaf, without divergent branches: the interior arithmetic, the push,
+					// the pop of an empty leaf and the hand-over of a non-empty leaf are all predicated / selected.
 					const uint2 nd = __ldg(&s.nodes[r.node]);
 					const uint32_t axis = nd.y & 3u;
-					if(axis != 3u)
+					const uint32_t payload = nd.y >> 2; // interior: right child, leaf: primitive count
+					const bool is_leaf = (axis == 3u);
+					const float split = __uint_as_float(nd.x);
+					const bool a1 = (axis == 1u), a2 = (axis == 2u);
+					const float o = selectf(a2, r.oz, selectf(a1, r.oy, r.ox));
+					const float inv = selectf(a2, r.iz, selectf(a1, r.iy, r.ix));
+					const float t_plane = (split - o) * inv;
+					const bool neg = inv < 0.f;
+					const uint32_t left = r.node + 1u;
+					const uint32_t near = selectu(neg, payload, left), far = selectu(neg, left, payload);
+					const float limit = (QUERY == kClosest) ? fminf(r.seg_hi, r.t_max) : r.seg_hi;
+					const bool far_only = t_plane <= r.seg_lo;
+					const bool both = !is_leaf && !(t_plane >= limit) && !far_only;
+					// top of the ring (read before this step's speculative store; different slot)
+					const int top = (r.sp - 1) & (kShortStack - 1);
+					const uint32_t pop_node = sh_node[top][tid];
+					const float pop_far = sh_far[top][tid];
+					if(!is_leaf)
 					{
-						// branch-free node step
-						const float split = __uint_as_float(nd.x);
-						const bool a1 = (axis == 1u), a2 = (axis == 2u);
-						const float o = selectf(a2, r.oz, selectf(a1, r.oy, r.ox));
-						const float inv = selectf(a2, r.iz, selectf(a1, r.iy, r.ix));
-						const float t_plane = (split - o) * inv;
-						const bool neg = inv < 0.f;
-						const uint32_t left = r.node + 1u, right = nd.y >> 2;
-						const uint32_t near = selectu(neg, right, left), far = selectu(neg, left, right);
-						const float limit = (QUERY == kClosest) ? fminf(r.seg_hi, r.t_max) : r.seg_hi;
-						const bool far_only = t_plane <= r.seg_lo;
-						const bool both = !(t_plane >= limit) && !far_only;
 						const int slot = r.sp & (kShortStack - 1);
 						sh_node[slot][tid] = far;
 						sh_far[slot][tid] = r.seg_hi;
-						floor = max(floor, r.sp + 1 - kShortStack); // the store above has clobbered the oldest slot of a full ring, pushed or not
-						r.sp += both ? 1 : 0;
-						r.node = selectu(far_only, far, near);
-						r.seg_hi = selectf(both, t_plane, r.seg_hi);
+						floor = max(floor, r.sp + 1 - kShortStack); // the store has clobbered the oldest slot of a full ring, pushed or not
 					}
-					else
+					const bool empty_leaf = is_leaf && payload == 0u;
+					// closest: once the best hit is not beyond the end of this leaf nothing nearer can follow (accelerator_kdtree_common.h:232)
+					const bool closest_done = (QUERY == kClosest) && r.best_prim != B200RT_MISS && r.t_max <= r.seg_hi;
+					const bool has_stack = r.sp > floor;
+					const bool do_pop = empty_leaf && !closest_done && has_stack;
+					const bool lost = empty_leaf && !closest_done && !has_stack && floor != 0;
+					finished = empty_leaf && !do_pop && !lost;
+					pending = is_leaf && !empty_leaf;
+					leaf_count = payload;
+					leaf_first = nd.x;
+					r.node = is_leaf ? selectu(do_pop, pop_node, r.node) : selectu(far_only, far, near);
+					r.seg_lo = selectf(do_pop, r.seg_hi, r.seg_lo);
+					r.seg_hi = selectf(do_pop, pop_far, selectf(both, t_plane, r.seg_hi));
+					r.sp += (both ? 1 : 0) - (do_pop ? 1 : 0);
+					if(lost)
 					{
-						leaf_count = nd.y >> 2;
-						leaf_first = nd.x;
-#if B200RT_POP_IN_LEAF_PHASE
-						pending = true;
-#else
-						if(leaf_count != 0u) pending = true;
-						else finished = popNode();
-#endif
+						// ring entries were overwritten: restart from the root behind the leaf just left (kd-restart)
+						r.sp = 0;
+						floor = 0;
+						r.node = 0u;
+						r.seg_lo = r.seg_hi;
+						r.seg_hi = t_exit;
+						finished = !(r.seg_lo < t_exit);
 					}
 				}
 			}
