@@ -170,7 +170,7 @@ __device__ __forceinline__ float polyIntersect(const float4 q0, const float4 q1,
 #define B200RT_BLOCK 128
 #endif
 #ifndef B200RT_MIN_BLOCKS
-#define B200RT_MIN_BLOCKS 8
+#define B200RT_MIN_BLOCKS 9
 #endif
 #ifndef B200RT_REFILL
 #define B200RT_REFILL 8
@@ -183,6 +183,9 @@ __device__ __forceinline__ float polyIntersect(const float4 q0, const float4 q1,
 #endif
 #ifndef B200RT_STREAM_IO
 #define B200RT_STREAM_IO 1
+#endif
+#ifndef B200RT_SMEM_RAY
+#define B200RT_SMEM_RAY 1
 #endif
 #ifndef B200RT_STEPS
 #define B200RT_STEPS 8
@@ -351,8 +354,10 @@ template <int QUERY>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
                                                                  typename OutType<QUERY>::type *__restrict__ out, uint32_t *__restrict__ cursor, int max_depth, bool tree_space)
 {
-	__shared__ uint32_t sh_node[kShortStack][kBlock];
-	__shared__ float sh_far[kShortStack][kBlock];
+	__shared__ uint2 sh_stack[kShortStack][kBlock];
+#if B200RT_SMEM_RAY
+	__shared__ float2 sh_axis[3][kBlock];          // per axis: (origin, inverse direction) of the lane's ray
+#endif // x = node index, y = float bits of the far end of its interval
 	const unsigned tid = threadIdx.x;
 	const unsigned lane = tid & 31u;
 	const unsigned lanes_below = (1u << lane) - 1u;
@@ -376,9 +381,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 		if(r.sp > floor)
 		{
 			--r.sp;
-			r.node = sh_node[r.sp & (kShortStack - 1)][tid];
+			const uint2 e = sh_stack[r.sp & (kShortStack - 1)][tid];
+			r.node = e.x;
 			r.seg_lo = r.seg_hi;
-			r.seg_hi = sh_far[r.sp & (kShortStack - 1)][tid];
+			r.seg_hi = __uint_as_float(e.y);
 			return false;
 		}
 		if(floor == 0) return true;
@@ -435,6 +441,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 					floor = 0;
 					alive = setupRay<QUERY>(s, a, b, r, tree_space);
 					t_exit = r.seg_hi;
+#if B200RT_SMEM_RAY
+					sh_axis[0][tid] = make_float2(r.ox, r.ix);
+					sh_axis[1][tid] = make_float2(r.oy, r.iy);
+					sh_axis[2][tid] = make_float2(r.oz, r.iz);
+#endif
 					if(!alive) writeResult<QUERY>(out, r, false, ts); // missed the tree bound
 				}
 				pool_next += min(avail, uint32_t(__popc(idle)));
@@ -512,9 +523,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 					const uint32_t payload = nd.y >> 2; // interior: right child, leaf: primitive count
 					const bool is_leaf = (axis == 3u);
 					const float split = __uint_as_float(nd.x);
+#if B200RT_SMEM_RAY
+					const float2 oi = sh_axis[axis < 3u ? axis : 0u][tid];
+					const float o = oi.x, inv = oi.y;
+#else
 					const bool a1 = (axis == 1u), a2 = (axis == 2u);
 					const float o = selectf(a2, r.oz, selectf(a1, r.oy, r.ox));
 					const float inv = selectf(a2, r.iz, selectf(a1, r.iy, r.ix));
+#endif
 					const float t_plane = (split - o) * inv;
 					const bool neg = inv < 0.f;
 					const uint32_t left = r.node + 1u;
@@ -524,13 +540,13 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 					const bool both = !is_leaf && !(t_plane >= limit) && !far_only;
 					// top of the ring (read before this step's speculative store; different slot)
 					const int top = (r.sp - 1) & (kShortStack - 1);
-					const uint32_t pop_node = sh_node[top][tid];
-					const float pop_far = sh_far[top][tid];
+					const uint2 popped = sh_stack[top][tid];
+					const uint32_t pop_node = popped.x;
+					const float pop_far = __uint_as_float(popped.y);
 					if(!is_leaf)
 					{
 						const int slot = r.sp & (kShortStack - 1);
-						sh_node[slot][tid] = far;
-						sh_far[slot][tid] = r.seg_hi;
+						sh_stack[slot][tid] = make_uint2(far, __float_as_uint(r.seg_hi));
 						floor = max(floor, r.sp + 1 - kShortStack); // the store has clobbered the oldest slot of a full ring, pushed or not
 					}
 					const bool empty_leaf = is_leaf && payload == 0u;
