@@ -168,10 +168,36 @@ enum
 };
 enum
 {
-	B200RT_RAYS_TREE_SPACE = 1
+	B200RT_RAYS_TREE_SPACE = 1,
+	B200RT_BUFFERS_PINNED = 2 /* host-buffer calls: rays and out come from b200rt_host_alloc (skips the pointer query) */
 };
 int b200rt_trace(b200rt_scene *scene, int query, unsigned flags, const b200rt_ray *rays, size_t n, void *out, int max_depth);
 int b200rt_trace_device(b200rt_scene *scene, int query, unsigned flags, const b200rt_ray *d_rays, size_t n, void *d_out, int max_depth, void *stream);
+
+/* Several host-buffer batches in one call -- what one flush of the renderer's wavefront ray queue holds (closest,
+ * shadow and transparent-shadow rays of the pixels in flight on one render thread; Accelerator::intersect / isShadowed /
+ * isShadowedTransparentShadow call sites of integrator_montecarlo.cc:148,240,362, integrator_path_tracer.cc:145,210,251).
+ * Batches in pinned memory of up to 65 536 rays are traced in place (the kernels read the rays and write the results
+ * across PCIe, no staging copies), all jobs concurrently on their own streams, one wait per job at the end; larger or
+ * unpinned batches take the staged path of b200rt_trace one after the other.  Returns the first error. */
+typedef struct b200rt_job
+{
+	b200rt_scene *scene;
+	int query;          /* B200RT_QUERY_* */
+	unsigned flags;     /* B200RT_RAYS_TREE_SPACE | B200RT_BUFFERS_PINNED */
+	const b200rt_ray *rays;
+	size_t n;
+	void *out;
+	int max_depth;      /* transparent shadows only */
+} b200rt_job;
+int b200rt_trace_jobs(const b200rt_job *jobs, size_t n_jobs);
+/* The same in two halves, so that a render thread can shade one group of pixels while the rays of another group are
+ * on the GPU: _begin enqueues the in-place jobs and returns (jobs that need staging are traced before it returns);
+ * _end waits for them, releases the flight and returns the first error of either half.  The job buffers must stay
+ * untouched between the two calls; the job array itself may go away after _begin. */
+typedef struct b200rt_flight b200rt_flight;
+int b200rt_trace_jobs_begin(const b200rt_job *jobs, size_t n_jobs, b200rt_flight **flight);
+int b200rt_trace_jobs_end(b200rt_flight *flight);
 
 /* Pinned host memory for ray / result buffers (makes the host-buffer queries copy at full PCIe rate). */
 int b200rt_host_alloc(void **ptr, size_t bytes);

@@ -11,6 +11,10 @@
 #define LIBYAFARAY_ACCELERATOR_B200_H
 
 #include "accelerator/accelerator.h"
+#include "render/wavefront_b200.h"
+#include <atomic>
+#include <memory>
+#include <mutex>
 #include <vector>
 
 struct b200rt_scene;
@@ -39,6 +43,19 @@ class AcceleratorB200 final : public Accelerator
 		/* isShadowedTransparentShadowBatch is Accelerator::isShadowedTransparentShadow(ray, max_depth, camera). */
 		bool isShadowedTransparentShadowBatch(const Ray *rays, size_t n, int max_depth, const Camera *camera, bool *shadowed, Rgb *colors, const Primitive **occluders) const;
 
+		/* Wavefront rendering (render/wavefront_b200.h): TiledIntegrator::renderWorkerWavefront runs the reference's
+		 * renderTile() on wavefrontFibers() fibers per render thread; the three per-ray virtuals below then park their ray
+		 * in the calling fiber's queue instead of launching a one-ray kernel.  0 fibers = the per-ray path only. */
+		int wavefrontFibers() const { return scene_ ? params_.wavefront_fibers_ : 0; }
+		int wavefrontGroups() const { return params_.wavefront_groups_; }
+		int wavefrontBlock() const { return params_.wavefront_block_; }
+		size_t wavefrontStackBytes() const { return static_cast<size_t>(std::max(64, params_.wavefront_stack_kb_)) << 10; }
+		/* Ray queues (fiber stacks + pinned buffers) are kept between render passes: a render worker borrows one and returns it. */
+		std::unique_ptr<b200::RayQueue> acquireRayQueue() const;
+		void releaseRayQueue(std::unique_ptr<b200::RayQueue> queue) const;
+		void addWavefrontStats(const b200::RayQueue::Stats &stats) const;
+		void logWavefrontStats() const; //!< one Info line with the totals since the last call, then resets them
+
 	private:
 		[[nodiscard]] Type type() const override { return Type::B200KdTree; }
 		const struct Params
@@ -51,6 +68,10 @@ class AcceleratorB200 final : public Accelerator
 			PARAM_DECL(float, empty_bonus_, 0.f, "empty_bonus", "0 = library default");
 			PARAM_DECL(int, device_, 0, "device", "CUDA device index");
 			PARAM_DECL(int, num_threads_, 0, "accelerator_threads", "host threads for the tree build; 0 = all");
+			PARAM_DECL(int, wavefront_fibers_, 1024, "wavefront_fibers", "rays in flight per render thread (fibers running renderTile on pixel blocks); 0 = per-ray calls only");
+			PARAM_DECL(int, wavefront_groups_, 2, "wavefront_groups", "groups the fibers of a thread are split into; one group shades while the rays of another are on the GPU");
+			PARAM_DECL(int, wavefront_block_, 4, "wavefront_block", "side of the pixel block one fiber renders");
+			PARAM_DECL(int, wavefront_stack_kb_, 256, "wavefront_stack_kb", "stack per fiber, KiB (mapped lazily)");
 		} params_;
 		[[nodiscard]] ParamMap getAsParamMap(bool only_non_default) const override;
 
@@ -62,6 +83,9 @@ class AcceleratorB200 final : public Accelerator
 		std::vector<const Primitive *> primitives_; //!< face id (upload order) -> primitive; copies the factory's temporary vector
 		b200rt_scene *scene_ = nullptr;             //!< owned; device memory lives behind this handle
 		Bound<float> bound_{{{0.f, 0.f, 0.f}}, {{0.f, 0.f, 0.f}}};
+		mutable std::mutex queues_mutex_;
+		mutable std::vector<std::unique_ptr<b200::RayQueue>> idle_queues_;
+		mutable std::atomic<uint64_t> wf_rays_[3]{}, wf_batches_{0}, wf_calls_{0}, wf_switches_{0}, wf_trace_us_{0}, wf_run_us_{0}, wf_per_ray_calls_{0};
 };
 
 } //namespace yafaray

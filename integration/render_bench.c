@@ -1,0 +1,233 @@
+/* integration/render_bench.c -- a client of libYafaRay's PUBLIC C API only (yafaray_c_api.h), in the style of the
+ * reference's tests/testNN clients: builds a synthetic height-field scene of the S1M-hf shape with a
+ * few boxes standing on it, one point light and one area light, and renders it with the integrator and the accelerator
+ * type named on the command line.  Used to time `yafaray_render` end to end with the stock CPU kd-tree against the
+ * "b200-kdtree" accelerator and to compare the two images (tests/test_render.py, tools/render_compare.py).
+ *
+ *   render_bench <accelerator-type> <integrator> <cells> <width> <height> <aa_samples> <out.tga> [threads] [key=value ...]
+ *     accelerator-type  yafaray-kdtree-original | yafaray-kdtree-multi-thread | b200-kdtree
+ *     integrator        directlighting | pathtracing
+ *     key=value         extra integer accelerator parameters (e.g. wavefront_fibers=0 wavefront_block=4)
+ *     i:key=value       extra integer integrator parameters (e.g. i:AO_samples=32 i:bounces=5)
+ *     b:key=0|1         extra boolean integrator parameters (e.g. b:do_AO=1)
+ *     f:key=value       extra float integrator parameters (e.g. f:AO_distance=2.5)
+ */
+#include "yafaray_c_api.h"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+static double now(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+}
+
+static unsigned lcg_state = 12345u;
+static double lcg(void)
+{
+	lcg_state = lcg_state * 1664525u + 1013904223u;
+	return (double) (lcg_state >> 8) / 16777216.0;
+}
+
+static void add_box(yafaray_Scene *scene, const char *name, double x0, double y0, double z0, double x1, double y1, double z1, const char *material)
+{
+	size_t object_id = 0, material_id = 0;
+	yafaray_ParamMap *pm = yafaray_createParamMap();
+	yafaray_setParamMapInt(pm, "num_faces", 6);
+	yafaray_setParamMapInt(pm, "num_vertices", 8);
+	yafaray_setParamMapString(pm, "type", "mesh");
+	yafaray_createObject(scene, &object_id, name, pm);
+	for(int k = 0; k < 8; ++k) yafaray_addVertex(scene, object_id, (k & 4) ? x1 : x0, (k & 2) ? y1 : y0, (k & 1) ? z1 : z0);
+	yafaray_getMaterialId(scene, &material_id, material);
+	yafaray_addQuad(scene, object_id, 2, 0, 1, 3, material_id);
+	yafaray_addQuad(scene, object_id, 3, 7, 6, 2, material_id);
+	yafaray_addQuad(scene, object_id, 7, 5, 4, 6, material_id);
+	yafaray_addQuad(scene, object_id, 0, 4, 5, 1, material_id);
+	yafaray_addQuad(scene, object_id, 0, 2, 6, 4, material_id);
+	yafaray_addQuad(scene, object_id, 5, 7, 3, 1, material_id);
+	yafaray_initObject(scene, object_id, material_id);
+	yafaray_destroyParamMap(pm);
+}
+
+int main(int argc, char **argv)
+{
+	if(argc < 8)
+	{
+		fprintf(stderr, "usage: %s <accelerator-type> <integrator> <cells> <width> <height> <aa_samples> <out.tga> [threads] [key=value ...]\n", argv[0]);
+		return 2;
+	}
+	const char *accel = argv[1], *integrator = argv[2], *out_path = argv[7];
+	const int cells = atoi(argv[3]), width = atoi(argv[4]), height = atoi(argv[5]), aa_samples = atoi(argv[6]);
+	const int threads = argc > 8 ? atoi(argv[8]) : -1;
+	const double scale = 10.0; /* scene spans [0,10]^2 */
+
+	yafaray_Logger *logger = yafaray_createLogger("", NULL, NULL, YAFARAY_DISPLAY_CONSOLE_NORMAL);
+	yafaray_setConsoleLogColorsEnabled(logger, YAFARAY_BOOL_FALSE);
+	yafaray_setConsoleVerbosityLevel(logger, YAFARAY_LOG_LEVEL_INFO);
+	yafaray_Scene *scene = yafaray_createScene(logger, "scene");
+	yafaray_ParamMap *pm = yafaray_createParamMap();
+	yafaray_ParamMapList *pml = yafaray_createParamMapList();
+	size_t material_id = 0, object_id = 0;
+
+	/* materials */
+	yafaray_setParamMapColor(pm, "color", 0.75f, 0.7f, 0.6f, 1.f);
+	yafaray_setParamMapFloat(pm, "diffuse_reflect", 1.f);
+	yafaray_setParamMapString(pm, "type", "shinydiffusemat");
+	yafaray_createMaterial(scene, &material_id, "ground", pm, pml);
+	yafaray_clearParamMap(pm);
+	yafaray_setParamMapColor(pm, "color", 0.3f, 0.45f, 0.8f, 1.f);
+	yafaray_setParamMapFloat(pm, "diffuse_reflect", 0.9f);
+	yafaray_setParamMapFloat(pm, "specular_reflect", 0.15f);
+	yafaray_setParamMapString(pm, "type", "shinydiffusemat");
+	yafaray_createMaterial(scene, &material_id, "boxes", pm, pml);
+
+	/* height-field: cells x cells quads split in two triangles, z as S1M-hf plus a little noise */
+	const double t_scene = now();
+	const int nv = cells + 1;
+	yafaray_clearParamMap(pm);
+	yafaray_setParamMapInt(pm, "num_faces", 2 * cells * cells);
+	yafaray_setParamMapInt(pm, "num_vertices", nv * nv);
+	yafaray_setParamMapString(pm, "type", "mesh");
+	yafaray_createObject(scene, &object_id, "heightfield", pm);
+	for(int j = 0; j < nv; ++j)
+		for(int i = 0; i < nv; ++i)
+		{
+			const double x = (double) i / cells, y = (double) j / cells;
+			const double z = 0.15 * sin(17.0 * x) * cos(13.0 * y) + 0.05 * sin(71.0 * x + 3.0 * y) + 0.002 * lcg();
+			yafaray_addVertex(scene, object_id, scale * x, scale * y, scale * 0.35 * z);
+		}
+	yafaray_getMaterialId(scene, &material_id, "ground");
+	for(int j = 0; j < cells; ++j)
+		for(int i = 0; i < cells; ++i)
+		{
+			const int v00 = j * nv + i, v10 = v00 + 1, v01 = v00 + nv, v11 = v01 + 1;
+			yafaray_addTriangle(scene, object_id, v00, v10, v11, material_id);
+			yafaray_addTriangle(scene, object_id, v00, v11, v01, material_id);
+		}
+	yafaray_initObject(scene, object_id, material_id);
+	/* boxes standing in the field (occluders for the shadow rays) */
+	for(int k = 0; k < 12; ++k)
+	{
+		char name[32];
+		snprintf(name, sizeof name, "box%02d", k);
+		const double cx = scale * (0.15 + 0.7 * lcg()), cy = scale * (0.15 + 0.7 * lcg()), s = scale * (0.02 + 0.03 * lcg()), h = scale * (0.08 + 0.12 * lcg());
+		add_box(scene, name, cx - s, cy - s, -0.6, cx + s, cy + s, h, "boxes");
+	}
+
+	/* lights */
+	yafaray_clearParamMap(pm);
+	yafaray_setParamMapColor(pm, "color", 1.f, 0.95f, 0.9f, 1.f);
+	yafaray_setParamMapVector(pm, "from", 0.2 * scale, 0.1 * scale, 0.9 * scale);
+	yafaray_setParamMapFloat(pm, "power", 60.f);
+	yafaray_setParamMapString(pm, "type", "pointlight");
+	yafaray_createLight(scene, "point", pm);
+	yafaray_clearParamMap(pm);
+	yafaray_setParamMapColor(pm, "color", 0.9f, 0.95f, 1.f, 1.f);
+	yafaray_setParamMapVector(pm, "corner", 0.7 * scale, 0.6 * scale, 0.8 * scale);
+	yafaray_setParamMapVector(pm, "point1", 0.9 * scale, 0.6 * scale, 0.8 * scale);
+	yafaray_setParamMapVector(pm, "point2", 0.7 * scale, 0.8 * scale, 0.8 * scale);
+	yafaray_setParamMapFloat(pm, "power", 25.f);
+	yafaray_setParamMapInt(pm, "samples", 4);
+	yafaray_setParamMapString(pm, "type", "arealight");
+	yafaray_createLight(scene, "area", pm);
+
+	yafaray_clearParamMap(pm);
+	yafaray_setParamMapColor(pm, "color", 0.5f, 0.6f, 0.8f, 1.f);
+	yafaray_setParamMapFloat(pm, "power", 0.4f);
+	yafaray_setParamMapString(pm, "type", "constant");
+	yafaray_defineBackground(scene, pm);
+
+	/* accelerator: exactly what tests/test02/test02.c:5193-5197 does */
+	yafaray_clearParamMap(pm);
+	yafaray_setParamMapString(pm, "type", accel);
+	for(int a = 9; a < argc; ++a)
+	{
+		char key[64];
+		const char *eq = strchr(argv[a], '=');
+		if(!eq || (size_t) (eq - argv[a]) >= sizeof key || argv[a][1] == ':') continue;
+		memcpy(key, argv[a], (size_t) (eq - argv[a]));
+		key[eq - argv[a]] = 0;
+		yafaray_setParamMapInt(pm, key, atoi(eq + 1));
+	}
+	yafaray_setSceneAcceleratorParams(scene, pm);
+
+	/* integrator */
+	yafaray_clearParamMap(pm);
+	yafaray_setParamMapString(pm, "type", integrator);
+	yafaray_setParamMapInt(pm, "raydepth", 3);
+	yafaray_setParamMapInt(pm, "threads", threads);
+	if(strcmp(integrator, "pathtracing") == 0)
+	{
+		yafaray_setParamMapInt(pm, "bounces", 3);
+		yafaray_setParamMapInt(pm, "path_samples", 1);
+		yafaray_setParamMapString(pm, "caustic_type", "none");
+	}
+	for(int a = 9; a < argc; ++a)
+	{
+		char key[64];
+		const char *eq = strchr(argv[a], '=');
+		if(!eq || argv[a][1] != ':' || (size_t) (eq - argv[a] - 2) >= sizeof key) continue;
+		memcpy(key, argv[a] + 2, (size_t) (eq - argv[a] - 2));
+		key[eq - argv[a] - 2] = 0;
+		if(argv[a][0] == 'i') yafaray_setParamMapInt(pm, key, atoi(eq + 1));
+		else if(argv[a][0] == 'b') yafaray_setParamMapBool(pm, key, atoi(eq + 1) ? YAFARAY_BOOL_TRUE : YAFARAY_BOOL_FALSE);
+		else if(argv[a][0] == 'f') yafaray_setParamMapFloat(pm, key, (float) atof(eq + 1));
+	}
+	yafaray_SurfaceIntegrator *surface_integrator = yafaray_createSurfaceIntegrator(logger, "surface integrator", pm);
+
+	/* film, layer, camera, output */
+	yafaray_clearParamMap(pm);
+	yafaray_setParamMapInt(pm, "width", width);
+	yafaray_setParamMapInt(pm, "height", height);
+	yafaray_setParamMapInt(pm, "AA_passes", 1);
+	yafaray_setParamMapInt(pm, "AA_minsamples", aa_samples);
+	yafaray_setParamMapInt(pm, "threads", threads);
+	yafaray_Film *film = yafaray_createFilm(logger, surface_integrator, "film", pm);
+	yafaray_clearParamMap(pm);
+	yafaray_setParamMapString(pm, "exported_image_name", "Combined");
+	yafaray_setParamMapString(pm, "exported_image_type", "ColorAlpha");
+	yafaray_setParamMapString(pm, "image_type", "ColorAlpha");
+	yafaray_setParamMapString(pm, "type", "combined");
+	yafaray_defineLayer(film, pm);
+	yafaray_clearParamMap(pm);
+	yafaray_setParamMapFloat(pm, "focal", 1.1f);
+	yafaray_setParamMapVector(pm, "from", 0.5 * scale, -0.45 * scale, 0.55 * scale);
+	yafaray_setParamMapVector(pm, "to", 0.5 * scale, 0.5 * scale, 0.0);
+	yafaray_setParamMapVector(pm, "up", 0.5 * scale, -0.45 * scale, 0.55 * scale + 1.0);
+	yafaray_setParamMapInt(pm, "resx", width);
+	yafaray_setParamMapInt(pm, "resy", height);
+	yafaray_setParamMapString(pm, "type", "perspective");
+	yafaray_defineCamera(film, pm);
+	yafaray_clearParamMap(pm);
+	yafaray_setParamMapString(pm, "image_path", out_path);
+	yafaray_setParamMapBool(pm, "denoise_enabled", YAFARAY_BOOL_FALSE);
+	yafaray_createOutput(film, "output_tga", pm);
+	const double t_built = now();
+
+	yafaray_RenderMonitor *render_monitor = yafaray_createRenderMonitor(NULL, NULL, YAFARAY_DISPLAY_CONSOLE_HIDDEN);
+	yafaray_RenderControl *render_control = yafaray_createRenderControl();
+	yafaray_setRenderControlForNormalStart(render_control);
+	yafaray_SceneModifiedFlags flags = yafaray_checkAndClearSceneModifiedFlags(scene);
+	yafaray_preprocessScene(scene, render_control, flags);
+	const double t_pre = now();
+	yafaray_preprocessSurfaceIntegrator(render_monitor, surface_integrator, render_control, scene);
+	const double t_render0 = now();
+	yafaray_render(render_control, render_monitor, surface_integrator, film);
+	const double t_render1 = now();
+	printf("RENDER_BENCH {\"accelerator\": \"%s\", \"integrator\": \"%s\", \"triangles\": %d, \"width\": %d, \"height\": %d, \"aa_samples\": %d, \"threads\": %d, "
+	       "\"scene_seconds\": %.3f, \"preprocess_seconds\": %.3f, \"render_seconds\": %.3f}\n",
+	       accel, integrator, 2 * cells * cells + 72, width, height, aa_samples, threads, t_built - t_scene, t_pre - t_built, t_render1 - t_render0);
+	yafaray_destroyRenderControl(render_control);
+	yafaray_destroyRenderMonitor(render_monitor);
+	yafaray_destroyFilm(film);
+	yafaray_destroySurfaceIntegrator(surface_integrator);
+	yafaray_destroyScene(scene);
+	yafaray_destroyLogger(logger);
+	yafaray_destroyParamMapList(pml);
+	yafaray_destroyParamMap(pm);
+	return 0;
+}

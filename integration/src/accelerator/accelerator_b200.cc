@@ -23,6 +23,10 @@ std::map<std::string, const ParamMeta *> AcceleratorB200::Params::getParamMetaMa
 	PARAM_META(empty_bonus_);
 	PARAM_META(device_);
 	PARAM_META(num_threads_);
+	PARAM_META(wavefront_fibers_);
+	PARAM_META(wavefront_groups_);
+	PARAM_META(wavefront_block_);
+	PARAM_META(wavefront_stack_kb_);
 	return param_meta_map;
 }
 
@@ -34,6 +38,10 @@ AcceleratorB200::Params::Params(ParamResult &param_result, const ParamMap &param
 	PARAM_LOAD(empty_bonus_);
 	PARAM_LOAD(device_);
 	PARAM_LOAD(num_threads_);
+	PARAM_LOAD(wavefront_fibers_);
+	PARAM_LOAD(wavefront_groups_);
+	PARAM_LOAD(wavefront_block_);
+	PARAM_LOAD(wavefront_stack_kb_);
 }
 
 ParamMap AcceleratorB200::getAsParamMap(bool only_non_default) const
@@ -46,6 +54,10 @@ ParamMap AcceleratorB200::getAsParamMap(bool only_non_default) const
 	PARAM_SAVE(empty_bonus_);
 	PARAM_SAVE(device_);
 	PARAM_SAVE(num_threads_);
+	PARAM_SAVE(wavefront_fibers_);
+	PARAM_SAVE(wavefront_groups_);
+	PARAM_SAVE(wavefront_block_);
+	PARAM_SAVE(wavefront_stack_kb_);
 	return param_map;
 }
 
@@ -150,6 +162,7 @@ AcceleratorB200::AcceleratorB200(Logger &logger, ParamResult &param_result, cons
 
 AcceleratorB200::~AcceleratorB200()
 {
+	idle_queues_.clear(); //pinned buffers go before the scene (and its CUDA context use) does
 	if(scene_) b200rt_destroy(scene_);
 }
 
@@ -161,7 +174,9 @@ IntersectData AcceleratorB200::intersect(const Ray &ray, float t_max) const
 	IntersectData data;
 	data.t_max_ = t_max;
 	if(!scene_) return data;
-	if(b200rt_trace(scene_, B200RT_QUERY_CLOSEST, B200RT_RAYS_TREE_SPACE, &r, 1, &hit, 0) != B200RT_OK || hit.prim == B200RT_MISS) return data;
+	if(b200::RayQueue *queue{b200::RayQueue::current()}) hit = queue->closest(scene_, r); //on a fiber: joins the thread's next batch
+	else if(++wf_per_ray_calls_, b200rt_trace(scene_, B200RT_QUERY_CLOSEST, B200RT_RAYS_TREE_SPACE, &r, 1, &hit, 0) != B200RT_OK) return data;
+	if(hit.prim == B200RT_MISS) return data;
 	data.t_hit_ = hit.t;
 	data.t_max_ = hit.t;
 	data.uv_ = {hit.u, hit.v};
@@ -175,7 +190,9 @@ IntersectData AcceleratorB200::intersectShadow(const Ray &ray, float t_max) cons
 	uint32_t occluder = B200RT_MISS;
 	IntersectData data;
 	if(!scene_) return data;
-	if(b200rt_trace(scene_, B200RT_QUERY_SHADOW, B200RT_RAYS_TREE_SPACE, &r, 1, &occluder, 0) != B200RT_OK || occluder == B200RT_MISS) return data;
+	if(b200::RayQueue *queue{b200::RayQueue::current()}) occluder = queue->shadow(scene_, r);
+	else if(++wf_per_ray_calls_, b200rt_trace(scene_, B200RT_QUERY_SHADOW, B200RT_RAYS_TREE_SPACE, &r, 1, &occluder, 0) != B200RT_OK) return data;
+	if(occluder == B200RT_MISS) return data;
 	data.t_hit_ = 1.f; //any value > 0: callers only use isHit() and primitive_ (accelerator.h:110)
 	data.primitive_ = primitives_[occluder];
 	return data;
@@ -188,7 +205,8 @@ IntersectData AcceleratorB200::intersectTransparentShadow(const Ray &ray, int ma
 	IntersectData data;
 	if(max_depth > B200RT_TSHADOW_MAX) max_depth = B200RT_TSHADOW_MAX; //documented limit of the result record
 	if(!scene_) return data;
-	if(b200rt_trace(scene_, B200RT_QUERY_TSHADOW, B200RT_RAYS_TREE_SPACE, &r, 1, &res, max_depth) != B200RT_OK) return data;
+	if(b200::RayQueue *queue{b200::RayQueue::current()}) res = queue->transparentShadow(scene_, r, max_depth);
+	else if(++wf_per_ray_calls_, b200rt_trace(scene_, B200RT_QUERY_TSHADOW, B200RT_RAYS_TREE_SPACE, &r, 1, &res, max_depth) != B200RT_OK) return data;
 	if(res.shadowed)
 	{
 		data.t_hit_ = 1.f;
@@ -205,6 +223,51 @@ IntersectData AcceleratorB200::intersectTransparentShadow(const Ray &ray, int ma
 		if(sp) data.color_ *= sp->getTransparency(ray.dir_, camera);
 	}
 	return data; //setNoHit(): t_hit_ = 0, primitive_ = nullptr, colour kept (accelerator_kdtree_common.h:246-250)
+}
+
+// ---- wavefront ray queues ---------------------------------------------------------------------------------
+std::unique_ptr<b200::RayQueue> AcceleratorB200::acquireRayQueue() const
+{
+	{
+		std::lock_guard<std::mutex> lock(queues_mutex_);
+		if(!idle_queues_.empty())
+		{
+			auto queue{std::move(idle_queues_.back())};
+			idle_queues_.pop_back();
+			return queue;
+		}
+	}
+	return std::make_unique<b200::RayQueue>(wavefrontFibers(), wavefrontGroups(), wavefrontStackBytes());
+}
+
+void AcceleratorB200::releaseRayQueue(std::unique_ptr<b200::RayQueue> queue) const
+{
+	if(!queue || !queue->ok()) return; //a failed queue is dropped
+	addWavefrontStats(queue->stats());
+	queue->resetStats();
+	std::lock_guard<std::mutex> lock(queues_mutex_);
+	idle_queues_.push_back(std::move(queue));
+}
+
+// ---- wavefront statistics ---------------------------------------------------------------------------------
+void AcceleratorB200::addWavefrontStats(const b200::RayQueue::Stats &stats) const
+{
+	for(int kind = 0; kind < 3; ++kind) wf_rays_[kind] += stats.rays[kind];
+	wf_batches_ += stats.batches;
+	wf_calls_ += stats.calls;
+	wf_switches_ += stats.switches;
+	wf_trace_us_ += static_cast<uint64_t>(stats.trace_seconds * 1e6);
+	wf_run_us_ += static_cast<uint64_t>(stats.run_seconds * 1e6);
+}
+
+void AcceleratorB200::logWavefrontStats() const
+{
+	const uint64_t closest{wf_rays_[0].exchange(0)}, shadow{wf_rays_[1].exchange(0)}, tshadow{wf_rays_[2].exchange(0)};
+	const uint64_t batches{wf_batches_.exchange(0)}, calls{wf_calls_.exchange(0)}, per_ray{wf_per_ray_calls_.exchange(0)};
+	const double trace_s{static_cast<double>(wf_trace_us_.exchange(0)) * 1e-6}, run_s{static_cast<double>(wf_run_us_.exchange(0)) * 1e-6};
+	wf_switches_ = 0;
+	logger_.logInfo(getClassName(), ": wavefront rays closest=", closest, " shadow=", shadow, " transparent-shadow=", tshadow, " in ", batches, " batches / ", calls,
+					" libb200rt calls (", batches ? (closest + shadow + tshadow) / batches : 0, " rays per batch), ", trace_s, " thread-seconds inside libb200rt of ", run_s, " thread-seconds in the render workers; per-ray calls outside fibers: ", per_ray);
 }
 
 // ---- batched entry points ---------------------------------------------------------------------------------

@@ -5,6 +5,8 @@
  *                                       exactly what tests/test02/test02.c:5193-5197 does by hand
  *   B200_DETERMINISTIC=1             -> threads=1 on integrator and film, tiles_order=linear
  *   B200_AA_PASSES=n                 -> overrides AA_passes of the film (shorter renders on the per-ray path)
+ *   B200_WAVEFRONT_FIBERS=n          -> accelerator parameter "wavefront_fibers" (0 = per-ray calls only)
+ *   B200_WAVEFRONT_BLOCK=n           -> accelerator parameter "wavefront_block"
  * TEST INFRASTRUCTURE ONLY. */
 #ifndef B200_TEST_HOOK_H
 #define B200_TEST_HOOK_H
@@ -18,6 +20,9 @@ static yafaray_Bool b200_hook_preprocessScene(yafaray_Scene *scene, const yafara
 	{
 		yafaray_ParamMap *pm = yafaray_createParamMap();
 		yafaray_setParamMapString(pm, "type", type);
+		if(getenv("B200_WAVEFRONT_FIBERS")) yafaray_setParamMapInt(pm, "wavefront_fibers", atoi(getenv("B200_WAVEFRONT_FIBERS")));
+		if(getenv("B200_WAVEFRONT_GROUPS")) yafaray_setParamMapInt(pm, "wavefront_groups", atoi(getenv("B200_WAVEFRONT_GROUPS")));
+		if(getenv("B200_WAVEFRONT_BLOCK")) yafaray_setParamMapInt(pm, "wavefront_block", atoi(getenv("B200_WAVEFRONT_BLOCK")));
 		yafaray_setSceneAcceleratorParams(scene, pm);
 		yafaray_destroyParamMap(pm);
 		flags = (yafaray_SceneModifiedFlags) (flags | yafaray_checkAndClearSceneModifiedFlags(scene));

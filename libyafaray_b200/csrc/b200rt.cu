@@ -36,6 +36,7 @@ int fail(int code, const std::string &msg)
 constexpr uint32_t kTriangle = 0xFFFFFFFFu;
 constexpr size_t kChunkBytes = size_t(32) << 20; // staging granularity of the host-buffer queries
 constexpr int kLanesPerCall = 3;
+constexpr size_t kDirectRays = size_t(1) << 16;  // pinned batches up to this size are traced in place (no staging copies)
 
 // One staging lane: a stream with pinned host and device buffers for rays in / results out.
 struct Lane
@@ -96,6 +97,16 @@ struct b200rt_scene
 	}
 };
 
+// Jobs enqueued by b200rt_trace_jobs_begin and not yet waited for.
+struct b200rt_flight
+{
+	struct Entry { b200rt_scene *scene; std::unique_ptr<Lane> lane; };
+	std::vector<Entry> lanes;
+	int first_error = B200RT_OK;
+	std::string error_text;
+	void note(int rc) { if(first_error == B200RT_OK) { first_error = rc; error_text = g_last_error; } }
+};
+
 namespace {
 
 int ensureLane(Lane &l, size_t in_bytes, size_t out_bytes, bool need_h_in, bool need_h_out)
@@ -133,12 +144,41 @@ bool isPinned(const void *p)
 }
 
 template <typename Out, typename LaunchFn>
-int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, LaunchFn launch)
+int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, LaunchFn launch, bool known_pinned = false)
 {
 	if(!s || (!rays && n) || (!out && n)) return fail(B200RT_E_INVALID, "null argument");
 	if(!s->built) return fail(B200RT_E_INVALID, "scene not built: call b200rt_build first");
 	if(n == 0) return B200RT_OK;
 	CUDA_TRY(cudaSetDevice(s->device));
+	// a batch of one is the per-ray compatibility path (stack variables of the caller): not worth the pointer query
+	const bool in_pinned = known_pinned || (n > 1 && isPinned(rays)), out_pinned = known_pinned || (n > 1 && isPinned(out));
+	if(in_pinned && out_pinned && n <= kDirectRays)
+	{
+		// Batches in pinned memory (the wavefront ray queue of the renderer, integration/src/render): the kernel
+		// reads the rays and writes the results across PCIe itself -- one cursor reset, one launch and one stream
+		// synchronisation per call, no staging copies.
+		std::unique_ptr<Lane> lane;
+		{
+			std::lock_guard<std::mutex> lock(s->lane_mutex);
+			if(!s->free_lanes.empty()) { lane = std::move(s->free_lanes.back()); s->free_lanes.pop_back(); }
+		}
+		if(!lane) lane = std::make_unique<Lane>();
+		int rc = B200RT_OK;
+		if(!lane->stream)
+		{
+			const cudaError_t e = cudaStreamCreateWithFlags(&lane->stream, cudaStreamNonBlocking);
+			if(e != cudaSuccess) rc = fail(B200RT_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+		}
+		if(rc == B200RT_OK) rc = launch(rays, n, out, lane->stream, true);
+		if(rc == B200RT_OK)
+		{
+			const cudaError_t e = cudaStreamSynchronize(lane->stream);
+			if(e != cudaSuccess) rc = fail(B200RT_E_CUDA, std::string("direct trace: ") + cudaGetErrorString(e));
+		}
+		std::lock_guard<std::mutex> lock(s->lane_mutex);
+		s->free_lanes.push_back(std::move(lane));
+		return rc;
+	}
 	if(n <= size_t(b200rt::kPoolRays))
 	{
 		// Small batches (the per-ray compatibility path of the Accelerator virtuals): no staging copies at all.  The
@@ -170,7 +210,6 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, La
 	const size_t chunk = std::max<size_t>(1024, kChunkBytes / per_ray);
 	const size_t n_chunks = (n + chunk - 1) / chunk;
 	const int n_lanes = int(std::min<size_t>(kLanesPerCall, n_chunks));
-	const bool in_pinned = isPinned(rays), out_pinned = isPinned(out);
 
 	std::vector<std::unique_ptr<Lane>> lanes;
 	{
@@ -249,7 +288,9 @@ int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b2
 {
 	if(cursorless)
 	{
-		b200rt::traceKernel<Q><<<1, b200rt::kBlock, 0, stream>>>(s->view, d_rays, uint32_t(n), d_out, nullptr, max_depth, (flags & B200RT_RAYS_TREE_SPACE) != 0u);
+		// small batch (n <= kDirectRays): no ray cursor, so nothing to reset before the launch; warp w owns rays [32 w, 32 w + 32)
+		const unsigned grid = unsigned((n + b200rt::kBlock - 1) / b200rt::kBlock);
+		b200rt::traceKernel<Q><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays, uint32_t(n), d_out, nullptr, max_depth, (flags & B200RT_RAYS_TREE_SPACE) != 0u);
 		++g_launches;
 		CUDA_TRY(cudaGetLastError());
 		return B200RT_OK;
@@ -577,6 +618,119 @@ int b200rt_trace(b200rt_scene *s, int query, unsigned flags, const b200rt_ray *r
 			});
 		default: return fail(B200RT_E_INVALID, "unknown query kind");
 	}
+}
+
+int b200rt_trace_jobs_begin(const b200rt_job *jobs, size_t n_jobs, b200rt_flight **out_flight)
+{
+	if((!jobs && n_jobs) || !out_flight) return fail(B200RT_E_INVALID, "null argument");
+	*out_flight = nullptr;
+	b200rt_flight *flight = new(std::nothrow) b200rt_flight;
+	if(!flight) return fail(B200RT_E_MEMORY, "out of host memory");
+	// in-place jobs of one scene with different query kinds share ONE launch (traceMixedKernel): with 16 render threads
+	// flushing small batches the driver's launch path is the contended resource, not the GPU
+	struct Bundle { b200rt_scene *scene; unsigned tree_space; const b200rt_job *job[3]; };
+	std::vector<Bundle> bundles;
+	std::vector<size_t> staged;
+	auto launchBundle = [&](const Bundle &bundle) {
+		b200rt_scene *s = bundle.scene;
+		std::unique_ptr<Lane> lane;
+		{
+			std::lock_guard<std::mutex> lock(s->lane_mutex);
+			if(!s->free_lanes.empty()) { lane = std::move(s->free_lanes.back()); s->free_lanes.pop_back(); }
+		}
+		if(!lane) lane = std::make_unique<Lane>();
+		int rc = B200RT_OK;
+		cudaError_t e = cudaSetDevice(s->device);
+		if(e == cudaSuccess && !lane->stream) e = cudaStreamCreateWithFlags(&lane->stream, cudaStreamNonBlocking);
+		if(e != cudaSuccess) rc = fail(B200RT_E_CUDA, std::string("b200rt_trace_jobs: ") + cudaGetErrorString(e));
+		const int kinds = (bundle.job[0] ? 1 : 0) + (bundle.job[1] ? 1 : 0) + (bundle.job[2] ? 1 : 0);
+		if(rc == B200RT_OK && kinds == 1)
+		{
+			const b200rt_job &job = *(bundle.job[0] ? bundle.job[0] : bundle.job[1] ? bundle.job[1] : bundle.job[2]);
+			switch(job.query)
+			{
+				case B200RT_QUERY_CLOSEST: rc = launchTrace<b200rt::kClosest>(s, job.rays, job.n, static_cast<b200rt_hit *>(job.out), lane->stream, 0, job.flags, true); break;
+				case B200RT_QUERY_SHADOW: rc = launchTrace<b200rt::kShadow>(s, job.rays, job.n, static_cast<uint32_t *>(job.out), lane->stream, 0, job.flags, true); break;
+				default: rc = launchTrace<b200rt::kTShadow>(s, job.rays, job.n, static_cast<b200rt_tshadow *>(job.out), lane->stream, job.max_depth, job.flags, true); break;
+			}
+		}
+		else if(rc == B200RT_OK)
+		{
+			b200rt::MixedBatch batch{};
+			size_t warps = 0;
+			for(int k = 0; k < 3; ++k)
+			{
+				if(!bundle.job[k]) continue;
+				batch.rays[k] = bundle.job[k]->rays;
+				batch.out[k] = bundle.job[k]->out;
+				batch.n[k] = uint32_t(bundle.job[k]->n);
+				warps += (bundle.job[k]->n + 31) / 32;
+			}
+			const unsigned grid = unsigned((warps + b200rt::kBlock / 32 - 1) / (b200rt::kBlock / 32));
+			b200rt::traceMixedKernel<<<grid, b200rt::kBlock, 0, lane->stream>>>(s->view, batch, bundle.job[2] ? bundle.job[2]->max_depth : 0, bundle.tree_space != 0u);
+			++g_launches;
+			e = cudaGetLastError();
+			if(e != cudaSuccess) rc = fail(B200RT_E_CUDA, std::string("traceMixedKernel: ") + cudaGetErrorString(e));
+		}
+		if(rc != B200RT_OK) flight->note(rc);
+		flight->lanes.push_back({s, std::move(lane)});
+	};
+	for(size_t j = 0; j < n_jobs; ++j)
+	{
+		const b200rt_job &job = jobs[j];
+		if(job.n == 0) continue;
+		int rc = checkDeviceCall(job.scene, job.rays, job.n, job.out);
+		if(rc == B200RT_OK && (job.query < B200RT_QUERY_CLOSEST || job.query > B200RT_QUERY_TSHADOW)) rc = fail(B200RT_E_INVALID, "unknown query kind");
+		if(rc == B200RT_OK && job.query == B200RT_QUERY_TSHADOW && (job.max_depth < 0 || job.max_depth > B200RT_TSHADOW_MAX)) rc = fail(B200RT_E_INVALID, "max_depth must be in [0, B200RT_TSHADOW_MAX]");
+		if(rc != B200RT_OK) { flight->note(rc); continue; }
+		const bool pinned = (job.flags & B200RT_BUFFERS_PINNED) != 0u || (isPinned(job.rays) && isPinned(job.out));
+		if(!pinned || job.n > kDirectRays) { staged.push_back(j); continue; }
+		const unsigned tree_space = job.flags & B200RT_RAYS_TREE_SPACE;
+		Bundle *home = nullptr;
+		for(Bundle &bundle : bundles)
+			if(bundle.scene == job.scene && bundle.tree_space == tree_space && !bundle.job[job.query]) { home = &bundle; break; }
+		if(!home)
+		{
+			bundles.push_back(Bundle{job.scene, tree_space, {nullptr, nullptr, nullptr}});
+			home = &bundles.back();
+		}
+		home->job[job.query] = &job;
+	}
+	for(const Bundle &bundle : bundles) launchBundle(bundle);
+	for(size_t j : staged)
+	{
+		const int rc = b200rt_trace(jobs[j].scene, jobs[j].query, jobs[j].flags, jobs[j].rays, jobs[j].n, jobs[j].out, jobs[j].max_depth);
+		if(rc != B200RT_OK) flight->note(rc);
+	}
+	*out_flight = flight;
+	return flight->first_error;
+}
+
+int b200rt_trace_jobs_end(b200rt_flight *flight)
+{
+	if(!flight) return fail(B200RT_E_INVALID, "null argument");
+	for(auto &f : flight->lanes)
+	{
+		if(f.lane->stream)
+		{
+			const cudaError_t e = cudaStreamSynchronize(f.lane->stream);
+			if(e != cudaSuccess && flight->first_error == B200RT_OK) { flight->first_error = B200RT_E_CUDA; flight->error_text = std::string("b200rt_trace_jobs: ") + cudaGetErrorString(e); }
+		}
+		std::lock_guard<std::mutex> lock(f.scene->lane_mutex);
+		f.scene->free_lanes.push_back(std::move(f.lane));
+	}
+	const int rc = flight->first_error;
+	if(rc != B200RT_OK) g_last_error = flight->error_text;
+	delete flight;
+	return rc;
+}
+
+int b200rt_trace_jobs(const b200rt_job *jobs, size_t n_jobs)
+{
+	b200rt_flight *flight = nullptr;
+	const int rc = b200rt_trace_jobs_begin(jobs, n_jobs, &flight);
+	if(!flight) return rc;
+	return b200rt_trace_jobs_end(flight);
 }
 
 int b200rt_host_alloc(void **ptr, size_t bytes)

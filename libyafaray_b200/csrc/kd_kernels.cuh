@@ -149,7 +149,8 @@ __device__ __forceinline__ float polyIntersect(const float4 q0, const float4 q1,
 // Persistent-warp traversal ("while-while" with ray replacement).
 //
 // A warp owns 32 ray slots.  Whenever at least kRefill slots are idle, the idle lanes take the next rays of
-// the warp's pool (the pool is refilled kPoolRays at a time with one atomicAdd on a global cursor), so a warp's
+// the warp's pool (the pool is refilled kPoolRays at a time with one atomicAdd on a global cursor; small batches are
+// launched without a cursor, warp w of the grid owning rays [32 w, 32 w + 32)), so a warp's
 // lifetime is no longer the maximum over its 32 first rays: measured with the one-thread-per-ray kernel, only
 // 3.3 of 32 lanes were active per issued instruction (profiles/r1a_*), here they are kept busy.
 // Every lane then alternates between
@@ -350,14 +351,13 @@ __device__ __forceinline__ uint32_t selectu(bool p, uint32_t a, uint32_t b)
 	return r;
 }
 
+// The traversal proper.  Called by every thread of the block; warps are independent of each other (no block-level
+// synchronisation).  sh_stack / sh_axis are the block's shared arrays; static_base is the first ray of the calling warp's
+// static pool in a cursor-less launch (ignored when `cursor` is given).
 template <int QUERY>
-__global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
-                                                                 typename OutType<QUERY>::type *__restrict__ out, uint32_t *__restrict__ cursor, int max_depth, bool tree_space)
+__device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray *__restrict__ rays, uint32_t n, typename OutType<QUERY>::type *__restrict__ out,
+                                           uint32_t *__restrict__ cursor, int max_depth, bool tree_space, uint2 (*sh_stack)[kBlock], float2 (*sh_axis)[kBlock], uint32_t static_base)
 {
-	__shared__ uint2 sh_stack[kShortStack][kBlock];
-#if B200RT_SMEM_RAY
-	__shared__ float2 sh_axis[3][kBlock];          // per axis: (origin, inverse direction) of the lane's ray
-#endif // x = node index, y = float bits of the far end of its interval
 	const unsigned tid = threadIdx.x;
 	const unsigned lane = tid & 31u;
 	const unsigned lanes_below = (1u << lane) - 1u;
@@ -413,13 +413,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 					if(lane == 0u) base = atomicAdd(cursor, uint32_t(kPoolRays));
 					base = __shfl_sync(kFullMask, base, 0);
 				}
-				else if(first_pool && blockIdx.x == 0 && tid < 32u) base = 0u; // cursor-less launch: one warp, one pool (n <= kPoolRays)
+				else if(first_pool) base = static_base; // cursor-less launch: the warp owns rays [static_base, static_base + 32)
 				first_pool = false;
 				if(base >= n) exhausted = true;
 				else
 				{
 					pool_next = base;
-					pool_end = (n - base < uint32_t(kPoolRays)) ? n : base + uint32_t(kPoolRays);
+					const uint32_t pool = (cursor != nullptr) ? uint32_t(kPoolRays) : 32u;
+					pool_end = (n - base < pool) ? n : base + pool;
 				}
 			}
 			if(!exhausted)
@@ -583,6 +584,37 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
 			alive = false;
 		}
 	}
+}
+
+
+template <int QUERY>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
+                                                                 typename OutType<QUERY>::type *__restrict__ out, uint32_t *__restrict__ cursor, int max_depth, bool tree_space)
+{
+	__shared__ uint2 sh_stack[kShortStack][kBlock]; // x = node index, y = float bits of the far end of its interval
+	__shared__ float2 sh_axis[3][kBlock];          // per axis: (origin, inverse direction) of the lane's ray
+	traceWarps<QUERY>(s, rays, n, out, cursor, max_depth, tree_space, sh_stack, sh_axis, (blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5)) * 32u);
+}
+
+// One launch for the closest, shadow and transparent-shadow rays of one flush of the renderer's ray queue
+// (b200rt_trace_jobs): cursor-less, warp w of the grid takes 32 rays of whichever kind its index falls into.  Launches
+// are what 16 render threads contend for in the driver, so three kinds in one launch matter more than code size.
+struct MixedBatch
+{
+	const b200rt_ray *rays[3];
+	void *out[3];
+	uint32_t n[3];
+};
+
+__global__ void __launch_bounds__(kBlock, 4) traceMixedKernel(SceneView s, MixedBatch b, int max_depth, bool tree_space)
+{
+	__shared__ uint2 sh_stack[kShortStack][kBlock];
+	__shared__ float2 sh_axis[3][kBlock];
+	const uint32_t warp = blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5);
+	const uint32_t w0 = (b.n[0] + 31u) / 32u, w1 = (b.n[1] + 31u) / 32u;
+	if(warp < w0) traceWarps<kClosest>(s, b.rays[0], b.n[0], static_cast<b200rt_hit *>(b.out[0]), nullptr, 0, tree_space, sh_stack, sh_axis, warp * 32u);
+	else if(warp < w0 + w1) traceWarps<kShadow>(s, b.rays[1], b.n[1], static_cast<uint32_t *>(b.out[1]), nullptr, 0, tree_space, sh_stack, sh_axis, (warp - w0) * 32u);
+	else traceWarps<kTShadow>(s, b.rays[2], b.n[2], static_cast<b200rt_tshadow *>(b.out[2]), nullptr, max_depth, tree_space, sh_stack, sh_axis, (warp - w0 - w1) * 32u);
 }
 
 } // namespace b200rt

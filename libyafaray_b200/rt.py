@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("B200RT_LIB") or os.path.join(_HERE, "libb200rt.so")  
 MISS = 0xFFFFFFFF
 QUERY_CLOSEST, QUERY_SHADOW, QUERY_TSHADOW = 0, 1, 2
 RAYS_TREE_SPACE = 1
+BUFFERS_PINNED = 2
 TSHADOW_MAX = 8
 
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("tmin", np.float32), ("d", np.float32, 3), ("tmax", np.float32)])
@@ -39,6 +40,11 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class Job(C.Structure):
+    """b200rt_job (include/b200rt.h)."""
+    _fields_ = [("scene", C.c_void_p), ("query", C.c_int), ("flags", C.c_uint), ("rays", C.c_void_p), ("n", C.c_size_t), ("out", C.c_void_p), ("max_depth", C.c_int)]
+
+
 class B200RTError(RuntimeError):
     def __init__(self, code, text):
         super().__init__(f"libb200rt error {code}: {text}")
@@ -50,7 +56,7 @@ SYMBOLS = [
     "b200rt_device_count", "b200rt_create", "b200rt_destroy", "b200rt_add_mesh", "b200rt_build", "b200rt_get_bound",
     "b200rt_get_stats", "b200rt_update_face_flags", "b200rt_trace_closest", "b200rt_trace_shadow", "b200rt_trace_tshadow",
     "b200rt_trace_closest_device", "b200rt_trace_shadow_device", "b200rt_trace_tshadow_device", "b200rt_trace",
-    "b200rt_trace_device", "b200rt_host_alloc",
+    "b200rt_trace_device", "b200rt_trace_jobs", "b200rt_trace_jobs_begin", "b200rt_trace_jobs_end", "b200rt_host_alloc",
     "b200rt_host_free", "b200rt_host_tree_build", "b200rt_host_tree_sizes", "b200rt_host_tree_export",
     "b200rt_host_tree_destroy", "b200rt_launch_count", "b200rt_last_error", "b200rt_version",
 ]
@@ -83,6 +89,9 @@ def lib():
         L.b200rt_trace_tshadow_device.argtypes = [P, P, Z, C.c_int, P, P]
         L.b200rt_trace.argtypes = [P, C.c_int, C.c_uint, P, Z, P, C.c_int]
         L.b200rt_trace_device.argtypes = [P, C.c_int, C.c_uint, P, Z, P, C.c_int, P]
+        L.b200rt_trace_jobs.argtypes = [P, Z]
+        L.b200rt_trace_jobs_begin.argtypes = [P, Z, P]
+        L.b200rt_trace_jobs_end.argtypes = [P]
         L.b200rt_host_alloc.argtypes = [P, Z]
         L.b200rt_host_free.argtypes = [P]
         L.b200rt_host_tree_build.argtypes = [P, Z, P, Z, P, P]
@@ -243,6 +252,23 @@ class Scene:
 
     def trace_tshadow_device(self, d_rays: int, n: int, max_depth: int, d_out: int, stream: int = 0):
         _check(lib().b200rt_trace_tshadow_device(self._h, C.c_void_p(d_rays), n, int(max_depth), C.c_void_p(d_out), C.c_void_p(stream)))
+
+
+def trace_jobs(jobs, split=False):
+    """b200rt_trace_jobs over a list of (scene, query, flags, rays[n,8] float32, out array, max_depth); split=True goes through
+    the _begin / _end pair.  The arrays must stay alive (and, for the in-place path, be PinnedBuffer arrays)."""
+    arr = (Job * len(jobs))()
+    for k, (scene, query, flags, rays, out, max_depth) in enumerate(jobs):
+        arr[k] = Job(scene._h, int(query), int(flags), rays.ctypes.data, rays.shape[0], out.ctypes.data, int(max_depth))
+    if not split:
+        _check(lib().b200rt_trace_jobs(arr, len(jobs)))
+        return
+    flight = C.c_void_p(0)
+    rc = lib().b200rt_trace_jobs_begin(arr, len(jobs), C.byref(flight))
+    if flight.value:
+        rc2 = lib().b200rt_trace_jobs_end(flight)
+        rc = rc or rc2
+    _check(rc)
 
 
 def host_tree(xyz, idx, params: BuildParams | None = None) -> dict:

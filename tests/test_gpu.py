@@ -318,3 +318,53 @@ def test_tree_space_rays_equal_wrapped_rays(built):
     with pytest.raises(rt.B200RTError):
         s.trace(7, closest)
     s.close()
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_trace_jobs_bundles_match_single_queries(built, split):
+    """b200rt_trace_jobs[_begin/_end]: what one flush of the renderer's wavefront ray queue hands over -- closest, shadow and
+    transparent-shadow batches in pinned memory, traced in place by ONE mixed-kind launch per scene (traceMixedKernel), plus
+    a second scene and an unpinned job in the same call -- must be byte-identical to the single-kind queries."""
+    xyz, idx, _ = scenes.objects(30000, n_spheres=10)
+    flags = helpers.flag_mix(idx.shape[0], seed=4)
+    s1 = make_scene(xyz, idx, flags)
+    s2 = make_scene(*scenes.cube_scene())
+    launches0 = rt.launch_count()
+    for n in (1, 31, 700, 5000):
+        closest, shadow = helpers.ray_zoo(s1.bound(), n=n, seed=50 + n)
+        closest, shadow = closest[:n], shadow[:n]
+        c2, _ = helpers.ray_zoo(s2.bound(), n=max(n // 2, 1), seed=60 + n)
+        c2 = c2[: max(n // 2, 1)]
+        bufs = {}
+        def pin(name, src_or_shape, dtype=None):
+            if dtype is None:
+                b = rt.PinnedBuffer(src_or_shape.shape, np.float32); b.array[:] = src_or_shape
+            else:
+                b = rt.PinnedBuffer(src_or_shape, dtype)
+            bufs[name] = b
+            return b.array
+        fl = rt.RAYS_TREE_SPACE | rt.BUFFERS_PINNED
+        out_unpinned = np.empty(shadow.shape[0], np.uint32)
+        jobs = [
+            (s1, rt.QUERY_CLOSEST, fl, pin("rc", closest), pin("oc", (n,), rt.HIT_DTYPE), 0),
+            (s1, rt.QUERY_SHADOW, fl, pin("rs", shadow), pin("os", (n,), np.uint32), 0),
+            (s1, rt.QUERY_TSHADOW, fl, pin("rt", shadow), pin("ot", (n,), rt.TSHADOW_DTYPE), 3),
+            (s1, rt.QUERY_TSHADOW, fl, pin("rt2", shadow), pin("ot2", (n,), rt.TSHADOW_DTYPE), 1),   # same scene and kind again: its own launch
+            (s2, rt.QUERY_CLOSEST, fl, pin("rc2", c2), pin("oc2", (c2.shape[0],), rt.HIT_DTYPE), 0),
+            (s1, rt.QUERY_SHADOW, rt.RAYS_TREE_SPACE, np.ascontiguousarray(shadow), out_unpinned, 0),  # pageable memory: staged path
+        ]
+        rt.trace_jobs(jobs, split=split)
+        assert bufs["oc"].array.tobytes() == s1.trace(rt.QUERY_CLOSEST, closest, flags=rt.RAYS_TREE_SPACE).tobytes()
+        assert bufs["os"].array.tobytes() == s1.trace(rt.QUERY_SHADOW, shadow, flags=rt.RAYS_TREE_SPACE).tobytes()
+        for name, depth in (("ot", 3), ("ot2", 1)):
+            ref = s1.trace(rt.QUERY_TSHADOW, shadow, flags=rt.RAYS_TREE_SPACE, max_depth=depth)
+            got = bufs[name].array
+            assert np.array_equal(got["shadowed"], ref["shadowed"]) and np.array_equal(got["n_transparent"], ref["n_transparent"])
+        assert bufs["oc2"].array.tobytes() == s2.trace(rt.QUERY_CLOSEST, c2, flags=rt.RAYS_TREE_SPACE).tobytes()
+        assert np.array_equal(out_unpinned, bufs["os"].array)
+        for b in bufs.values():
+            b.free()
+    assert rt.launch_count() > launches0
+    with pytest.raises(rt.B200RTError):
+        rt.trace_jobs([(s1, 9, 0, np.zeros((4, 8), np.float32), np.zeros(4, np.uint32), 0)])
+    s1.close(); s2.close()

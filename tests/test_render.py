@@ -61,12 +61,16 @@ def needs_build(name):
 
 @pytest.mark.gpu
 @needs_build("yafaray_test01")
-@pytest.mark.parametrize("test,deterministic", [("test01", True), ("test01", False), ("test09", True)])
-def test_reference_scene_renders_through_b200_accelerator(built, test, deterministic):
+@pytest.mark.parametrize("test,deterministic,fibers", [("test01", True, 0), ("test01", True, 1024), ("test01", False, 1024), ("test09", True, 1024)])
+def test_reference_scene_renders_through_b200_accelerator(built, test, deterministic, fibers):
+    """fibers = 0: every Accelerator virtual is a one-ray libb200rt call (the compatibility path; byte-identical image).
+    fibers > 0: the wavefront ray queue (integration/src/render/wavefront_b200.cc) -- the reference's renderTile() runs on
+    fibers, pixel blocks are evaluated in a different order than the tile loop, so order-dependent sampler state
+     makes the image equal within the PSNR bar rather than byte for byte."""
     binary = os.path.join(BUILD, "yafaray_" + test)
     if not os.path.exists(binary):
         pytest.skip(binary + " not prebuilt")
-    extra = {"B200_AA_PASSES": "1"}
+    extra = {"B200_AA_PASSES": "1", "B200_WAVEFRONT_FIBERS": str(fibers)}
     if deterministic:
         extra["B200_DETERMINISTIC"] = "1"
     images = {}
@@ -76,6 +80,8 @@ def test_reference_scene_renders_through_b200_accelerator(built, test, determini
             if accel:
                 assert "Added AcceleratorB200 (b200-kdtree)" in log or "(b200-kdtree)" in log, "the b200 accelerator was not selected"
                 assert "no usable accelerator" not in log, "libb200rt failed to build the scene on this box"
+                if fibers:
+                    assert "wavefront rays closest=" in log and "per-ray calls outside fibers: 0" in log, "the render did not go through the wavefront ray queue"
             else:
                 assert "(yafaray-kdtree-original)" in log
             out = [f for f in os.listdir(d) if f.endswith(".tga")]
@@ -87,9 +93,11 @@ def test_reference_scene_renders_through_b200_accelerator(built, test, determini
     # the film rows only (the badge is 78 identical black rows at the top of test01's 480x348 output)
     badge = a.shape[0] - 270 if a.shape[0] > 270 else 0
     value = psnr(a[badge:], b[badge:])
-    print(f"{test} deterministic={deterministic}: PSNR {value:.2f} dB, differing bytes {(a[badge:] != b[badge:]).sum()} of {a[badge:].size}")
+    print(f"{test} deterministic={deterministic} fibers={fibers}: PSNR {value:.2f} dB, differing bytes {(a[badge:] != b[badge:]).sum()} of {a[badge:].size}")
     assert value >= PSNR_FLOOR_DB
     assert a[badge:].std() > 5.0, "reference image is flat: nothing was rendered"
+    if fibers == 0 and deterministic:
+        assert np.array_equal(a[badge:], b[badge:]), "the per-ray path is expected to be byte-identical with threads=1"
 
 
 @needs_build("yafaray_test01")
