@@ -68,9 +68,9 @@ class AcceleratorB200 final : public Accelerator
 			PARAM_DECL(float, empty_bonus_, 0.f, "empty_bonus", "0 = library default");
 			PARAM_DECL(int, device_, 0, "device", "CUDA device index");
 			PARAM_DECL(int, num_threads_, 0, "accelerator_threads", "host threads for the tree build; 0 = all");
-			PARAM_DECL(int, wavefront_fibers_, 1024, "wavefront_fibers", "rays in flight per render thread (fibers running renderTile on pixel blocks); 0 = per-ray calls only");
+			PARAM_DECL(int, wavefront_fibers_, 512, "wavefront_fibers", "rays in flight per render thread (fibers running renderTile on pixel blocks); 0 = per-ray calls only");
 			PARAM_DECL(int, wavefront_groups_, 2, "wavefront_groups", "groups the fibers of a thread are split into; one group shades while the rays of another are on the GPU");
-			PARAM_DECL(int, wavefront_block_, 4, "wavefront_block", "side of the pixel block one fiber renders");
+			PARAM_DECL(int, wavefront_block_, 2, "wavefront_block", "side of the pixel block one fiber renders");
 			PARAM_DECL(int, wavefront_stack_kb_, 256, "wavefront_stack_kb", "stack per fiber, KiB (mapped lazily)");
 		} params_;
 		[[nodiscard]] ParamMap getAsParamMap(bool only_non_default) const override;

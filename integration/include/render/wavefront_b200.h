@@ -113,6 +113,7 @@ class RayQueue final
 		const int n_fibers_;
 		std::vector<Fiber> fibers_;
 		std::vector<Group> groups_;
+		char *slab_ = nullptr;     //!< the pinned memory every group's ray / answer arrays are carved from
 		Fiber *running_ = nullptr;
 		void *scheduler_sp_ = nullptr;
 		const std::function<void()> *body_ = nullptr;

@@ -104,6 +104,11 @@ RayQueue::RayQueue(int n_fibers, int n_groups, size_t stack_bytes) : n_fibers_{s
 	n_groups = std::max(1, std::min(n_groups, n_fibers_));
 	groups_.resize(size_t(n_groups));
 	const size_t per_group = (size_t(n_fibers_) + size_t(n_groups) - 1) / size_t(n_groups);
+	// one pinned slab for the rays and answers of all groups (a pinned allocation costs the driver a fraction of a millisecond and
+	// sixteen render threads create their queues at the same moment)
+	const size_t per_slot = 3 * sizeof(b200rt_ray) + kOutSize[0] + kOutSize[1] + kOutSize[2];
+	slab_ = static_cast<char *>(pinned(size_t(n_groups) * per_group * per_slot + 64, error_));
+	char *cursor = slab_;
 	for(size_t g = 0; g < groups_.size(); ++g)
 	{
 		Group &group = groups_[g];
@@ -112,14 +117,19 @@ RayQueue::RayQueue(int n_fibers, int n_groups, size_t stack_bytes) : n_fibers_{s
 			fibers_[i].group = &group;
 			group.fibers.push_back(&fibers_[i]);
 		}
-		group.capacity = uint32_t(group.fibers.size());
+		group.capacity = uint32_t(per_group);
 		group.parked.reserve(group.capacity);
-		for(int kind = 0; kind < 3; ++kind)
+		for(int kind = 0; kind < 3 && slab_; ++kind)
 		{
-			group.rays[kind] = static_cast<b200rt_ray *>(pinned(size_t(group.capacity) * sizeof(b200rt_ray), error_));
-			group.outs[kind] = pinned(size_t(group.capacity) * kOutSize[kind], error_);
-			group.requests[kind].resize(group.capacity);
+			group.rays[kind] = reinterpret_cast<b200rt_ray *>(cursor);
+			cursor += per_group * sizeof(b200rt_ray);
 		}
+		for(int kind = 2; kind >= 0 && slab_; --kind) // 144-byte records first: keeps every array 16-byte aligned
+		{
+			group.outs[kind] = cursor;
+			cursor += per_group * kOutSize[kind];
+		}
+		for(auto &r : group.requests) r.resize(group.capacity);
 	}
 	resuming_.reserve(per_group);
 }
@@ -131,12 +141,11 @@ RayQueue::~RayQueue()
 		if(group.flying && group.flight) b200rt_trace_jobs_end(group.flight);
 		for(int kind = 0; kind < 3; ++kind)
 		{
-			b200rt_host_free(group.rays[kind]);
-			b200rt_host_free(group.outs[kind]);
 			b200rt_host_free(group.sorted_rays[kind]);
 			b200rt_host_free(group.sorted_out[kind]);
 		}
 	}
+	b200rt_host_free(slab_);
 	for(Fiber &f : fibers_) if(f.stack) munmap(f.stack, f.stack_bytes);
 }
 

@@ -61,7 +61,7 @@ def needs_build(name):
 
 @pytest.mark.gpu
 @needs_build("yafaray_test01")
-@pytest.mark.parametrize("test,deterministic,fibers", [("test01", True, 0), ("test01", True, 1024), ("test01", False, 1024), ("test09", True, 1024)])
+@pytest.mark.parametrize("test,deterministic,fibers", [("test01", True, 0), ("test01", True, 512), ("test01", False, 512), ("test09", True, 512)])
 def test_reference_scene_renders_through_b200_accelerator(built, test, deterministic, fibers):
     """fibers = 0: every Accelerator virtual is a one-ray libb200rt call (the compatibility path; byte-identical image).
     fibers > 0: the wavefront ray queue (integration/src/render/wavefront_b200.cc) -- the reference's renderTile() runs on
@@ -98,6 +98,10 @@ def test_reference_scene_renders_through_b200_accelerator(built, test, determini
     assert a[badge:].std() > 5.0, "reference image is flat: nothing was rendered"
     if fibers == 0 and deterministic:
         assert np.array_equal(a[badge:], b[badge:]), "the per-ray path is expected to be byte-identical with threads=1"
+    if test == "test01" and deterministic:
+        # measured: with the wavefront queue only the alpha byte differs (254 <-> 255: the film sums the same splats in a
+        # different order, alpha = sum(w) / sum(w) rounds to 1 - ulp or 1 and the 8-bit conversion truncates)
+        assert np.array_equal(a[badge:, :, :3], b[badge:, :, :3]), "colour channels are expected to be byte-identical with threads=1"
 
 
 @needs_build("yafaray_test01")
