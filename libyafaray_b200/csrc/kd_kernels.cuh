@@ -189,12 +189,19 @@ __device__ __forceinline__ float polyIntersect(const float4 q0, const float4 q1,
 #define B200RT_SMEM_RAY 1
 #endif
 #ifndef B200RT_STEPS
-#define B200RT_STEPS 8
+#define B200RT_STEPS 16
+#endif
+#ifndef B200RT_UNROLL
+#define B200RT_UNROLL 4
+#endif
+#ifndef B200RT_BREAK
+#define B200RT_BREAK 1
 #endif
 static constexpr int kBlock = B200RT_BLOCK;
 static constexpr int kPoolRays = 256;               // rays taken from the global cursor per atomicAdd
 static constexpr int kRefill = B200RT_REFILL;       // idle lanes that trigger a refill
 static constexpr int kLeafBatch = B200RT_LEAF_BATCH; // lanes holding a leaf that trigger the leaf phase
+static constexpr int kUnroll = B200RT_UNROLL;       // unroll factor of the descent loop
 static constexpr int kSteps = B200RT_STEPS;         // node steps per lane between two warp votes
 static constexpr int kMinBlocks = B200RT_MIN_BLOCKS; // blocks per SM the register allocation is held to
 static constexpr unsigned kFullMask = 0xFFFFFFFFu;
@@ -211,7 +218,7 @@ struct RayState
 	uint32_t node;
 	uint32_t index;               // ray index in the batch
 	uint32_t neg;                 // bit k set: direction component k is negative
-	int sp;
+	int sp;                       // ring depth in bytes (kRingStride per entry)
 };
 
 // Ray setup: root slab test (bound.h:156-198), bias (accelerator.h:64), traversal interval.  Returns false when
@@ -337,6 +344,8 @@ __device__ __forceinline__ void writeResult(typename OutType<QUERY>::type *out, 
 #endif
 static constexpr int kShortStack = B200RT_SHORT_STACK;
 static_assert((kShortStack & (kShortStack - 1)) == 0, "ring size must be a power of two");
+static constexpr int kRingStride = kBlock * int(sizeof(uint2));        // bytes between two entries of one thread's ring
+static constexpr int kRingMask = (kShortStack - 1) * kRingStride;
 
 __device__ __forceinline__ float selectf(bool p, float a, float b)
 {
@@ -361,6 +370,8 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 	const unsigned tid = threadIdx.x;
 	const unsigned lane = tid & 31u;
 	const unsigned lanes_below = (1u << lane) - 1u;
+	// the thread's column of the ring; r.sp and floor count in bytes of it (kRingStride per entry), which saves the shifts
+	char *const ring = reinterpret_cast<char *>(&sh_stack[0][tid]);
 	RayState r;
 	TShadowState ts;
 	ts.depth = 0;
@@ -380,8 +391,8 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 		if(QUERY == kClosest && r.best_prim != B200RT_MISS && r.t_max <= r.seg_hi) return true;
 		if(r.sp > floor)
 		{
-			--r.sp;
-			const uint2 e = sh_stack[r.sp & (kShortStack - 1)][tid];
+			r.sp -= kRingStride;
+			const uint2 e = *reinterpret_cast<const uint2 *>(ring + (r.sp & kRingMask));
 			r.node = e.x;
 			r.seg_lo = r.seg_hi;
 			r.seg_hi = __uint_as_float(e.y);
@@ -512,59 +523,68 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 		else
 		{
 			// ---------------- descend: up to kSteps nodes per lane; empty leaves are consumed here ----------------
-#pragma unroll 1
+			// Lanes that descend in this round; a lane drops out at a leaf it cannot pop past: a non-empty leaf, the end of its ray,
+			// or an empty ring with lost entries.  Which of the three is decided after the loop, from state the step left untouched.
+			const bool descending = alive && !pending;
+			bool go = descending;
+#pragma unroll kUnroll
 			for(int step = 0; step < kSteps; ++step)
 			{
-				if(alive && !pending && !finished)
+#if B200RT_BREAK
+				if(!go) break;
+#else
+				if(go)
+#endif
 				{
-					// One node per step, interior or leaf, without divergent branches: the interior arithmetic, the push,
-					// the pop of an empty leaf and the hand-over of a non-empty leaf are all predicated / selected.
+					// One node per step, interior or leaf, without divergent branches: the interior arithmetic, the push and
+					// the pop of an empty leaf are all predicated / selected.
 					const uint2 nd = __ldg(&s.nodes[r.node]);
 					const uint32_t axis = nd.y & 3u;
 					const uint32_t payload = nd.y >> 2; // interior: right child, leaf: primitive count
 					const bool is_leaf = (axis == 3u);
 					const float split = __uint_as_float(nd.x);
-#if B200RT_SMEM_RAY
-					const float2 oi = sh_axis[axis < 3u ? axis : 0u][tid];
+					const float2 oi = sh_axis[axis][tid]; // row 3 (leaves) is never written: its value is not used
 					const float o = oi.x, inv = oi.y;
-#else
-					const bool a1 = (axis == 1u), a2 = (axis == 2u);
-					const float o = selectf(a2, r.oz, selectf(a1, r.oy, r.ox));
-					const float inv = selectf(a2, r.iz, selectf(a1, r.iy, r.ix));
-#endif
 					const float t_plane = (split - o) * inv;
-					const bool neg = inv < 0.f;
+					// near / far child without a predicate: m = all ones for a negative direction component
+					const uint32_t m = uint32_t(__float_as_int(inv) >> 31);
 					const uint32_t left = r.node + 1u;
-					const uint32_t near = selectu(neg, payload, left), far = selectu(neg, left, payload);
+					const uint32_t swap = (left ^ payload) & m;
+					const uint32_t near = left ^ swap, far = payload ^ swap;
 					const float limit = (QUERY == kClosest) ? fminf(r.seg_hi, r.t_max) : r.seg_hi;
 					const bool far_only = t_plane <= r.seg_lo;
 					const bool both = !is_leaf && !(t_plane >= limit) && !far_only;
 					// top of the ring (read before this step's speculative store; different slot)
-					const int top = (r.sp - 1) & (kShortStack - 1);
-					const uint2 popped = sh_stack[top][tid];
+					const uint2 popped = *reinterpret_cast<const uint2 *>(ring + ((r.sp - kRingStride) & kRingMask));
 					const uint32_t pop_node = popped.x;
 					const float pop_far = __uint_as_float(popped.y);
 					if(!is_leaf)
 					{
-						const int slot = r.sp & (kShortStack - 1);
-						sh_stack[slot][tid] = make_uint2(far, __float_as_uint(r.seg_hi));
-						floor = max(floor, r.sp + 1 - kShortStack); // the store has clobbered the oldest slot of a full ring, pushed or not
+						*reinterpret_cast<uint2 *>(ring + (r.sp & kRingMask)) = make_uint2(far, __float_as_uint(r.seg_hi));
+						floor = max(floor, r.sp + (1 - kShortStack) * kRingStride); // the store has clobbered the oldest slot of a full ring, pushed or not
 					}
-					const bool empty_leaf = is_leaf && payload == 0u;
 					// closest: once the best hit is not beyond the end of this leaf nothing nearer can follow (accelerator_kdtree_common.h:232)
 					const bool closest_done = (QUERY == kClosest) && r.best_prim != B200RT_MISS && r.t_max <= r.seg_hi;
-					const bool has_stack = r.sp > floor;
-					const bool do_pop = empty_leaf && !closest_done && has_stack;
-					const bool lost = empty_leaf && !closest_done && !has_stack && floor != 0;
-					finished = empty_leaf && !do_pop && !lost;
-					pending = is_leaf && !empty_leaf;
+					const bool do_pop = nd.y == 3u && !closest_done && r.sp > floor; // an empty leaf (count 0, axis bits 3) with something to pop
 					leaf_count = payload;
 					leaf_first = nd.x;
 					r.node = is_leaf ? selectu(do_pop, pop_node, r.node) : selectu(far_only, far, near);
 					r.seg_lo = selectf(do_pop, r.seg_hi, r.seg_lo);
 					r.seg_hi = selectf(do_pop, pop_far, selectf(both, t_plane, r.seg_hi));
-					r.sp += (both ? 1 : 0) - (do_pop ? 1 : 0);
-					if(lost)
+					if(both) r.sp += kRingStride;
+					if(do_pop) r.sp -= kRingStride;
+					go = !is_leaf || do_pop;
+				}
+			}
+			if(descending && !go)
+			{
+				// stopped at a leaf (leaf_count = its primitive count); node, interval and ring are as the step found them
+				if(leaf_count != 0u) pending = true;
+				else
+				{
+					const bool closest_done = (QUERY == kClosest) && r.best_prim != B200RT_MISS && r.t_max <= r.seg_hi;
+					if(closest_done || floor == 0) finished = true;
+					else
 					{
 						// ring entries were overwritten: restart from the root behind the leaf just left (kd-restart)
 						r.sp = 0;
@@ -592,7 +612,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, c
                                                                  typename OutType<QUERY>::type *__restrict__ out, uint32_t *__restrict__ cursor, int max_depth, bool tree_space)
 {
 	__shared__ uint2 sh_stack[kShortStack][kBlock]; // x = node index, y = float bits of the far end of its interval
-	__shared__ float2 sh_axis[3][kBlock];          // per axis: (origin, inverse direction) of the lane's ray
+	__shared__ float2 sh_axis[4][kBlock];          // per axis: (origin, inverse direction) of the lane's ray; row 3 is read (not used) at leaves
 	traceWarps<QUERY>(s, rays, n, out, cursor, max_depth, tree_space, sh_stack, sh_axis, (blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5)) * 32u);
 }
 
@@ -609,7 +629,7 @@ struct MixedBatch
 __global__ void __launch_bounds__(kBlock, 4) traceMixedKernel(SceneView s, MixedBatch b, int max_depth, bool tree_space)
 {
 	__shared__ uint2 sh_stack[kShortStack][kBlock];
-	__shared__ float2 sh_axis[3][kBlock];
+	__shared__ float2 sh_axis[4][kBlock];
 	const uint32_t warp = blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5);
 	const uint32_t w0 = (b.n[0] + 31u) / 32u, w1 = (b.n[1] + 31u) / 32u;
 	if(warp < w0) traceWarps<kClosest>(s, b.rays[0], b.n[0], static_cast<b200rt_hit *>(b.out[0]), nullptr, 0, tree_space, sh_stack, sh_axis, warp * 32u);
