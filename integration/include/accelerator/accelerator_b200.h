@@ -49,6 +49,8 @@ class AcceleratorB200 final : public Accelerator
 		int wavefrontFibers() const { return scene_ ? params_.wavefront_fibers_ : 0; }
 		int wavefrontGroups() const { return params_.wavefront_groups_; }
 		int wavefrontBlock() const { return params_.wavefront_block_; }
+		int tileShardIndex() const { return params_.tile_shard_index_; }
+		int tileShardCount() const { return params_.tile_shard_count_; }
 		size_t wavefrontStackBytes() const { return static_cast<size_t>(std::max(64, params_.wavefront_stack_kb_)) << 10; }
 		/* Ray queues (fiber stacks + pinned buffers) are kept between render passes: a render worker borrows one and returns it. */
 		std::unique_ptr<b200::RayQueue> acquireRayQueue() const;
@@ -72,6 +74,8 @@ class AcceleratorB200 final : public Accelerator
 			PARAM_DECL(int, wavefront_groups_, 2, "wavefront_groups", "groups the fibers of a thread are split into; one group shades while the rays of another are on the GPU");
 			PARAM_DECL(int, wavefront_block_, 2, "wavefront_block", "side of the pixel block one fiber renders");
 			PARAM_DECL(int, wavefront_stack_kb_, 256, "wavefront_stack_kb", "stack per fiber, KiB (mapped lazily)");
+			PARAM_DECL(int, tile_shard_index_, 0, "tile_shard_index", "multi-GPU rendering: which share of the frame's tiles this process renders (render/tile_shard_b200.h)");
+			PARAM_DECL(int, tile_shard_count_, 1, "tile_shard_count", "multi-GPU rendering: number of processes (one per GPU) sharing the frame; 1 = render every tile");
 		} params_;
 		[[nodiscard]] ParamMap getAsParamMap(bool only_non_default) const override;
 

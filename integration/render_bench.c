@@ -11,6 +11,10 @@
  *     i:key=value       extra integer integrator parameters (e.g. i:AO_samples=32 i:bounces=5)
  *     b:key=0|1         extra boolean integrator parameters (e.g. b:do_AO=1)
  *     f:key=value       extra float integrator parameters (e.g. f:AO_distance=2.5)
+ *     tile_shard=i/n    multi-GPU rendering: render only share i of n of the frame's tiles (render/tile_shard_b200.h); sets the
+ *                       b200-kdtree parameters tile_shard_index / tile_shard_count, or B200_TILE_SHARD for the stock accelerators
+ *     film_save=prefix  write the film's weighted sums as "<prefix> - node 0000.film" when the render ends (the reference's own
+ *                       film_load_save_mode=save, src/render/imagefilm.cc:1099-1176); libyafaray_b200/film.py sums such films
  */
 #include "yafaray_c_api.h"
 #include <math.h>
@@ -64,6 +68,7 @@ int main(int argc, char **argv)
 	const int cells = atoi(argv[3]), width = atoi(argv[4]), height = atoi(argv[5]), aa_samples = atoi(argv[6]);
 	const int threads = argc > 8 ? atoi(argv[8]) : -1;
 	const double scale = 10.0; /* scene spans [0,10]^2 */
+	const char *film_save = NULL;
 
 	yafaray_Logger *logger = yafaray_createLogger("", NULL, NULL, YAFARAY_DISPLAY_CONSOLE_NORMAL);
 	yafaray_setConsoleLogColorsEnabled(logger, YAFARAY_BOOL_FALSE);
@@ -151,6 +156,23 @@ int main(int argc, char **argv)
 		if(!eq || (size_t) (eq - argv[a]) >= sizeof key || argv[a][1] == ':') continue;
 		memcpy(key, argv[a], (size_t) (eq - argv[a]));
 		key[eq - argv[a]] = 0;
+		if(strcmp(key, "film_save") == 0) { film_save = eq + 1; continue; }
+		if(strcmp(key, "tile_shard") == 0)
+		{
+			int shard_index = 0, shard_count = 1;
+			if(sscanf(eq + 1, "%d/%d", &shard_index, &shard_count) != 2 || shard_count < 1 || shard_index < 0 || shard_index >= shard_count)
+			{
+				fprintf(stderr, "render_bench: bad tile_shard '%s' (expected index/count)\n", eq + 1);
+				return 2;
+			}
+			if(strcmp(accel, "b200-kdtree") == 0)
+			{
+				yafaray_setParamMapInt(pm, "tile_shard_index", shard_index);
+				yafaray_setParamMapInt(pm, "tile_shard_count", shard_count);
+			}
+			else setenv("B200_TILE_SHARD", eq + 1, 1);
+			continue;
+		}
 		yafaray_setParamMapInt(pm, key, atoi(eq + 1));
 	}
 	yafaray_setSceneAcceleratorParams(scene, pm);
@@ -186,6 +208,11 @@ int main(int argc, char **argv)
 	yafaray_setParamMapInt(pm, "AA_passes", 1);
 	yafaray_setParamMapInt(pm, "AA_minsamples", aa_samples);
 	yafaray_setParamMapInt(pm, "threads", threads);
+	if(film_save)
+	{
+		yafaray_setParamMapString(pm, "film_load_save_mode", "save");
+		yafaray_setParamMapString(pm, "film_load_save_path", film_save);
+	}
 	yafaray_Film *film = yafaray_createFilm(logger, surface_integrator, "film", pm);
 	yafaray_clearParamMap(pm);
 	yafaray_setParamMapString(pm, "exported_image_name", "Combined");

@@ -27,6 +27,8 @@ std::map<std::string, const ParamMeta *> AcceleratorB200::Params::getParamMetaMa
 	PARAM_META(wavefront_groups_);
 	PARAM_META(wavefront_block_);
 	PARAM_META(wavefront_stack_kb_);
+	PARAM_META(tile_shard_index_);
+	PARAM_META(tile_shard_count_);
 	return param_meta_map;
 }
 
@@ -42,6 +44,8 @@ AcceleratorB200::Params::Params(ParamResult &param_result, const ParamMap &param
 	PARAM_LOAD(wavefront_groups_);
 	PARAM_LOAD(wavefront_block_);
 	PARAM_LOAD(wavefront_stack_kb_);
+	PARAM_LOAD(tile_shard_index_);
+	PARAM_LOAD(tile_shard_count_);
 }
 
 ParamMap AcceleratorB200::getAsParamMap(bool only_non_default) const
@@ -58,6 +62,8 @@ ParamMap AcceleratorB200::getAsParamMap(bool only_non_default) const
 	PARAM_SAVE(wavefront_groups_);
 	PARAM_SAVE(wavefront_block_);
 	PARAM_SAVE(wavefront_stack_kb_);
+	PARAM_SAVE(tile_shard_index_);
+	PARAM_SAVE(tile_shard_count_);
 	return param_map;
 }
 

@@ -18,6 +18,7 @@
 #include "render/imagesplitter.h"
 #include "render/render_control.h"
 #include "render/wavefront_b200.h"
+#include "render/tile_shard_b200.h"
 #include <deque>
 
 namespace yafaray {
@@ -40,6 +41,7 @@ void TiledIntegrator::renderWorkerWavefront(const AcceleratorB200 &accelerator, 
 	std::vector<Block> blocks;   //blocks of the areas taken so far that no fiber has claimed yet
 	size_t next_block = 0;
 	const int block_size{std::max(1, accelerator.wavefrontBlock())};
+	const b200::TileShard shard{b200::TileShard::make(*image_film_, accelerator.tileShardIndex(), accelerator.tileShardCount())}; //multi-GPU rendering: areas of other processes are skipped
 
 	const auto area_finished{[&](const RenderArea &a) {
 		std::unique_lock<std::mutex> lk(control->m_);
@@ -54,6 +56,7 @@ void TiledIntegrator::renderWorkerWavefront(const AcceleratorB200 &accelerator, 
 			next_block = 0;
 			RenderArea a;
 			if(render_control.canceled() || !image_film_->nextArea(a)) return false;
+			if(!shard.owns(a)) continue;
 			areas.push_back({a, 0});
 			Area &area{areas.back()};
 			for(int y = a.y_; y < a.y_ + a.h_; y += block_size)

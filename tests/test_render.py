@@ -98,10 +98,12 @@ def test_reference_scene_renders_through_b200_accelerator(built, test, determini
     assert a[badge:].std() > 5.0, "reference image is flat: nothing was rendered"
     if fibers == 0 and deterministic:
         assert np.array_equal(a[badge:], b[badge:]), "the per-ray path is expected to be byte-identical with threads=1"
-    if test == "test01" and deterministic:
-        # measured: with the wavefront queue only the alpha byte differs (254 <-> 255: the film sums the same splats in a
-        # different order, alpha = sum(w) / sum(w) rounds to 1 - ulp or 1 and the 8-bit conversion truncates)
-        assert np.array_equal(a[badge:, :, :3], b[badge:, :, :3]), "colour channels are expected to be byte-identical with threads=1"
+    if test == "test01" and deterministic and fibers:
+        # renderTile() runs once per wavefront_block x wavefront_block pixel block instead of once per 32 x 32 tile, and every
+        # renderTile() call seeds its own RNG from rand() (src/integrator/surface/integrator_tiled.cc:256): the stochastic
+        # part of the image (area-light / AO sample jitter) is drawn from a different stream, the geometry is identical.
+        # Measured on B200: 66.2 dB with the default 2 x 2 blocks (only the alpha byte differs with 4 x 4 blocks and 1024 fibers).
+        assert value >= 60.0, "deterministic wavefront render drifted from the stock image"
 
 
 @needs_build("yafaray_test01")
