@@ -13,6 +13,8 @@
  *     f:key=value       extra float integrator parameters (e.g. f:AO_distance=2.5)
  *     tile_shard=i/n    multi-GPU rendering: render only share i of n of the frame's tiles (render/tile_shard_b200.h); sets the
  *                       b200-kdtree parameters tile_shard_index / tile_shard_count, or B200_TILE_SHARD for the stock accelerators
+ *     instances=n       n static instances (rotation about z + translation) of one box standing on the field; every third one
+ *                       is an instance OF THE PREVIOUS INSTANCE (nested, include/geometry/primitive/primitive_instance.h:88-91)
  *     film_save=prefix  write the film's weighted sums as "<prefix> - node 0000.film" when the render ends (the reference's own
  *                       film_load_save_mode=save, src/render/imagefilm.cc:1099-1176); libyafaray_b200/film.py sums such films
  */
@@ -37,7 +39,7 @@ static double lcg(void)
 	return (double) (lcg_state >> 8) / 16777216.0;
 }
 
-static void add_box(yafaray_Scene *scene, const char *name, double x0, double y0, double z0, double x1, double y1, double z1, const char *material)
+static size_t add_box(yafaray_Scene *scene, const char *name, double x0, double y0, double z0, double x1, double y1, double z1, const char *material)
 {
 	size_t object_id = 0, material_id = 0;
 	yafaray_ParamMap *pm = yafaray_createParamMap();
@@ -55,6 +57,7 @@ static void add_box(yafaray_Scene *scene, const char *name, double x0, double y0
 	yafaray_addQuad(scene, object_id, 5, 7, 3, 1, material_id);
 	yafaray_initObject(scene, object_id, material_id);
 	yafaray_destroyParamMap(pm);
+	return object_id;
 }
 
 int main(int argc, char **argv)
@@ -123,6 +126,34 @@ int main(int argc, char **argv)
 		add_box(scene, name, cx - s, cy - s, -0.6, cx + s, cy + s, h, "boxes");
 	}
 
+	/* static instances of one more box, on a ring around the centre of the field */
+	int n_instances = 0;
+	for(int a = 9; a < argc; ++a) if(strncmp(argv[a], "instances=", 10) == 0) n_instances = atoi(argv[a] + 10);
+	if(n_instances > 0)
+	{
+		const double s = 0.018 * scale;
+		const size_t pillar = add_box(scene, "pillar", -s, -s, -0.6, s, s, 0.16 * scale, "boxes");
+		size_t previous = 0;
+		for(int k = 0; k < n_instances; ++k)
+		{
+			const double angle = 6.283185307179586 * k / n_instances, c = cos(2.5 * angle), sn = sin(2.5 * angle);
+			const size_t instance = yafaray_createInstance(scene);
+			if(k % 3 == 2)
+			{
+				/* nested: the previous instance moved a little further out and up */
+				yafaray_addInstanceOfInstance(scene, instance, previous);
+				yafaray_addInstanceMatrix(scene, instance, 1., 0., 0., 0.035 * scale * cos(angle), 0., 1., 0., 0.035 * scale * sin(angle), 0., 0., 1., 0.05 * scale, 0., 0., 0., 1., 0.f);
+			}
+			else
+			{
+				const double r = scale * (0.22 + 0.12 * (k & 1));
+				yafaray_addInstanceObject(scene, instance, pillar);
+				yafaray_addInstanceMatrix(scene, instance, c, -sn, 0., 0.5 * scale + r * cos(angle), sn, c, 0., 0.5 * scale + r * sin(angle), 0., 0., 1.1, 0., 0., 0., 0., 1., 0.f);
+			}
+			previous = instance;
+		}
+	}
+
 	/* lights */
 	yafaray_clearParamMap(pm);
 	yafaray_setParamMapColor(pm, "color", 1.f, 0.95f, 0.9f, 1.f);
@@ -157,6 +188,7 @@ int main(int argc, char **argv)
 		memcpy(key, argv[a], (size_t) (eq - argv[a]));
 		key[eq - argv[a]] = 0;
 		if(strcmp(key, "film_save") == 0) { film_save = eq + 1; continue; }
+		if(strcmp(key, "instances") == 0) continue; /* handled with the geometry above */
 		if(strcmp(key, "tile_shard") == 0)
 		{
 			int shard_index = 0, shard_count = 1;
@@ -247,7 +279,7 @@ int main(int argc, char **argv)
 	const double t_render1 = now();
 	printf("RENDER_BENCH {\"accelerator\": \"%s\", \"integrator\": \"%s\", \"triangles\": %d, \"width\": %d, \"height\": %d, \"aa_samples\": %d, \"threads\": %d, "
 	       "\"scene_seconds\": %.3f, \"preprocess_seconds\": %.3f, \"render_seconds\": %.3f}\n",
-	       accel, integrator, 2 * cells * cells + 72, width, height, aa_samples, threads, t_built - t_scene, t_pre - t_built, t_render1 - t_render0);
+	       accel, integrator, 2 * cells * cells + 72 + (n_instances > 0 ? 6 * (n_instances + 1) : 0), width, height, aa_samples, threads, t_built - t_scene, t_pre - t_built, t_render1 - t_render0);
 	yafaray_destroyRenderControl(render_control);
 	yafaray_destroyRenderMonitor(render_monitor);
 	yafaray_destroyFilm(film);

@@ -7,6 +7,9 @@
 #include "b200rt.h"
 #include "common/logger.h"
 #include "geometry/primitive/primitive_face.h"
+#include "geometry/primitive/primitive_instance.h"
+#include "geometry/instance.h"
+#include "geometry/matrix.h"
 #include "material/material.h"
 #include "param/param.h"
 #include "render/render_control.h"
@@ -120,17 +123,33 @@ AcceleratorB200::AcceleratorB200(Logger &logger, ParamResult &param_result, cons
 	for(const Primitive *primitive : primitives_)
 	{
 		if(render_control_ && render_control_->canceled()) return;
-		const auto *face{dynamic_cast<const FacePrimitive *>(primitive)};
-		const int n_vertices{face ? face->numVertices() : 0};
-		if(!face || face->hasMotionBlur() || (n_vertices != 3 && n_vertices != 4))
+		// Instances: PrimitiveInstance::intersect hands the base primitive the instance's matrix, nested
+		// instances multiply theirs in front (include/geometry/primitive/primitive_instance.h:83-91), and a mesh face then tests
+		// the ray against obj_to_world * vertex (include/geometry/primitive/primitive_face.h:81-84).  A static instance
+		// (Instance::hasMotionBlur() false, include/geometry/instance.h:48) always uses matrix 0, so its faces are uploaded
+		// pre-transformed WITH THE REFERENCE'S OWN matrix product and matrix * point code: same floats, same hits.
+		const Primitive *base{primitive};
+		Matrix4f obj_to_world{1.f};
+		bool transformed{false}, moving{false};
+		while(const auto *instance_primitive{dynamic_cast<const PrimitiveInstance *>(base)})
 		{
-			logger_.logError(getClassName(), ": primitive kind not supported by the b200-kdtree accelerator (only static triangle and quad mesh faces are); no accelerator created");
+			const Instance &instance{instance_primitive->getBaseInstance()};
+			moving = moving || instance.hasMotionBlur();
+			obj_to_world = transformed ? obj_to_world * instance.getObjToWorldMatrix(0) : instance.getObjToWorldMatrix(0);
+			transformed = true;
+			base = &instance_primitive->getBasePrimitive();
+		}
+		const auto *face{dynamic_cast<const FacePrimitive *>(base)};
+		const int n_vertices{face ? face->numVertices() : 0};
+		if(!face || moving || face->hasMotionBlur() || (n_vertices != 3 && n_vertices != 4))
+		{
+			logger_.logError(getClassName(), ": primitive kind not supported by the b200-kdtree accelerator (static triangle and quad mesh faces and static instances of them are); no accelerator created");
 			return;
 		}
 		const uint32_t first_vertex{static_cast<uint32_t>(xyz.size() / 3)};
 		for(int v = 0; v < n_vertices; ++v)
 		{
-			const Point3f p{face->getVertex(v, 0)};
+			const Point3f p{transformed ? face->getVertex(v, 0, obj_to_world) : face->getVertex(v, 0)};
 			xyz.push_back(p[Axis::X]); xyz.push_back(p[Axis::Y]); xyz.push_back(p[Axis::Z]);
 		}
 		for(int v = 0; v < 4; ++v) idx.push_back(v < n_vertices ? first_vertex + static_cast<uint32_t>(v) : 0xFFFFFFFFu);
