@@ -7,7 +7,7 @@
  *   reference interface                                                    replaced by
  *   -------------------------------------------------------------------    ---------------------------------
  *   AcceleratorKdTree ctor / Accelerator::factory                          b200rt_create + b200rt_add_mesh
- *     (src/accelerator/accelerator_kdtree_original.cc:57-141,               + b200rt_build
+ *     (src/accelerator/accelerator_kdtree_original.cc:57-141,               [+ b200rt_add_spheres] + b200rt_build
  *      src/accelerator/accelerator.cc:44-55)
  *   Accelerator::getBound()  (include/accelerator/accelerator.h:53)        b200rt_get_bound
  *   Accelerator::intersect(ray,t_max) / intersect(ray,camera)              b200rt_trace_closest[_device]
@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B200RT_VERSION 1
+#define B200RT_VERSION 2
 #define B200RT_MISS 0xFFFFFFFFu
 
 enum
@@ -109,6 +109,7 @@ typedef struct b200rt_stats
 	uint32_t max_depth, max_leaf_prims;
 	double build_seconds, upload_seconds;
 	uint64_t device_bytes;
+	uint64_t n_spheres;
 } b200rt_stats;
 
 typedef struct b200rt_scene b200rt_scene;
@@ -126,6 +127,13 @@ void b200rt_destroy(b200rt_scene *scene);
  * caster).  Face ids continue across calls in upload order, like the primitive vector Scene::preprocess
  * hands to the factory (src/scene/scene.cc:320-341). */
 int b200rt_add_mesh(b200rt_scene *scene, const float *xyz, size_t n_verts, const uint32_t *idx, size_t n_faces, const uint8_t *flags);
+
+/* Append spheres (SpherePrimitive, src/geometry/primitive/primitive_sphere.cc:71-102; objects of type "sphere",
+ * src/geometry/object/object.cc:80-90).  center_radius: 4 floats per sphere (cx cy cz radius).  flags as for faces.
+ * Every sphere takes the next face id, in call order with b200rt_add_mesh.  A hit on a sphere reports u = v = 0 like the
+ * reference.  An instance of a sphere is the same sphere: the reference ignores the instance matrix for spheres
+ * (primitive_sphere.cc:104-122), so upload it unchanged. */
+int b200rt_add_spheres(b200rt_scene *scene, const float *center_radius, size_t n_spheres, const uint8_t *flags);
 
 /* Build the kd-tree on the host, flatten it and upload it.  Must precede any trace call; calling it
  * again after more b200rt_add_mesh calls rebuilds. */
@@ -206,7 +214,10 @@ int b200rt_host_free(void *ptr);
 /* ---- diagnostics: the host-side builder alone (no CUDA device needed).  Used by the CPU test-suite to
  * validate the tree (every face reachable, same hits as the reference traversal run over it) and by tools.
  * Export format: node i = (a[i], b[i]); interior: a = float bits of the split, b = (right child << 2) | axis,
- * left child = i + 1; leaf: a = first index into refs, b = (count << 2) | 3; refs = face ids. */
+ * left child = i + 1; leaf: a = first index into refs, b = (count << 2) | 3; refs = face ids.
+ * Here (and only here) a sphere is passed inside the mesh arrays: a face with idx[4f+2] == 0xFFFFFFFE and
+ * idx[4f+3] == 0xFFFFFFFF whose vertex idx[4f+0] is the centre and whose vertex idx[4f+1] carries the radius in x --
+ * the layout b200rt_add_spheres stores internally. */
 typedef struct b200rt_host_tree b200rt_host_tree;
 int b200rt_host_tree_build(const float *xyz, size_t n_verts, const uint32_t *idx, size_t n_faces, const b200rt_build_params *params, b200rt_host_tree **out);
 int b200rt_host_tree_sizes(const b200rt_host_tree *tree, size_t *n_nodes, size_t *n_refs);

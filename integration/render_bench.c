@@ -15,6 +15,7 @@
  *                       b200-kdtree parameters tile_shard_index / tile_shard_count, or B200_TILE_SHARD for the stock accelerators
  *     instances=n       n static instances (rotation about z + translation) of one box standing on the field; every third one
  *                       is an instance OF THE PREVIOUS INSTANCE (nested, include/geometry/primitive/primitive_instance.h:88-91)
+ *     spheres=n         n objects of type "sphere" (SpherePrimitive) resting on / floating above the field
  *     film_save=prefix  write the film's weighted sums as "<prefix> - node 0000.film" when the render ends (the reference's own
  *                       film_load_save_mode=save, src/render/imagefilm.cc:1099-1176); libyafaray_b200/film.py sums such films
  */
@@ -154,6 +155,22 @@ int main(int argc, char **argv)
 		}
 	}
 
+	/* spheres: objects of type "sphere", src/geometry/object/object.cc:80-90 */
+	int n_spheres = 0;
+	for(int a = 9; a < argc; ++a) if(strncmp(argv[a], "spheres=", 8) == 0) n_spheres = atoi(argv[a] + 8);
+	for(int k = 0; k < n_spheres; ++k)
+	{
+		char name[32];
+		snprintf(name, sizeof name, "sphere%03d", k);
+		const double angle = 2.399963229728653 * k, rad = scale * 0.42 * sqrt((k + 0.5) / n_spheres);
+		yafaray_clearParamMap(pm);
+		yafaray_setParamMapString(pm, "type", "sphere");
+		yafaray_setParamMapVector(pm, "center", 0.5 * scale + rad * cos(angle), 0.5 * scale + rad * sin(angle), scale * (0.06 + 0.05 * (k % 4)));
+		yafaray_setParamMapFloat(pm, "radius", (float) (scale * (0.012 + 0.004 * (k % 5))));
+		yafaray_setParamMapString(pm, "material", (k & 1) ? "boxes" : "ground");
+		yafaray_createObject(scene, &object_id, name, pm);
+	}
+
 	/* lights */
 	yafaray_clearParamMap(pm);
 	yafaray_setParamMapColor(pm, "color", 1.f, 0.95f, 0.9f, 1.f);
@@ -188,7 +205,7 @@ int main(int argc, char **argv)
 		memcpy(key, argv[a], (size_t) (eq - argv[a]));
 		key[eq - argv[a]] = 0;
 		if(strcmp(key, "film_save") == 0) { film_save = eq + 1; continue; }
-		if(strcmp(key, "instances") == 0) continue; /* handled with the geometry above */
+		if(strcmp(key, "instances") == 0 || strcmp(key, "spheres") == 0) continue; /* handled with the geometry above */
 		if(strcmp(key, "tile_shard") == 0)
 		{
 			int shard_index = 0, shard_count = 1;
@@ -279,7 +296,7 @@ int main(int argc, char **argv)
 	const double t_render1 = now();
 	printf("RENDER_BENCH {\"accelerator\": \"%s\", \"integrator\": \"%s\", \"triangles\": %d, \"width\": %d, \"height\": %d, \"aa_samples\": %d, \"threads\": %d, "
 	       "\"scene_seconds\": %.3f, \"preprocess_seconds\": %.3f, \"render_seconds\": %.3f}\n",
-	       accel, integrator, 2 * cells * cells + 72 + (n_instances > 0 ? 6 * (n_instances + 1) : 0), width, height, aa_samples, threads, t_built - t_scene, t_pre - t_built, t_render1 - t_render0);
+	       accel, integrator, 2 * cells * cells + 72 + (n_instances > 0 ? 6 * (n_instances + 1) : 0) + n_spheres, width, height, aa_samples, threads, t_built - t_scene, t_pre - t_built, t_render1 - t_render0);
 	yafaray_destroyRenderControl(render_control);
 	yafaray_destroyRenderMonitor(render_monitor);
 	yafaray_destroyFilm(film);

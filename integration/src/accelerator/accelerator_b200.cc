@@ -8,6 +8,7 @@
 #include "common/logger.h"
 #include "geometry/primitive/primitive_face.h"
 #include "geometry/primitive/primitive_instance.h"
+#include "geometry/primitive/primitive_sphere.h"
 #include "geometry/instance.h"
 #include "geometry/matrix.h"
 #include "material/material.h"
@@ -120,9 +121,28 @@ AcceleratorB200::AcceleratorB200(Logger &logger, ParamResult &param_result, cons
 	xyz.reserve(primitives_.size() * 12);
 	idx.reserve(primitives_.size() * 4);
 	flags.reserve(primitives_.size());
+	b200rt_build_params build_params{};
+	build_params.max_depth = params_.max_depth_;
+	build_params.max_leaf_size = params_.max_leaf_size_;
+	build_params.cost_ratio = params_.cost_ratio_;
+	build_params.empty_bonus = params_.empty_bonus_;
+	build_params.build_threads = params_.num_threads_;
+	b200rt_scene *scene = nullptr;
+	int rc = b200rt_create(params_.device_, &build_params, &scene);
+	// faces gathered so far go to the library before a sphere does, so that face ids follow the primitive order
+	const auto flush_mesh{[&]() {
+		if(rc == B200RT_OK && !flags.empty()) rc = b200rt_add_mesh(scene, xyz.data(), xyz.size() / 3, idx.data(), idx.size() / 4, flags.data());
+		xyz.clear();
+		idx.clear();
+		flags.clear();
+	}};
 	for(const Primitive *primitive : primitives_)
 	{
-		if(render_control_ && render_control_->canceled()) return;
+		if(render_control_ && render_control_->canceled())
+		{
+			if(scene) b200rt_destroy(scene);
+			return;
+		}
 		// Instances: PrimitiveInstance::intersect hands the base primitive the instance's matrix, nested
 		// instances multiply theirs in front (include/geometry/primitive/primitive_instance.h:83-91), and a mesh face then tests
 		// the ray against obj_to_world * vertex (include/geometry/primitive/primitive_face.h:81-84).  A static instance
@@ -139,11 +159,30 @@ AcceleratorB200::AcceleratorB200(Logger &logger, ParamResult &param_result, cons
 			transformed = true;
 			base = &instance_primitive->getBasePrimitive();
 		}
+		if(const auto *sphere{dynamic_cast<const SpherePrimitive *>(base)})
+		{
+			// Spheres (src/geometry/primitive/primitive_sphere.cc:71-102): centre and radius are the primitive's own parameters;
+			// the instance matrix is ignored for them, as the reference does (primitive_sphere.cc:77-81,104-122).
+			Vec3f center{0.f};
+			float radius{1.f};
+			const ParamMap sphere_params{sphere->getAsParamMap(false)};
+			sphere_params.getParam("center", center);
+			sphere_params.getParam("radius", radius);
+			flush_mesh();
+			if(rc == B200RT_OK)
+			{
+				const float center_radius[4]{center[Axis::X], center[Axis::Y], center[Axis::Z], radius};
+				const uint8_t sphere_flags{faceFlags(primitive)};
+				rc = b200rt_add_spheres(scene, center_radius, 1, &sphere_flags);
+			}
+			continue;
+		}
 		const auto *face{dynamic_cast<const FacePrimitive *>(base)};
 		const int n_vertices{face ? face->numVertices() : 0};
 		if(!face || moving || face->hasMotionBlur() || (n_vertices != 3 && n_vertices != 4))
 		{
-			logger_.logError(getClassName(), ": primitive kind not supported by the b200-kdtree accelerator (static triangle and quad mesh faces and static instances of them are); no accelerator created");
+			logger_.logError(getClassName(), ": primitive kind not supported by the b200-kdtree accelerator (static triangle and quad mesh faces, spheres and static instances of them are); no accelerator created");
+			if(scene) b200rt_destroy(scene);
 			return;
 		}
 		const uint32_t first_vertex{static_cast<uint32_t>(xyz.size() / 3)};
@@ -155,15 +194,7 @@ AcceleratorB200::AcceleratorB200(Logger &logger, ParamResult &param_result, cons
 		for(int v = 0; v < 4; ++v) idx.push_back(v < n_vertices ? first_vertex + static_cast<uint32_t>(v) : 0xFFFFFFFFu);
 		flags.push_back(faceFlags(primitive));
 	}
-	b200rt_build_params build_params{};
-	build_params.max_depth = params_.max_depth_;
-	build_params.max_leaf_size = params_.max_leaf_size_;
-	build_params.cost_ratio = params_.cost_ratio_;
-	build_params.empty_bonus = params_.empty_bonus_;
-	build_params.build_threads = params_.num_threads_;
-	b200rt_scene *scene = nullptr;
-	int rc = b200rt_create(params_.device_, &build_params, &scene);
-	if(rc == B200RT_OK) rc = b200rt_add_mesh(scene, xyz.data(), xyz.size() / 3, idx.data(), idx.size() / 4, flags.data());
+	flush_mesh();
 	if(rc == B200RT_OK) rc = b200rt_build(scene);
 	float bound[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 	if(rc == B200RT_OK) rc = b200rt_get_bound(scene, bound);

@@ -34,6 +34,7 @@ int fail(int code, const std::string &msg)
 	} while(0)
 
 constexpr uint32_t kTriangle = 0xFFFFFFFFu;
+constexpr uint32_t kSphere = 0xFFFFFFFEu; // idx[2] of a sphere face (kd_build.h)
 constexpr size_t kChunkBytes = size_t(32) << 20; // staging granularity of the host-buffer queries
 constexpr int kLanesPerCall = 3;
 constexpr size_t kDirectRays = size_t(1) << 16;  // pinned batches up to this size are traced in place (no staging copies)
@@ -373,7 +374,7 @@ int b200rt_add_mesh(b200rt_scene *s, const float *xyz, size_t n_verts, const uin
 {
 	if(!s || (!xyz && n_verts) || (!idx && n_faces)) return fail(B200RT_E_INVALID, "null argument");
 	const size_t base = s->xyz.size() / 3;
-	if(base + n_verts >= size_t(kTriangle)) return fail(B200RT_E_INVALID, "too many vertices");
+	if(base + n_verts >= size_t(kSphere)) return fail(B200RT_E_INVALID, "too many vertices");
 	if(s->idx.size() / 4 + n_faces >= (size_t(1) << 30)) return fail(B200RT_E_INVALID, "too many faces");
 	for(size_t f = 0; f < n_faces; ++f)
 		for(int k = 0; k < 4; ++k)
@@ -400,6 +401,29 @@ int b200rt_add_mesh(b200rt_scene *s, const float *xyz, size_t n_verts, const uin
 	return B200RT_OK;
 }
 
+int b200rt_add_spheres(b200rt_scene *s, const float *center_radius, size_t n_spheres, const uint8_t *flags)
+{
+	if(!s || (!center_radius && n_spheres)) return fail(B200RT_E_INVALID, "null argument");
+	const size_t base = s->xyz.size() / 3;
+	if(base + 2 * n_spheres >= size_t(kSphere)) return fail(B200RT_E_INVALID, "too many vertices");
+	if(s->idx.size() / 4 + n_spheres >= (size_t(1) << 30)) return fail(B200RT_E_INVALID, "too many faces");
+	try
+	{
+		// stored in the mesh arrays: two vertices (centre; radius in x) and one marker face per sphere
+		for(size_t k = 0; k < n_spheres; ++k)
+		{
+			const float *c = center_radius + 4 * k;
+			s->xyz.insert(s->xyz.end(), {c[0], c[1], c[2], c[3], 0.f, 0.f});
+			s->idx.insert(s->idx.end(), {uint32_t(base + 2 * k), uint32_t(base + 2 * k + 1), kSphere, kTriangle});
+		}
+		if(flags) s->flags.insert(s->flags.end(), flags, flags + n_spheres);
+		else s->flags.insert(s->flags.end(), n_spheres, uint8_t(B200RT_FACE_VISIBLE | B200RT_FACE_CASTS_SHADOWS));
+	}
+	catch(const std::bad_alloc &) { return fail(B200RT_E_MEMORY, "out of host memory"); }
+	s->built = false;
+	return B200RT_OK;
+}
+
 int b200rt_build(b200rt_scene *s)
 {
 	if(!s) return fail(B200RT_E_INVALID, "null argument");
@@ -418,8 +442,8 @@ int b200rt_build(b200rt_scene *s)
 		s->record_of_ref.assign(tree.leaf_refs.size(), 0u);
 		tris.reserve(tree.leaf_refs.size() * 3 + 4);
 		nodes.resize(tree.nodes.size());
-		uint64_t n_tri = 0, n_quad = 0;
-		for(size_t f = 0; f < n_faces; ++f) (s->idx[4 * f + 3] == kTriangle ? n_tri : n_quad)++;
+		uint64_t n_tri = 0, n_quad = 0, n_sphere = 0;
+		for(size_t f = 0; f < n_faces; ++f) (s->idx[4 * f + 2] == kSphere ? n_sphere : s->idx[4 * f + 3] == kTriangle ? n_tri : n_quad)++;
 		for(size_t i = 0; i < tree.nodes.size(); ++i)
 		{
 			const b200rt::HostNode hn = tree.nodes[i];
@@ -436,6 +460,19 @@ int b200rt_build(b200rt_scene *s)
 				uint32_t fl = s->flags[face] & 7u;
 				if(quad) fl |= b200rt::kFlagQuad;
 				float4 q;
+				if(id[2] == kSphere)
+				{
+					// sphere record, same 3-vector stride as a triangle: q0 = centre | face id, q1 = radius,0,0 | flags, q2 = 0
+					fl |= b200rt::kFlagSphere;
+					q.x = v0[0]; q.y = v0[1]; q.z = v0[2];
+					std::memcpy(&q.w, &face, 4);
+					tris.push_back(q);
+					q.x = s->xyz[3 * size_t(id[1])]; q.y = 0.f; q.z = 0.f;
+					std::memcpy(&q.w, &fl, 4);
+					tris.push_back(q);
+					tris.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
+					continue;
+				}
 				q.x = v0[0]; q.y = v0[1]; q.z = v0[2];
 				std::memcpy(&q.w, &face, 4);
 				tris.push_back(q);
@@ -457,6 +494,7 @@ int b200rt_build(b200rt_scene *s)
 		s->stats.n_faces = n_faces;
 		s->stats.n_triangles = n_tri;
 		s->stats.n_quads = n_quad;
+		s->stats.n_spheres = n_sphere;
 		s->stats.n_nodes = tree.nodes.size();
 		s->stats.n_interior = tree.n_interior;
 		s->stats.n_leaves = tree.n_leaves;
@@ -525,6 +563,7 @@ int b200rt_update_face_flags(b200rt_scene *s, const uint8_t *flags, size_t n_fac
 		const uint32_t face = s->tree.leaf_refs[r];
 		uint32_t fl = s->flags[face] & 7u;
 		if(s->idx[4 * size_t(face) + 3] != kTriangle) fl |= b200rt::kFlagQuad;
+		if(s->idx[4 * size_t(face) + 2] == kSphere) fl |= b200rt::kFlagSphere;
 		std::memcpy(&tris[size_t(s->record_of_ref[r]) + 1].w, &fl, 4);
 	}
 	CUDA_TRY(cudaMemcpy(s->d_tris, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
@@ -783,6 +822,7 @@ int b200rt_host_tree_build(const float *xyz, size_t n_verts, const uint32_t *idx
 		{
 			const uint32_t v = idx[4 * f + k];
 			if(k == 3 && v == kTriangle) continue;
+			if(k == 2 && v == kSphere && idx[4 * f + 3] == kTriangle) continue; // sphere face (kd_build.h)
 			if(v >= n_verts) return fail(B200RT_E_INVALID, "face references a vertex >= n_verts");
 		}
 	try

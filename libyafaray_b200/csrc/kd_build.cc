@@ -24,6 +24,9 @@ constexpr size_t kExactThreshold = 384;
 constexpr size_t kClipThreshold = 64;
 constexpr size_t kSpawnThreshold = 40000; // references; below this a subtree is built serially
 constexpr uint32_t kTriangle = 0xFFFFFFFFu;
+constexpr uint32_t kSphere = 0xFFFFFFFEu; // idx[2] of a sphere "face": vertex idx[0] = centre, x of vertex idx[1] = radius (kd_build.h)
+
+void faceBound(const MeshView &mesh, size_t f, float lo[3], float hi[3]);
 
 struct Ref
 {
@@ -225,6 +228,19 @@ inline float roundUp(double x) { float f = float(x); return (double(f) < x) ? st
 bool clipRef(const Context &c, uint32_t prim, const Box &box, Ref &out)
 {
 	const uint32_t *id = c.mesh.idx + 4 * size_t(prim);
+	if(id[2] == kSphere)
+	{
+		// no clipping for spheres (SpherePrimitive has no clippingSupport() either): the padded bound cut to the box
+		out.prim = prim;
+		faceBound(c.mesh, prim, out.lo, out.hi);
+		for(int k = 0; k < 3; ++k)
+		{
+			out.lo[k] = std::max(out.lo[k], box.lo[k]);
+			out.hi[k] = std::min(out.hi[k], box.hi[k]);
+			if(out.lo[k] > out.hi[k]) return false;
+		}
+		return true;
+	}
 	const float *v0 = c.mesh.xyz + 3 * size_t(id[0]), *v1 = c.mesh.xyz + 3 * size_t(id[1]), *v2 = c.mesh.xyz + 3 * size_t(id[2]);
 	double lo[3], hi[3];
 	for(int k = 0; k < 3; ++k)
@@ -365,6 +381,19 @@ void buildNode(const Context &c, Subtree &st, std::vector<Ref> &refs, const Box 
 void faceBound(const MeshView &mesh, size_t f, float lo[3], float hi[3])
 {
 	const uint32_t *id = mesh.idx + 4 * f;
+	if(id[2] == kSphere)
+	{
+		// SpherePrimitive::getBound (src/geometry/primitive/primitive_sphere.cc:71-75): r = radius * 1.0001f, centre -+ r.
+		// Part of the tree bound, hence of the ray bias: the same float operations.
+		volatile float r = mesh.xyz[3 * size_t(id[1])] * 1.0001f;
+		for(int k = 0; k < 3; ++k)
+		{
+			volatile float a = mesh.xyz[3 * size_t(id[0]) + k] - r, g = mesh.xyz[3 * size_t(id[0]) + k] + r;
+			lo[k] = a;
+			hi[k] = g;
+		}
+		return;
+	}
 	const int nv = (id[3] == kTriangle) ? 3 : 4;
 	for(int k = 0; k < 3; ++k) lo[k] = hi[k] = mesh.xyz[3 * size_t(id[0]) + k];
 	for(int v = 1; v < nv; ++v)

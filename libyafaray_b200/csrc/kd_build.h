@@ -41,6 +41,7 @@ struct HostTree
 };
 
 // Flat mesh view shared by builder and flattener.  idx: 4 per face, idx[3] == 0xFFFFFFFF => triangle.
+// A face with idx[2] == 0xFFFFFFFE is a sphere: vertex idx[0] is its centre, the x of vertex idx[1] its radius.
 struct MeshView
 {
 	const float *xyz;

@@ -41,6 +41,7 @@ enum Query { kClosest = 0, kShadow = 1, kTShadow = 2 };
 
 static constexpr int kStackSize = 64;
 static constexpr uint32_t kFlagQuad = 8u;
+static constexpr uint32_t kFlagSphere = 16u;
 
 __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz)
 {
@@ -143,6 +144,27 @@ __device__ __forceinline__ float polyIntersect(const float4 q0, const float4 q1,
 	out_u = 0.f;
 	out_v = 0.f;
 	return 0.f;
+}
+
+// SpherePrimitive::intersect, src/geometry/primitive/primitive_sphere.cc:83-102, on a sphere record (q0 = centre, q1.x =
+// radius).  math::sqrt is std::sqrt in the reference build (include/math/math.h:148-173): IEEE, __fsqrt_rn.  Returns t (0 = miss).
+__device__ __forceinline__ float sphereIntersect(const float4 q0, float radius, float ox, float oy, float oz, float dx, float dy, float dz)
+{
+	const float vx = __fsub_rn(ox, q0.x), vy = __fsub_rn(oy, q0.y), vz = __fsub_rn(oz, q0.z); // vf = from - center
+	const float ea = dot3(dx, dy, dz, dx, dy, dz);
+	const float eb = __fmul_rn(2.f, dot3(vx, vy, vz, dx, dy, dz));
+	const float ec = __fsub_rn(dot3(vx, vy, vz, vx, vy, vz), __fmul_rn(radius, radius));
+	float osc = __fsub_rn(__fmul_rn(eb, eb), __fmul_rn(__fmul_rn(4.f, ea), ec));
+	if(osc < 0.f) return 0.f;
+	osc = __fsqrt_rn(osc);
+	const float two_ea = __fmul_rn(2.f, ea);
+	float sol = __fdiv_rn(__fsub_rn(-eb, osc), two_ea);
+	if(sol < 0.f)
+	{
+		sol = __fdiv_rn(__fadd_rn(-eb, osc), two_ea);
+		if(sol < 0.f) return 0.f;
+	}
+	return sol;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -484,8 +506,9 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
 					const uint32_t flags = __float_as_uint(q1.w);
 					const bool quad = (flags & kFlagQuad) != 0u;
-					float u, v;
-					const float t = polyIntersect(q0, q1, q2, rec + 3, quad, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, u, v);
+					float u, v, t;
+					if(flags & kFlagSphere) { t = sphereIntersect(q0, q1.x, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz); u = 0.f; v = 0.f; }
+					else t = polyIntersect(q0, q1, q2, rec + 3, quad, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, u, v);
 					rec += quad ? 4 : 3;
 					--leaf_count;
 					// accept rules, accelerator.h:125-127 / :137-139 / :150-154

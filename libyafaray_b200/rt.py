@@ -34,7 +34,8 @@ class Stats(C.Structure):
     _fields_ = [("n_faces", C.c_uint64), ("n_triangles", C.c_uint64), ("n_quads", C.c_uint64),
                 ("n_nodes", C.c_uint64), ("n_interior", C.c_uint64), ("n_leaves", C.c_uint64), ("n_empty_leaves", C.c_uint64),
                 ("n_leaf_refs", C.c_uint64), ("max_depth", C.c_uint32), ("max_leaf_prims", C.c_uint32),
-                ("build_seconds", C.c_double), ("upload_seconds", C.c_double), ("device_bytes", C.c_uint64)]
+                ("build_seconds", C.c_double), ("upload_seconds", C.c_double), ("device_bytes", C.c_uint64),
+                ("n_spheres", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -53,7 +54,7 @@ class B200RTError(RuntimeError):
 
 #: every symbol include/b200rt.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "b200rt_device_count", "b200rt_create", "b200rt_destroy", "b200rt_add_mesh", "b200rt_build", "b200rt_get_bound",
+    "b200rt_device_count", "b200rt_create", "b200rt_destroy", "b200rt_add_mesh", "b200rt_add_spheres", "b200rt_build", "b200rt_get_bound",
     "b200rt_get_stats", "b200rt_update_face_flags", "b200rt_trace_closest", "b200rt_trace_shadow", "b200rt_trace_tshadow",
     "b200rt_trace_closest_device", "b200rt_trace_shadow_device", "b200rt_trace_tshadow_device", "b200rt_trace",
     "b200rt_trace_device", "b200rt_trace_jobs", "b200rt_trace_jobs_begin", "b200rt_trace_jobs_end", "b200rt_host_alloc",
@@ -77,6 +78,7 @@ def lib():
         L.b200rt_destroy.argtypes = [P]
         L.b200rt_destroy.restype = None
         L.b200rt_add_mesh.argtypes = [P, P, Z, P, Z, P]
+        L.b200rt_add_spheres.argtypes = [P, P, Z, P]
         L.b200rt_build.argtypes = [P]
         L.b200rt_get_bound.argtypes = [P, P]
         L.b200rt_get_stats.argtypes = [P, P]
@@ -195,6 +197,16 @@ class Scene:
                 raise ValueError("one flag byte per face")
         _check(lib().b200rt_add_mesh(self._h, _p(xyz), xyz.shape[0], _p(idx), idx.shape[0], _p(flags)))
         self.n_faces += idx.shape[0]
+
+    def add_spheres(self, center_radius, flags=None):
+        """Spheres as rows cx, cy, cz, radius (b200rt_add_spheres); they take the next face ids."""
+        cr = np.ascontiguousarray(center_radius, dtype=np.float32).reshape(-1, 4)
+        if flags is not None:
+            flags = np.ascontiguousarray(flags, dtype=np.uint8)
+            if flags.shape[0] != cr.shape[0]:
+                raise ValueError("one flag byte per sphere")
+        _check(lib().b200rt_add_spheres(self._h, _p(cr), cr.shape[0], _p(flags)))
+        self.n_faces += cr.shape[0]
 
     def build(self):
         _check(lib().b200rt_build(self._h))

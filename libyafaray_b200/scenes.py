@@ -225,3 +225,38 @@ def rays_edge_cases(bound_lo, bound_hi, seed: int = 7):
         rows.append([*lo, 0.0, *d, -1.0])                        # origin on the bound corner
         rows.append([*(hi + ext), 0.0, *(c - hi - ext), -1.0])   # from outside through the centre
     return np.asarray(rows, dtype=np.float32)
+
+
+SPHERE = 0xFFFFFFFE  # face marker in idx[:, 2]: vertex idx[:, 0] = centre, x of vertex idx[:, 1] = radius (include/b200rt.h)
+
+
+def with_spheres(xyz, idx, flags, spheres, sphere_flags=None):
+    """Append spheres (rows cx, cy, cz, radius -- SpherePrimitive, src/geometry/primitive/primitive_sphere.cc) to a mesh in the
+    flat encoding the oracle and the host-tree diagnostics read: two extra vertices and one marker face per sphere.
+    The product path takes spheres through rt.Scene.add_spheres (b200rt_add_spheres) instead; face ids come out the same
+    (mesh faces first, then the spheres in order)."""
+    spheres = np.ascontiguousarray(spheres, dtype=np.float32).reshape(-1, 4)
+    n = spheres.shape[0]
+    base = xyz.shape[0]
+    extra = np.zeros((2 * n, 3), dtype=np.float32)
+    extra[0::2] = spheres[:, :3]
+    extra[1::2, 0] = spheres[:, 3]
+    faces = np.empty((n, 4), dtype=np.uint32)
+    faces[:, 0] = base + 2 * np.arange(n)
+    faces[:, 1] = base + 2 * np.arange(n) + 1
+    faces[:, 2] = SPHERE
+    faces[:, 3] = TRI
+    if sphere_flags is None:
+        sphere_flags = np.full(n, F_NORMAL, dtype=np.uint8)
+    return (np.concatenate([xyz, extra]).astype(np.float32), np.concatenate([idx, faces]).astype(np.uint32),
+            np.concatenate([flags, np.asarray(sphere_flags, dtype=np.uint8)]).astype(np.uint8))
+
+
+def sphere_field(n: int = 200, seed: int = 5, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0), r_lo: float = 0.01, r_hi: float = 0.06):
+    """n random spheres inside [lo, hi]: rows cx, cy, cz, radius."""
+    rng = np.random.default_rng(seed)
+    lo, hi = np.asarray(lo, np.float32), np.asarray(hi, np.float32)
+    out = np.empty((n, 4), dtype=np.float32)
+    out[:, :3] = lo + rng.random((n, 3), dtype=np.float32) * (hi - lo)
+    out[:, 3] = r_lo + rng.random(n, dtype=np.float32) * (r_hi - r_lo)
+    return out

@@ -131,9 +131,38 @@ float kdo_poly_intersect(const float *v0, const float *v1, const float *v2, cons
 	return 0.f;
 }
 
+/* SpherePrimitive::intersect, src/geometry/primitive/primitive_sphere.cc:83-102 (math::sqrt is std::sqrt on x86-64,
+ * include/math/math.h:148-173,214-221).  Returns t (0 = miss); uv is {0, 0} (`return {sol, {}}`). */
+float kdo_sphere_intersect(const float center[3], float radius, const float from[3], const float dir[3])
+{
+	float vf[3];
+	sub3(from, center, vf);
+	const float ea = dot3(dir, dir);
+	const float eb = 2.f * dot3(vf, dir);
+	const float ec = dot3(vf, vf) - radius * radius;
+	float osc = eb * eb - 4.f * ea * ec;
+	if(osc < 0) return 0.f;
+	osc = sqrtf(osc);
+	const float sol_1 = (-eb - osc) / (2.f * ea);
+	const float sol_2 = (-eb + osc) / (2.f * ea);
+	float sol = sol_1;
+	if(sol < 0.f)
+	{
+		sol = sol_2;
+		if(sol < 0.f) return 0.f;
+	}
+	return sol;
+}
+
 static inline float primIntersect(const kdo_mesh *m, uint32_t prim, const float from[3], const float dir[3], float *u, float *v)
 {
 	const uint32_t *i = m->idx + 4 * (size_t) prim;
+	if(i[2] == KDO_SPHERE)
+	{
+		*u = 0.f;
+		*v = 0.f;
+		return kdo_sphere_intersect(m->xyz + 3 * (size_t) i[0], m->xyz[3 * (size_t) i[1]], from, dir);
+	}
 	const int nv = (i[3] == 0xFFFFFFFFu) ? 3 : 4;
 	return kdo_poly_intersect(m->xyz + 3 * (size_t) i[0], m->xyz + 3 * (size_t) i[1], m->xyz + 3 * (size_t) i[2],
 	                          nv == 4 ? m->xyz + 3 * (size_t) i[3] : NULL, nv, from, dir, u, v);
@@ -459,6 +488,17 @@ void kdo_brute_closest(const kdo_mesh *mesh, const float bound6[6], const float 
 static void primBound(const kdo_mesh *m, size_t f, float lo[3], float hi[3])
 {
 	const uint32_t *i = m->idx + 4 * f;
+	if(i[2] == KDO_SPHERE)
+	{
+		/* SpherePrimitive::getBound, src/geometry/primitive/primitive_sphere.cc:71-75: r = radius * 1.0001f, centre -+ r */
+		const float r = m->xyz[3 * (size_t) i[1]] * 1.0001f;
+		for(int a = 0; a < 3; ++a)
+		{
+			lo[a] = m->xyz[3 * (size_t) i[0] + a] - r;
+			hi[a] = m->xyz[3 * (size_t) i[0] + a] + r;
+		}
+		return;
+	}
 	const int nv = (i[3] == 0xFFFFFFFFu) ? 3 : 4;
 	for(int a = 0; a < 3; ++a) lo[a] = hi[a] = m->xyz[3 * (size_t) i[0] + a];
 	for(int k = 1; k < nv; ++k)

@@ -26,6 +26,9 @@ extern "C" {
  *   xyz  float[3*n_verts]; idx uint32[4*n_faces] with idx[4f+3]==0xFFFFFFFF for a triangle;
  *   flags uint8[n_faces]: bit0 Visible, bit1 CastsShadows (object AND material, accelerator.h:126-127),
  *                         bit2 material isTransparent() (material.h:85). */
+/* A face with idx[4f+2] == KDO_SPHERE is a sphere (SpherePrimitive, src/geometry/primitive/primitive_sphere.cc):
+ * vertex idx[4f+0] is its centre, the x component of vertex idx[4f+1] its radius, idx[4f+3] = 0xFFFFFFFF. */
+#define KDO_SPHERE 0xFFFFFFFEu
 typedef struct kdo_mesh
 {
 	const float *xyz;
@@ -92,6 +95,9 @@ void kdo_brute_closest(const kdo_mesh *mesh, const float bound6[6], const float 
 /* One polygon test, exported for unit tests (shape_polygon.h:126-176).  nv = 3 or 4.  Returns t (0 = miss). */
 float kdo_poly_intersect(const float *v0, const float *v1, const float *v2, const float *v3, int nv,
                          const float from[3], const float dir[3], float *u, float *v);
+
+/* One sphere test, exported for unit tests (primitive_sphere.cc:83-102).  Returns t (0 = miss). */
+float kdo_sphere_intersect(const float center[3], float radius, const float from[3], const float dir[3]);
 
 /* Bound<float>::cross (bound.h:156-198). Returns crossed; enter/leave written when crossed. */
 int kdo_bound_cross(const float bound6[6], const float from[3], const float dir[3], float t_max, float *enter, float *leave);

@@ -155,6 +155,26 @@ int yref_add_mesh(void *h, const float *xyz, size_t n_verts, const uint32_t *idx
 	return static_cast<int>(object_id);
 }
 
+/* One "sphere" object (Object::factory -> SpherePrimitive, src/geometry/object/object.cc:80-90,
+ * src/geometry/primitive/primitive_sphere.cc).  material: index returned by yref_add_material. */
+int yref_add_sphere(void *h, float cx, float cy, float cz, float radius, int material, const char *object_visibility)
+{
+	auto *s = static_cast<RefScene *>(h);
+	if(material < 0 || static_cast<size_t>(material) >= s->material_ids.size()) return -1;
+	yafaray_ParamMap *pm = yafaray_createParamMap();
+	yafaray_setParamMapString(pm, "type", "sphere");
+	yafaray_setParamMapVector(pm, "center", cx, cy, cz);
+	yafaray_setParamMapFloat(pm, "radius", radius);
+	yafaray_setParamMapString(pm, "material", ("oracle_mat_" + std::to_string(material)).c_str());
+	yafaray_setParamMapString(pm, "visibility", object_visibility ? object_visibility : "normal");
+	size_t object_id = 0;
+	const std::string name = "oracle_sphere_" + std::to_string(s->n_objects++);
+	const yafaray_ResultFlags res = yafaray_createObject(s->scene, &object_id, name.c_str(), pm);
+	yafaray_destroyParamMap(pm);
+	if(res & YAFARAY_RESULT_ERROR_WHILE_CREATING) return -2;
+	return static_cast<int>(object_id);
+}
+
 /* accel_type NULL => no accelerator params at all (reference default, like tests/test01).
  * depth/max_leaf/cost_ratio/empty_bonus < 0 => leave at the reference default. */
 int yref_build(void *h, const char *accel_type, int depth, int max_leaf_size, float cost_ratio, float empty_bonus)

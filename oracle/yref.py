@@ -32,6 +32,8 @@ def lib():
         L.yref_scene_destroy.argtypes = [C.c_void_p]
         L.yref_add_material.argtypes = [C.c_void_p, C.c_char_p, C.c_float]
         L.yref_add_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_char_p]
+        L.yref_add_sphere.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_char_p]
+        L.yref_add_sphere.restype = C.c_int
         L.yref_build.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_float, C.c_float]
         L.yref_build_seconds.restype = C.c_double
         L.yref_build_seconds.argtypes = [C.c_void_p]
@@ -82,8 +84,19 @@ class RefScene:
                 raise RuntimeError("reference refused the material")
             mat_of[cmb] = m
         face_mat = np.array([mat_of[int(f) & 7] for f in flags], dtype=np.int32) if len(combos) > 1 else np.zeros(n_faces, dtype=np.int32)
-        if L.yref_add_mesh(self.h, _p(xyz), xyz.shape[0], _p(idx), n_faces, _p(face_mat), b"normal") < 0:
+        # sphere faces (idx[:, 2] == 0xFFFFFFFE, libyafaray_b200/scenes.py::with_spheres) become "sphere" objects created
+        # after the mesh, so that the reference's primitive order (objects in creation order, src/scene/scene.cc:320-326)
+        # is the face order of the arrays; they must therefore be the LAST faces
+        is_sphere = idx[:, 2] == 0xFFFFFFFE if n_faces else np.zeros(0, bool)
+        n_mesh = int(n_faces - is_sphere.sum())
+        if is_sphere[:n_mesh].any():
+            raise ValueError("sphere faces must follow all mesh faces")
+        if n_mesh and L.yref_add_mesh(self.h, _p(xyz), xyz.shape[0], _p(np.ascontiguousarray(idx[:n_mesh])), n_mesh, _p(np.ascontiguousarray(face_mat[:n_mesh])), b"normal") < 0:
             raise RuntimeError("reference refused the mesh")
+        for f in range(n_mesh, n_faces):
+            c = xyz[idx[f, 0]]
+            if L.yref_add_sphere(self.h, float(c[0]), float(c[1]), float(c[2]), float(xyz[idx[f, 1], 0]), int(face_mat[f]), b"normal") < 0:
+                raise RuntimeError("reference refused the sphere")
         rc = L.yref_build(self.h, accel_type.encode() if accel_type else None, depth, max_leaf_size, cost_ratio, empty_bonus)
         if rc != 0:
             raise RuntimeError(f"reference preprocess failed ({rc})")

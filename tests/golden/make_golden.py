@@ -33,6 +33,9 @@ def main():
         "soup": scenes.soup(1500, seed=4),
         "objects": scenes.objects(2500, n_spheres=6, seed=9),
     }
+    # SpherePrimitive objects next to mesh faces (scenes.with_spheres encoding: marker faces after the mesh faces)
+    sx, si, sf = scenes.objects(1200, n_spheres=4, seed=14)
+    cases["spheres"] = scenes.with_spheres(sx, si, sf, scenes.sphere_field(40, seed=15, lo=sx.min(0), hi=sx.max(0)))
     for i, (name, (xyz, idx, _)) in enumerate(cases.items()):
         flags = flag_mix(idx.shape[0], seed=20 + i) if name != "hf" else np.full(idx.shape[0], 3, np.uint8)
         ref = yref.RefScene(xyz, idx, flags)

@@ -26,6 +26,9 @@ def scene_zoo(small=True):
         "soup": scenes.soup(3000 * k * k),
         "objects": scenes.objects(6000 * k * k, n_spheres=12),
     }
+    # spheres (SpherePrimitive) among mesh objects: mesh faces first, then the spheres (scenes.with_spheres)
+    oxyz, oidx, ofl = scenes.objects(3000 * k * k, n_spheres=8, seed=21)
+    zoo["spheres"] = scenes.with_spheres(oxyz, oidx, ofl, scenes.sphere_field(60 * k * k, seed=22, lo=oxyz.min(0), hi=oxyz.max(0)))
     out = {}
     for i, (name, (xyz, idx, fl)) in enumerate(zoo.items()):
         out[name] = (xyz, idx, fl)
@@ -81,3 +84,29 @@ def check_closest_parity(got_prim, got_t, got_u, got_v, ref, min_agree=0.9999, r
         rel = np.abs(got_t[diff] - ref["t"][diff]) / np.maximum(np.abs(ref["t"][diff]), 1e-30)
         assert np.all(rel <= rtol), f"non-tie id mismatch, max rel t diff {rel.max()}"
     return agree
+
+
+def make_rt_scene(rt, xyz, idx, flags=None, params=None, device=0):
+    """rt.Scene from the flat arrays of the zoo: mesh faces through add_mesh, sphere marker faces (scenes.SPHERE) through
+    add_spheres, in face order, so that face ids equal array rows."""
+    idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1, 4)
+    s = rt.Scene(device, params)
+    is_sphere = idx[:, 2] == scenes.SPHERE
+    if not is_sphere.any():
+        s.add_mesh(xyz, idx, flags)
+    else:
+        f = 0
+        n = idx.shape[0]
+        while f < n:
+            e = f
+            while e < n and is_sphere[e] == is_sphere[f]:
+                e += 1
+            fl = None if flags is None else flags[f:e]
+            if is_sphere[f]:
+                cr = np.concatenate([xyz[idx[f:e, 0]], xyz[idx[f:e, 1], :1]], axis=1)
+                s.add_spheres(cr, fl)
+            else:
+                s.add_mesh(xyz, idx[f:e], fl)
+            f = e
+    s.build()
+    return s

@@ -185,3 +185,31 @@ def test_tile_shards_through_the_b200_accelerator_sum_to_the_whole_frame(tmp_pat
     a, b = film.psnr(film.normalized(total), film.normalized(whole)), film.psnr(film.normalized(total), film.normalized(stock))
     print(f"sharded b200 vs unsharded b200: {a:.1f} dB; vs stock kd-tree: {b:.1f} dB")
     assert a > 50.0 and b > 50.0
+
+
+@pytest.mark.gpu
+@needs_render_bench
+def test_static_and_nested_instances_render_like_the_reference(tmp_path):
+    """static instances (and instances of instances) are uploaded pre-transformed with the reference's
+    own matrix code, so the b200 render of a scene with 9 instanced boxes equals the stock kd-tree render."""
+    stock = _render_film(tmp_path, "stock", "directlighting", "0/1", size=(240, 150), extra=("instances=9",))
+    b200 = _render_film(tmp_path, "b200", "directlighting", "0/1", size=(240, 150), extra=("instances=9",), accel="b200-kdtree")
+    plain = _render_film(tmp_path, "plain", "directlighting", "0/1", size=(240, 150))
+    assert film.psnr(film.normalized(stock), film.normalized(plain)) < 45.0, "the instances are not visible in this view: the test would prove nothing"
+    value = film.psnr(film.normalized(b200), film.normalized(stock))
+    print(f"instances: b200 vs stock kd-tree {value:.1f} dB")
+    assert value > 50.0
+
+
+@pytest.mark.gpu
+@needs_render_bench
+def test_sphere_objects_render_like_the_reference(tmp_path):
+    """objects of type "sphere" travel through AcceleratorB200 -> b200rt_add_spheres -> the sphere
+    branch of the leaf loop; 40 spheres over the field, b200 render against the stock kd-tree render."""
+    stock = _render_film(tmp_path, "stock", "directlighting", "0/1", size=(240, 150), extra=("spheres=40",))
+    b200 = _render_film(tmp_path, "b200", "directlighting", "0/1", size=(240, 150), extra=("spheres=40",), accel="b200-kdtree")
+    plain = _render_film(tmp_path, "plain", "directlighting", "0/1", size=(240, 150))
+    assert film.psnr(film.normalized(stock), film.normalized(plain)) < 45.0, "the spheres are not visible in this view"
+    value = film.psnr(film.normalized(b200), film.normalized(stock))
+    print(f"spheres: b200 vs stock kd-tree {value:.1f} dB")
+    assert value > 50.0

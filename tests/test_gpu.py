@@ -20,10 +20,7 @@ NCPU = os.cpu_count() or 1
 
 
 def make_scene(xyz, idx, flags=None, params=None):
-    s = rt.Scene(0, params)
-    s.add_mesh(xyz, idx, flags)
-    s.build()
-    return s
+    return helpers.make_rt_scene(rt, xyz, idx, flags, params)
 
 
 def tie_floor(name):
@@ -82,7 +79,7 @@ def test_zoo_against_oracle(built, name):
 
 
 @pytest.mark.skipif(not yref.available(), reason="oracle/_ref/libyafref.so did not travel")
-@pytest.mark.parametrize("name", ["hf_flags", "objects_flags", "soup", "hf_quads"])
+@pytest.mark.parametrize("name", ["hf_flags", "objects_flags", "soup", "hf_quads", "spheres_flags"])
 def test_zoo_against_live_reference(built, name):
     xyz, idx, flags = ZOO[name]
     s = make_scene(xyz, idx, flags)

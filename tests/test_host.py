@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(built):
     L = rt.lib()
     for name in sorted(declared):
         assert hasattr(L, name), f"libb200rt.so does not export {name}"
-    assert L.b200rt_version() == 1
+    assert L.b200rt_version() == 2
 
 
 def test_struct_sizes_match_header():

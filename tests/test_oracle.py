@@ -68,7 +68,7 @@ def test_brute_force_agrees(built, path):
 
 
 @pytest.mark.skipif(not yref.available(), reason="oracle/_ref/libyafref.so not built (needs /root/reference)")
-@pytest.mark.parametrize("name", ["hf_flags", "hf_quads_flags", "cubes_flags", "soup_flags", "objects_flags"])
+@pytest.mark.parametrize("name", ["hf_flags", "hf_quads_flags", "cubes_flags", "soup_flags", "objects_flags", "spheres_flags", "spheres"])
 def test_oracle_vs_live_reference(built, name):
     xyz, idx, flags = helpers.scene_zoo()[name]
     ref = yref.RefScene(xyz, idx, flags)
