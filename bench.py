@@ -33,6 +33,9 @@ UNIT = "Mrays/s"
 # (counting oracle, tools/count_bytes.py).  IO = 32 B ray + 16 B hit (closest) / + 4 B (shadow).
 ALGO_BYTES = {"closest": 345.0, "shadow": 230.8}
 SHADOW_TMAX = 0.25
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE closest launch on this workload, from the ncu --set full capture kept
+# under profiles/ (r1h_descent_loop.txt: 1.571 GB read + 0.282 GB written); a constant of the profile, not measured live
+NCU_DRAM_TRAFFIC_BYTES = {"closest": 1.571421e9 + 0.282247e9, "source": "profiles/r1h_descent_loop.txt"}
 
 
 def parse():
@@ -315,7 +318,9 @@ def run_b200(args):
                        "closest_mrays_per_gpu": n / (closest_ms * 1e-3) / 1e6, "shadow_mrays_per_gpu": n / (shadow_ms * 1e-3) / 1e6,
                        "closest_ms": closest_ms, "shadow_ms": shadow_ms, "tree": {k: stats[k] for k in ("n_nodes", "n_leaf_refs", "max_depth", "device_bytes", "build_seconds")}},
             "roofline": {"bound": "hbm", "kernel": "traceClosestKernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": NCU_DRAM_TRAFFIC_BYTES["closest"] if n == (1 << 24) and args.cells == 707 else None,
+                         "traffic_source": NCU_DRAM_TRAFFIC_BYTES["source"], "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": ALGO_BYTES["closest"] * n,
                          "algorithmic_bytes_per_ray": ALGO_BYTES["closest"], "launch_ms": closest_ms,
                          "note": "latency/issue-bound gather (DESIGN.md): the algorithmic-byte fraction is small by construction"},
             "gpu_launches": int(launches),
