@@ -74,6 +74,7 @@ struct b200rt_scene
 	std::vector<uint8_t> flags;
 	// built state
 	bool built = false;
+	bool has_spheres = false;               // selects the kernel variant with the sphere branch
 	b200rt::HostTree tree;
 	std::vector<uint32_t> record_of_ref; // float4 offset of every leaf reference's record (for flag updates)
 	uint2 *d_nodes = nullptr;
@@ -291,7 +292,8 @@ int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b2
 	{
 		// small batch (n <= kDirectRays): no ray cursor, so nothing to reset before the launch; warp w owns rays [32 w, 32 w + 32)
 		const unsigned grid = unsigned((n + b200rt::kBlock - 1) / b200rt::kBlock);
-		b200rt::traceKernel<Q><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays, uint32_t(n), d_out, nullptr, max_depth, (flags & B200RT_RAYS_TREE_SPACE) != 0u);
+		if(s->has_spheres) b200rt::traceKernel<Q, true><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays, uint32_t(n), d_out, nullptr, max_depth, (flags & B200RT_RAYS_TREE_SPACE) != 0u);
+		else b200rt::traceKernel<Q, false><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays, uint32_t(n), d_out, nullptr, max_depth, (flags & B200RT_RAYS_TREE_SPACE) != 0u);
 		++g_launches;
 		CUDA_TRY(cudaGetLastError());
 		return B200RT_OK;
@@ -303,24 +305,32 @@ int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b2
 		CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), stream));
 		const unsigned wanted = unsigned((size_t(count) + b200rt::kBlock - 1) / b200rt::kBlock);
 		const unsigned grid = std::max(1u, std::min(wanted, unsigned(s->resident_blocks[Q])));
-		b200rt::traceKernel<Q><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, cursor, max_depth, (flags & B200RT_RAYS_TREE_SPACE) != 0u);
+		if(s->has_spheres) b200rt::traceKernel<Q, true><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, cursor, max_depth, (flags & B200RT_RAYS_TREE_SPACE) != 0u);
+		else b200rt::traceKernel<Q, false><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, cursor, max_depth, (flags & B200RT_RAYS_TREE_SPACE) != 0u);
 		++g_launches;
 		CUDA_TRY(cudaGetLastError());
 	}
 	return B200RT_OK;
 }
 
-template <int Q>
-int queryResidency(b200rt_scene *s)
+template <int Q, bool SPHERES>
+int queryResidencyOf(b200rt_scene *s, int &blocks)
 {
 	int per_sm = 0, sms = 0;
 #ifdef B200RT_CARVEOUT
-	CUDA_TRY(cudaFuncSetAttribute(b200rt::traceKernel<Q>, cudaFuncAttributePreferredSharedMemoryCarveout, B200RT_CARVEOUT));
+	CUDA_TRY(cudaFuncSetAttribute(b200rt::traceKernel<Q, SPHERES>, cudaFuncAttributePreferredSharedMemoryCarveout, B200RT_CARVEOUT));
 #endif
-	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b200rt::traceKernel<Q>, b200rt::kBlock, 0));
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b200rt::traceKernel<Q, SPHERES>, b200rt::kBlock, 0));
 	CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-	s->resident_blocks[Q] = std::max(1, per_sm) * std::max(1, sms);
+	blocks = std::max(1, per_sm) * std::max(1, sms);
 	return B200RT_OK;
+}
+
+// one resident wave of the kernel variant this scene launches (with or without the sphere branch)
+template <int Q>
+int queryResidency(b200rt_scene *s)
+{
+	return s->has_spheres ? queryResidencyOf<Q, true>(s, s->resident_blocks[Q]) : queryResidencyOf<Q, false>(s, s->resident_blocks[Q]);
 }
 
 } // namespace
@@ -495,6 +505,7 @@ int b200rt_build(b200rt_scene *s)
 		s->stats.n_triangles = n_tri;
 		s->stats.n_quads = n_quad;
 		s->stats.n_spheres = n_sphere;
+		s->has_spheres = n_sphere != 0;
 		s->stats.n_nodes = tree.nodes.size();
 		s->stats.n_interior = tree.n_interior;
 		s->stats.n_leaves = tree.n_leaves;
@@ -706,7 +717,8 @@ int b200rt_trace_jobs_begin(const b200rt_job *jobs, size_t n_jobs, b200rt_flight
 				warps += (bundle.job[k]->n + 31) / 32;
 			}
 			const unsigned grid = unsigned((warps + b200rt::kBlock / 32 - 1) / (b200rt::kBlock / 32));
-			b200rt::traceMixedKernel<<<grid, b200rt::kBlock, 0, lane->stream>>>(s->view, batch, bundle.job[2] ? bundle.job[2]->max_depth : 0, bundle.tree_space != 0u);
+			if(s->has_spheres) b200rt::traceMixedKernel<true><<<grid, b200rt::kBlock, 0, lane->stream>>>(s->view, batch, bundle.job[2] ? bundle.job[2]->max_depth : 0, bundle.tree_space != 0u);
+			else b200rt::traceMixedKernel<false><<<grid, b200rt::kBlock, 0, lane->stream>>>(s->view, batch, bundle.job[2] ? bundle.job[2]->max_depth : 0, bundle.tree_space != 0u);
 			++g_launches;
 			e = cudaGetLastError();
 			if(e != cudaSuccess) rc = fail(B200RT_E_CUDA, std::string("traceMixedKernel: ") + cudaGetErrorString(e));

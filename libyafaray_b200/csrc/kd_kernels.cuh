@@ -385,7 +385,9 @@ __device__ __forceinline__ uint32_t selectu(bool p, uint32_t a, uint32_t b)
 // The traversal proper.  Called by every thread of the block; warps are independent of each other (no block-level
 // synchronisation).  sh_stack / sh_axis are the block's shared arrays; static_base is the first ray of the calling warp's
 // static pool in a cursor-less launch (ignored when `cursor` is given).
-template <int QUERY>
+// SPHERES: the scene holds sphere records (b200rt_add_spheres).  A compile-time switch, so that scenes of polygons only -- the
+// BASELINE workloads -- do not pay for the flag test and the extra code in the leaf loop (measured: 3 % on S1M-hf).
+template <int QUERY, bool SPHERES>
 __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray *__restrict__ rays, uint32_t n, typename OutType<QUERY>::type *__restrict__ out,
                                            uint32_t *__restrict__ cursor, int max_depth, bool tree_space, uint2 (*sh_stack)[kBlock], float2 (*sh_axis)[kBlock], uint32_t static_base)
 {
@@ -507,7 +509,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					const uint32_t flags = __float_as_uint(q1.w);
 					const bool quad = (flags & kFlagQuad) != 0u;
 					float u, v, t;
-					if(flags & kFlagSphere) { t = sphereIntersect(q0, q1.x, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz); u = 0.f; v = 0.f; }
+					if(SPHERES && (flags & kFlagSphere)) { t = sphereIntersect(q0, q1.x, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz); u = 0.f; v = 0.f; }
 					else t = polyIntersect(q0, q1, q2, rec + 3, quad, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, u, v);
 					rec += quad ? 4 : 3;
 					--leaf_count;
@@ -630,13 +632,13 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 }
 
 
-template <int QUERY>
+template <int QUERY, bool SPHERES>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
                                                                  typename OutType<QUERY>::type *__restrict__ out, uint32_t *__restrict__ cursor, int max_depth, bool tree_space)
 {
 	__shared__ uint2 sh_stack[kShortStack][kBlock]; // x = node index, y = float bits of the far end of its interval
 	__shared__ float2 sh_axis[4][kBlock];          // per axis: (origin, inverse direction) of the lane's ray; row 3 is read (not used) at leaves
-	traceWarps<QUERY>(s, rays, n, out, cursor, max_depth, tree_space, sh_stack, sh_axis, (blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5)) * 32u);
+	traceWarps<QUERY, SPHERES>(s, rays, n, out, cursor, max_depth, tree_space, sh_stack, sh_axis, (blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5)) * 32u);
 }
 
 // One launch for the closest, shadow and transparent-shadow rays of one flush of the renderer's ray queue
@@ -649,15 +651,16 @@ struct MixedBatch
 	uint32_t n[3];
 };
 
+template <bool SPHERES>
 __global__ void __launch_bounds__(kBlock, 4) traceMixedKernel(SceneView s, MixedBatch b, int max_depth, bool tree_space)
 {
 	__shared__ uint2 sh_stack[kShortStack][kBlock];
 	__shared__ float2 sh_axis[4][kBlock];
 	const uint32_t warp = blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5);
 	const uint32_t w0 = (b.n[0] + 31u) / 32u, w1 = (b.n[1] + 31u) / 32u;
-	if(warp < w0) traceWarps<kClosest>(s, b.rays[0], b.n[0], static_cast<b200rt_hit *>(b.out[0]), nullptr, 0, tree_space, sh_stack, sh_axis, warp * 32u);
-	else if(warp < w0 + w1) traceWarps<kShadow>(s, b.rays[1], b.n[1], static_cast<uint32_t *>(b.out[1]), nullptr, 0, tree_space, sh_stack, sh_axis, (warp - w0) * 32u);
-	else traceWarps<kTShadow>(s, b.rays[2], b.n[2], static_cast<b200rt_tshadow *>(b.out[2]), nullptr, max_depth, tree_space, sh_stack, sh_axis, (warp - w0 - w1) * 32u);
+	if(warp < w0) traceWarps<kClosest, SPHERES>(s, b.rays[0], b.n[0], static_cast<b200rt_hit *>(b.out[0]), nullptr, 0, tree_space, sh_stack, sh_axis, warp * 32u);
+	else if(warp < w0 + w1) traceWarps<kShadow, SPHERES>(s, b.rays[1], b.n[1], static_cast<uint32_t *>(b.out[1]), nullptr, 0, tree_space, sh_stack, sh_axis, (warp - w0) * 32u);
+	else traceWarps<kTShadow, SPHERES>(s, b.rays[2], b.n[2], static_cast<b200rt_tshadow *>(b.out[2]), nullptr, max_depth, tree_space, sh_stack, sh_axis, (warp - w0 - w1) * 32u);
 }
 
 } // namespace b200rt

@@ -213,3 +213,30 @@ def test_sphere_objects_render_like_the_reference(tmp_path):
     value = film.psnr(film.normalized(b200), film.normalized(stock))
     print(f"spheres: b200 vs stock kd-tree {value:.1f} dB")
     assert value > 50.0
+
+
+@pytest.mark.gpu
+@needs_render_bench
+@pytest.mark.parametrize("integrator,extra", [("photonmapping", ("i:diffuse_photons=200000", "i:caustic_photons=20000", "b:finalGather=0")),
+                                              ("SPPM", ("i:photons=100000", "i:passNums=2"))])
+def test_photon_passes_run_on_fibers(tmp_path, integrator, extra):
+    """SURVEY.md 8f row N4 (photon shooting): the reference's own photon worker functions run as logical workers on the fibers
+    of the wavefront queue (integration/include/render/photon_fibers_b200.h), so no photon bounce is a one-ray launch; the
+    image agrees with the stock render as well as two stock renders agree with each other (photon maps are stochastic:
+    radiance sub-sampling and Halton dimensions >= 50 draw from one shared LCG)."""
+    import re
+    stock = _render_film(tmp_path, "stock", integrator, "0/1", size=(240, 150), aa=1, threads=4, extra=extra)
+    again = _render_film(tmp_path, "again", integrator, "0/1", size=(240, 150), aa=1, threads=4, extra=extra)
+    prefix = str(tmp_path / "b200")
+    cmd = [RENDER_BENCH, "b200-kdtree", integrator, "48", "240", "150", "1", prefix + ".tga", "4", "film_save=" + prefix, *extra]
+    p = subprocess.run(cmd, cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, errors="replace", timeout=600)
+    assert p.returncode == 0 and "no usable accelerator" not in p.stdout, p.stdout[-2000:]
+    stats = re.findall(r"wavefront rays closest=(\d+) .*?per-ray calls outside fibers: (\d+)", p.stdout)
+    assert len(stats) >= 2, "expected one statistics line per photon pass and one per render pass"
+    assert all(int(per_ray) == 0 for _, per_ray in stats), f"rays were traced one per launch: {stats}"
+    assert int(stats[0][0]) > 50000, "the photon pass traced no rays through the queue"
+    b200 = film.read_film(film.film_path(prefix))
+    floor = film.psnr(film.normalized(again), film.normalized(stock))
+    value = film.psnr(film.normalized(b200), film.normalized(stock))
+    print(f"{integrator}: b200 vs stock {value:.1f} dB, stock vs stock {floor:.1f} dB")
+    assert value > min(floor - 3.0, 40.0)

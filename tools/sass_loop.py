@@ -8,7 +8,7 @@ lib = sys.argv[1] if len(sys.argv) > 1 else "libyafaray_b200/libb200rt.so"
 q = sys.argv[2] if len(sys.argv) > 2 else "0"
 out = subprocess.run(["cuobjdump", "-sass", lib], stdout=subprocess.PIPE, text=True).stdout
 blocks = out.split("Function : ")
-body = next(b for b in blocks if b.startswith(f"_ZN6b200rt11traceKernelILi{q}EEE"))
+body = next(b for b in blocks if b.startswith(f"_ZN6b200rt11traceKernelILi{q}ELb0EEE"))
 ins = []
 for line in body.splitlines():
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
