@@ -29,7 +29,9 @@ def main():
         def f(k):
             try: return float(r[ci[k]])
             except ValueError: return 0.0
-        data.append(dict(src=r[ci["Source"]], samples=f("# Samples"), inst=f("Instructions Executed"), tinst=f("Thread Instructions Executed"), pinst=f("Predicated-On Thread Instructions Executed"),
+        try: addr = int(r[ci["Address"]], 16) if not r[ci["Address"]].isdigit() else int(r[ci["Address"]])
+        except ValueError: addr = 0
+        data.append(dict(addr=addr, src=r[ci["Source"]], samples=f("# Samples"), inst=f("Instructions Executed"), tinst=f("Thread Instructions Executed"), pinst=f("Predicated-On Thread Instructions Executed"),
                          long_sb=f("stall_long_sb"), wait=f("stall_wait"), math=f("stall_math"), notsel=f("stall_not_selected"), sel=f("stall_selected"), br=f("stall_branch_resolving"), ssb=f("stall_short_sb"), mio=f("stall_mio")))
     tot_i = sum(d["inst"] for d in data); tot_s = sum(d["samples"] for d in data)
     if len(sys.argv) > 3 and sys.argv[3] == "dump":
@@ -41,12 +43,25 @@ def main():
         for i in range(start, len(data)):
             if pred(data[i]["src"]): return i
         return len(data)
-    i_ray = find(lambda s: "LDG.E.EF.128" in s)
+    import re
     i_node = find(lambda s: "LDG.E.64" in s)
     i_tri = find(lambda s: "LDG.E.128.CONSTANT" in s)
     i_exit = find(lambda s: s.strip().startswith("EXIT"))
-    # walk back from the node load to the loop head (BSSY before it), crude: 12 instructions
-    regions = [("refill+setup", 0, i_node - 14), ("descent loop", i_node - 14, i_tri - 6), ("leaf test + pop + write", i_tri - 6, i_exit + 1), ("cold paths (div slow path, BRA.DIV)", i_exit + 1, len(data))]
+    nodes = [i for i, d in enumerate(data) if "LDG.E.64" in d["src"]]
+    addr_of = [d["addr"] for d in data]
+    # the descent loop ends at the backward branch that follows the last (unrolled) node load and targets the first one
+    i_loop_end = nodes[-1]
+    for i in range(nodes[-1], len(data)):
+        m = re.search(r"BRA\s+(?:P\d,\s*)?0x([0-9a-f]+)", data[i]["src"])
+        if m and int(m.group(1), 16) <= addr_of[i_node] and int(m.group(1), 16) >= addr_of[max(i_node - 14, 0)]:
+            i_loop_end = i + 1
+            break
+    if i_tri < i_node:
+        # r1h layout: refill, votes, leaf phase, descent loop, stop-reason / restart / result write
+        regions = [("refill+setup+votes", 0, i_tri - 6), ("leaf test + pop", i_tri - 6, i_node - 3), ("descent loop", i_node - 3, i_loop_end),
+                   ("stop reason + restart + result write", i_loop_end, i_exit + 1), ("cold paths (div slow path, BRA.DIV)", i_exit + 1, len(data))]
+    else:
+        regions = [("refill+setup", 0, i_node - 14), ("descent loop", i_node - 14, i_tri - 6), ("leaf test + pop + write", i_tri - 6, i_exit + 1), ("cold paths (div slow path, BRA.DIV)", i_exit + 1, len(data))]
     print(f"{'region':40s} {'warp inst':>12s} {'share':>7s} {'thr/inst':>9s} {'pred-on/inst':>12s} {'samples':>9s} {'share':>7s} {'long_sb':>8s} {'wait':>7s} {'math':>7s} {'notsel':>7s} {'branch':>7s}")
     for name, a, b in regions:
         seg = data[max(a, 0):b]
