@@ -8,6 +8,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -35,8 +36,18 @@ int fail(int code, const std::string &msg)
 
 constexpr uint32_t kTriangle = 0xFFFFFFFFu;
 constexpr uint32_t kSphere = 0xFFFFFFFEu; // idx[2] of a sphere face (kd_build.h)
-constexpr size_t kChunkBytes = size_t(32) << 20; // staging granularity of the host-buffer queries
-constexpr int kLanesPerCall = 3;
+// staging granularity of the host-buffer queries and chunks in flight per call; the environment overrides are tuning aids
+// (tools/gpu_e2e_sweep.sh), read once
+size_t chunkBytes()
+{
+	static const size_t value = [] { const char *e = std::getenv("B200RT_CHUNK_MB"); const long mb = e ? std::atol(e) : 0; return size_t(mb > 0 ? mb : 32) << 20; }();
+	return value;
+}
+int lanesPerCall()
+{
+	static const int value = [] { const char *e = std::getenv("B200RT_LANES"); const long n = e ? std::atol(e) : 0; return int(n > 0 && n <= 16 ? n : 3); }();
+	return value;
+}
 constexpr size_t kDirectRays = size_t(1) << 16;  // pinned batches up to this size are traced in place (no staging copies)
 
 // One staging lane: a stream with pinned host and device buffers for rays in / results out.
@@ -209,9 +220,9 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, La
 		return rc;
 	}
 	const size_t per_ray = std::max(sizeof(b200rt_ray), sizeof(Out));
-	const size_t chunk = std::max<size_t>(1024, kChunkBytes / per_ray);
+	const size_t chunk = std::max<size_t>(1024, chunkBytes() / per_ray);
 	const size_t n_chunks = (n + chunk - 1) / chunk;
-	const int n_lanes = int(std::min<size_t>(kLanesPerCall, n_chunks));
+	const int n_lanes = int(std::min<size_t>(size_t(lanesPerCall()), n_chunks));
 
 	std::vector<std::unique_ptr<Lane>> lanes;
 	{

@@ -240,3 +240,20 @@ def test_photon_passes_run_on_fibers(tmp_path, integrator, extra):
     value = film.psnr(film.normalized(b200), film.normalized(stock))
     print(f"{integrator}: b200 vs stock {value:.1f} dB, stock vs stock {floor:.1f} dB")
     assert value > min(floor - 3.0, 40.0)
+
+
+@needs_render_bench
+@pytest.mark.parametrize("integrator,extra", [("photonmapping", ("i:diffuse_photons=20000", "i:caustic_photons=4000")), ("SPPM", ("i:photons=20000", "i:passNums=2"))])
+def test_patched_photon_launch_sites_keep_the_reference_behaviour_on_cpu(tmp_path, integrator, extra):
+    """With any accelerator but b200-kdtree, b200::PhotonWorkers::run starts one std::thread per worker -- the reference's own
+    code path (integration/include/render/photon_fibers_b200.h): the thread count in the log is the requested one and the
+    render completes with a lit image."""
+    import re
+    prefix = str(tmp_path / "cpu")
+    cmd = [RENDER_BENCH, "yafaray-kdtree-original", integrator, "32", "120", "80", "1", prefix + ".tga", "3", "film_save=" + prefix, "i:threads_photons=3", *extra]
+    p = subprocess.run(cmd, cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, errors="replace", timeout=600)
+    assert p.returncode == 0 and "RENDER_BENCH" in p.stdout, p.stdout[-2000:]
+    shots = re.findall(r"Shooting (\d+) photons across (\d+) threads", p.stdout)
+    assert shots and all(int(t) == 3 for _, t in shots), shots
+    img = film.normalized(film.read_film(film.film_path(prefix)))
+    assert float(img[..., :3].mean()) > 0.01 and (film.read_film(film.film_path(prefix)).weights > 0).all()
