@@ -37,15 +37,15 @@ int fail(int code, const std::string &msg)
 constexpr uint32_t kTriangle = 0xFFFFFFFFu;
 constexpr uint32_t kSphere = 0xFFFFFFFEu; // idx[2] of a sphere face (kd_build.h)
 // staging granularity of the host-buffer queries and chunks in flight per call; the environment overrides are tuning aids
-// (tools/gpu_e2e_sweep.sh), read once
+// (tools/gpu_e2e_sweep.sh), read once.  Defaults from the measured sweep (profiles/r1m_e2e_sweep.txt): 16 MiB x 6 in flight.
 size_t chunkBytes()
 {
-	static const size_t value = [] { const char *e = std::getenv("B200RT_CHUNK_MB"); const long mb = e ? std::atol(e) : 0; return size_t(mb > 0 ? mb : 32) << 20; }();
+	static const size_t value = [] { const char *e = std::getenv("B200RT_CHUNK_MB"); const long mb = e ? std::atol(e) : 0; return size_t(mb > 0 ? mb : 16) << 20; }();
 	return value;
 }
 int lanesPerCall()
 {
-	static const int value = [] { const char *e = std::getenv("B200RT_LANES"); const long n = e ? std::atol(e) : 0; return int(n > 0 && n <= 16 ? n : 3); }();
+	static const int value = [] { const char *e = std::getenv("B200RT_LANES"); const long n = e ? std::atol(e) : 0; return int(n > 0 && n <= 16 ? n : 6); }();
 	return value;
 }
 constexpr size_t kDirectRays = size_t(1) << 16;  // pinned batches up to this size are traced in place (no staging copies)
