@@ -1,0 +1,67 @@
+"""bench.py's output contract: one JSON line with the metric, the roofline and cpu_baseline objects, the end-to-end arm and
+the launch count; the reference arm runs on the CPU (rank 0 only under torchrun); without a GPU the product arm fails loudly."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BENCH = os.path.join(ROOT, "bench.py")
+SMALL = ["--rays", "65536", "--cells", "48", "--steps", "2", "--warmup", "1", "--cpu-seconds", "0.5"]
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "e2e"}
+
+
+def run_bench(args, env=None):
+    e = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        e.pop(k, None)
+    e.update(env or {})
+    return subprocess.run([sys.executable, BENCH] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900, env=e)
+
+
+def test_reference_arm_prints_the_contract_line(built):
+    p = run_bench(["--impl", "reference"] + SMALL)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    rec = json.loads(lines[0])
+    assert BASE_KEYS <= set(rec) and rec["impl"] == "reference"
+    assert rec["unit"] == "Mrays/s" and rec["higher_is_better"] is True and rec["value"] > 0
+    assert rec["e2e"] == {"value": rec["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    base = rec["cpu_baseline"]
+    assert base["kind"] in ("reference", "port") and base["cores"] >= 1 and base["value"] == rec["value"] and "sample" in base
+    assert rec["gpu_launches"] == 0 and "workload" in rec["config"]
+
+
+def test_reference_arm_other_ranks_exit_quietly(built):
+    p = run_bench(["--impl", "reference", "--gpus", "2"] + SMALL, env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_product_arm_has_no_cpu_fallback(built):
+    from libyafaray_b200 import rt
+    if rt.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    p = run_bench(SMALL)
+    assert p.returncode != 0 and "no CUDA device" in (p.stderr + p.stdout)
+    assert not any(l.startswith("{") for l in p.stdout.splitlines()), "a bench line was printed without a GPU"
+
+
+@pytest.mark.gpu
+def test_product_arm_line_on_the_gpu(built):
+    p = run_bench(["--rays", str(1 << 20), "--cells", "128", "--steps", "3", "--warmup", "3", "--cpu-seconds", "1"])
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    rec = json.loads(lines[0])
+    assert BASE_KEYS <= set(rec) and "impl" not in rec
+    assert rec["n_gpus"] == 1 and rec["scaling"] == "weak" and rec["dtype"] == "f32" and rec["vs_baseline"] is None
+    assert rec["gpu_launches"] == 2 * rec["steps"], "one closest and one shadow launch per step"
+    roof = rec["roofline"]
+    assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and roof["peak"] > 1000 and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
+    e2e = rec["e2e"]
+    assert e2e["h2d_bytes_per_step"] == 2 * (1 << 20) * 32 and e2e["d2h_bytes_per_step"] == (1 << 20) * 20 and 0 < e2e["value"] < rec["value"]
+    assert rec["cpu_baseline"]["value"] > 0 and rec["cpu_baseline"]["kind"] in ("reference", "port")
+    assert rec["clocks"]["sm_mhz"] and not set(rec["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
