@@ -15,6 +15,7 @@ ap.add_argument("--leaf", type=int, default=0)
 ap.add_argument("--cost", type=float, default=0.0)
 ap.add_argument("--bonus", type=float, default=0.0)
 ap.add_argument("--tag", default="")
+ap.add_argument("--sort", default="", help="reorder the rays before tracing: 'morton' (origin cell, 10 bits per axis), 'octmorton' (direction octant, then origin), 'dirmorton' (origin 7 bits/axis + direction 3 bits/axis interleaved)")
 a = ap.parse_args()
 mesh = {"hf": lambda: scenes.heightfield(707), "obj": lambda: scenes.objects(1_000_000), "soup": lambda: scenes.soup(1_000_000)}[a.scene]()
 sc = rt.Scene(0, rt.make_params(max_leaf_size=a.leaf, cost_ratio=a.cost, empty_bonus=a.bonus))
@@ -23,6 +24,26 @@ st = sc.stats()
 n = a.rays
 b = sc.bound()
 rays = scenes.rays_incoherent(n, seed=12345, lo=b[:3] if a.scene != "hf" else (0, 0, 0), hi=b[3:] if a.scene != "hf" else (1, 1, 1))
+def part1by2(x):
+    x = x.astype(np.uint64) & 0x3FF
+    x = (x | (x << 16)) & 0x30000FF
+    x = (x | (x << 8)) & 0x300F00F
+    x = (x | (x << 4)) & 0x30C30C3
+    x = (x | (x << 2)) & 0x9249249
+    return x
+if a.sort:
+    lo = np.asarray(b[:3], np.float64); ext = np.maximum(np.asarray(b[3:], np.float64) - lo, 1e-30)
+    q = np.clip(((rays[:, 0:3] - lo) / ext * 1024).astype(np.int64), 0, 1023)
+    key = part1by2(q[:, 0]) | (part1by2(q[:, 1]) << 1) | (part1by2(q[:, 2]) << 2)
+    if a.sort == "octmorton":
+        octant = ((rays[:, 4] < 0).astype(np.uint64)) | ((rays[:, 5] < 0).astype(np.uint64) << 1) | ((rays[:, 6] < 0).astype(np.uint64) << 2)
+        key = key | (octant << 30)
+    elif a.sort == "dirmorton":
+        d = rays[:, 4:7] / np.linalg.norm(rays[:, 4:7], axis=1, keepdims=True)
+        dq = np.clip(((d + 1) * 4).astype(np.int64), 0, 7)
+        dkey = part1by2(dq[:, 0]) | (part1by2(dq[:, 1]) << 1) | (part1by2(dq[:, 2]) << 2)
+        key = ((key >> 9) << 9) | dkey  # 7 bits per axis of origin, then 3 bits per axis of direction
+    rays = np.ascontiguousarray(rays[np.argsort(key, kind="stable")])
 srays = rays.copy(); srays[:, 3] = 0.0005; srays[:, 7] = 0.25
 d_r = torch.from_numpy(rays).cuda(); d_s = torch.from_numpy(srays).cuda()
 d_h = torch.empty((n, 4), dtype=torch.float32, device="cuda"); d_o = torch.empty(n, dtype=torch.int32, device="cuda")
