@@ -30,7 +30,7 @@ METRIC = "Mrays/s closest-hit+shadow per B200 (1/2/4/8 GPU) vs host-CPU kd-tree"
 UNIT = "Mrays/s"
 # ALGORITHMIC bytes per ray (DESIGN.md "Roofline"): IO + 8 B x (interior + leaf nodes visited) + 4 B x leaf refs
 # + 36 B x triangle tests, visit counts taken from the REFERENCE's own kd-tree traversing this very workload
-# (counting oracle, tools/count_bytes.py).  IO = 32 B ray + 16 B hit (closest) / + 4 B (shadow).
+# (counting oracle, tests/tools/count_bytes.py).  IO = 32 B ray + 16 B hit (closest) / + 4 B (shadow).
 ALGO_BYTES = {"closest": 345.0, "shadow": 230.8}
 SHADOW_TMAX = 0.25
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE closest launch on this workload, from the ncu --set full capture kept

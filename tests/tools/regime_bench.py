@@ -7,7 +7,7 @@ judged number): the HBM-resident 10 M-triangle scene of BASELINE.json configs[3]
 Parity sample: the first --check rays are also traced by the oracle's C restatement ON THE TREE libb200rt's host
 builder produced (exported through b200rt_host_tree_*), so a 10 M-triangle check needs no second build."""
 import argparse, json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from libyafaray_b200 import rt, scenes
