@@ -89,6 +89,10 @@ class ClockSampler:
     def window(self, t0, t1):
         if not self.ok:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "error": getattr(self, "err", "nvml unavailable")}
+        for _ in range(100):  # a timed region shorter than one sampling period: wait for the first samples around it
+            if len(self.rows) >= 2:
+                break
+            time.sleep(0.002)
         rows = [r for r in self.rows if t0 <= r[0] <= t1]
         if len(rows) < 2:  # region shorter than two periods: take the nearest samples around it
             rows = sorted(self.rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))[:4]

@@ -17,7 +17,8 @@ ap.add_argument("--bonus", type=float, default=0.0)
 ap.add_argument("--tag", default="")
 ap.add_argument("--sort", default="", help="reorder the rays before tracing: 'morton' (origin cell, 10 bits per axis), 'octmorton' (direction octant, then origin), 'dirmorton' (origin 7 bits/axis + direction 3 bits/axis interleaved)")
 a = ap.parse_args()
-mesh = {"hf": lambda: scenes.heightfield(707), "obj": lambda: scenes.objects(1_000_000), "soup": lambda: scenes.soup(1_000_000)}[a.scene]()
+mesh = {"hf": lambda: scenes.heightfield(707), "obj": lambda: scenes.objects(1_000_000), "soup": lambda: scenes.soup(1_000_000),
+        "obj10": lambda: scenes.objects(10_000_000)}[a.scene]()
 sc = rt.Scene(0, rt.make_params(max_leaf_size=a.leaf, cost_ratio=a.cost, empty_bonus=a.bonus))
 sc.add_mesh(*mesh); sc.build()
 st = sc.stats()
