@@ -9,6 +9,9 @@
 #include "geometry/primitive/primitive_face.h"
 #include "geometry/primitive/primitive_instance.h"
 #include "geometry/primitive/primitive_sphere.h"
+#include "geometry/shape/shape_polygon.h"
+#include <cstdio>
+#include <cstdlib>
 #include "geometry/instance.h"
 #include "geometry/matrix.h"
 #include "material/material.h"
@@ -130,12 +133,25 @@ AcceleratorB200::AcceleratorB200(Logger &logger, ParamResult &param_result, cons
 	b200rt_scene *scene = nullptr;
 	int rc = b200rt_create(params_.device_, &build_params, &scene);
 	// faces gathered so far go to the library before a sphere does, so that face ids follow the primitive order
+	// diagnostic (B200_DUMP_SCENE=<file>): the flattened geometry as libb200rt receives it -- per add_mesh call one record
+	// {uint64 n_verts, uint64 n_faces, float xyz[3 n_verts], uint32 idx[4 n_faces], uint8 flags[n_faces]}; read by tests/tools/dump_compare.py
+	std::FILE *dump{std::getenv("B200_DUMP_SCENE") ? std::fopen(std::getenv("B200_DUMP_SCENE"), "wb") : nullptr};
 	const auto flush_mesh{[&]() {
+		if(dump && !flags.empty())
+		{
+			const uint64_t counts[2]{xyz.size() / 3, flags.size()};
+			std::fwrite(counts, sizeof(uint64_t), 2, dump);
+			std::fwrite(xyz.data(), sizeof(float), xyz.size(), dump);
+			std::fwrite(idx.data(), sizeof(uint32_t), idx.size(), dump);
+			std::fwrite(flags.data(), 1, flags.size(), dump);
+		}
 		if(rc == B200RT_OK && !flags.empty()) rc = b200rt_add_mesh(scene, xyz.data(), xyz.size() / 3, idx.data(), idx.size() / 4, flags.data());
 		xyz.clear();
 		idx.clear();
 		flags.clear();
 	}};
+	const bool verify_extraction{std::getenv("B200_VERIFY_EXTRACTION") != nullptr};
+	size_t verify_tests{0}, verify_hits{0}, verify_mismatches{0};
 	for(const Primitive *primitive : primitives_)
 	{
 		if(render_control_ && render_control_->canceled())
@@ -193,8 +209,31 @@ AcceleratorB200::AcceleratorB200(Logger &logger, ParamResult &param_result, cons
 		}
 		for(int v = 0; v < 4; ++v) idx.push_back(v < n_vertices ? first_vertex + static_cast<uint32_t>(v) : 0xFFFFFFFFu);
 		flags.push_back(faceFlags(primitive));
+		if(verify_extraction)
+		{
+			// diagnostic (B200_VERIFY_EXTRACTION=1): the vertices just extracted, tested with the reference's own polygon code, must
+			// give bit for bit what the primitive's virtual intersect() gives -- for a ray through the face and for one that grazes it
+			const float *p{xyz.data() + 3 * size_t(first_vertex)};
+			const Point3f v_0{{p[0], p[1], p[2]}}, v_1{{p[3], p[4], p[5]}}, v_2{{p[6], p[7], p[8]}};
+			const Vec3f normal{(v_1 - v_0) ^ (v_2 - v_0)};
+			const Point3f centre{(v_0 + v_1 + v_2) * (1.f / 3.f)};
+			for(int k = 0; k < 2; ++k)
+			{
+				const Point3f from{centre + normal * (k == 0 ? 1.f : 0.37f) + (v_1 - v_0) * (k == 0 ? 0.f : 0.21f)};
+				const Vec3f dir{k == 0 ? -normal : -(normal + (v_2 - v_0) * 0.4f)};
+				const auto expected{primitive->intersect(from, dir, 0.f)};
+				std::pair<float, Uv<float>> got;
+				if(n_vertices == 3) got = ShapePolygon<float, 3>{{v_0, v_1, v_2}}.intersect(from, dir);
+				else got = ShapePolygon<float, 4>{{v_0, v_1, v_2, Point3f{{p[9], p[10], p[11]}}}}.intersect(from, dir);
+				++verify_tests;
+				if(got.first != expected.first || got.second.u_ != expected.second.u_ || got.second.v_ != expected.second.v_) ++verify_mismatches;
+				if(expected.first > 0.f) ++verify_hits;
+			}
+		}
 	}
+	if(verify_extraction) logger_.logInfo(getClassName(), ": extraction check: ", verify_tests, " test rays, ", verify_hits, " hits, ", verify_mismatches, " differ from Primitive::intersect");
 	flush_mesh();
+	if(dump) std::fclose(dump);
 	if(rc == B200RT_OK) rc = b200rt_build(scene);
 	float bound[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 	if(rc == B200RT_OK) rc = b200rt_get_bound(scene, bound);

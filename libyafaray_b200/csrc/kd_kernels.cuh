@@ -182,9 +182,13 @@ __device__ __forceinline__ float sphereIntersect(const float4 q0, float radius, 
 // from inside), so that the compiler's reconvergence points sit right after each phase.
 //
 // The traversal is t-interval based: [seg_lo, seg_hi] is the ray parameter range inside the current node.
-//   t_plane >= min(seg_hi, closest so far)  -> near child only
-//   t_plane <= seg_lo                       -> far child only
+//   t_plane >  min(seg_hi, closest so far)  -> near child only
+//   t_plane <  seg_lo                       -> far child only
 //   otherwise near first, far child pushed with the current seg_hi
+// The comparisons are STRICT on purpose: a slab thinner than the resolution of t along this ray (a 1-ulp slab around an
+// axis-aligned face, say) has t_plane == seg_lo on entry, and the faces inside it must still be met -- with "<=" whole cube
+// faces of the reference's tests/test02 scene were skipped.  (split - o) * inv is monotonic in split, so entry and exit of
+// a slab can coincide but never swap; a zero-length interval is traversed like any other.
 // "near" is decided by the sign of the direction component (of its inverse, so that a zero component, whose
 // inverse is +FLT_MAX as in math::inverse, math.h:71-77, behaves as "positive").
 // -------------------------------------------------------------------------------------------------
@@ -357,8 +361,9 @@ __device__ __forceinline__ void writeResult(typename OutType<QUERY>::type *out, 
 // kShortStack entries per thread, laid out [entry][thread] so that a warp's accesses are conflict-free
 // whatever the lanes' stack depths are (bank = thread % 32).  It is a ring: a push onto a full ring
 // overwrites the OLDEST entry and raises `floor`; popping down to a raised floor means entries were lost,
-// and the ray then restarts from the root with seg_lo advanced to the end of the leaf it just left
-// (kd-restart).  Pushes are unconditional stores (the slot is simply not committed when the ray visits
+// and the ray then REPLAYS its descent from the root along the path to the leaf it just left, postponing the
+// far children of that path again (the ring keeps the deepest ones, the ones needed next), and pops (an exact
+// kd-restart: progress does not depend on t, so zero-length intervals cannot make it loop).  Pushes are unconditional stores (the slot is simply not committed when the ray visits
 // one child only), which keeps the node step free of divergent branches; the price is that the ring
 // effectively holds kShortStack - 1 entries.
 #ifndef B200RT_SHORT_STACK
@@ -403,14 +408,63 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 	bool alive = false, pending = false;
 	uint32_t leaf_count = 0u, leaf_first = 0u;
 	int floor = 0;          // ring entries below this index were overwritten
-	float t_exit = 0.f;     // where the ray leaves the tree bound (or its t_max)
 	uint32_t pool_next = 0u, pool_end = 0u; // warp-uniform
 	bool exhausted = false;                 // warp-uniform
 	bool first_pool = true;                 // warp-uniform
 
+	// Exact kd-restart.  `target` is the leaf the ray has just left (ring empty, older entries lost).  The tree is stored
+	// depth first (left child = node + 1, the right subtree starts at `right`), so "target < right" tells which child holds
+	// it.  On the way down the decisions of the first descent are taken again -- the child without the target is
+	// postponed when the ray enters it AFTER the target's side, and skipped when it lies before (already traversed) --
+	// then the next postponed subtree is popped.  Returns true when nothing is left.  Rare path (the ring holds the 7
+	// deepest entries), divergent on purpose.
+	bool need_replay = false;
+	auto replayTo = [&](const uint32_t target) -> bool {
+		r.sp = 0;
+		floor = 0;
+		uint32_t node = 0u;
+		const float2 whole = sh_axis[3][tid]; // the interval the ray was set up with
+		float lo = whole.x, hi = whole.y;
+		while(node != target)
+		{
+			const uint2 nd = __ldg(&s.nodes[node]); // interior: the target lies below it
+			const uint32_t right = nd.y >> 2;
+			const float2 oi = sh_axis[nd.y & 3u][tid];
+			const float t_plane = (__uint_as_float(nd.x) - oi.x) * oi.y;
+			const bool negative = __float_as_int(oi.y) < 0;
+			const uint32_t left = node + 1u;
+			const uint32_t near = negative ? right : left, far = negative ? left : right;
+			const bool target_near = ((target < right) != negative);
+			if(target_near)
+			{
+				const float limit = (QUERY == kClosest) ? fminf(hi, r.t_max) : hi;
+				if(!(t_plane > limit) && !(t_plane < lo))
+				{
+					*reinterpret_cast<uint2 *>(ring + (r.sp & kRingMask)) = make_uint2(far, __float_as_uint(hi));
+					floor = max(floor, r.sp + (1 - kShortStack) * kRingStride);
+					r.sp += kRingStride;
+					hi = t_plane;
+				}
+				node = near;
+			}
+			else
+			{
+				lo = fmaxf(lo, t_plane); // the near side lies before the target: done
+				node = far;
+			}
+		}
+		if(r.sp <= floor) return true; // nothing was postponed behind the target
+		r.sp -= kRingStride;
+		const uint2 e = *reinterpret_cast<const uint2 *>(ring + (r.sp & kRingMask));
+		r.node = e.x;
+		r.seg_lo = hi;
+		r.seg_hi = __uint_as_float(e.y);
+		return false;
+	};
+
 	// Leave the current leaf.  Closest queries stop once the best hit is not beyond the end of this leaf
-	// (accelerator_kdtree_common.h:232); otherwise continue with the nearest postponed subtree, or restart
-	// from the root behind this leaf when ring entries were lost.  Returns true when the ray has ended.
+	// (accelerator_kdtree_common.h:232); otherwise continue with the nearest postponed subtree, or replay the descent
+	// when ring entries were lost.  Returns true when the ray has ended.
 	auto popNode = [&]() -> bool {
 		if(QUERY == kClosest && r.best_prim != B200RT_MISS && r.t_max <= r.seg_hi) return true;
 		if(r.sp > floor)
@@ -423,12 +477,8 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 			return false;
 		}
 		if(floor == 0) return true;
-		r.sp = 0;
-		floor = 0;
-		r.node = 0u;
-		r.seg_lo = r.seg_hi;
-		r.seg_hi = t_exit;
-		return !(r.seg_lo < t_exit);
+		need_replay = true; // done once, after the phase (one copy of the replay code)
+		return false;
 	};
 
 	for(;;)
@@ -476,11 +526,11 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					ts.depth = 0;
 					floor = 0;
 					alive = setupRay<QUERY>(s, a, b, r, tree_space);
-					t_exit = r.seg_hi;
 #if B200RT_SMEM_RAY
 					sh_axis[0][tid] = make_float2(r.ox, r.ix);
 					sh_axis[1][tid] = make_float2(r.oy, r.iy);
 					sh_axis[2][tid] = make_float2(r.oz, r.iz);
+					sh_axis[3][tid] = make_float2(r.seg_lo, r.seg_hi); // where the ray enters and leaves the tree bound (replayTo); row 3 is also what a leaf's "axis" reads, unused there
 #endif
 					if(!alive) writeResult<QUERY>(out, r, false, ts); // missed the tree bound
 				}
@@ -577,8 +627,8 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					const uint32_t swap = (left ^ payload) & m;
 					const uint32_t near = left ^ swap, far = payload ^ swap;
 					const float limit = (QUERY == kClosest) ? fminf(r.seg_hi, r.t_max) : r.seg_hi;
-					const bool far_only = t_plane <= r.seg_lo;
-					const bool both = !is_leaf && !(t_plane >= limit) && !far_only;
+					const bool far_only = t_plane < r.seg_lo;
+					const bool both = !is_leaf && !(t_plane > limit) && !far_only;
 					// top of the ring (read before this step's speculative store; different slot)
 					const uint2 popped = *reinterpret_cast<const uint2 *>(ring + ((r.sp - kRingStride) & kRingMask));
 					const uint32_t pop_node = popped.x;
@@ -609,20 +659,16 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 				{
 					const bool closest_done = (QUERY == kClosest) && r.best_prim != B200RT_MISS && r.t_max <= r.seg_hi;
 					if(closest_done || floor == 0) finished = true;
-					else
-					{
-						// ring entries were overwritten: restart from the root behind the leaf just left (kd-restart)
-						r.sp = 0;
-						floor = 0;
-						r.node = 0u;
-						r.seg_lo = r.seg_hi;
-						r.seg_hi = t_exit;
-						finished = !(r.seg_lo < t_exit);
-					}
+					else need_replay = true; // ring entries were overwritten: exact kd-restart behind the leaf just left
 				}
 			}
 		}
 
+		if(need_replay)
+		{
+			need_replay = false;
+			finished = replayTo(r.node);
+		}
 		if(finished)
 		{
 			writeResult<QUERY>(out, r, (QUERY == kClosest) ? (r.best_prim != B200RT_MISS) : hit, ts);

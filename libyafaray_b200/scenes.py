@@ -260,3 +260,29 @@ def sphere_field(n: int = 200, seed: int = 5, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 
     out[:, :3] = lo + rng.random((n, 3), dtype=np.float32) * (hi - lo)
     out[:, 3] = r_lo + rng.random(n, dtype=np.float32) * (r_hi - r_lo)
     return out
+
+
+def cube_grid(n_per_axis: int = 9, scale: float = 0.06, distance: float = 0.35, floor: bool = True):
+    """A grid of small axis-aligned cubes, the instanced "Cube" of the reference's tests/test02/test02.c:3546-3569: two of its
+    vertices are off by 1e-6, so that after the instance transform (scale 0.06 + translation, in float) the faces are planar only
+    up to one ulp.  A SAH builder cuts 1-ulp slabs around such faces, thinner than the resolution of t along most rays -- the
+    case in which a t-interval traversal must still enter a slab whose entry and exit parameter coincide (kd_kernels.cuh)."""
+    base = np.array([[1, 1, -1], [1, -1, -1], [-1, -1, -1], [-1, 1, -1], [1, 0.999999, 1], [0.999999, -1, 1], [-1, -1, 1], [-1, 1, 1]], dtype=np.float32)
+    faces = np.array([[0, 1, 2], [0, 2, 3], [4, 7, 6], [4, 6, 5], [0, 4, 5], [0, 5, 1], [1, 5, 6], [1, 6, 2], [2, 6, 7], [2, 7, 3], [4, 0, 3], [4, 3, 7]], dtype=np.uint32)
+    s = np.float32(scale)
+    xyz, idx = [], []
+    start = np.float32(-0.5 * distance * (n_per_axis - 1))
+    for i in range(n_per_axis):
+        for j in range(n_per_axis):
+            for k in range(n_per_axis):
+                offset = np.array([start + np.float32(distance) * i, start + np.float32(distance) * j, start + np.float32(distance) * k], dtype=np.float32)
+                idx.append(np.concatenate([faces + np.uint32(8 * len(xyz)), np.full((12, 1), TRI, np.uint32)], axis=1))
+                xyz.append((base * s + offset).astype(np.float32))  # m00 * x + m03, one float multiply and one float add like Matrix4f * Point3f
+    xyz, idx = np.concatenate(xyz), np.concatenate(idx)
+    if floor:
+        e = np.float32(1.2 * abs(float(start)) + 2 * scale)
+        z = np.float32(float(start) - 2 * scale)
+        base_v = xyz.shape[0]
+        xyz = np.concatenate([xyz, np.array([[-e, -e, z], [e, -e, z], [e, e, z], [-e, e, z]], dtype=np.float32)])
+        idx = np.concatenate([idx, np.array([[base_v, base_v + 1, base_v + 2, base_v + 3]], dtype=np.uint32)])
+    return _finish(xyz, idx)

@@ -29,6 +29,8 @@ def scene_zoo(small=True):
     # spheres (SpherePrimitive) among mesh objects: mesh faces first, then the spheres (scenes.with_spheres)
     oxyz, oidx, ofl = scenes.objects(3000 * k * k, n_spheres=8, seed=21)
     zoo["spheres"] = scenes.with_spheres(oxyz, oidx, ofl, scenes.sphere_field(60 * k * k, seed=22, lo=oxyz.min(0), hi=oxyz.max(0)))
+    # instanced axis-aligned cubes with faces planar up to one ulp (the reference's tests/test02): 1-ulp kd slabs
+    zoo["cube_grid"] = scenes.cube_grid(5 if small else 9)
     out = {}
     for i, (name, (xyz, idx, fl)) in enumerate(zoo.items()):
         out[name] = (xyz, idx, fl)
@@ -36,19 +38,23 @@ def scene_zoo(small=True):
     return out
 
 
-def ray_zoo(bound, n=20000, seed=3):
+def ray_zoo(bound, n=20000, seed=3, edge_cases=True):
+    """edge_cases=False leaves out the axis-parallel / exact-diagonal rays of scenes.rays_edge_cases: through a SYMMETRIC grid of
+    axis-aligned cubes (cube_grid) they pass exactly through cube corners, where which of the eight cells around the corner a
+    kd traversal walks through -- the reference's included -- depends on the rounding of three equal plane distances and on the
+    tree, so two valid trees may disagree on such a ray (a corner leak, not a tie in t)."""
     lo, hi = bound[:3].astype(np.float64), bound[3:].astype(np.float64)
     ext = hi - lo
     diag = float(np.linalg.norm(ext))
     closest = np.concatenate([
         scenes.rays_incoherent(n, seed=seed, lo=lo - 0.1 * ext, hi=hi + 0.1 * ext),
         scenes.rays_incoherent(n // 4, seed=seed + 1, lo=lo, hi=hi, tmax=0.3 * diag, tmin=0.01 * diag),
-        scenes.rays_edge_cases(lo, hi, seed=seed + 2),
+        scenes.rays_edge_cases(lo, hi, seed=seed + 2) if edge_cases else np.zeros((0, 8), np.float32),
     ])
     shadow = np.concatenate([
         scenes.rays_shadow(n, seed=seed + 3, lo=lo, hi=hi, t_max=0.25 * diag),
         scenes.rays_incoherent(n // 4, seed=seed + 4, lo=lo, hi=hi, tmax=-1.0, tmin=0.0005),
-        scenes.rays_edge_cases(lo, hi, seed=seed + 5),
+        scenes.rays_edge_cases(lo, hi, seed=seed + 5) if edge_cases else np.zeros((0, 8), np.float32),
     ])
     return closest, shadow
 
