@@ -223,6 +223,7 @@ __device__ __forceinline__ float sphereIntersect(const float4 q0, float radius, 
 #ifndef B200RT_BREAK
 #define B200RT_BREAK 1
 #endif
+
 static constexpr int kBlock = B200RT_BLOCK;
 static constexpr int kPoolRays = 256;               // rays taken from the global cursor per atomicAdd
 static constexpr int kRefill = B200RT_REFILL;       // idle lanes that trigger a refill
@@ -424,7 +425,10 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 		floor = 0;
 		uint32_t node = 0u;
 		const float2 whole = sh_axis[3][tid]; // the interval the ray was set up with
-		float lo = whole.x, hi = whole.y;
+		// the leaf just left reaches the end of the ray's stay in the (inflated, hence empty at its faces) tree bound: nothing
+		// can follow.  Most rays whose ring ever overflowed end this way, and are spared the descent.
+		if(!(r.seg_hi < whole.y)) return true;
+		float hi = whole.y;
 		while(node != target)
 		{
 			const uint2 nd = __ldg(&s.nodes[node]); // interior: the target lies below it
@@ -438,7 +442,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 			if(target_near)
 			{
 				const float limit = (QUERY == kClosest) ? fminf(hi, r.t_max) : hi;
-				if(!(t_plane > limit) && !(t_plane < lo))
+				if(!(t_plane > limit)) // (t_plane < interval start cannot be: the first descent would have taken the far child only)
 				{
 					*reinterpret_cast<uint2 *>(ring + (r.sp & kRingMask)) = make_uint2(far, __float_as_uint(hi));
 					floor = max(floor, r.sp + (1 - kShortStack) * kRingStride);
@@ -447,11 +451,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 				}
 				node = near;
 			}
-			else
-			{
-				lo = fmaxf(lo, t_plane); // the near side lies before the target: done
-				node = far;
-			}
+			else node = far; // the near side lies before the target: done
 		}
 		if(r.sp <= floor) return true; // nothing was postponed behind the target
 		r.sp -= kRingStride;
