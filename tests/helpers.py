@@ -116,3 +116,30 @@ def make_rt_scene(rt, xyz, idx, flags=None, params=None, device=0):
             f = e
     s.build()
     return s
+
+
+def load_scene_dump(path):
+    """Geometry dumped by AcceleratorB200 (B200_DUMP_SCENE, integration/src/accelerator/accelerator_b200.cc): one record per
+    b200rt_add_mesh call {uint64 n_verts, uint64 n_faces, float xyz[3 n_verts], uint32 idx[4 n_faces], uint8 flags[n_faces]}."""
+    raw = open(path, "rb").read()
+    off, xs, ids, fs, base = 0, [], [], [], 0
+    while off < len(raw):
+        nv, nf = (int(x) for x in np.frombuffer(raw, "<u8", 2, off)); off += 16
+        x = np.frombuffer(raw, "<f4", 3 * nv, off).reshape(nv, 3); off += 12 * nv
+        i = np.frombuffer(raw, "<u4", 4 * nf, off).reshape(nf, 4).copy(); off += 16 * nf
+        f = np.frombuffer(raw, "u1", nf, off); off += nf
+        tri = i[:, 3] == 0xFFFFFFFF
+        i[:, :3] += base
+        i[~tri, 3] += base
+        xs.append(x); ids.append(i); fs.append(f); base += nv
+    return np.concatenate(xs), np.concatenate(ids), np.concatenate(fs)
+
+
+def surface_rays(rays, t, seed, tmin=0.0005):
+    """Secondary rays as the integrators shoot them: origin = from + t * dir of a hit (float arithmetic), random direction."""
+    rng = np.random.default_rng(seed)
+    hit = t > 0
+    p = (rays[hit, 0:3] + t[hit, None] * rays[hit, 4:7]).astype(np.float32)
+    out = np.zeros((p.shape[0], 8), np.float32)
+    out[:, 0:3] = p; out[:, 3] = tmin; out[:, 4:7] = rng.normal(size=p.shape).astype(np.float32); out[:, 7] = -1.0
+    return out

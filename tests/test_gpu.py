@@ -365,3 +365,30 @@ def test_trace_jobs_bundles_match_single_queries(built, split):
     with pytest.raises(rt.B200RTError):
         rt.trace_jobs([(s1, 9, 0, np.zeros((4, 8), np.float32), np.zeros(4, np.uint32), 0)])
     s1.close(); s2.close()
+
+
+REF_SCENES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_scenes", "*.bin")))
+
+
+@pytest.mark.parametrize("path", REF_SCENES, ids=[os.path.basename(p)[:-4] for p in REF_SCENES])
+def test_reference_test_scenes_primary_and_surface_rays(built, path):
+    """The geometry of the reference's own tests/test00, test01, test03 clients as AcceleratorB200 extracts it (dumped with
+    B200_DUMP_SCENE; axis-aligned boxes and planes -- the kind of scene whose kd slabs have zero thickness in t), traced with
+    primary rays and with rays that START ON SURFACES like bounce / shadow rays do.  Checked against the oracle and, when it
+    travelled, the live reference.  (tests/test02's 21 MB dump is not committed; scenes.cube_grid reproduces its slabs.)"""
+    xyz, idx, flags = helpers.load_scene_dump(path)
+    s = make_scene(xyz, idx, flags)
+    o = kdo.Oracle(xyz, idx, flags)
+    assert np.array_equal(s.bound(), o.bound())
+    b = s.bound().astype(np.float64)
+    ext = b[3:] - b[:3]
+    primary = scenes.rays_incoherent(300000, seed=31, lo=b[:3] - 0.2 * ext, hi=b[3:] + 0.2 * ext)
+    checkers = [("oracle", o)] + ([("live reference", yref.RefScene(xyz, idx, flags))] if yref.available() else [])
+    for what, ref in checkers:
+        r1 = ref.trace_closest(primary, threads=NCPU)
+        surface = helpers.surface_rays(primary, r1["t"], seed=32)
+        for rays, rr in ((primary, r1), (surface, ref.trace_closest(surface, threads=NCPU))):
+            h = s.trace_closest(rays)
+            helpers.check_closest_parity(helpers.prim_signed(h["prim"]), h["t"], h["u"], h["v"], rr, min_agree=0.97)  # shared box edges tie
+            assert np.array_equal((s.trace_shadow(rays) != rt.MISS).astype(np.uint8), ref.trace_shadow(rays, threads=NCPU)["shadowed"]), what
+    s.close()

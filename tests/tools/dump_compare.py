@@ -15,30 +15,11 @@ from oracle import kdo, yref
 from tests.helpers import host_tree_as_oracle_tree
 
 
-def load_dump(path):
-    raw = open(path, "rb").read()
-    off, xs, is_, fs, base = 0, [], [], [], 0
-    while off < len(raw):
-        nv, nf = np.frombuffer(raw, "<u8", 2, off); off += 16
-        nv, nf = int(nv), int(nf)
-        x = np.frombuffer(raw, "<f4", 3 * nv, off).reshape(nv, 3); off += 12 * nv
-        i = np.frombuffer(raw, "<u4", 4 * nf, off).reshape(nf, 4).copy(); off += 16 * nf
-        f = np.frombuffer(raw, "u1", nf, off); off += nf
-        tri = i[:, 3] == 0xFFFFFFFF
-        i[:, :3] += base
-        i[~tri, 3] += base
-        xs.append(x); is_.append(i); fs.append(f); base += nv
-    return np.concatenate(xs), np.concatenate(is_), np.concatenate(fs)
+from tests.helpers import load_scene_dump as load_dump, surface_rays
 
 
 def secondary(rays, t, n, seed):
-    rng = np.random.default_rng(seed)
-    hit = t > 0
-    p = (rays[hit, 0:3] + t[hit, None] * rays[hit, 4:7]).astype(np.float32)[:n]
-    d = rng.normal(size=p.shape).astype(np.float32)
-    out = np.zeros((p.shape[0], 8), np.float32)
-    out[:, 0:3] = p; out[:, 3] = 0.0005; out[:, 4:7] = d; out[:, 7] = -1.0
-    return out
+    return surface_rays(rays, t, seed)[:n]
 
 
 def report(name, got, ref):
