@@ -392,3 +392,62 @@ def test_reference_test_scenes_primary_and_surface_rays(built, path):
             helpers.check_closest_parity(helpers.prim_signed(h["prim"]), h["t"], h["u"], h["v"], rr, min_agree=0.97)  # shared box edges tie
             assert np.array_equal((s.trace_shadow(rays) != rt.MISS).astype(np.uint8), ref.trace_shadow(rays, threads=NCPU)["shadowed"]), what
     s.close()
+
+
+def _adversarial_scenes():
+    out = {}
+    x, i, f = scenes.objects(20000, n_spheres=10, seed=41)
+    out["far_from_origin"] = ((x + np.array([1000.0, 2000.0, -500.0], np.float32)).astype(np.float32), i, f)  # coarse float grid: 6e-5 ulps
+    x, i, f = scenes.cube_grid(5)
+    out["cube_grid_far"] = ((x + np.array([300.0, 300.0, 300.0], np.float32)).astype(np.float32), i, f)         # thin slabs AND coarse t
+    x, i, f = scenes.heightfield(60)
+    flat = x.copy(); flat[:, 2] = 0.25
+    out["flat_with_duplicates"] = (np.concatenate([flat, flat]), np.concatenate([i, i + np.uint32(np.where(i == scenes.TRI, 0, flat.shape[0]))]).astype(np.uint32),
+                                   np.concatenate([f, f]))                                                        # zero-extent bound on z, every face twice
+    rng = np.random.default_rng(43)
+    n = 4000
+    a = rng.random((n, 3), dtype=np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    e = rng.normal(size=(n, 3)).astype(np.float32) * 1e-4
+    sl = np.stack([a - d, a + d, a + e], axis=1).reshape(-1, 3).astype(np.float32)                                # needle triangles crossing the whole scene
+    x, i, f = scenes.soup(20000, seed=44)
+    si = np.concatenate([np.arange(3 * n, dtype=np.uint32).reshape(n, 3) + np.uint32(x.shape[0]), np.full((n, 1), scenes.TRI, np.uint32)], axis=1)
+    out["needles_in_soup"] = (np.concatenate([x, sl]), np.concatenate([i, si]), np.concatenate([f, np.full(n, 3, np.uint8)]))
+    return out
+
+
+@pytest.mark.parametrize("name", ["far_from_origin", "cube_grid_far", "flat_with_duplicates", "needles_in_soup"])
+def test_adversarial_scenes(built, name):
+    """Geometry chosen to break a t-interval kd traversal: coordinates far from the origin (coarse float grid, slabs below the
+    resolution of t), a flat scene (zero-extent tree bound on one axis) with every face duplicated (exact ties everywhere),
+    needle triangles that cross the whole scene (referenced by thousands of leaves).  Primary and on-surface rays against the oracle."""
+    xyz, idx, flags = _adversarial_scenes()[name]
+    s = make_scene(xyz, idx, flags)
+    o = kdo.Oracle(xyz, idx, flags)
+    assert np.array_equal(s.bound(), o.bound())
+    b = s.bound().astype(np.float64)
+    ext = np.maximum(b[3:] - b[:3], 1e-3)
+    primary = scenes.rays_incoherent(300000, seed=51, lo=b[:3] - 0.3 * ext, hi=b[3:] + 0.3 * ext)
+    r1 = o.trace_closest(primary, threads=NCPU)
+    surface = helpers.surface_rays(primary, r1["t"], seed=52, tmin=0.0005 * float(np.linalg.norm(ext)))
+    floor = 0.45 if name == "flat_with_duplicates" else 0.9999  # duplicates: either copy may win
+    for rays, rr in ((primary, r1), (surface, o.trace_closest(surface, threads=NCPU))):
+        h = s.trace_closest(rays)
+        shadow_differs = (s.trace_shadow(rays) != rt.MISS).astype(np.uint8) != o.trace_shadow(rays, threads=NCPU)["shadowed"]
+        if name == "cube_grid_far":
+            # At coordinates of 300 (ulp 3e-5) with faces planar up to one ulp, the REFERENCE traversal itself stops being
+            # tree-independent: run over two valid trees (the oracle's and libb200rt's) it disagrees on ~2 rays in 100 000 that
+            # graze cube edges -- hit/miss included (measured on the CPU, no GPU involved).  Those are neither ties nor
+            # errors of either tree; the bar here is the north-star's 99.99 % without the tie classification.
+            prim = helpers.prim_signed(h["prim"])
+            same = prim == rr["prim"]
+            rel = np.abs(h["t"] - rr["t"]) / np.maximum(np.abs(rr["t"]), 1e-30)
+            non_tie = (~same) & ((rel > 1e-5) | ((prim >= 0) != (rr["prim"] >= 0)))
+            assert np.array_equal(h["t"][same], rr["t"][same])
+            assert non_tie.mean() <= 1e-4 and shadow_differs.mean() <= 1e-4, (int(non_tie.sum()), int(shadow_differs.sum()))
+            assert same.mean() >= 0.97
+            continue
+        helpers.check_closest_parity(helpers.prim_signed(h["prim"]), h["t"], h["u"], h["v"], rr, min_agree=floor)
+        assert not shadow_differs.any()
+    s.close()
