@@ -18,6 +18,7 @@
 #include "param/param.h"
 #include "render/render_control.h"
 #include <limits>
+#include <memory>
 
 namespace yafaray {
 
@@ -135,7 +136,8 @@ AcceleratorB200::AcceleratorB200(Logger &logger, ParamResult &param_result, cons
 	// faces gathered so far go to the library before a sphere does, so that face ids follow the primitive order
 	// diagnostic (B200_DUMP_SCENE=<file>): the flattened geometry as libb200rt receives it -- per add_mesh call one record
 	// {uint64 n_verts, uint64 n_faces, float xyz[3 n_verts], uint32 idx[4 n_faces], uint8 flags[n_faces]}; read by tests/tools/dump_compare.py
-	std::FILE *dump{std::getenv("B200_DUMP_SCENE") ? std::fopen(std::getenv("B200_DUMP_SCENE"), "wb") : nullptr};
+	const std::unique_ptr<std::FILE, int (*)(std::FILE *)> dump_file{std::getenv("B200_DUMP_SCENE") ? std::fopen(std::getenv("B200_DUMP_SCENE"), "wb") : nullptr, &std::fclose};
+	std::FILE *const dump{dump_file.get()};
 	const auto flush_mesh{[&]() {
 		if(dump && !flags.empty())
 		{
@@ -233,7 +235,7 @@ AcceleratorB200::AcceleratorB200(Logger &logger, ParamResult &param_result, cons
 	}
 	if(verify_extraction) logger_.logInfo(getClassName(), ": extraction check: ", verify_tests, " test rays, ", verify_hits, " hits, ", verify_mismatches, " differ from Primitive::intersect");
 	flush_mesh();
-	if(dump) std::fclose(dump);
+	if(dump) std::fflush(dump);
 	if(rc == B200RT_OK) rc = b200rt_build(scene);
 	float bound[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 	if(rc == B200RT_OK) rc = b200rt_get_bound(scene, bound);
