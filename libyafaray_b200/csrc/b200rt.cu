@@ -14,6 +14,8 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <system_error>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -149,6 +151,34 @@ int ensureLane(Lane &l, size_t in_bytes, size_t out_bytes, bool need_h_in, bool 
 	return B200RT_OK;
 }
 
+// Staging copy between a caller's pageable buffer and a pinned lane buffer.  One thread moves ~10 GB/s, a fifth of what the
+// copy engine then needs; chunks of 4 MiB and more are split over a few short-lived threads (the caller's thread takes a share).
+// Measured (tools/e2e_pageable.py, profiles/r2i_pageable.jsonl): 213 Mrays/s with the caller's thread alone, 549 with 5 helpers;
+// pinned buffers (b200rt_host_alloc) remain the fast path at 1570 Mrays/s.
+void stagingCopy(void *dst, const void *src, size_t bytes)
+{
+	constexpr size_t kSplitAbove = size_t(4) << 20;
+	static const unsigned helpers = [] {
+		const char *e = std::getenv("B200RT_STAGING_HELPERS"); // tuning aid (tools/e2e_pageable.py), read once
+		if(e) return unsigned(std::min(7L, std::max(0L, std::atol(e))));
+		return std::min(5u, std::max(1u, std::thread::hardware_concurrency() / 2) - 1u);
+	}();
+	if(bytes < kSplitAbove || helpers == 0u) { std::memcpy(dst, src, bytes); return; }
+	const size_t parts = helpers + 1u, share = ((bytes / parts) + 4095) & ~size_t(4095);
+	std::thread workers[7];
+	unsigned started = 0;
+	for(; started < helpers; ++started)
+	{
+		const size_t begin = (started + 1u) * share;
+		if(begin >= bytes) break;
+		const size_t count = std::min(share, bytes - begin);
+		try { workers[started] = std::thread([=]() { std::memcpy(static_cast<char *>(dst) + begin, static_cast<const char *>(src) + begin, count); }); }
+		catch(const std::system_error &) { std::memcpy(static_cast<char *>(dst) + begin, static_cast<const char *>(src) + begin, bytes - begin); break; }
+	}
+	std::memcpy(dst, src, std::min(share, bytes));
+	for(unsigned k = 0; k < started; ++k) if(workers[k].joinable()) workers[k].join();
+}
+
 bool isPinned(const void *p)
 {
 	cudaPointerAttributes a;
@@ -241,7 +271,7 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, La
 	auto drain = [&](Lane &l) -> int {
 		if(!l.pending_dst) return B200RT_OK;
 		CUDA_TRY(cudaEventSynchronize(l.done));
-		if(!l.pending_direct) std::memcpy(l.pending_dst, l.h_out, l.pending_bytes);
+		if(!l.pending_direct) stagingCopy(l.pending_dst, l.h_out, l.pending_bytes);
 		l.pending_dst = nullptr;
 		return B200RT_OK;
 	};
@@ -260,7 +290,7 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, La
 		if(rc != B200RT_OK) break;
 		const size_t begin = c * chunk, count = std::min(chunk, n - begin);
 		const void *src = rays + begin;
-		if(!in_pinned) { std::memcpy(l.h_in, src, count * sizeof(b200rt_ray)); src = l.h_in; }
+		if(!in_pinned) { stagingCopy(l.h_in, src, count * sizeof(b200rt_ray)); src = l.h_in; }
 		cudaError_t e = cudaMemcpyAsync(l.d_in, src, count * sizeof(b200rt_ray), cudaMemcpyHostToDevice, l.stream);
 		if(e == cudaSuccess)
 		{
