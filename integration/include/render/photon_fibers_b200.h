@@ -36,6 +36,7 @@ class PhotonWorkers final
 		PhotonWorkers(const Accelerator *accelerator, int &num_threads, int n_photons) : num_threads_{num_threads}, os_threads_{std::max(1, num_threads)}
 		{
 			b200_ = dynamic_cast<const AcceleratorB200 *>(accelerator);
+			if(b200_) b200_->refreshFaceFlags(); //materials may have been replaced since the accelerator was built
 			if(b200_ && b200_->wavefrontFibers() > 0)
 			{
 				const int per_thread{std::clamp(n_photons / (os_threads_ * kMinPhotonsPerWorker), 1, b200_->wavefrontFibers())};

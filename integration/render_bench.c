@@ -16,6 +16,9 @@
  *     instances=n       n static instances (rotation about z + translation) of one box standing on the field; every third one
  *                       is an instance OF THE PREVIOUS INSTANCE (nested, include/geometry/primitive/primitive_instance.h:88-91)
  *     spheres=n         n objects of type "sphere" (SpherePrimitive) resting on / floating above the field
+ *     rerender_hidden=1 after the render, replace the material of the boxes by an INVISIBLE one (no object is touched, so the scene keeps
+ *                       its accelerator, src/scene/scene.cc:318) and render again into the same outputs: what the files hold is the
+ *                       second frame -- the boxes and their shadows must be gone (AcceleratorB200::refreshFaceFlags)
  *     film_save=prefix  write the film's weighted sums as "<prefix> - node 0000.film" when the render ends (the reference's own
  *                       film_load_save_mode=save, src/render/imagefilm.cc:1099-1176); libyafaray_b200/film.py sums such films
  */
@@ -205,7 +208,7 @@ int main(int argc, char **argv)
 		memcpy(key, argv[a], (size_t) (eq - argv[a]));
 		key[eq - argv[a]] = 0;
 		if(strcmp(key, "film_save") == 0) { film_save = eq + 1; continue; }
-		if(strcmp(key, "instances") == 0 || strcmp(key, "spheres") == 0) continue; /* handled with the geometry above */
+		if(strcmp(key, "instances") == 0 || strcmp(key, "spheres") == 0 || strcmp(key, "rerender_hidden") == 0) continue; /* handled elsewhere */
 		if(strcmp(key, "tile_shard") == 0)
 		{
 			int shard_index = 0, shard_count = 1;
@@ -293,7 +296,24 @@ int main(int argc, char **argv)
 	yafaray_preprocessSurfaceIntegrator(render_monitor, surface_integrator, render_control, scene);
 	const double t_render0 = now();
 	yafaray_render(render_control, render_monitor, surface_integrator, film);
-	const double t_render1 = now();
+	double t_render1 = now();
+	int rerender_hidden = 0;
+	for(int a = 9; a < argc; ++a) if(strncmp(argv[a], "rerender_hidden=", 16) == 0) rerender_hidden = atoi(argv[a] + 16);
+	if(rerender_hidden)
+	{
+		yafaray_clearParamMap(pm);
+		yafaray_setParamMapColor(pm, "color", 0.3f, 0.45f, 0.8f, 1.f);
+		yafaray_setParamMapFloat(pm, "diffuse_reflect", 0.9f);
+		yafaray_setParamMapString(pm, "visibility", "invisible");
+		yafaray_setParamMapString(pm, "type", "shinydiffusemat");
+		yafaray_createMaterial(scene, &material_id, "boxes", pm, pml); /* same name: replaces the material the faces refer to */
+		flags = yafaray_checkAndClearSceneModifiedFlags(scene);
+		yafaray_preprocessScene(scene, render_control, flags);
+		yafaray_preprocessSurfaceIntegrator(render_monitor, surface_integrator, render_control, scene);
+		yafaray_setRenderControlForNormalStart(render_control);
+		yafaray_render(render_control, render_monitor, surface_integrator, film);
+		t_render1 = now();
+	}
 	printf("RENDER_BENCH {\"accelerator\": \"%s\", \"integrator\": \"%s\", \"triangles\": %d, \"width\": %d, \"height\": %d, \"aa_samples\": %d, \"threads\": %d, "
 	       "\"scene_seconds\": %.3f, \"preprocess_seconds\": %.3f, \"render_seconds\": %.3f}\n",
 	       accel, integrator, 2 * cells * cells + 72 + (n_instances > 0 ? 6 * (n_instances + 1) : 0) + n_spheres, width, height, aa_samples, threads, t_built - t_scene, t_pre - t_built, t_render1 - t_render0);

@@ -191,6 +191,7 @@ AcceleratorB200::AcceleratorB200(Logger &logger, ParamResult &param_result, cons
 			{
 				const float center_radius[4]{center[Axis::X], center[Axis::Y], center[Axis::Z], radius};
 				const uint8_t sphere_flags{faceFlags(primitive)};
+				face_flags_.push_back(sphere_flags);
 				rc = b200rt_add_spheres(scene, center_radius, 1, &sphere_flags);
 			}
 			continue;
@@ -211,6 +212,7 @@ AcceleratorB200::AcceleratorB200(Logger &logger, ParamResult &param_result, cons
 		}
 		for(int v = 0; v < 4; ++v) idx.push_back(v < n_vertices ? first_vertex + static_cast<uint32_t>(v) : 0xFFFFFFFFu);
 		flags.push_back(faceFlags(primitive));
+		face_flags_.push_back(flags.back());
 		if(verify_extraction)
 		{
 			// diagnostic (B200_VERIFY_EXTRACTION=1): the vertices just extracted, tested with the reference's own polygon code, must
@@ -344,6 +346,21 @@ void AcceleratorB200::releaseRayQueue(std::unique_ptr<b200::RayQueue> queue) con
 	queue->resetStats();
 	std::lock_guard<std::mutex> lock(queues_mutex_);
 	idle_queues_.push_back(std::move(queue));
+}
+
+void AcceleratorB200::refreshFaceFlags() const
+{
+	if(!scene_ || face_flags_.size() != primitives_.size()) return;
+	std::lock_guard<std::mutex> lock(queues_mutex_);
+	size_t changed{0};
+	for(size_t i = 0; i < primitives_.size(); ++i)
+	{
+		const uint8_t flags{faceFlags(primitives_[i])};
+		if(flags != face_flags_[i]) { face_flags_[i] = flags; ++changed; }
+	}
+	if(changed == 0) return;
+	if(b200rt_update_face_flags(scene_, face_flags_.data(), face_flags_.size()) != B200RT_OK) logger_.logError(getClassName(), ": b200rt_update_face_flags failed: ", b200rt_last_error());
+	else logger_.logInfo(getClassName(), ": visibility / transparency of ", changed, " primitives changed since the build; flags updated on the device");
 }
 
 // ---- wavefront statistics ---------------------------------------------------------------------------------

@@ -257,3 +257,25 @@ def test_patched_photon_launch_sites_keep_the_reference_behaviour_on_cpu(tmp_pat
     assert shots and all(int(t) == 3 for _, t in shots), shots
     img = film.normalized(film.read_film(film.film_path(prefix)))
     assert float(img[..., :3].mean()) > 0.01 and (film.read_film(film.film_path(prefix)).weights > 0).all()
+
+
+@pytest.mark.gpu
+@needs_render_bench
+def test_replaced_material_is_seen_without_a_rebuild(tmp_path):
+    """the reference reads visibility LIVE at every hit, the GPU scene bakes it per face, and the scene keeps
+    its accelerator when only a material is replaced (src/scene/scene.cc:318).  render_bench renders, replaces the boxes'
+    material by an invisible one and renders again: AcceleratorB200::refreshFaceFlags must patch the flags on the device, so the
+    second frame has neither boxes nor their shadows -- exactly like the stock kd-tree's second frame."""
+    stock = _render_film(tmp_path, "stock", "directlighting", "0/1", size=(240, 150), extra=("rerender_hidden=1",))
+    prefix = str(tmp_path / "b200")
+    cmd = [RENDER_BENCH, "b200-kdtree", "directlighting", "48", "240", "150", "2", prefix + ".tga", "2", "film_save=" + prefix, "rerender_hidden=1"]
+    p = subprocess.run(cmd, cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, errors="replace", timeout=600)
+    assert p.returncode == 0 and "no usable accelerator" not in p.stdout, p.stdout[-2000:]
+    assert "flags updated on the device" in p.stdout, "the adaptor did not notice the replaced material"
+    assert p.stdout.count("AcceleratorB200: Starting build") == 1, "the accelerator was rebuilt: the test no longer exercises the flag update"
+    b200 = film.read_film(film.film_path(prefix))
+    visible = _render_film(tmp_path, "visible", "directlighting", "0/1", size=(240, 150))
+    assert film.psnr(film.normalized(stock), film.normalized(visible)) < 30.0, "hiding the boxes changes nothing in this view"
+    value = film.psnr(film.normalized(b200), film.normalized(stock))
+    print(f"second frame after the material was replaced: b200 vs stock {value:.1f} dB")
+    assert value > 50.0
