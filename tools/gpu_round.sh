@@ -1,10 +1,11 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, both bench arms, the ncu launch list of the bench command and one full
+# One GPU-box visit: smoke(), parity tests, both bench arms, the ncu launch list of the bench command and one full
 # ncu capture of the closest + shadow kernels.  Outputs under gpurun_out/ (summaries are copied to profiles/).
 #   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh <tag>'
 tag=${1:-run}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_smi.txt 2>&1
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; tail -1 gpurun_out/${tag}_smoke.log
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${tag}_pytest.log
 tail -3 gpurun_out/${tag}_pytest.log
 timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -c 3000 gpurun_out/${tag}_bench.json
