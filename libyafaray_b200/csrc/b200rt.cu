@@ -50,6 +50,7 @@ int lanesPerCall()
 	static const int value = [] { const char *e = std::getenv("B200RT_LANES"); const long n = e ? std::atol(e) : 0; return int(n > 0 && n <= 16 ? n : 6); }();
 	return value;
 }
+constexpr size_t kSmallBatchRays = 256;           // unpinned batches up to this size go through a pinned lane buffer, one cursor-less launch
 constexpr size_t kDirectRays = size_t(1) << 16;  // pinned batches up to this size are traced in place (no staging copies)
 
 // One staging lane: a stream with pinned host and device buffers for rays in / results out.
@@ -222,7 +223,7 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, La
 		s->free_lanes.push_back(std::move(lane));
 		return rc;
 	}
-	if(n <= size_t(b200rt::kPoolRays))
+	if(n <= kSmallBatchRays)
 	{
 		// Small batches (the per-ray compatibility path of the Accelerator virtuals): no staging copies at all.  The
 		// kernel reads the rays from, and writes the results to, pinned host memory (device-addressable under UVA), as
@@ -233,7 +234,7 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, La
 			if(!s->free_lanes.empty()) { lane = std::move(s->free_lanes.back()); s->free_lanes.pop_back(); }
 		}
 		if(!lane) lane = std::make_unique<Lane>();
-		int rc = ensureLane(*lane, b200rt::kPoolRays * sizeof(b200rt_ray), b200rt::kPoolRays * sizeof(Out), true, true);
+		int rc = ensureLane(*lane, kSmallBatchRays * sizeof(b200rt_ray), kSmallBatchRays * sizeof(Out), true, true);
 		if(rc == B200RT_OK)
 		{
 			std::memcpy(lane->h_in, rays, n * sizeof(b200rt_ray));

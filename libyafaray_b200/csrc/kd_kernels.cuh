@@ -225,7 +225,10 @@ __device__ __forceinline__ float sphereIntersect(const float4 q0, float radius, 
 #endif
 
 static constexpr int kBlock = B200RT_BLOCK;
-static constexpr int kPoolRays = 256;               // rays taken from the global cursor per atomicAdd
+#ifndef B200RT_POOL
+#define B200RT_POOL 256
+#endif
+static constexpr int kPoolRays = B200RT_POOL;       // rays taken from the global cursor per atomicAdd
 static constexpr int kRefill = B200RT_REFILL;       // idle lanes that trigger a refill
 static constexpr int kLeafBatch = B200RT_LEAF_BATCH; // lanes holding a leaf that trigger the leaf phase
 static constexpr int kUnroll = B200RT_UNROLL;       // unroll factor of the descent loop
