@@ -264,7 +264,8 @@ def test_build_parameters_do_not_change_hits(built):
 
 def test_restart_path_with_tiny_stack(built):
     """libb200rt_stack2.so is the same source built with a 2-entry short stack: nearly every ray overflows the ring
-    and takes the kd-restart path.  Results must be byte-identical to the regular build's."""
+    and replays its descent (the exact kd-restart of kd_kernels.cuh), on a mixed scene and on the thin-slab cube grid.  Results must
+    be byte-identical to the regular build's -- face ids included, i.e. the replay preserves the visiting order."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -279,7 +280,11 @@ def test_restart_path_with_tiny_stack(built):
         "c, sh = helpers.ray_zoo(s.bound(), n=300000, seed=17)\n"
         "h = hashlib.md5()\n"
         "h.update(s.trace_closest(c).tobytes()); h.update((s.trace_shadow(sh) != rt.MISS).tobytes())\n"
-        "h.update(s.trace_tshadow(sh, 2)['shadowed'].tobytes()); print(h.hexdigest())\n" % root)
+        "h.update(s.trace_tshadow(sh, 2)['shadowed'].tobytes())\n"
+        "xyz, idx, fl = scenes.cube_grid(9)\n"  # 1-ulp slabs: zero-length intervals meet the replay
+        "s2 = rt.Scene(0); s2.add_mesh(xyz, idx, fl); s2.build()\n"
+        "c, sh = helpers.ray_zoo(s2.bound(), n=300000, seed=18, edge_cases=False)\n"
+        "h.update(s2.trace_closest(c).tobytes()); h.update((s2.trace_shadow(sh) != rt.MISS).tobytes()); print(h.hexdigest())\n" % root)
     digests = []
     for lib in ("", stress):
         env = dict(os.environ)
