@@ -117,3 +117,17 @@ def test_b200_accelerator_fails_loudly_without_a_device(built):
     with tempfile.TemporaryDirectory() as d:
         log = render(os.path.join(BUILD, "yafaray_test01"), d, "b200-kdtree", {"B200_AA_PASSES": "1", "B200_DETERMINISTIC": "1"})
         assert "libb200rt failed" in log and "no usable accelerator" in log
+
+
+@needs_build("yafaray_test02")
+def test_accelerator_type_and_parameters_are_exported_with_the_scene(built):
+    """SURVEY.md 8a row F: the reference's tests/test02 client exports its scene as XML (inherited Accelerator::exportToString,
+    include/accelerator/accelerator.h:171-179); with the b200-kdtree type selected the <accelerator> element carries the new type
+    name and the non-default parameters, so a saved scene selects the GPU path again.  Needs no GPU (the export happens anyway)."""
+    with tempfile.TemporaryDirectory() as d:
+        render(os.path.join(BUILD, "yafaray_test02"), d, "b200-kdtree", {"B200_AA_PASSES": "1", "B200_DETERMINISTIC": "1", "B200_WAVEFRONT_FIBERS": "256"})
+        xml = open(os.path.join(d, "test02-output.xml")).read()
+    block = xml[xml.index("<accelerator>"):xml.index("</accelerator>")]
+    assert '<type sval="b200-kdtree"/>' in block
+    assert '<wavefront_fibers ival="256"/>' in block
+    assert "yafaray-kdtree" not in block
