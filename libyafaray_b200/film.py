@@ -155,3 +155,22 @@ def psnr(a: np.ndarray, b: np.ndarray, peak: float = 1.0) -> float:
     b = np.clip(np.asarray(b, dtype=np.float64), 0.0, peak)
     mse = float(np.mean((a - b) ** 2))
     return float("inf") if mse == 0.0 else 10.0 * np.log10(peak * peak / mse)
+
+
+def write_tga(path: str, film: Film, layer: int = 0, srgb: bool = True) -> None:
+    """The normalised layer as an uncompressed 32-bit TGA (bottom-up BGRA, the container the reference's built-in TGA output
+    writes).  srgb=True applies the sRGB transfer curve to the colour channels; the reference's own colour-space and badge
+    handling (src/image/image_output.cc) is NOT reproduced -- load the summed .film into a stock libYafaRay for that."""
+    img = np.clip(normalized(film, layer), 0.0, 1.0).astype(np.float64)
+    rgb = img[..., :3]
+    if srgb:
+        rgb = np.where(rgb <= 0.0031308, 12.92 * rgb, 1.055 * np.power(np.maximum(rgb, 1e-12), 1.0 / 2.4) - 0.055)
+    out = np.empty((film.height, film.width, 4), dtype=np.uint8)
+    out[..., 0] = np.round(rgb[..., 2] * 255.0)
+    out[..., 1] = np.round(rgb[..., 1] * 255.0)
+    out[..., 2] = np.round(rgb[..., 0] * 255.0)
+    out[..., 3] = np.round(img[..., 3] * 255.0)
+    header = struct.pack("<BBBHHBHHHHBB", 0, 0, 2, 0, 0, 0, 0, 0, film.width, film.height, 32, 8)
+    with open(path, "wb") as f:
+        f.write(header)
+        f.write(np.ascontiguousarray(out[::-1]).tobytes())  # film rows run top to bottom, TGA's default origin is bottom left

@@ -74,6 +74,19 @@ def test_sum_and_normalise_follow_the_reference_merge():
     assert film.psnr(img, img) == float("inf")
 
 
+def test_tga_writer_round_trips_through_the_test_suite_reader(tmp_path):
+    from tests.test_render import read_tga
+    f = film.Film(5, 3, np.ones((3, 5), np.float32), np.zeros((1, 3, 5, 4), np.float32))
+    f.layers[0, 0, 0] = [1.0, 0.0, 0.0, 1.0]     # top-left pixel red
+    f.layers[0, 2, 4] = [0.0, 0.0, 0.5, 1.0]     # bottom-right pixel half blue (linear)
+    p = str(tmp_path / "x.tga")
+    film.write_tga(p, f)
+    img = read_tga(p)                             # rows as stored: bottom-up, BGRA
+    assert img.shape == (3, 5, 4)
+    assert img[2, 0].tolist() == [0.0, 0.0, 255.0, 255.0]
+    assert img[0, 4, 0] == 188.0 and img[0, 4, 3] == 255.0   # sRGB(0.5) = 0.7354 -> 188
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

@@ -63,6 +63,7 @@ def main():
     ap.add_argument("--compare", action="store_true", help="rank 0 also renders every tile in one process and reports the PSNR")
     ap.add_argument("--extra", default="", help="extra render_bench arguments, e.g. 'wavefront_fibers=1024 i:bounces=5'")
     ap.add_argument("--save", default="", help="rank 0 writes the summed film here (the reference's .film format)")
+    ap.add_argument("--image", default="", help="rank 0 writes the normalised first layer here as a 32-bit TGA (sRGB)")
     args = ap.parse_args()
 
     import numpy as np
@@ -111,6 +112,8 @@ def main():
                     "shard_pixels_with_weight_sum": int(count[1])}
             if args.save:
                 film.write_film(args.save, total)
+            if args.image:
+                film.write_tga(args.image, total)
             if args.compare:
                 single_extra = ["tile_shard=0/1"] + ([f"device={local}"] if args.accelerator == "b200-kdtree" else [])
                 rec1, rays1, single = render(args, d, "single", args.threads or (os.cpu_count() or 1), single_extra)
