@@ -2,7 +2,7 @@
 """Kernel timing + parity sample in the regimes bench.py does not cover (tuning / DESIGN.md evidence; bench.py is the
 judged number): the HBM-resident 10 M-triangle scene of BASELINE.json configs[3], S1M-obj and S1M-soup.
 
-    python tools/regime_bench.py --scene obj --tris 10000000 [--rays 16777216] [--check 200000]
+    python tests/tools/regime_bench.py --scene obj --tris 10000000 [--rays 16777216] [--check 200000]
 
 Parity sample: the first --check rays are also traced by the oracle's C restatement ON THE TREE libb200rt's host
 builder produced (exported through b200rt_host_tree_*), so a 10 M-triangle check needs no second build."""
