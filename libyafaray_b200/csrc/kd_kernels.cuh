@@ -378,6 +378,18 @@ static_assert((kShortStack & (kShortStack - 1)) == 0, "ring size must be a power
 static constexpr int kRingStride = kBlock * int(sizeof(uint2));        // bytes between two entries of one thread's ring
 static constexpr int kRingMask = (kShortStack - 1) * kRingStride;
 
+// The largest float below x (x finite).  Used for the traversal copy of the ray origin on axes where the direction is exactly
+// zero: such a ray never crosses a plane of that axis, it lies on one side of it or IN it, and for "in it" the reference takes
+// the left child only (entry[axis] <= split and exit[axis] <= split, accelerator_kdtree_common.h:148-174).  With the origin
+// one ulp lower, (split - o) * FLT_MAX is +huge for o <= split (near = left only) and <= 0 for o > split (right), the same
+// choice -- measured on the thin-slab cube grid, 18 % of the reference's hits on in-plane rays lay in leaves the unshifted
+// rule did not open.  The leaf tests use the true origin.
+__device__ __forceinline__ float floatBelow(float x)
+{
+	const int bits = __float_as_int(x);
+	return (x > 0.f) ? __int_as_float(bits - 1) : ((x < 0.f) ? __int_as_float(bits + 1) : -1.401298464e-45f);
+}
+
 __device__ __forceinline__ float selectf(bool p, float a, float b)
 {
 	float r;
@@ -530,9 +542,9 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					floor = 0;
 					alive = setupRay<QUERY>(s, a, b, r, tree_space);
 #if B200RT_SMEM_RAY
-					sh_axis[0][tid] = make_float2(r.ox, r.ix);
-					sh_axis[1][tid] = make_float2(r.oy, r.iy);
-					sh_axis[2][tid] = make_float2(r.oz, r.iz);
+					sh_axis[0][tid] = make_float2((r.dx == 0.f) ? floatBelow(r.ox) : r.ox, r.ix);
+					sh_axis[1][tid] = make_float2((r.dy == 0.f) ? floatBelow(r.oy) : r.oy, r.iy);
+					sh_axis[2][tid] = make_float2((r.dz == 0.f) ? floatBelow(r.oz) : r.oz, r.iz);
 					sh_axis[3][tid] = make_float2(r.seg_lo, r.seg_hi); // where the ray enters and leaves the tree bound (replayTo); row 3 is also what a leaf's "axis" reads, unused there
 #endif
 					if(!alive) writeResult<QUERY>(out, r, false, ts); // missed the tree bound

@@ -456,3 +456,31 @@ def test_adversarial_scenes(built, name):
         helpers.check_closest_parity(helpers.prim_signed(h["prim"]), h["t"], h["u"], h["v"], rr, min_agree=floor)
         assert not shadow_differs.any()
     s.close()
+
+
+def test_rays_lying_in_split_planes(built):
+    """Rays whose direction component is exactly zero and whose origin lies exactly on a kd split plane (axis-parallel light
+    and camera rays in axis-aligned scenes): the kernel must give what the REFERENCE TRAVERSAL gives on the same tree
+    (exported host tree -> oracle), hit/miss included.  Against another valid tree even the reference differs on such rays."""
+    xyz, idx, flags = scenes.cube_grid(7)
+    tree = rt.host_tree(xyz, idx)
+    a, b = tree["a"], tree["b"]
+    split = a.view(np.float32)
+    interior = np.nonzero((b & 3) != 3)[0]
+    rng = np.random.default_rng(2)
+    lo, ext = tree["bound"][:3], tree["bound"][3:] - tree["bound"][:3]
+    rays = np.zeros((20000, 8), np.float32)
+    for k, node in enumerate(rng.choice(interior, size=rays.shape[0])):
+        axis = int(b[node]) & 3
+        o = (lo - 0.3 * ext + rng.random(3).astype(np.float32) * 1.6 * ext).astype(np.float32)
+        d = rng.normal(size=3).astype(np.float32)
+        o[axis], d[axis] = split[node], 0.0
+        rays[k] = [o[0], o[1], o[2], 0.0, d[0], d[1], d[2], -1.0]
+    s = make_scene(xyz, idx, flags)
+    same_tree = kdo.Oracle(xyz, idx, flags, tree=helpers.host_tree_as_oracle_tree(tree), bound=tree["bound"])
+    ref = same_tree.trace_closest(rays, threads=NCPU)
+    h = s.trace_closest(rays)
+    assert (ref["prim"] >= 0).mean() > 0.2
+    helpers.check_closest_parity(helpers.prim_signed(h["prim"]), h["t"], h["u"], h["v"], ref, min_agree=0.97)
+    assert np.array_equal((s.trace_shadow(rays) != rt.MISS).astype(np.uint8), same_tree.trace_shadow(rays, threads=NCPU)["shadowed"])
+    s.close()

@@ -113,6 +113,8 @@ def _visited_faces(tree, ray, strict):
     a, b, refs, bound = tree["a"], tree["b"], tree["refs"], tree["bound"]
     split = a.view(np.float32)
     o, d = ray[0:3].astype(np.float32), ray[4:7].astype(np.float32)
+    if strict:  # the kernel's traversal copy of the origin: one ulp lower where the direction component is exactly zero
+        o = np.where(d == 0, np.nextafter(o, np.float32(-np.inf)), o).astype(np.float32)
     with np.errstate(all="ignore"):
         inv = np.where(d == 0, np.float32(3.4e38), np.float32(1) / np.where(d == 0, np.float32(1), d)).astype(np.float32)
         t0, t1 = (bound[:3] - o) * inv, (bound[3:] - o) * inv
@@ -153,3 +155,27 @@ def test_strict_interval_rule_opens_one_ulp_slabs(built):
     missed_loose = sum(int(ref["prim"][i]) not in _visited_faces(tree, closest[i], False) for i in hit)
     assert missed_strict == 0
     assert missed_loose > 0, "the scene no longer produces the thin slabs this test is about"
+
+
+def test_rays_lying_in_split_planes_take_the_reference_side(built):
+    """A ray whose direction component is exactly zero and whose origin lies exactly on a split plane of that axis: the
+    reference descends into the LEFT child only (accelerator_kdtree_common.h:148-174).  The kernel's rule (origin copy one ulp
+    lower on such axes) must open every leaf in which the reference traversal -- run over the same tree -- finds its hit."""
+    xyz, idx, flags = scenes.cube_grid(5)
+    tree = rt.host_tree(xyz, idx)
+    a, b = tree["a"], tree["b"]
+    split = a.view(np.float32)
+    interior = np.nonzero((b & 3) != 3)[0]
+    rng = np.random.default_rng(1)
+    lo, ext = tree["bound"][:3], tree["bound"][3:] - tree["bound"][:3]
+    rays = np.zeros((1200, 8), np.float32)
+    for k, node in enumerate(rng.choice(interior, size=rays.shape[0])):
+        axis = int(b[node]) & 3
+        o = (lo - 0.3 * ext + rng.random(3).astype(np.float32) * 1.6 * ext).astype(np.float32)
+        d = rng.normal(size=3).astype(np.float32)
+        o[axis], d[axis] = split[node], 0.0
+        rays[k] = [o[0], o[1], o[2], 0.0, d[0], d[1], d[2], -1.0]
+    same_tree = kdo.Oracle(xyz, idx, flags, tree=helpers.host_tree_as_oracle_tree(tree), bound=tree["bound"]).trace_closest(rays, threads=4)
+    hit = np.nonzero(same_tree["prim"] >= 0)[0]
+    assert len(hit) > 300
+    assert sum(int(same_tree["prim"][i]) not in _visited_faces(tree, rays[i], True) for i in hit) == 0
