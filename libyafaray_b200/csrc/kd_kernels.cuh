@@ -542,9 +542,16 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					floor = 0;
 					alive = setupRay<QUERY>(s, a, b, r, tree_space);
 #if B200RT_SMEM_RAY
-					sh_axis[0][tid] = make_float2((r.dx == 0.f) ? floatBelow(r.ox) : r.ox, r.ix);
-					sh_axis[1][tid] = make_float2((r.dy == 0.f) ? floatBelow(r.oy) : r.oy, r.iy);
-					sh_axis[2][tid] = make_float2((r.dz == 0.f) ? floatBelow(r.oz) : r.oz, r.iz);
+					sh_axis[0][tid] = make_float2(r.ox, r.ix);
+					sh_axis[1][tid] = make_float2(r.oy, r.iy);
+					sh_axis[2][tid] = make_float2(r.oz, r.iz);
+					if(__builtin_expect(r.dx == 0.f || r.dy == 0.f || r.dz == 0.f, 0))
+					{
+						// axis-parallel ray: traversal copy of the origin one ulp lower on the zero-direction axes (floatBelow)
+						if(r.dx == 0.f) sh_axis[0][tid].x = floatBelow(r.ox);
+						if(r.dy == 0.f) sh_axis[1][tid].x = floatBelow(r.oy);
+						if(r.dz == 0.f) sh_axis[2][tid].x = floatBelow(r.oz);
+					}
 					sh_axis[3][tid] = make_float2(r.seg_lo, r.seg_hi); // where the ray enters and leaves the tree bound (replayTo); row 3 is also what a leaf's "axis" reads, unused there
 #endif
 					if(!alive) writeResult<QUERY>(out, r, false, ts); // missed the tree bound
