@@ -34,8 +34,8 @@ UNIT = "Mrays/s"
 ALGO_BYTES = {"closest": 345.0, "shadow": 230.8}
 SHADOW_TMAX = 0.25
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE closest launch on this workload, from the ncu --set full capture kept
-# under profiles/ (r2a_final_kernels.txt: 1.573 GB read + 0.282 GB written); a constant of the profile, not measured live
-NCU_DRAM_TRAFFIC_BYTES = {"closest": 1.573425e9 + 0.282297e9, "source": "profiles/r2a_final_kernels.txt"}
+# under profiles/ (r2v_final_kernels.txt: 1.588 GB read + 0.292 GB written); a constant of the profile, not measured live
+NCU_DRAM_TRAFFIC_BYTES = {"closest": 1.587585e9 + 0.292205e9, "source": "profiles/r2v_final_kernels.txt"}
 
 
 def parse():
