@@ -179,3 +179,22 @@ def test_rays_lying_in_split_planes_take_the_reference_side(built):
     hit = np.nonzero(same_tree["prim"] >= 0)[0]
     assert len(hit) > 300
     assert sum(int(same_tree["prim"][i]) not in _visited_faces(tree, rays[i], True) for i in hit) == 0
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(ZOO) if not n.endswith("_flags")])
+def test_kernel_rule_opens_every_leaf_in_which_the_reference_finds_its_hit(built, name):
+    """The kernel's descent rule restated on the CPU (_visited_faces: strict t-interval comparisons, origin copy one ulp lower on
+    zero-direction axes) against the REFERENCE traversal run over the same exported tree: for primary, edge-case and
+    on-surface rays (tmin 0) every leaf that holds the reference's hit must be among the leaves the rule opens."""
+    import warnings
+    xyz, idx, flags = ZOO[name]
+    tree = rt.host_tree(xyz, idx)
+    same_tree = kdo.Oracle(xyz, idx, flags, tree=helpers.host_tree_as_oracle_tree(tree), bound=tree["bound"])
+    closest, _ = helpers.ray_zoo(tree["bound"], n=400, seed=9)
+    surface = helpers.surface_rays(closest, same_tree.trace_closest(closest, threads=4)["t"], seed=10, tmin=0.0)[:600]
+    rays = np.concatenate([closest, surface])
+    ref = same_tree.trace_closest(rays, threads=4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        missed = [int(i) for i in np.nonzero(ref["prim"] >= 0)[0] if int(ref["prim"][i]) not in _visited_faces(tree, rays[i], True)]
+    assert not missed, missed[:10]
