@@ -198,3 +198,88 @@ def test_kernel_rule_opens_every_leaf_in_which_the_reference_finds_its_hit(built
         warnings.simplefilter("ignore")
         missed = [int(i) for i in np.nonzero(ref["prim"] >= 0)[0] if int(ref["prim"][i]) not in _visited_faces(tree, rays[i], True)]
     assert not missed, missed[:10]
+
+
+def _leaf_order(tree, ray, ring_entries=None):
+    """Leaves in the order the kernel's descent opens them.  ring_entries=None: unbounded stack.  Otherwise the kernel's short
+    stack restated: a ring that keeps the newest `ring_entries` - 1 usable entries (pushes are unconditional stores), `floor`
+    marking lost entries, and the exact kd-restart (replayTo in kd_kernels.cuh): replay the descent from the root along the path
+    to the leaf just left -- "target < right" tells the child in depth-first order -- re-postponing the far children, then pop."""
+    a, b, bound = tree["a"], tree["b"], tree["bound"]
+    split = a.view(np.float32)
+    o, d = ray[0:3].astype(np.float32), ray[4:7].astype(np.float32)
+    o = np.where(d == 0, np.nextafter(o, np.float32(-np.inf)), o).astype(np.float32)
+    with np.errstate(all="ignore"):
+        inv = np.where(d == 0, np.float32(3.4e38), np.float32(1) / np.where(d == 0, np.float32(1), d)).astype(np.float32)
+        t0, t1 = (bound[:3] - ray[0:3].astype(np.float32)) * inv, (bound[3:] - ray[0:3].astype(np.float32)) * inv
+        lo, hi = np.float32(max(np.minimum(t0, t1).max(), 0)), np.float32(np.maximum(t0, t1).min())
+    order = []
+    if not lo <= hi:
+        return order
+    t_exit = hi
+    ring, sp, floor = {}, 0, 0   # ring slot -> entry; sp counts pushes minus pops; entries below floor are lost
+
+    def plane(node):
+        axis = int(b[node]) & 3
+        with np.errstate(all="ignore"):
+            t_plane = np.float32((split[node] - o[axis]) * inv[axis])
+        left, right = node + 1, int(b[node]) >> 2
+        return t_plane, ((left, right) if inv[axis] >= 0 else (right, left)), right, inv[axis] < 0
+
+    def push(entry):
+        nonlocal sp, floor
+        if ring_entries is None:
+            ring[sp] = entry
+        else:
+            ring[sp % ring_entries] = entry
+            floor = max(floor, sp + 1 - ring_entries + 1)  # the kernel's speculative store also clobbers one more slot: K - 1 usable
+        sp += 1
+
+    node, seg_lo, seg_hi = 0, lo, hi
+    for _ in range(100000):
+        if (int(b[node]) & 3) != 3:
+            t_plane, (near, far), _, _ = plane(node)
+            if t_plane > seg_hi:
+                node = near
+            elif t_plane < seg_lo:
+                node = far
+            else:
+                push((far, seg_hi)); node = near; seg_hi = t_plane
+            continue
+        order.append(node)
+        if sp > floor:
+            sp -= 1
+            entry = ring[sp if ring_entries is None else sp % ring_entries]
+            node, seg_lo, seg_hi = entry[0], seg_hi, entry[1]
+            continue
+        if floor == 0 or not seg_hi < t_exit:
+            return order
+        # exact kd-restart
+        target, sp, floor, cur, r_hi = node, 0, 0, 0, t_exit
+        while cur != target:
+            t_plane, (near, far), right, negative = plane(cur)
+            if (target < right) != negative:
+                if not t_plane > r_hi:
+                    push((far, r_hi)); r_hi = t_plane
+                cur = near
+            else:
+                cur = far
+        if sp <= floor:
+            return order
+        sp -= 1
+        entry = ring[sp % ring_entries]
+        node, seg_lo, seg_hi = entry[0], r_hi, entry[1]
+    raise AssertionError("the descent did not terminate")
+
+
+@pytest.mark.parametrize("name", ["cube_grid", "objects", "soup"])
+def test_replay_restart_visits_the_same_leaves_in_the_same_order(built, name):
+    """The exact kd-restart, restated: with a ring of 2, 3 or 8 entries the descent must open exactly the leaves, in exactly the
+    order, of the unbounded-stack descent -- and terminate -- also through the zero-length intervals of the thin-slab scene."""
+    xyz, idx, flags = ZOO[name]
+    tree = rt.host_tree(xyz, idx)
+    closest, _ = helpers.ray_zoo(tree["bound"], n=150, seed=12)
+    for ray in closest[::3]:
+        want = _leaf_order(tree, ray)
+        for entries in (2, 3, 8):
+            assert _leaf_order(tree, ray, entries) == want, (name, entries, ray.tolist())
