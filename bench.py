@@ -1,22 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- BASELINE.json's metric: Mrays/s closest-hit + shadow per B200 vs the host-CPU kd-tree.
 
-Workload (BASELINE.json configs[1]): synthetic 1 M-triangle scene (S1M-hf, 999 698 triangles),
-16 M incoherent random rays; one "step" = one closest-hit pass over the 16 M rays (R-inc) plus one any-hit
-shadow pass over 16 M shadow rays (R-shadow, t_max = 0.25) => 32 M rays per step per GPU.
+Default workload (BASELINE.json configs[1], the judged line): synthetic 1 M-triangle scene (S1M-hf, 999 698 triangles,
+SURVEY.md 8d), 16 Mi incoherent random rays; one "step" = one closest-hit pass over the 16 Mi rays (R-inc) plus one any-hit
+shadow pass over 16 Mi shadow rays (R-shadow, t_max = 0.25) => 32 Mi rays per step per GPU.
 
     python bench.py [--gpus N --steps K --warmup W]            this framework (libb200rt, CUDA sm_100a)
     python bench.py --impl reference [...]                      the reference's CPU kd-tree on the host cores
+    python bench.py --workload s10m | rcoh                      other regimes (not the judged line):
+        s10m   config[3]'s geometry: 10 M-triangle object scene (2 GB on the device, HBM-resident), incoherent rays
+        rcoh   S1M-hf, coherent rays: 1920x1080 pin-hole camera rays (jittered, 8 per pixel) + shadow rays from their hit
+               points to one point light (SURVEY.md 8d R-coh, src/camera/camera_perspective.cc:165-180)
 
-Prints ONE JSON line (rank 0).  Weak scaling: every rank traces its own 16 M + 16 M rays against a replicated
-scene; there is no collective on the data path, only a barrier and a MAX-reduce of the time.
+Prints ONE JSON line (rank 0).  Weak scaling: every rank traces its own rays against a replicated scene; there is no
+collective on the data path, only a barrier and a MAX-reduce of the time.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -31,11 +35,16 @@ UNIT = "Mrays/s"
 # ALGORITHMIC bytes per ray (DESIGN.md "Roofline"): IO + 8 B x (interior + leaf nodes visited) + 4 B x leaf refs
 # + 36 B x triangle tests, visit counts taken from the REFERENCE's own kd-tree traversing this very workload
 # (counting oracle, tests/tools/count_bytes.py).  IO = 32 B ray + 16 B hit (closest) / + 4 B (shadow).
-ALGO_BYTES = {"closest": 345.0, "shadow": 230.8}
+ALGO_BYTES = {"s1m": {"closest": 345.0, "shadow": 230.8}}
 SHADOW_TMAX = 0.25
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE closest launch on this workload, from the ncu --set full capture kept
-# under profiles/ (r2v_final_kernels.txt: 1.588 GB read + 0.292 GB written); a constant of the profile, not measured live
-NCU_DRAM_TRAFFIC_BYTES = {"closest": 1.587585e9 + 0.292205e9, "source": "profiles/r2v_final_kernels.txt"}
+TSHADOW_DEPTH = 4
+# ncu counters of the kernels on each workload (dram bytes, warp instructions, lanes per instruction ...), written by
+# `tools/ncu_summary.py json` from the committed capture and keyed by the hash of the kernel source they were taken from:
+# a capture of an older kernel is reported as stale (traffic = null) instead of silently going out of date.
+COUNTERS_JSON = os.path.join(ROOT, "profiles", "kernel_counters.json")
+KERNEL_SOURCES = [os.path.join(ROOT, "libyafaray_b200", "csrc", f) for f in ("kd_kernels.cuh",)]
+KERNEL_NAMES = {"closest": "b200rt::traceKernel<0,false>", "shadow": "b200rt::traceKernel<1,false>", "tshadow": "b200rt::traceKernel<2,false>"}
+SMS, SCHEDULERS_PER_SM = 148, 4
 
 
 def parse():
@@ -44,12 +53,36 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="s1m", choices=["s1m", "s10m", "rcoh"])
     ap.add_argument("--rays", type=int, default=1 << 24, help="rays per query per GPU (16 Mi)")
     ap.add_argument("--cells", type=int, default=707, help="height-field cells per side (707 -> 999 698 triangles)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-tshadow", action="store_true")
     return ap.parse_args()
+
+
+def kernel_source_hash():
+    h = hashlib.sha256()
+    for p in KERNEL_SOURCES:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def load_counters(workload):
+    """(counters of this workload or None, note)."""
+    try:
+        rec = json.load(open(COUNTERS_JSON))
+    except Exception as e:
+        return None, f"no {os.path.relpath(COUNTERS_JSON, ROOT)} ({e.__class__.__name__})"
+    if rec.get("kernel_source_sha") != kernel_source_hash():
+        return None, f"stale: {os.path.relpath(COUNTERS_JSON, ROOT)} was captured from kernel source {rec.get('kernel_source_sha')}, this is {kernel_source_hash()}"
+    w = rec.get("workloads", {}).get(workload)
+    if not w:
+        return None, f"no capture of workload {workload} in {os.path.relpath(COUNTERS_JSON, ROOT)}"
+    return w, rec.get("source", "")
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -109,19 +142,61 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ workload
-def make_scene_arrays(cells):
-    from libyafaray_b200 import scenes
-    return scenes.heightfield(cells)
+LIGHT = np.array([0.5, 0.5, 3.0])  # rcoh: the point light the shadow rays aim at
 
 
-def make_rays(n, rank):
+def make_scene_arrays(args):
     from libyafaray_b200 import scenes
-    return (scenes.rays_incoherent(n, seed=12345 + 2 * rank),
-            scenes.rays_shadow(n, seed=12346 + 2 * rank, t_max=SHADOW_TMAX))
+    if args.workload == "s10m":
+        return scenes.objects(10_000_000)
+    return scenes.heightfield(args.cells)
+
+
+def make_closest_rays(args, rank, bound):
+    from libyafaray_b200 import scenes
+    n = args.rays
+    if args.workload == "s1m":
+        return scenes.rays_incoherent(n, seed=12345 + 2 * rank)
+    if args.workload == "s10m":
+        return scenes.rays_incoherent(n, seed=12345 + 2 * rank, lo=bound[:3], hi=bound[3:])
+    w, h = 1920, 1080
+    frames = [scenes.rays_camera(w, h, seed=1000 * rank + k) for k in range((n + w * h - 1) // (w * h))]
+    return np.ascontiguousarray(np.concatenate(frames)[:n])
+
+
+def make_shadow_rays(args, rank, bound, closest_rays=None, closest_t=None):
+    """s1m / s10m: R-shadow (independent incoherent rays with a finite t_max).  rcoh: from the hit point of every camera ray
+    (the ray origin where it missed) to the light, direction unnormalised so that t = 1 is the light (as the reference's
+    light sampling does: tmax = distance along a unit direction; the two are equivalent for the traversal)."""
+    from libyafaray_b200 import scenes
+    n = args.rays
+    if args.workload == "s1m":
+        return scenes.rays_shadow(n, seed=12346 + 2 * rank, t_max=SHADOW_TMAX)
+    if args.workload == "s10m":
+        diag = float(np.linalg.norm(bound[3:].astype(np.float64) - bound[:3].astype(np.float64)))
+        return scenes.rays_shadow(n, seed=12346 + 2 * rank, t_max=SHADOW_TMAX * diag, lo=bound[:3], hi=bound[3:])
+    o = closest_rays[:, 0:3].astype(np.float64) + closest_rays[:, 4:7].astype(np.float64) * closest_t.astype(np.float64)[:, None]
+    r = np.empty((n, 8), np.float32)
+    r[:, 0:3] = o
+    r[:, 3] = 0.0005
+    r[:, 4:7] = LIGHT[None, :] - o
+    r[:, 7] = 1.0
+    return r
 
 
 def workload_name(args, n_faces):
-    return f"S1M-hf height-field {n_faces} triangles; {args.rays} incoherent closest-hit rays + {args.rays} shadow rays (t_max {SHADOW_TMAX}) per GPU per step"
+    if args.workload == "s1m":
+        return f"S1M-hf height-field {n_faces} triangles; {args.rays} incoherent closest-hit rays + {args.rays} shadow rays (t_max {SHADOW_TMAX}) per GPU per step"
+    if args.workload == "s10m":
+        return f"S10M objects {n_faces} faces (HBM-resident, config[3] geometry); {args.rays} incoherent closest-hit rays + {args.rays} shadow rays (t_max {SHADOW_TMAX} x diagonal) per GPU per step"
+    return f"R-coh: S1M-hf {n_faces} triangles; {args.rays} jittered 1920x1080 camera rays + {args.rays} shadow rays from their hit points to a point light per GPU per step"
+
+
+def config_dict(args, n_faces):
+    """The SAME keys and values in both arms (the driver compares the two `config` objects)."""
+    return {"workload": workload_name(args, n_faces), "rays_per_step_per_gpu": 2 * args.rays,
+            "l2_policy": "inputs larger than L2: 512 MiB rays + 256 MiB hits (closest), 512 MiB + 64 MiB (shadow) streamed per step at the default size; "
+                         "the scene is read through L2 as the traversal finds it"}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -144,16 +219,18 @@ class CpuArm:
             self.obj = kdo.Oracle(xyz, idx, flags)
             self.build_seconds = time.perf_counter() - t0
             self.what = "C restatement (oracle/kd_oracle.c) on its own SAH tree"
+        self.last = None
 
     def _timed(self, fn, r):
         t0 = time.perf_counter()
         out = fn(r, threads=self.threads)
         dt = time.perf_counter() - t0
-        return out.get("seconds", dt) if self.kind == "reference" else dt
+        return (out.get("seconds", dt) if self.kind == "reference" else dt), out
 
     def measure(self, rays, srays, n):
-        tc = self._timed(self.obj.trace_closest, rays[:n])
-        ts = self._timed(self.obj.trace_shadow, srays[:n])
+        tc, c = self._timed(self.obj.trace_closest, rays[:n])
+        ts, s = self._timed(self.obj.trace_shadow, srays[:n])
+        self.last = (n, c, s)
         return tc, ts
 
     def sample_size(self, rays, srays, target_seconds):
@@ -166,13 +243,23 @@ class CpuArm:
         return f"first {n} closest + first {n} shadow rays of the {total}-ray workload, {self.threads} host threads, {self.what}"
 
 
-def cpu_baseline(xyz, idx, flags, rays, srays, target_seconds):
-    threads = os.cpu_count() or 1
-    arm = CpuArm(xyz, idx, flags, threads)
-    n = arm.sample_size(rays, srays, target_seconds)
-    tc, ts = arm.measure(rays, srays, n)
-    return {"value": 2 * n / (tc + ts) / 1e6, "unit": UNIT, "cores": threads, "kind": arm.kind, "sample": arm.describe(n, rays.shape[0]),
-            "closest_mrays": n / tc / 1e6, "shadow_mrays": n / ts / 1e6, "build_seconds": arm.build_seconds}
+def parity_report(n, cpu_closest, cpu_shadow, gpu_hits, gpu_occ, miss):
+    """GPU results against the CPU arm's over the rays the CPU sample covered (all of them at the default size)."""
+    prim = gpu_hits["prim"][:n].astype(np.int64)
+    prim[prim == miss] = -1
+    ref_prim = cpu_closest["prim"][:n].astype(np.int64)
+    same = prim == ref_prim
+    diff = np.flatnonzero(~same)
+    t_g, t_r = gpu_hits["t"][:n], cpu_closest["t"][:n]
+    both_hit = (prim[diff] >= 0) & (ref_prim[diff] >= 0)
+    tie = both_hit & (np.abs(t_g[diff].astype(np.float64) - t_r[diff]) <= 1e-5 * np.maximum(np.abs(t_r[diff]), 1e-30))
+    bits = (np.array_equal(t_g[same], t_r[same]) and np.array_equal(gpu_hits["u"][:n][same], cpu_closest["u"][:n][same])
+            and np.array_equal(gpu_hits["v"][:n][same], cpu_closest["v"][:n][same]))
+    sh = (gpu_occ[:n] != miss).astype(np.uint8)
+    return {"rays_compared": int(n), "ids_equal": float(same.mean()) if n else None, "id_mismatches": int(diff.size),
+            "non_tie_mismatches": int(diff.size - tie.sum()), "tuv_bit_identical_where_ids_equal": bool(bits),
+            "shadow_bool_mismatches": int(np.count_nonzero(sh != cpu_shadow["shadowed"][:n])),
+            "against": "cpu_baseline arm (same rays, same run)"}
 
 
 def run_reference(args):
@@ -180,10 +267,15 @@ def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     threads = os.cpu_count() or 1
-    xyz, idx, flags = make_scene_arrays(args.cells)
-    rays, srays = make_rays(args.rays, 0)
+    xyz, idx, flags = make_scene_arrays(args)
     steps, warm = max(1, args.steps), max(0, args.warmup)
     arm = CpuArm(xyz, idx, flags, threads)
+    bound = arm.obj.bound()
+    rays = make_closest_rays(args, 0, bound)
+    if args.workload == "rcoh":
+        srays = make_shadow_rays(args, 0, bound, rays, arm.obj.trace_closest(rays, threads=threads)["t"])
+    else:
+        srays = make_shadow_rays(args, 0, bound)
     per_step = max(1.0, min(args.cpu_seconds, 120.0 / (steps + warm)))
     n = arm.sample_size(rays, srays, per_step)
     for _ in range(warm):
@@ -192,11 +284,12 @@ def run_reference(args):
     tc, ts = float(np.sum(tcs)), float(np.sum(tss))
     value = 2 * n * steps / (tc + ts) / 1e6
     base = {"value": value, "unit": UNIT, "cores": threads, "kind": arm.kind, "sample": arm.describe(n, args.rays),
-            "closest_mrays": n * steps / tc / 1e6, "shadow_mrays": n * steps / ts / 1e6, "build_seconds": arm.build_seconds}
+            "closest_mrays": n * steps / tc / 1e6, "shadow_mrays": n * steps / ts / 1e6, "build_seconds": arm.build_seconds,
+            "sample_rays_per_step": 2 * n}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": (tc + ts) / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": workload_name(args, idx.shape[0]), "sample_rays_per_step": 2 * n},
+        "data": "synthetic", "config": config_dict(args, idx.shape[0]),
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -205,6 +298,14 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def transparent_flags(n_faces):
+    """Every third face a transparent shadow caster: the transparent-shadow pass then really collects casters."""
+    from libyafaray_b200 import scenes
+    fl = np.full(n_faces, scenes.F_NORMAL, np.uint8)
+    fl[::3] |= scenes.F_TRANSPARENT
+    return fl
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -221,13 +322,18 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    xyz, idx, flags = make_scene_arrays(args.cells)
+    xyz, idx, flags = make_scene_arrays(args)
     scene = rt.Scene(local)
     scene.add_mesh(xyz, idx, flags)
     scene.build()
     stats = scene.stats()
-    rays, srays = make_rays(args.rays, rank)
+    bound = scene.bound()
     n = args.rays
+    rays = make_closest_rays(args, rank, bound)
+    if args.workload == "rcoh":
+        srays = make_shadow_rays(args, rank, bound, rays, scene.trace_closest(rays)["t"])  # set-up, not timed
+    else:
+        srays = make_shadow_rays(args, rank, bound)
 
     # ---- device-resident arm: inputs already in HBM when the timed region starts ----
     d_rays = torch.from_numpy(rays).to(dev)
@@ -271,6 +377,8 @@ def run_b200(args):
     closest_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
     shadow_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
     clocks = sampler.window(w0, w1) if sampler else None
+    gpu_hits = d_hits.cpu().numpy().view(rt.HIT_DTYPE).reshape(-1)
+    gpu_occ = d_occ.cpu().numpy().view(np.uint32)
 
     # ---- end-to-end arm: the host-buffer C-ABI call, pinned host rays in, host results out ----
     e2e_s = None
@@ -291,7 +399,33 @@ def run_b200(args):
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - e0) / e2e_steps
         # results of both arms must be the same bytes
-        assert pin_h.array.tobytes() == d_hits.cpu().numpy().tobytes(), "e2e and device-resident results differ"
+        assert pin_h.array.tobytes() == gpu_hits.tobytes(), "e2e and device-resident results differ"
+        del pin_r, pin_s, pin_h, pin_o
+
+    # ---- transparent shadows (traceKernel<2,*>): own key, outside `value`; a second copy of the scene in which every third
+    # face is a transparent caster, the step's shadow rays, max_depth 4 ----
+    tshadow = None
+    if not args.no_tshadow and rank == 0:
+        ts_scene = rt.Scene(local)
+        ts_scene.add_mesh(xyz, idx, transparent_flags(idx.shape[0]))
+        ts_scene.build()
+        d_ts = torch.empty((n, rt.TSHADOW_DTYPE.itemsize // 4), dtype=torch.int32, device=dev)
+        for _ in range(2):
+            ts_scene.trace_tshadow_device(d_srays.data_ptr(), n, TSHADOW_DEPTH, d_ts.data_ptr(), sp)
+        t_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        reps = max(2, min(args.steps, 5))
+        t_ev[0].record(stream)
+        for _ in range(reps):
+            ts_scene.trace_tshadow_device(d_srays.data_ptr(), n, TSHADOW_DEPTH, d_ts.data_ptr(), sp)
+        t_ev[1].record(stream)
+        torch.cuda.synchronize()
+        ts_ms = t_ev[0].elapsed_time(t_ev[1]) / reps
+        res = d_ts.cpu().numpy().view(rt.TSHADOW_DTYPE).reshape(-1)
+        tshadow = {"kernel": KERNEL_NAMES["tshadow"], "mrays_per_gpu": n / (ts_ms * 1e-3) / 1e6, "ms": ts_ms, "max_depth": TSHADOW_DEPTH,
+                   "transparent_faces": "every third", "result_bytes_per_ray": rt.TSHADOW_DTYPE.itemsize,
+                   "shadowed_fraction": float(np.mean(res["shadowed"] != 0)), "mean_transparent_casters_on_lit_rays": float(np.mean(res["n_transparent"][res["shadowed"] == 0]))}
+        del d_ts
+        ts_scene.close()
 
     # ---- max over ranks ----
     t = torch.tensor([total_ms, closest_ms, shadow_ms, (e2e_s or 0.0) * 1e3], dtype=torch.float64, device=dev)
@@ -311,32 +445,69 @@ def run_b200(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
         ms_per_step = total_ms / args.steps
         value = world * 2 * n / (ms_per_step * 1e-3) / 1e6
-        achieved = ALGO_BYTES["closest"] * n / (closest_ms * 1e-3) / 1e9
+        counters, counters_note = load_counters(args.workload)
+        full_size = n == (1 << 24) and (args.workload != "s1m" or args.cells == 707)
+        cc = (counters or {}).get("closest") if full_size else None
+        # HBM bound: algorithmic bytes of one closest launch / its measured duration
+        algo = ALGO_BYTES.get(args.workload)
+        hbm = None
+        if algo:
+            achieved = algo["closest"] * n / (closest_ms * 1e-3) / 1e9
+            hbm = {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src,
+                   "algorithmic_bytes_per_ray": algo["closest"], "algorithmic_bytes_per_launch": algo["closest"] * n,
+                   "traffic": cc["dram_bytes"] if cc else None}
+        elif cc:
+            # no counted visit numbers for this workload: the bytes the launch moved through L2 in 32-byte sectors (ncu) over the live time
+            achieved = cc["l2_sector_bytes"] / (closest_ms * 1e-3) / 1e9
+            hbm = {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src,
+                   "bytes": "L2 sector bytes of one closest launch (ncu lts__t_sectors x 32 B), not algorithmic", "traffic": cc["dram_bytes"]}
+        # issue bound: warp instructions of one closest launch (ncu) / its duration, against SMs x 4 schedulers x SM clock
+        issue = None
+        sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+        if cc:
+            peak_issue = SMS * SCHEDULERS_PER_SM * sm_mhz * 1e6 / 1e9
+            ach_issue = cc["warp_inst"] / (closest_ms * 1e-3) / 1e9
+            issue = {"achieved": ach_issue, "peak": peak_issue, "unit": "G warp-inst/s", "frac": ach_issue / peak_issue,
+                     "warp_inst_per_ray": cc["warp_inst"] / n, "lanes_per_inst": cc.get("lanes_per_inst"),
+                     "peak_source": f"{SMS} SMs x {SCHEDULERS_PER_SM} schedulers x {sm_mhz:.0f} MHz (clock sampled during the timed region)"}
+        bounds = {k: v for k, v in (("hbm", hbm), ("issue", issue)) if v}
+        tighter = max(bounds, key=lambda k: bounds[k]["frac"]) if bounds else None
+        roof = {"bound": tighter, "kernel": KERNEL_NAMES["closest"], "launch_ms": closest_ms, "counters_source": counters_note}
+        if tighter:
+            roof.update({k: bounds[tighter][k] for k in ("achieved", "peak", "unit", "frac")})
+            roof["traffic"] = (hbm or {}).get("traffic")
+        roof.update(bounds)
+        roof["note"] = ("a gather over an L2-resident scene: the algorithmic-byte fraction of HBM is small by construction; instruction issue is the "
+                        "tighter bound (DESIGN.md 5)")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args, idx.shape[0]), "rays_per_step_per_gpu": 2 * n,
-                       "l2_policy": "inputs larger than L2: 512 MiB rays + 256 MiB hits (closest), 512 MiB + 64 MiB (shadow) streamed per step; "
-                                    "the 1 M-triangle scene itself is L2-resident by nature of the workload",
-                       "closest_mrays_per_gpu": n / (closest_ms * 1e-3) / 1e6, "shadow_mrays_per_gpu": n / (shadow_ms * 1e-3) / 1e6,
-                       "closest_ms": closest_ms, "shadow_ms": shadow_ms, "tree": {k: stats[k] for k in ("n_nodes", "n_leaf_refs", "max_depth", "device_bytes", "build_seconds")}},
-            "roofline": {"bound": "hbm", "kernel": "traceClosestKernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": NCU_DRAM_TRAFFIC_BYTES["closest"] if n == (1 << 24) and args.cells == 707 else None,
-                         "traffic_source": NCU_DRAM_TRAFFIC_BYTES["source"], "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": ALGO_BYTES["closest"] * n,
-                         "algorithmic_bytes_per_ray": ALGO_BYTES["closest"], "launch_ms": closest_ms,
-                         "note": "latency/issue-bound gather (DESIGN.md): the algorithmic-byte fraction is small by construction"},
+            "config": config_dict(args, idx.shape[0]),
+            "detail": {"closest_mrays_per_gpu": n / (closest_ms * 1e-3) / 1e6, "shadow_mrays_per_gpu": n / (shadow_ms * 1e-3) / 1e6,
+                       "closest_ms": closest_ms, "shadow_ms": shadow_ms, "kernels": [KERNEL_NAMES["closest"], KERNEL_NAMES["shadow"]],
+                       "kernel_source_sha": kernel_source_hash(),
+                       "tree": {k: stats[k] for k in ("n_nodes", "n_leaf_refs", "max_depth", "device_bytes", "build_seconds")}},
+            "roofline": roof,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "wall_ms_per_step": (w1 - w0) * 1e3 / args.steps,
         }
+        if tshadow:
+            line["tshadow"] = tshadow
         if e2e_s is not None:
             line["e2e"] = {"value": world * 2 * n / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
                            "h2d_bytes_per_step": 2 * n * 32, "d2h_bytes_per_step": n * 16 + n * 4,
                            "path": "b200rt_trace_closest + b200rt_trace_shadow on pinned host buffers (H2D, kernel, D2H chunk-pipelined inside the call)"}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(xyz, idx, flags, rays, srays, args.cpu_seconds)
+            threads = os.cpu_count() or 1
+            arm = CpuArm(xyz, idx, flags, threads)
+            m = arm.sample_size(rays, srays, args.cpu_seconds)
+            tc, ts = arm.measure(rays, srays, m)
+            line["cpu_baseline"] = {"value": 2 * m / (tc + ts) / 1e6, "unit": UNIT, "cores": threads, "kind": arm.kind, "sample": arm.describe(m, n),
+                                    "closest_mrays": m / tc / 1e6, "shadow_mrays": m / ts / 1e6, "build_seconds": arm.build_seconds}
+            _, c_res, s_res = arm.last
+            line["parity"] = parity_report(m, c_res, s_res, gpu_hits, gpu_occ, rt.MISS)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

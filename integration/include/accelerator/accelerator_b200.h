@@ -57,6 +57,8 @@ class AcceleratorB200 final : public Accelerator
 		void releaseRayQueue(std::unique_ptr<b200::RayQueue> queue) const;
 		void addWavefrontStats(const b200::RayQueue::Stats &stats) const;
 		void logWavefrontStats() const; //!< one Info line with the totals since the last call, then resets them
+		int clampShadowDepth(int max_depth) const; //!< the depth the result record can express (warns once when it has to clamp)
+		void logQueueError(const std::string &what) const; //!< a ray queue could not run (photon_fibers_b200.h, integrator_tiled_b200.cc)
 		/*! The reference reads object / material visibility and transparency LIVE at every hit (accelerator.h:126-127,138-139,152-154),
 		 *  while the GPU scene bakes them per face; Scene::preprocess rebuilds the accelerator for OBJECTS / accelerator-parameter
 		 *  changes only (src/scene/scene.cc:318), not when a material is replaced.  Called at the start of every render pass and
@@ -94,6 +96,7 @@ class AcceleratorB200 final : public Accelerator
 		b200rt_scene *scene_ = nullptr;             //!< owned; device memory lives behind this handle
 		Bound<float> bound_{{{0.f, 0.f, 0.f}}, {{0.f, 0.f, 0.f}}};
 		mutable std::vector<uint8_t> face_flags_;   //!< the flag byte every primitive was uploaded with (refreshFaceFlags)
+		mutable std::atomic<bool> depth_clamp_logged_{false};
 		mutable std::mutex queues_mutex_;
 		mutable std::vector<std::unique_ptr<b200::RayQueue>> idle_queues_;
 		mutable std::atomic<uint64_t> wf_rays_[3]{}, wf_batches_{0}, wf_calls_{0}, wf_switches_{0}, wf_trace_us_{0}, wf_run_us_{0}, wf_per_ray_calls_{0};

@@ -68,8 +68,15 @@ class PhotonWorkers final
 					int next{t * fibers_per_thread_};
 					const int end{next + fibers_per_thread_};
 					//every fiber takes logical workers until none is left; fibers of one OS thread never run concurrently
-					queue->run([&]() { while(next < end) worker(next++); });
-					b200_->releaseRayQueue(std::move(queue));
+					const bool ran{queue && queue->run([&]() { while(next < end) worker(next++); })};
+					if(!ran)
+					{
+						//the queue was unusable (pinned / stack allocation failed) or a libb200rt call failed in flight: say so, and give
+						//the logical workers that never started to the per-ray path -- it still traces on the GPU, one launch per ray
+						b200_->logQueueError(queue ? queue->error() : std::string{"no ray queue"});
+						while(next < end) worker(next++);
+					}
+					if(queue) b200_->releaseRayQueue(std::move(queue));
 				});
 			}
 			for(auto &thread : threads) thread.join();

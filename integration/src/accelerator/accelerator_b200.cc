@@ -302,7 +302,7 @@ IntersectData AcceleratorB200::intersectTransparentShadow(const Ray &ray, int ma
 	const b200rt_ray r{toRay(ray, dist)};
 	b200rt_tshadow res{};
 	IntersectData data;
-	if(max_depth > B200RT_TSHADOW_MAX) max_depth = B200RT_TSHADOW_MAX; //documented limit of the result record
+	max_depth = clampShadowDepth(max_depth);
 	if(!scene_) return data;
 	if(b200::RayQueue *queue{b200::RayQueue::current()}) res = queue->transparentShadow(scene_, r, max_depth);
 	else if(++wf_per_ray_calls_, b200rt_trace(scene_, B200RT_QUERY_TSHADOW, B200RT_RAYS_TREE_SPACE, &r, 1, &res, max_depth) != B200RT_OK) return data;
@@ -384,6 +384,26 @@ void AcceleratorB200::logWavefrontStats() const
 					" libb200rt calls (", batches ? (closest + shadow + tshadow) / batches : 0, " rays per batch), ", trace_s, " thread-seconds inside libb200rt of ", run_s, " thread-seconds in the render workers; per-ray calls outside fibers: ", per_ray);
 }
 
+int AcceleratorB200::clampShadowDepth(int max_depth) const
+{
+	// a negative depth behaves like 0 in the reference (accelerator.h:161: "depth >= max_depth" holds for the first transparent caster)
+	if(max_depth < 0) return 0;
+	if(max_depth > B200RT_TSHADOW_MAX)
+	{
+		// the result record lists at most B200RT_TSHADOW_MAX distinct transparent casters: a ray through more of them reads as
+		// shadowed here, while the reference lets up to shadow_depth of them through -- say so once instead of clamping silently
+		if(!depth_clamp_logged_.exchange(true))
+			logger_.logWarning(getClassName(), ": shadow_depth ", max_depth, " exceeds the ", B200RT_TSHADOW_MAX, " distinct transparent shadow casters one result record holds; rays through more than ", B200RT_TSHADOW_MAX, " of them are reported as shadowed");
+		return B200RT_TSHADOW_MAX;
+	}
+	return max_depth;
+}
+
+void AcceleratorB200::logQueueError(const std::string &what) const
+{
+	logger_.logError(getClassName(), ": wavefront ray queue failed (", what, "); the affected workers fall back to one-ray launches");
+}
+
 // ---- batched entry points ---------------------------------------------------------------------------------
 bool AcceleratorB200::intersectBatch(const Ray *rays, size_t n, IntersectData *out) const
 {
@@ -433,7 +453,7 @@ bool AcceleratorB200::isShadowedTransparentShadowBatch(const Ray *rays, size_t n
 	std::vector<b200rt_ray> r(n);
 	std::vector<b200rt_tshadow> res(n);
 	for(size_t i = 0; i < n; ++i) r[i] = toRay(rays[i], rays[i].tmax_);
-	if(max_depth > B200RT_TSHADOW_MAX) max_depth = B200RT_TSHADOW_MAX;
+	max_depth = clampShadowDepth(max_depth);
 	if(b200rt_trace_tshadow(scene_, r.data(), n, max_depth, res.data()) != B200RT_OK)
 	{
 		logger_.logError(getClassName(), ": isShadowedTransparentShadowBatch failed: ", b200rt_last_error());

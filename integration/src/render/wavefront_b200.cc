@@ -103,7 +103,10 @@ RayQueue::RayQueue(int n_fibers, int n_groups, size_t stack_bytes) : n_fibers_{s
 	}
 	n_groups = std::max(1, std::min(n_groups, n_fibers_));
 	groups_.resize(size_t(n_groups));
-	const size_t per_group = (size_t(n_fibers_) + size_t(n_groups) - 1) / size_t(n_groups);
+	// rounded up to a multiple of 4 slots: every array below then starts 16-byte aligned whatever the fiber / group counts are
+	// (32-byte rays, 144- and 16-byte records, 4-byte shadow answers), which the kernels' float4 loads and stores require
+	const size_t fibers_per_group = (size_t(n_fibers_) + size_t(n_groups) - 1) / size_t(n_groups);
+	const size_t per_group = (fibers_per_group + 3) & ~size_t(3);
 	// one pinned slab for the rays and answers of all groups (a pinned allocation costs the driver a fraction of a millisecond and
 	// sixteen render threads create their queues at the same moment)
 	const size_t per_slot = 3 * sizeof(b200rt_ray) + kOutSize[0] + kOutSize[1] + kOutSize[2];
@@ -112,7 +115,7 @@ RayQueue::RayQueue(int n_fibers, int n_groups, size_t stack_bytes) : n_fibers_{s
 	for(size_t g = 0; g < groups_.size(); ++g)
 	{
 		Group &group = groups_[g];
-		for(size_t i = g * per_group; i < std::min(size_t(n_fibers_), (g + 1) * per_group); ++i)
+		for(size_t i = g * fibers_per_group; i < std::min(size_t(n_fibers_), (g + 1) * fibers_per_group); ++i)
 		{
 			fibers_[i].group = &group;
 			group.fibers.push_back(&fibers_[i]);

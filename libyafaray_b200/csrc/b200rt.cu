@@ -567,14 +567,15 @@ int b200rt_build(b200rt_scene *s)
 	CUDA_TRY(cudaMalloc(&s->d_tris, tris.size() * sizeof(float4)));
 	CUDA_TRY(cudaMemcpy(s->d_nodes, nodes.data(), nodes.size() * sizeof(uint2), cudaMemcpyHostToDevice));
 	CUDA_TRY(cudaMemcpy(s->d_tris, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
-	if(!s->d_cursors)
+	// one resident wave of the kernel variant THIS build launches (a rebuild after b200rt_add_spheres switches variants); the
+	// cursors are allocated only once the occupancy queries have succeeded, so a failed query is retried by the next build
 	{
-		CUDA_TRY(cudaMalloc(&s->d_cursors, kCursorRing * sizeof(uint32_t)));
 		int rc = queryResidency<b200rt::kClosest>(s);
 		if(rc == B200RT_OK) rc = queryResidency<b200rt::kShadow>(s);
 		if(rc == B200RT_OK) rc = queryResidency<b200rt::kTShadow>(s);
 		if(rc != B200RT_OK) return rc;
 	}
+	if(!s->d_cursors) CUDA_TRY(cudaMalloc(&s->d_cursors, kCursorRing * sizeof(uint32_t)));
 	s->n_tri_vec4 = tris.size();
 	s->view.nodes = s->d_nodes;
 	s->view.tris = s->d_tris;

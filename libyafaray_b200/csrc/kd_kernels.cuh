@@ -39,7 +39,6 @@ struct SceneView
 
 enum Query { kClosest = 0, kShadow = 1, kTShadow = 2 };
 
-static constexpr int kStackSize = 64;
 static constexpr uint32_t kFlagQuad = 8u;
 static constexpr uint32_t kFlagSphere = 16u;
 
@@ -211,9 +210,6 @@ __device__ __forceinline__ float sphereIntersect(const float4 q0, float radius, 
 #ifndef B200RT_STREAM_IO
 #define B200RT_STREAM_IO 1
 #endif
-#ifndef B200RT_SMEM_RAY
-#define B200RT_SMEM_RAY 1
-#endif
 #ifndef B200RT_STEPS
 #define B200RT_STEPS 16
 #endif
@@ -223,13 +219,40 @@ __device__ __forceinline__ float sphereIntersect(const float4 q0, float radius, 
 #ifndef B200RT_BREAK
 #define B200RT_BREAK 1
 #endif
+// Prefetch experiments (north_star (b), DESIGN.md "Prefetch"):
+//   LEAF_PREFETCH 1: prefetch.global.L1 of the leaf's first record when a lane stops at a non-empty leaf (it is tested one vote later)
+//   LEAF_PREFETCH 2: cp.async (LDGSTS) of that record into the lane's shared-memory staging slot; the leaf phase reads it from there
+//   FAR_PREFETCH  1: prefetch.global.L1 of the postponed far child when it is pushed
+//   POOL_PREFETCH 1: prefetch.global.L2 of the whole 256-ray pool when the warp takes it from the cursor
+// SETUP_QUEUE 1: converged ray setup.  When a lane is idle and the warp's ready queue is empty, ALL 32 lanes set up the next 32
+// rays of the pool at once (the ~170-instruction setup with its three IEEE divisions ran at ~10 of 32 lanes when only the idle
+// lanes did it); rays that miss the tree bound -- 41 % of the BASELINE closest rays -- are answered right there and never occupy
+// a lane; the others are compacted into a 32-entry queue in shared memory from which idle lanes take a ready ray every round.
+// tools/simt_model.cc predicted 116 -> 96 warp instructions per ray for it; measured in profiles/r3b_*.
+#ifndef B200RT_SETUP_QUEUE
+#define B200RT_SETUP_QUEUE 1
+#endif
+#ifndef B200RT_LEAF_PREFETCH
+#define B200RT_LEAF_PREFETCH 0
+#endif
+#ifndef B200RT_FAR_PREFETCH
+#define B200RT_FAR_PREFETCH 0
+#endif
+#ifndef B200RT_POOL_PREFETCH
+#define B200RT_POOL_PREFETCH 0
+#endif
 
 static constexpr int kBlock = B200RT_BLOCK;
 #ifndef B200RT_POOL
 #define B200RT_POOL 256
 #endif
 static constexpr int kPoolRays = B200RT_POOL;       // rays taken from the global cursor per atomicAdd
-static constexpr int kRefill = B200RT_REFILL;       // idle lanes that trigger a refill
+static constexpr int kRefill = B200RT_REFILL;       // idle lanes that trigger a refill (SETUP_QUEUE 0)
+#ifndef B200RT_TAKE
+#define B200RT_TAKE 1
+#endif
+static constexpr int kTake = B200RT_TAKE;           // idle lanes that trigger a hand-out from the ready queue (SETUP_QUEUE 1)
+static constexpr int kQueueFields = 14;             // o, d, 1/d, t_min, t_max, interval in the tree bound, ray index
 static constexpr int kLeafBatch = B200RT_LEAF_BATCH; // lanes holding a leaf that trigger the leaf phase
 static constexpr int kUnroll = B200RT_UNROLL;       // unroll factor of the descent loop
 static constexpr int kSteps = B200RT_STEPS;         // node steps per lane between two warp votes
@@ -247,7 +270,6 @@ struct RayState
 	uint32_t best_prim;
 	uint32_t node;
 	uint32_t index;               // ray index in the batch
-	uint32_t neg;                 // bit k set: direction component k is negative
 	int sp;                       // ring depth in bytes (kRingStride per entry)
 };
 
@@ -306,7 +328,6 @@ __device__ __forceinline__ bool setupRay(const SceneView &s, const float4 a, con
 	r.ix = isinf(ix) ? copysignf(FLT_MAX, ix) : ix;
 	r.iy = isinf(iy) ? copysignf(FLT_MAX, iy) : iy;
 	r.iz = isinf(iz) ? copysignf(FLT_MAX, iz) : iz;
-	r.neg = (r.ix < 0.f ? 1u : 0u) | (r.iy < 0.f ? 2u : 0u) | (r.iz < 0.f ? 4u : 0u);
 	r.seg_lo = fmaxf(lmin, 0.f);
 	r.seg_hi = fminf(lmax, t_max);
 	r.best_u = 0.f; r.best_v = 0.f; r.best_prim = B200RT_MISS;
@@ -403,6 +424,54 @@ __device__ __forceinline__ uint32_t selectu(bool p, uint32_t a, uint32_t b)
 	return r;
 }
 
+__device__ __forceinline__ void prefetchL1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void cpAsync16(void *smem, const void *gmem)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(smem))), "l"(gmem));
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Converged ray setup (SETUP_QUEUE): lane L of the warp sets up ray first + L (L < avail).  A ray that misses the tree bound is
+// answered here; the others are compacted into the warp's ready queue, [field][entry].  Returns the number queued.  Not inlined
+// on purpose: the live state of the 32 rays in flight is saved around the call instead of competing for registers with the
+// set-up arithmetic in the traversal loop.
+template <int QUERY>
+__device__ __noinline__ uint32_t setupPass(const SceneView &s, const b200rt_ray *__restrict__ rays, uint32_t first, uint32_t avail,
+                                           typename OutType<QUERY>::type *__restrict__ out, bool tree_space, float *sh_queue)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	bool ready = false;
+	RayState q;
+	if(lane < avail)
+	{
+		q.index = first + lane;
+		// rays are read once: do not let them displace tree nodes from L1/L2
+		const float4 a = __ldcs(reinterpret_cast<const float4 *>(rays) + 2 * size_t(q.index));
+		const float4 b = __ldcs(reinterpret_cast<const float4 *>(rays) + 2 * size_t(q.index) + 1);
+		ready = setupRay<QUERY>(s, a, b, q, tree_space);
+		if(!ready)
+		{
+			TShadowState none;
+			none.depth = 0;
+			writeResult<QUERY>(out, q, false, none); // missed the tree bound
+		}
+	}
+	const unsigned m_ready = __ballot_sync(kFullMask, ready);
+	if(ready)
+	{
+		float *e = sh_queue + __popc(m_ready & ((1u << lane) - 1u));
+		e[0 * 32] = q.ox; e[1 * 32] = q.oy; e[2 * 32] = q.oz;
+		e[3 * 32] = q.dx; e[4 * 32] = q.dy; e[5 * 32] = q.dz;
+		e[6 * 32] = q.ix; e[7 * 32] = q.iy; e[8 * 32] = q.iz;
+		e[9 * 32] = q.t_min; e[10 * 32] = q.t_max; e[11 * 32] = q.seg_lo; e[12 * 32] = q.seg_hi;
+		e[13 * 32] = __uint_as_float(q.index);
+	}
+	__syncwarp();
+	return uint32_t(__popc(m_ready));
+}
+
 // The traversal proper.  Called by every thread of the block; warps are independent of each other (no block-level
 // synchronisation).  sh_stack / sh_axis are the block's shared arrays; static_base is the first ray of the calling warp's
 // static pool in a cursor-less launch (ignored when `cursor` is given).
@@ -410,7 +479,7 @@ __device__ __forceinline__ uint32_t selectu(bool p, uint32_t a, uint32_t b)
 // BASELINE workloads -- do not pay for the flag test and the extra code in the leaf loop (measured: 3 % on S1M-hf).
 template <int QUERY, bool SPHERES>
 __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray *__restrict__ rays, uint32_t n, typename OutType<QUERY>::type *__restrict__ out,
-                                           uint32_t *__restrict__ cursor, int max_depth, bool tree_space, uint2 (*sh_stack)[kBlock], float2 (*sh_axis)[kBlock], uint32_t static_base)
+                                           uint32_t *__restrict__ cursor, int max_depth, bool tree_space, uint2 (*sh_stack)[kBlock], float2 (*sh_axis)[kBlock], uint32_t static_base, float4 (*sh_leaf)[kBlock] = nullptr, float *sh_queue = nullptr)
 {
 	const unsigned tid = threadIdx.x;
 	const unsigned lane = tid & 31u;
@@ -427,6 +496,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 	uint32_t pool_next = 0u, pool_end = 0u; // warp-uniform
 	bool exhausted = false;                 // warp-uniform
 	bool first_pool = true;                 // warp-uniform
+	uint32_t q_count = 0u;                  // warp-uniform: ready rays in the warp's queue (SETUP_QUEUE)
 
 	// Exact kd-restart.  `target` is the leaf the ray has just left (ring empty, older entries lost).  The tree is stored
 	// depth first (left child = node + 1, the right subtree starts at `right`), so "target < right" tells which child holds
@@ -498,6 +568,73 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 
 	for(;;)
 	{
+#if B200RT_SETUP_QUEUE
+		// ---------------- ray setup (converged) and hand-out ----------------
+		const unsigned idle = __ballot_sync(kFullMask, !alive);
+		if(__popc(idle) >= kTake)
+		{
+			if(q_count == 0u && !exhausted)
+			{
+				if(pool_next == pool_end)
+				{
+					uint32_t base = n;
+					if(cursor != nullptr)
+					{
+						if(lane == 0u) base = atomicAdd(cursor, uint32_t(kPoolRays));
+						base = __shfl_sync(kFullMask, base, 0);
+					}
+					else if(first_pool) base = static_base; // cursor-less launch: the warp owns rays [static_base, static_base + 32)
+					first_pool = false;
+					if(base >= n) exhausted = true;
+					else
+					{
+						pool_next = base;
+						const uint32_t pool = (cursor != nullptr) ? uint32_t(kPoolRays) : 32u;
+						pool_end = (n - base < pool) ? n : base + pool;
+					}
+				}
+				if(!exhausted)
+				{
+					// all 32 lanes set up the next 32 rays of the pool, whatever their own ray is doing
+					const uint32_t avail = min(32u, pool_end - pool_next);
+					q_count = setupPass<QUERY>(s, rays, pool_next, avail, out, tree_space, sh_queue);
+					pool_next += avail;
+				}
+			}
+			if(q_count != 0u)
+			{
+				const uint32_t rank = __popc(idle & lanes_below);
+				if(!alive && rank < q_count)
+				{
+					const float *e = sh_queue + (q_count - 1u - rank);
+					r.ox = e[0 * 32]; r.oy = e[1 * 32]; r.oz = e[2 * 32];
+					r.dx = e[3 * 32]; r.dy = e[4 * 32]; r.dz = e[5 * 32];
+					r.ix = e[6 * 32]; r.iy = e[7 * 32]; r.iz = e[8 * 32];
+					r.t_min = e[9 * 32]; r.t_max = e[10 * 32]; r.seg_lo = e[11 * 32]; r.seg_hi = e[12 * 32];
+					r.index = __float_as_uint(e[13 * 32]);
+					r.best_u = 0.f; r.best_v = 0.f; r.best_prim = B200RT_MISS;
+					r.node = 0u;
+					r.sp = 0;
+					ts.depth = 0;
+					floor = 0;
+					alive = true;
+					sh_axis[0][tid] = make_float2(r.ox, r.ix);
+					sh_axis[1][tid] = make_float2(r.oy, r.iy);
+					sh_axis[2][tid] = make_float2(r.oz, r.iz);
+					if(__builtin_expect(r.dx == 0.f || r.dy == 0.f || r.dz == 0.f, 0))
+					{
+						// axis-parallel ray: traversal copy of the origin one ulp lower on the zero-direction axes (floatBelow)
+						if(r.dx == 0.f) sh_axis[0][tid].x = floatBelow(r.ox);
+						if(r.dy == 0.f) sh_axis[1][tid].x = floatBelow(r.oy);
+						if(r.dz == 0.f) sh_axis[2][tid].x = floatBelow(r.oz);
+					}
+					sh_axis[3][tid] = make_float2(r.seg_lo, r.seg_hi); // where the ray enters and leaves the tree bound (read by replayTo); a leaf's "axis" 3 also reads this row, value unused
+				}
+				q_count -= min(q_count, uint32_t(__popc(idle)));
+				__syncwarp();
+			}
+		}
+#else
 		// ---------------- refill idle lanes ----------------
 		// One pass per round: every idle lane takes the next ray of the warp's pool.  Rays that miss the tree bound
 		// are answered on the spot and leave their lane idle until the next round (looping here until every lane
@@ -521,6 +658,10 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					pool_next = base;
 					const uint32_t pool = (cursor != nullptr) ? uint32_t(kPoolRays) : 32u;
 					pool_end = (n - base < pool) ? n : base + pool;
+#if B200RT_POOL_PREFETCH
+					// the pool is 8 KB of rays that will be read 8..32 rays at a time over the next few thousand cycles: pull it from HBM into L2 now
+					for(uint32_t line = lane; line * 4u < pool_end - base; line += 32u) prefetchL2(rays + base + line * 4u);
+#endif
 				}
 			}
 			if(!exhausted)
@@ -541,7 +682,6 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					ts.depth = 0;
 					floor = 0;
 					alive = setupRay<QUERY>(s, a, b, r, tree_space);
-#if B200RT_SMEM_RAY
 					sh_axis[0][tid] = make_float2(r.ox, r.ix);
 					sh_axis[1][tid] = make_float2(r.oy, r.iy);
 					sh_axis[2][tid] = make_float2(r.oz, r.iz);
@@ -552,17 +692,17 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 						if(r.dy == 0.f) sh_axis[1][tid].x = floatBelow(r.oy);
 						if(r.dz == 0.f) sh_axis[2][tid].x = floatBelow(r.oz);
 					}
-					sh_axis[3][tid] = make_float2(r.seg_lo, r.seg_hi); // where the ray enters and leaves the tree bound (replayTo); row 3 is also what a leaf's "axis" reads, unused there
-#endif
+					sh_axis[3][tid] = make_float2(r.seg_lo, r.seg_hi); // where the ray enters and leaves the tree bound (read by replayTo); a leaf's "axis" 3 also reads this row, value unused
 					if(!alive) writeResult<QUERY>(out, r, false, ts); // missed the tree bound
 				}
 				pool_next += min(avail, uint32_t(__popc(idle)));
 			}
 		}
+#endif
 		const unsigned m_alive = __ballot_sync(kFullMask, alive);
 		if(m_alive == 0u)
 		{
-			if(exhausted) break;
+			if(exhausted && q_count == 0u) break;
 			continue;
 		}
 		const unsigned m_pending = __ballot_sync(kFullMask, pending);
@@ -575,9 +715,14 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 			if(pending)
 			{
 				const float4 *rec = s.tris + leaf_first;
-				while(leaf_count != 0u)
+#if B200RT_LEAF_PREFETCH == 2
+				cpAsyncWaitAll();
+				float4 q0 = sh_leaf[0][tid], q1 = sh_leaf[1][tid], q2 = sh_leaf[2][tid];
+#else
+				float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+#endif
+				for(;;)
 				{
-					const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
 					const uint32_t flags = __float_as_uint(q1.w);
 					const bool quad = (flags & kFlagQuad) != 0u;
 					float u, v, t;
@@ -612,6 +757,8 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 							}
 						}
 					}
+					if(leaf_count == 0u) break;
+					q0 = __ldg(rec); q1 = __ldg(rec + 1); q2 = __ldg(rec + 2);
 				}
 				pending = false;
 				finished = hit || popNode();
@@ -640,7 +787,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					const uint32_t payload = nd.y >> 2; // interior: right child, leaf: primitive count
 					const bool is_leaf = (axis == 3u);
 					const float split = __uint_as_float(nd.x);
-					const float2 oi = sh_axis[axis][tid]; // row 3 (leaves) is never written: its value is not used
+					const float2 oi = sh_axis[axis][tid]; // row 3 (read at leaves) holds the tree interval: the value is not used there
 					const float o = oi.x, inv = oi.y;
 					const float t_plane = (split - o) * inv;
 					// near / far child without a predicate: m = all ones for a negative direction component
@@ -670,13 +817,28 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					r.seg_hi = selectf(do_pop, pop_far, selectf(both, t_plane, r.seg_hi));
 					if(both) r.sp += kRingStride;
 					if(do_pop) r.sp -= kRingStride;
+#if B200RT_FAR_PREFETCH
+					if(both) prefetchL1(&s.nodes[far]);
+#endif
 					go = !is_leaf || do_pop;
 				}
 			}
 			if(descending && !go)
 			{
 				// stopped at a leaf (leaf_count = its primitive count); node, interval and ring are as the step found them
-				if(leaf_count != 0u) pending = true;
+				if(leaf_count != 0u)
+				{
+					pending = true;
+#if B200RT_LEAF_PREFETCH == 1
+					prefetchL1(s.tris + leaf_first);
+					prefetchL1(s.tris + leaf_first + 2); // a 48-byte record may straddle two sectors
+#elif B200RT_LEAF_PREFETCH == 2
+					cpAsync16(&sh_leaf[0][tid], s.tris + leaf_first);
+					cpAsync16(&sh_leaf[1][tid], s.tris + leaf_first + 1);
+					cpAsync16(&sh_leaf[2][tid], s.tris + leaf_first + 2);
+					cpAsyncCommit();
+#endif
+				}
 				else
 				{
 					const bool closest_done = (QUERY == kClosest) && r.best_prim != B200RT_MISS && r.t_max <= r.seg_hi;
@@ -701,12 +863,23 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 
 
 template <int QUERY, bool SPHERES>
-__global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
+__global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(const __grid_constant__ SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
                                                                  typename OutType<QUERY>::type *__restrict__ out, uint32_t *__restrict__ cursor, int max_depth, bool tree_space)
 {
 	__shared__ uint2 sh_stack[kShortStack][kBlock]; // x = node index, y = float bits of the far end of its interval
-	__shared__ float2 sh_axis[4][kBlock];          // per axis: (origin, inverse direction) of the lane's ray; row 3 is read (not used) at leaves
-	traceWarps<QUERY, SPHERES>(s, rays, n, out, cursor, max_depth, tree_space, sh_stack, sh_axis, (blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5)) * 32u);
+	__shared__ float2 sh_axis[4][kBlock];          // rows 0-2: (origin, inverse direction) of the lane's ray per axis; row 3: the interval inside the tree bound
+#if B200RT_LEAF_PREFETCH == 2
+	__shared__ float4 sh_leaf[3][kBlock];          // the first record of the leaf a lane has stopped at, staged by cp.async
+#else
+	float4 (*sh_leaf)[kBlock] = nullptr;
+#endif
+#if B200RT_SETUP_QUEUE
+	__shared__ float sh_queue[kBlock / 32][kQueueFields][32]; // per warp: up to 32 set-up rays waiting for a lane, [field][entry]
+	float *queue = &sh_queue[threadIdx.x >> 5][0][0];
+#else
+	float *queue = nullptr;
+#endif
+	traceWarps<QUERY, SPHERES>(s, rays, n, out, cursor, max_depth, tree_space, sh_stack, sh_axis, (blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5)) * 32u, sh_leaf, queue);
 }
 
 // One launch for the closest, shadow and transparent-shadow rays of one flush of the renderer's ray queue
@@ -720,15 +893,26 @@ struct MixedBatch
 };
 
 template <bool SPHERES>
-__global__ void __launch_bounds__(kBlock, 4) traceMixedKernel(SceneView s, MixedBatch b, int max_depth, bool tree_space)
+__global__ void __launch_bounds__(kBlock, 4) traceMixedKernel(const __grid_constant__ SceneView s, MixedBatch b, int max_depth, bool tree_space)
 {
 	__shared__ uint2 sh_stack[kShortStack][kBlock];
 	__shared__ float2 sh_axis[4][kBlock];
+#if B200RT_LEAF_PREFETCH == 2
+	__shared__ float4 sh_leaf[3][kBlock];
+#else
+	float4 (*sh_leaf)[kBlock] = nullptr;
+#endif
+#if B200RT_SETUP_QUEUE
+	__shared__ float sh_queue[kBlock / 32][kQueueFields][32];
+	float *queue = &sh_queue[threadIdx.x >> 5][0][0];
+#else
+	float *queue = nullptr;
+#endif
 	const uint32_t warp = blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5);
 	const uint32_t w0 = (b.n[0] + 31u) / 32u, w1 = (b.n[1] + 31u) / 32u;
-	if(warp < w0) traceWarps<kClosest, SPHERES>(s, b.rays[0], b.n[0], static_cast<b200rt_hit *>(b.out[0]), nullptr, 0, tree_space, sh_stack, sh_axis, warp * 32u);
-	else if(warp < w0 + w1) traceWarps<kShadow, SPHERES>(s, b.rays[1], b.n[1], static_cast<uint32_t *>(b.out[1]), nullptr, 0, tree_space, sh_stack, sh_axis, (warp - w0) * 32u);
-	else traceWarps<kTShadow, SPHERES>(s, b.rays[2], b.n[2], static_cast<b200rt_tshadow *>(b.out[2]), nullptr, max_depth, tree_space, sh_stack, sh_axis, (warp - w0 - w1) * 32u);
+	if(warp < w0) traceWarps<kClosest, SPHERES>(s, b.rays[0], b.n[0], static_cast<b200rt_hit *>(b.out[0]), nullptr, 0, tree_space, sh_stack, sh_axis, warp * 32u, sh_leaf, queue);
+	else if(warp < w0 + w1) traceWarps<kShadow, SPHERES>(s, b.rays[1], b.n[1], static_cast<uint32_t *>(b.out[1]), nullptr, 0, tree_space, sh_stack, sh_axis, (warp - w0) * 32u, sh_leaf, queue);
+	else traceWarps<kTShadow, SPHERES>(s, b.rays[2], b.n[2], static_cast<b200rt_tshadow *>(b.out[2]), nullptr, max_depth, tree_space, sh_stack, sh_axis, (warp - w0 - w1) * 32u, sh_leaf, queue);
 }
 
 } // namespace b200rt

@@ -143,3 +143,30 @@ def surface_rays(rays, t, seed, tmin=0.0005):
     out = np.zeros((p.shape[0], 8), np.float32)
     out[:, 0:3] = p; out[:, 3] = tmin; out[:, 4:7] = rng.normal(size=p.shape).astype(np.float32); out[:, 7] = -1.0
     return out
+
+
+def parity_counts(got_prim, got_t, ref, rtol=1e-5):
+    """(ids equal incl. ties, id mismatches, of which not ties: hit/miss differs or t apart by more than rtol)."""
+    same = got_prim == ref["prim"]
+    diff = np.flatnonzero(~same)
+    rel = np.abs(got_t[diff].astype(np.float64) - ref["t"][diff]) / np.maximum(np.abs(ref["t"][diff]), 1e-30)
+    non_tie = (rel > rtol) | ((got_prim[diff] >= 0) != (ref["prim"][diff] >= 0))
+    return float(same.mean()) if len(same) else 1.0, int(diff.size), int(non_tie.sum())
+
+
+def report(kind, **fields):
+    """Append one JSON line to gpurun_out/parity_report.jsonl (travels back from the GPU box; summarised under profiles/)."""
+    import json, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    try:
+        os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(root, "gpurun_out", "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps(dict(kind=kind, **fields)) + "\n")
+    except OSError:
+        pass
+
+
+def cube_grid_far():
+    """The thin-slab cube grid moved to coordinates of 300 (ulp 3e-5): 1-ulp slabs AND a coarse float grid."""
+    x, i, f = scenes.cube_grid(5)
+    return (x + np.array([300.0, 300.0, 300.0], np.float32)).astype(np.float32), i, f

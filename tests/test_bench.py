@@ -33,6 +33,10 @@ def test_reference_arm_prints_the_contract_line(built):
     base = rec["cpu_baseline"]
     assert base["kind"] in ("reference", "port") and base["cores"] >= 1 and base["value"] == rec["value"] and "sample" in base
     assert rec["gpu_launches"] == 0 and "workload" in rec["config"]
+    # both arms print the same config object (the driver compares them)
+    import bench
+    args = bench.parse.__globals__["argparse"].Namespace(workload="s1m", rays=65536, cells=48)
+    assert set(rec["config"]) == set(bench.config_dict(args, 1))
 
 
 def test_reference_arm_other_ranks_exit_quietly(built):
@@ -60,7 +64,13 @@ def test_product_arm_line_on_the_gpu(built):
     assert rec["n_gpus"] == 1 and rec["scaling"] == "weak" and rec["dtype"] == "f32" and rec["vs_baseline"] is None
     assert rec["gpu_launches"] == 2 * rec["steps"], "one closest and one shadow launch per step"
     roof = rec["roofline"]
-    assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and roof["peak"] > 1000 and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
+    assert roof["kernel"] == "b200rt::traceKernel<0,false>"
+    assert roof["bound"] in ("hbm", "issue") and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
+    assert roof["hbm"]["unit"] == "GB/s" and roof["hbm"]["peak"] > 1000 and abs(roof["hbm"]["frac"] - roof["hbm"]["achieved"] / roof["hbm"]["peak"]) < 1e-9
+    assert roof["traffic"] is None, "a reduced-size run must not carry the full-size ncu traffic figure"
+    par = rec["parity"]
+    assert par["rays_compared"] > 0 and par["non_tie_mismatches"] == 0 and par["shadow_bool_mismatches"] == 0 and par["tuv_bit_identical_where_ids_equal"]
+    assert rec["tshadow"]["mrays_per_gpu"] > 0 and rec["tshadow"]["mean_transparent_casters_on_lit_rays"] > 0
     e2e = rec["e2e"]
     assert e2e["h2d_bytes_per_step"] == 2 * (1 << 20) * 32 and e2e["d2h_bytes_per_step"] == (1 << 20) * 20 and 0 < e2e["value"] < rec["value"]
     assert rec["cpu_baseline"]["value"] > 0 and rec["cpu_baseline"]["kind"] in ("reference", "port")

@@ -403,8 +403,7 @@ def _adversarial_scenes():
     out = {}
     x, i, f = scenes.objects(20000, n_spheres=10, seed=41)
     out["far_from_origin"] = ((x + np.array([1000.0, 2000.0, -500.0], np.float32)).astype(np.float32), i, f)  # coarse float grid: 6e-5 ulps
-    x, i, f = scenes.cube_grid(5)
-    out["cube_grid_far"] = ((x + np.array([300.0, 300.0, 300.0], np.float32)).astype(np.float32), i, f)         # thin slabs AND coarse t
+    out["cube_grid_far"] = helpers.cube_grid_far()                                                               # thin slabs AND coarse t
     x, i, f = scenes.heightfield(60)
     flat = x.copy(); flat[:, 2] = 0.25
     out["flat_with_duplicates"] = (np.concatenate([flat, flat]), np.concatenate([i, i + np.uint32(np.where(i == scenes.TRI, 0, flat.shape[0]))]).astype(np.uint32),
@@ -441,17 +440,21 @@ def test_adversarial_scenes(built, name):
         h = s.trace_closest(rays)
         shadow_differs = (s.trace_shadow(rays) != rt.MISS).astype(np.uint8) != o.trace_shadow(rays, threads=NCPU)["shadowed"]
         if name == "cube_grid_far":
-            # At coordinates of 300 (ulp 3e-5) with faces planar up to one ulp, the REFERENCE traversal itself stops being
-            # tree-independent: run over two valid trees (the oracle's and libb200rt's) it disagrees on ~2 rays in 100 000 that
-            # graze cube edges -- hit/miss included (measured on the CPU, no GPU involved).  Those are neither ties nor
-            # errors of either tree; the bar here is the north-star's 99.99 % without the tie classification.
+            # At coordinates of 300 (ulp 3e-5) with faces planar up to one ulp no kd traversal is exact any more: the UNMODIFIED
+            # reference on its own tree differs from a brute-force test of all primitives on ~1e-4 of these rays, hit/miss
+            # included (pinned without any code of ours by tests/test_oracle.py::test_reference_itself_is_not_exact_on_cube_grid_far).
+            # Two bars instead of the tie classification: (1) against brute force the kernel may be wrong no more often than
+            # the reference is (2.5e-4, same bound as in that test); (2) on the SAME tree the kernel must agree with the
+            # reference traversal restated over it (below, test_same_tree_exactness) .
             prim = helpers.prim_signed(h["prim"])
-            same = prim == rr["prim"]
-            rel = np.abs(h["t"] - rr["t"]) / np.maximum(np.abs(rr["t"]), 1e-30)
-            non_tie = (~same) & ((rel > 1e-5) | ((prim >= 0) != (rr["prim"] >= 0)))
-            assert np.array_equal(h["t"][same], rr["t"][same])
-            assert non_tie.mean() <= 1e-4 and shadow_differs.mean() <= 1e-4, (int(non_tie.sum()), int(shadow_differs.sum()))
-            assert same.mean() >= 0.97
+            brute = o.brute_closest(rays, threads=NCPU)
+            agree, n_diff, n_bad = helpers.parity_counts(prim, h["t"], brute)
+            helpers.report("cube_grid_far_vs_brute", rays=int(rays.shape[0]), ids_equal=agree, id_mismatches=n_diff, non_tie=n_bad,
+                           shadow_differs_vs_other_tree=int(shadow_differs.sum()))
+            same = prim == brute["prim"]
+            assert np.array_equal(h["t"][same], brute["t"][same])
+            assert n_bad <= 2.5e-4 * rays.shape[0] and shadow_differs.mean() <= 2.5e-4, (n_diff, n_bad, int(shadow_differs.sum()))
+            assert agree >= 0.97
             continue
         helpers.check_closest_parity(helpers.prim_signed(h["prim"]), h["t"], h["u"], h["v"], rr, min_agree=floor)
         assert not shadow_differs.any()
@@ -483,4 +486,84 @@ def test_rays_lying_in_split_planes(built):
     assert (ref["prim"] >= 0).mean() > 0.2
     helpers.check_closest_parity(helpers.prim_signed(h["prim"]), h["t"], h["u"], h["v"], ref, min_agree=0.97)
     assert np.array_equal((s.trace_shadow(rays) != rt.MISS).astype(np.uint8), same_tree.trace_shadow(rays, threads=NCPU)["shadowed"])
+    s.close()
+
+
+SAME_TREE = dict(ZOO)
+SAME_TREE["cube_grid_far"] = helpers.cube_grid_far()
+
+
+@pytest.mark.parametrize("name", sorted(SAME_TREE))
+def test_same_tree_exactness(built, name):
+    """The kernel against the REFERENCE TRAVERSAL restated over the very tree the kernel walks (b200rt_host_tree_export ->
+    oracle), on the whole zoo and WITH the edge-case rays (axis-parallel, exact diagonals, origins on the bound) that the
+    cross-tree tests leave out on the cube grids: with the tree taken out of the comparison, hit/miss and t must agree on
+    every ray -- what orthographic cameras and directional lights shoot through axis-aligned geometry included -- and
+    ids may differ only where two primitives are hit at exactly the same t in different leaves or in another order (the kernel
+    orders leaves by t-interval, the reference by stored entry/exit points).  The counts go to gpurun_out/parity_report.jsonl."""
+    xyz, idx, flags = SAME_TREE[name]
+    is_sphere = idx[:, 2] == scenes.SPHERE
+    s = make_scene(xyz, idx, flags)
+    tree = rt.host_tree(xyz, idx)
+    o = kdo.Oracle(xyz, idx, flags, tree=helpers.host_tree_as_oracle_tree(tree), bound=tree["bound"])
+    assert np.array_equal(s.bound(), o.bound())
+    closest, shadow = helpers.ray_zoo(s.bound(), n=200000, seed=23, edge_cases=True)
+    n_edge = scenes.rays_edge_cases(s.bound()[:3], s.bound()[3:], seed=1).shape[0]
+    h = s.trace_closest(closest)
+    ref = o.trace_closest(closest, threads=NCPU)
+    prim = helpers.prim_signed(h["prim"])
+    agree, n_diff, n_bad = helpers.parity_counts(prim, h["t"], ref, rtol=0.0)   # rtol 0: a "tie" must be the same t exactly
+    e_agree, e_diff, e_bad = helpers.parity_counts(prim[-n_edge:], h["t"][-n_edge:], {k: v[-n_edge:] for k, v in ref.items() if k in ("prim", "t")}, rtol=0.0)
+    sh = (s.trace_shadow(shadow) != rt.MISS).astype(np.uint8)
+    rs = o.trace_shadow(shadow, threads=NCPU)["shadowed"]
+    helpers.report("same_tree", scene=name, rays=int(closest.shape[0]), ids_equal=agree, id_mismatches=n_diff, not_exact_t_ties=n_bad,
+                   edge_rays=int(n_edge), edge_id_mismatches=e_diff, edge_not_exact=e_bad, shadow_bool_mismatches=int((sh != rs).sum()),
+                   spheres=bool(is_sphere.any()))
+    same = prim == ref["prim"]
+    assert np.array_equal(h["t"][same], ref["t"][same]) and np.array_equal(h["u"][same], ref["u"][same]) and np.array_equal(h["v"][same], ref["v"][same])
+    assert n_bad == 0, f"{n_bad} rays differ in hit/miss or t on the same tree ({n_diff} id mismatches)"
+    assert agree >= (0.995 if "cube" in name else 0.99999), (agree, n_diff)
+    assert np.array_equal(sh, rs)
+    s.close()
+
+
+def _sample_parity_on_exported_tree(xyz, idx, flags, n_rays, seed, label):
+    s = make_scene(xyz, idx, flags)
+    tree = rt.host_tree(xyz, idx)
+    o = kdo.Oracle(xyz, idx, flags, tree=helpers.host_tree_as_oracle_tree(tree), bound=tree["bound"])
+    b = s.bound()
+    rays = scenes.rays_incoherent(n_rays, seed=seed, lo=b[:3], hi=b[3:])
+    diag = float(np.linalg.norm(b[3:].astype(np.float64) - b[:3]))
+    srays = scenes.rays_shadow(n_rays, seed=seed + 1, lo=b[:3], hi=b[3:], t_max=0.25 * diag)
+    h = s.trace_closest(rays)
+    ref = o.trace_closest(rays, threads=NCPU)
+    prim = helpers.prim_signed(h["prim"])
+    agree, n_diff, n_bad = helpers.parity_counts(prim, h["t"], ref)
+    sh = (s.trace_shadow(srays) != rt.MISS).astype(np.uint8)
+    rs = o.trace_shadow(srays, threads=NCPU)["shadowed"]
+    helpers.report("regime_sample", scene=label, faces=int(idx.shape[0]), rays=int(n_rays), ids_equal=agree, id_mismatches=n_diff, non_tie=n_bad,
+                   shadow_bool_mismatches=int((sh != rs).sum()), hit_fraction=float((prim >= 0).mean()), tree_nodes=int(tree["a"].shape[0]))
+    helpers.check_closest_parity(prim, h["t"], h["u"], h["v"], ref)
+    assert np.array_equal(sh, rs)
+    return s, rays, h
+
+
+def test_s10m_sample_against_oracle(built):
+    """BASELINE.json configs[3]'s geometry (10 M-triangle object scene, 2 GB on the device, HBM-resident): a 400 k-ray sample
+    against the reference traversal restated over the exported tree (a second 10 M-triangle build is not needed that way)."""
+    xyz, idx, flags = scenes.objects(10_000_000)
+    s, rays, h = _sample_parity_on_exported_tree(xyz, idx, flags, 400000, 71, "S10M-objects")
+    assert s.stats()["n_faces"] > 9_900_000
+    s.close()
+
+
+def test_soup_1m_sample_against_oracle_and_live_reference(built):
+    """The worst case for a kd-tree: 1 M random triangles (177 interior + 44 leaf visits and 34 primitive tests per ray)."""
+    xyz, idx, flags = scenes.soup(1_000_000)
+    s, rays, h = _sample_parity_on_exported_tree(xyz, idx, flags, 400000, 73, "S1M-soup")
+    if yref.available():
+        ref = yref.RefScene(xyz, idx, flags)
+        r = ref.trace_closest(rays[:200000], threads=NCPU)
+        helpers.check_closest_parity(helpers.prim_signed(h["prim"][:200000]), h["t"][:200000], h["u"][:200000], h["v"][:200000], r)
+        ref.close()
     s.close()

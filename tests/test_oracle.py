@@ -154,3 +154,33 @@ def test_empty_and_degenerate(built):
     idx = np.array([[0, 1, 2, 0xFFFFFFFF]], np.uint32)
     o = kdo.Oracle(xyz, idx)
     assert np.all(o.trace_closest(scenes.rays_incoherent(1000, lo=(0, 0, 0), hi=(2, 2, 2)))["prim"] == -1)
+
+
+@pytest.mark.skipif(not yref.available(), reason="oracle/_ref/libyafref.so was not built")
+def test_reference_itself_is_not_exact_on_cube_grid_far(built):
+    """Pins the claim behind the tolerance of tests/test_gpu.py::test_adversarial_scenes[cube_grid_far] WITHOUT any code of
+    ours in the loop: at coordinates of 300 with cube faces planar only up to one ulp, the UNMODIFIED reference on ITS OWN
+    kd-tree returns, for a few rays in 100 000, something else than a brute-force test of every primitive with the same
+    arithmetic and accept rules (it misses hits outright or reports a farther one: rays grazing cube edges walk through a
+    slab that is thinner than the resolution of its stored entry/exit points).  So on this scene no tree -- the reference's
+    included -- reproduces "the" answer, and two valid trees may differ by that much.  The rate is bounded here; the GPU test
+    holds the kernel to the same bound against brute force and to EXACT agreement with the reference traversal restated on
+    the same tree."""
+    xyz, idx, flags = helpers.cube_grid_far()
+    ref = yref.RefScene(xyz, idx, flags)
+    b = ref.bound().astype(np.float64)
+    ext = np.maximum(b[3:] - b[:3], 1e-3)
+    primary = scenes.rays_incoherent(300000, seed=51, lo=b[:3] - 0.3 * ext, hi=b[3:] + 0.3 * ext)
+    o = kdo.Oracle(xyz, idx, flags)
+    ncpu = os.cpu_count() or 1
+    r1 = ref.trace_closest(primary, threads=ncpu)
+    surface = helpers.surface_rays(primary, r1["t"], seed=52, tmin=0.0005 * float(np.linalg.norm(ext)))
+    total_bad = 0
+    for rays in (primary, surface):
+        r = ref.trace_closest(rays, threads=ncpu)
+        brute = o.brute_closest(rays, threads=ncpu)
+        _, n_diff, n_bad = helpers.parity_counts(r["prim"].astype(np.int64), r["t"], brute)
+        assert n_bad <= 2.5e-4 * rays.shape[0], (n_diff, n_bad)  # measured: 10 of 300 000 primary, 8 of 66 693 on-surface rays
+        total_bad += n_bad
+    assert total_bad > 0, "the reference agreed with brute force everywhere: tighten test_adversarial_scenes[cube_grid_far]"
+    ref.close()

@@ -3,6 +3,9 @@
 
     python tools/ncu_summary.py rep  gpurun_out/prof.ncu-rep  > profiles/r1_closest.txt
     python tools/ncu_summary.py list gpurun_out/launches.csv   > profiles/r1_launches.txt
+    python tools/ncu_summary.py json <workload> gpurun_out/prof.ncu-rep   merges the counters bench.py reads (roofline.traffic,
+        warp instructions per ray) into profiles/kernel_counters.json, keyed by the hash of the kernel source as it is NOW --
+        run it right after the capture, before editing kd_kernels.cuh
 """
 import csv
 import io
@@ -61,5 +64,52 @@ def launch_list(path):
         print(f"{k[:70]:70s} {len(v):8d} {sum(v) / len(v):14.1f} {sum(v):16.1f} {100 * sum(v) / total:6.1f}%")
 
 
+def to_json(workload, path):
+    import json, os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr = rows[0]
+    dest = bench.COUNTERS_JSON
+    try:
+        rec = json.load(open(dest))
+    except Exception:
+        rec = {}
+    sha = bench.kernel_source_hash()
+    if rec.get("kernel_source_sha") != sha:
+        rec = {"kernel_source_sha": sha, "workloads": {}}
+    rec["source"] = "ncu --set full --clock-control none captures summarised by tools/ncu_summary.py json; per launch"
+    kinds = {"0": "closest", "1": "shadow", "2": "tshadow"}
+    w = rec["workloads"].setdefault(workload, {})
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        m = re.search(r"traceKernel<\(int\)(\d)", d.get("Kernel Name", ""))
+        if not m or kinds[m.group(1)] in w:
+            continue  # the first launch of each kind
+        f = lambda k: float(d[k].replace(",", "")) if d.get(k) not in (None, "") else None
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        u = dict(zip(hdr, rows[1]))
+        dram = sum(f(k) * scale[u[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        t_unit = {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}[u["gpu__time_duration.sum"]]
+        w[kinds[m.group(1)]] = {
+            "kernel": d["Kernel Name"].split("(")[0].replace("void ", ""), "capture": os.path.basename(path),
+            "duration_ms_under_ncu": f("gpu__time_duration.sum") * t_unit, "dram_bytes": dram,
+            "dram_bytes_read": f("dram__bytes_read.sum") * scale[u["dram__bytes_read.sum"]],
+            "warp_inst": f("smsp__inst_executed.sum"), "lanes_per_inst": f("smsp__thread_inst_executed_per_inst_executed.ratio"),
+            "issue_active_pct": f("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "l2_sector_bytes": 32.0 * ((f("lts__t_sectors_op_read.sum") or 0.0) + (f("lts__t_sectors_op_write.sum") or 0.0)),
+            "l1_hit_pct": f("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": f("lts__t_sector_hit_rate.pct"),
+            "long_scoreboard_per_issue": f("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
+            "registers": f("launch__registers_per_thread"),
+        }
+    json.dump(rec, open(dest, "w"), indent=1, sort_keys=True)
+    print(json.dumps(rec["workloads"][workload], indent=1))
+
+
 if __name__ == "__main__":
-    (rep if sys.argv[1] == "rep" else launch_list)(sys.argv[2])
+    if sys.argv[1] == "json":
+        to_json(sys.argv[2], sys.argv[3])
+    else:
+        (rep if sys.argv[1] == "rep" else launch_list)(sys.argv[2])
