@@ -100,6 +100,8 @@ struct b200rt_scene
 	uint32_t *d_cursors = nullptr;          // ring of ray cursors, one per launch in flight
 	std::atomic<uint32_t> next_cursor{0};
 	int resident_blocks[3] = {0, 0, 0};     // blocks of traceKernel<Q> that fit the whole device
+	int resident_blocks_queued[3] = {0, 0, 0}; // the same for the queue-fed variant of the two-pass path
+	int setup_blocks = 0;                   // blocks of setupKernel for one resident wave
 	std::mutex lane_mutex;
 	std::vector<std::unique_ptr<Lane>> free_lanes;
 
@@ -317,6 +319,8 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, La
 
 constexpr uint32_t kCursorRing = 4096;
 constexpr size_t kMaxRaysPerLaunch = size_t(1) << 30;
+constexpr size_t kTwoPassRays = size_t(1) << 15;        // batches from this size on take the two-pass path (setup pass + queue-fed traversal)
+constexpr size_t kMaxRaysPerTwoPass = size_t(1) << 26;  // 64 Mi rays = 3.5 GiB of queue scratch at most per launch pair
 
 int checkDeviceCall(const b200rt_scene *s, const void *rays, size_t n, const void *out)
 {
@@ -340,6 +344,41 @@ int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b2
 		CUDA_TRY(cudaGetLastError());
 		return B200RT_OK;
 	}
+	const bool tree_space = (flags & B200RT_RAYS_TREE_SPACE) != 0u;
+#if B200RT_TWO_PASS
+	if(n >= kTwoPassRays)
+	{
+		// Two-pass batch (kd_kernels.cuh): setupKernel answers the rays that miss the tree bound and queues the others, set up,
+		// in HBM; traceKernel<.., QUEUED> pulls the queue through shared memory with TMA bulk copies.  The queue is stream-ordered
+		// scratch (cudaMallocAsync / cudaFreeAsync on the caller's stream: no synchronisation, the pool keeps the memory).
+		for(size_t begin = 0; begin < n; begin += kMaxRaysPerTwoPass)
+		{
+			const uint32_t count = uint32_t(std::min(kMaxRaysPerTwoPass, n - begin));
+			const uint32_t n_regions = (count + uint32_t(b200rt::kRegionRays) - 1u) / uint32_t(b200rt::kRegionRays);
+			float *queue = nullptr;
+			CUDA_TRY(cudaMallocAsync(&queue, size_t(n_regions) * b200rt::kRegionFloats * sizeof(float), stream));
+			uint32_t *cursor = s->d_cursors + (s->next_cursor.fetch_add(1) % kCursorRing);
+			cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(uint32_t), stream);
+			if(e == cudaSuccess)
+			{
+				const unsigned setup_grid = std::max(1u, std::min((n_regions + 7u) / 8u, unsigned(s->setup_blocks)));
+				b200rt::setupKernel<Q><<<setup_grid, 256, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, queue, tree_space);
+				++g_launches;
+				const unsigned wanted = unsigned((size_t(n_regions) + b200rt::kBlock / 32 - 1) / (b200rt::kBlock / 32));
+				const unsigned grid = std::max(1u, std::min(wanted, unsigned(s->resident_blocks_queued[Q])));
+				const b200rt_ray *as_rays = reinterpret_cast<const b200rt_ray *>(queue);
+				if(s->has_spheres) b200rt::traceKernel<Q, true, true><<<grid, b200rt::kBlock, 0, stream>>>(s->view, as_rays, n_regions, d_out + begin, cursor, max_depth, tree_space);
+				else b200rt::traceKernel<Q, false, true><<<grid, b200rt::kBlock, 0, stream>>>(s->view, as_rays, n_regions, d_out + begin, cursor, max_depth, tree_space);
+				++g_launches;
+				e = cudaGetLastError();
+			}
+			const cudaError_t e_free = cudaFreeAsync(queue, stream);
+			if(e != cudaSuccess) return fail(B200RT_E_CUDA, std::string("two-pass trace: ") + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+			CUDA_TRY(e_free);
+		}
+		return B200RT_OK;
+	}
+#endif
 	for(size_t begin = 0; begin < n; begin += kMaxRaysPerLaunch)
 	{
 		const uint32_t count = uint32_t(std::min(kMaxRaysPerLaunch, n - begin));
@@ -347,32 +386,41 @@ int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b2
 		CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), stream));
 		const unsigned wanted = unsigned((size_t(count) + b200rt::kBlock - 1) / b200rt::kBlock);
 		const unsigned grid = std::max(1u, std::min(wanted, unsigned(s->resident_blocks[Q])));
-		if(s->has_spheres) b200rt::traceKernel<Q, true><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, cursor, max_depth, (flags & B200RT_RAYS_TREE_SPACE) != 0u);
-		else b200rt::traceKernel<Q, false><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, cursor, max_depth, (flags & B200RT_RAYS_TREE_SPACE) != 0u);
+		if(s->has_spheres) b200rt::traceKernel<Q, true><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, cursor, max_depth, tree_space);
+		else b200rt::traceKernel<Q, false><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, cursor, max_depth, tree_space);
 		++g_launches;
 		CUDA_TRY(cudaGetLastError());
 	}
 	return B200RT_OK;
 }
 
-template <int Q, bool SPHERES>
+template <int Q, bool SPHERES, bool QUEUED>
 int queryResidencyOf(b200rt_scene *s, int &blocks)
 {
 	int per_sm = 0, sms = 0;
 #ifdef B200RT_CARVEOUT
-	CUDA_TRY(cudaFuncSetAttribute(b200rt::traceKernel<Q, SPHERES>, cudaFuncAttributePreferredSharedMemoryCarveout, B200RT_CARVEOUT));
+	CUDA_TRY(cudaFuncSetAttribute(b200rt::traceKernel<Q, SPHERES, QUEUED>, cudaFuncAttributePreferredSharedMemoryCarveout, B200RT_CARVEOUT));
 #endif
-	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b200rt::traceKernel<Q, SPHERES>, b200rt::kBlock, 0));
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b200rt::traceKernel<Q, SPHERES, QUEUED>, b200rt::kBlock, 0));
 	CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
 	blocks = std::max(1, per_sm) * std::max(1, sms);
 	return B200RT_OK;
 }
 
-// one resident wave of the kernel variant this scene launches (with or without the sphere branch)
+// one resident wave of the kernel variants this scene launches (with or without the sphere branch; single-kernel and queue-fed)
 template <int Q>
 int queryResidency(b200rt_scene *s)
 {
-	return s->has_spheres ? queryResidencyOf<Q, true>(s, s->resident_blocks[Q]) : queryResidencyOf<Q, false>(s, s->resident_blocks[Q]);
+	int rc = s->has_spheres ? queryResidencyOf<Q, true, false>(s, s->resident_blocks[Q]) : queryResidencyOf<Q, false, false>(s, s->resident_blocks[Q]);
+	if(rc == B200RT_OK) rc = s->has_spheres ? queryResidencyOf<Q, true, true>(s, s->resident_blocks_queued[Q]) : queryResidencyOf<Q, false, true>(s, s->resident_blocks_queued[Q]);
+	if(rc == B200RT_OK && Q == b200rt::kClosest)
+	{
+		int per_sm = 0, sms = 0;
+		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b200rt::setupKernel<b200rt::kClosest>, 256, 0));
+		CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+		s->setup_blocks = std::max(1, per_sm) * std::max(1, sms);
+	}
+	return rc;
 }
 
 } // namespace
@@ -405,6 +453,16 @@ int b200rt_create(int device, const b200rt_build_params *params, b200rt_scene **
 	if(device < 0 || device >= n) return fail(B200RT_E_INVALID, "device index out of range");
 	CUDA_TRY(cudaSetDevice(device));
 	CUDA_TRY(cudaFree(nullptr));
+	{
+		// the two-pass path takes its ray queue from the stream-ordered allocator: let the pool keep what it has handed out
+		cudaMemPool_t pool = nullptr;
+		if(cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool)
+		{
+			uint64_t keep = ~uint64_t(0);
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+		}
+		cudaGetLastError();
+	}
 	b200rt_scene *s = new(std::nothrow) b200rt_scene;
 	if(!s) return fail(B200RT_E_MEMORY, "out of host memory");
 	s->device = device;

@@ -224,13 +224,39 @@ __device__ __forceinline__ float sphereIntersect(const float4 q0, float radius, 
 //   LEAF_PREFETCH 2: cp.async (LDGSTS) of that record into the lane's shared-memory staging slot; the leaf phase reads it from there
 //   FAR_PREFETCH  1: prefetch.global.L1 of the postponed far child when it is pushed
 //   POOL_PREFETCH 1: prefetch.global.L2 of the whole 256-ray pool when the warp takes it from the cursor
-// SETUP_QUEUE 1: converged ray setup.  When a lane is idle and the warp's ready queue is empty, ALL 32 lanes set up the next 32
-// rays of the pool at once (the ~170-instruction setup with its three IEEE divisions ran at ~10 of 32 lanes when only the idle
-// lanes did it); rays that miss the tree bound -- 41 % of the BASELINE closest rays -- are answered right there and never occupy
-// a lane; the others are compacted into a 32-entry queue in shared memory from which idle lanes take a ready ray every round.
-// tools/simt_model.cc predicted 116 -> 96 warp instructions per ray for it; measured in profiles/r3b_*.
-#ifndef B200RT_SETUP_QUEUE
-#define B200RT_SETUP_QUEUE 1
+// Two-pass batches (setupKernel feeding traceKernel<.., QUEUED>): ray setup -- ~170 instructions with three IEEE divisions,
+// executed by ~10 of 32 lanes when idle lanes did it inside the traversal loop -- runs as its own fully converged,
+// bandwidth-bound pass that answers the rays missing the tree bound (41 % of the BASELINE closest rays) on the spot and writes
+// the others, set up, to a queue in HBM: 256-ray regions of 32-entry groups laid out [field][entry].  The traversal kernel's
+// warps pull whole groups into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier; SASS UBLKCP / SYNCS), issued
+// as soon as the previous group has been handed out, and idle lanes take a ready ray every round.  An in-kernel variant of the
+// same idea (a converged setup pass inside the traversal loop) executed 10 % fewer instructions at 18.8 instead of 16.0 lanes
+// but needed 72 registers; held to the 56 of 9 blocks/SM its spills (47 M local accesses per launch, 22 % L1 hits) made it 13 %
+// slower (profiles/r3d_*).  tools/simt_model.cc is the cost model both were designed with.  TWO_PASS 0 keeps large batches on
+// the single-kernel path (rays set up by idle lanes), which small batches and the renderer's mixed-kind flushes always use.
+#ifndef B200RT_TWO_PASS
+#define B200RT_TWO_PASS 1
+#endif
+// QUEUE_TMA 1: groups are staged in shared memory by bulk copies as described; 7 KB more shared memory per block moved the SM to
+// the 196 KB carve-out and left 32 KB of L1: 33 % instead of 54 % L1 hits on node loads, 2.67 ms for the traversal pass although it
+// executed 18 % fewer instructions (profiles/r3e_*).  QUEUE_TMA 0: lanes read their entry straight from the queue in HBM / L2
+// (coalesced, the next group prefetched into L2), shared memory stays at 12 KB per block.
+#ifndef B200RT_QUEUE_TMA
+#define B200RT_QUEUE_TMA 0
+#endif
+// TDONE 1: the descent reads one register, t_done = +inf until a hit is accepted and the hit's t from then on, instead of
+// (best_prim, t_max): "closest so far ends the ray" and the near/far limit become one compare and one min (same decisions: without
+// a hit seg_hi never exceeds the ray's t_max).  AXIS_MAD 1: the address of the per-axis row as one multiply-add.
+#ifndef B200RT_TDONE
+#define B200RT_TDONE 0
+#endif
+#ifndef B200RT_AXIS_MAD
+#define B200RT_AXIS_MAD 0
+#endif
+// RING_OR 1: the ring is aligned to its own size, so a slot's address is (column address | slot bits): one LOP3 instead of
+// LOP3 + IADD for the speculative store and for the read of the top entry.
+#ifndef B200RT_RING_OR
+#define B200RT_RING_OR 0
 #endif
 #ifndef B200RT_LEAF_PREFETCH
 #define B200RT_LEAF_PREFETCH 0
@@ -247,12 +273,21 @@ static constexpr int kBlock = B200RT_BLOCK;
 #define B200RT_POOL 256
 #endif
 static constexpr int kPoolRays = B200RT_POOL;       // rays taken from the global cursor per atomicAdd
-static constexpr int kRefill = B200RT_REFILL;       // idle lanes that trigger a refill (SETUP_QUEUE 0)
+static constexpr int kRefill = B200RT_REFILL;       // idle lanes that trigger a refill (single-kernel path)
 #ifndef B200RT_TAKE
 #define B200RT_TAKE 1
 #endif
-static constexpr int kTake = B200RT_TAKE;           // idle lanes that trigger a hand-out from the ready queue (SETUP_QUEUE 1)
-static constexpr int kQueueFields = 14;             // o, d, 1/d, t_min, t_max, interval in the tree bound, ray index
+static constexpr int kTake = B200RT_TAKE;           // idle lanes that trigger a hand-out from the ready queue (two-pass batches)
+// Ray queue between the two passes.  A REGION holds the rays of 256 consecutive batch indices that cross the tree bound, compacted,
+// in up to 8 GROUPS of 32 entries; a group is kQueueFields rows of 32 floats ([field][entry], 1792 bytes = one bulk copy):
+// rows 0-2 origin, 3-5 direction, 6-8 traversal 1/direction, 9 t_min, 10 t_max, 11-12 interval inside the tree bound, 13 ray index.
+// Entries past a region's last ray carry index B200RT_MISS in row 13 of the first group that is not full (that is how the
+// traversal pass learns a region's size without a second array).
+static constexpr int kQueueFields = 14;
+static constexpr int kRegionRays = 256;
+static constexpr int kGroupFloats = kQueueFields * 32;
+static constexpr int kGroupBytes = kGroupFloats * 4;
+static constexpr int kRegionFloats = (kRegionRays / 32) * kGroupFloats;
 static constexpr int kLeafBatch = B200RT_LEAF_BATCH; // lanes holding a leaf that trigger the leaf phase
 static constexpr int kUnroll = B200RT_UNROLL;       // unroll factor of the descent loop
 static constexpr int kSteps = B200RT_STEPS;         // node steps per lane between two warp votes
@@ -265,6 +300,7 @@ struct RayState
 	float ix, iy, iz;             // traversal inverse direction
 	float t_min;                  // ray bias
 	float t_max;                  // closest: shrinking; shadow: fixed
+	float t_done;                 // closest (TDONE): +inf until a hit is accepted, then its t
 	float seg_lo, seg_hi;
 	float best_u, best_v;
 	uint32_t best_prim;
@@ -272,6 +308,16 @@ struct RayState
 	uint32_t index;               // ray index in the batch
 	int sp;                       // ring depth in bytes (kRingStride per entry)
 };
+
+// closest: once the best hit is not beyond the end of the current leaf nothing nearer can follow (accelerator_kdtree_common.h:232)
+__device__ __forceinline__ bool closestDone(const RayState &r)
+{
+#if B200RT_TDONE
+	return r.t_done <= r.seg_hi;
+#else
+	return r.best_prim != B200RT_MISS && r.t_max <= r.seg_hi;
+#endif
+}
 
 // Ray setup: root slab test (bound.h:156-198), bias (accelerator.h:64), traversal interval.  Returns false when
 // the ray misses the tree bound.
@@ -331,6 +377,7 @@ __device__ __forceinline__ bool setupRay(const SceneView &s, const float4 a, con
 	r.seg_lo = fmaxf(lmin, 0.f);
 	r.seg_hi = fminf(lmax, t_max);
 	r.best_u = 0.f; r.best_v = 0.f; r.best_prim = B200RT_MISS;
+	r.t_done = __int_as_float(0x7f800000);
 	r.node = 0u;
 	r.sp = 0;
 	return crossed;
@@ -433,43 +480,25 @@ __device__ __forceinline__ void cpAsync16(void *smem, const void *gmem)
 __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Converged ray setup (SETUP_QUEUE): lane L of the warp sets up ray first + L (L < avail).  A ray that misses the tree bound is
-// answered here; the others are compacted into the warp's ready queue, [field][entry].  Returns the number queued.  Not inlined
-// on purpose: the live state of the 32 rays in flight is saved around the call instead of competing for registers with the
-// set-up arithmetic in the traversal loop.
-template <int QUERY>
-__device__ __noinline__ uint32_t setupPass(const SceneView &s, const b200rt_ray *__restrict__ rays, uint32_t first, uint32_t avail,
-                                           typename OutType<QUERY>::type *__restrict__ out, bool tree_space, float *sh_queue)
+// ---- 1-D TMA bulk copy global -> shared, completion on an mbarrier (one warp = one consumer, lane 0 = producer) ---------------
+__device__ __forceinline__ void mbarInit(uint32_t mbar, uint32_t count)
 {
-	const unsigned lane = threadIdx.x & 31u;
-	bool ready = false;
-	RayState q;
-	if(lane < avail)
-	{
-		q.index = first + lane;
-		// rays are read once: do not let them displace tree nodes from L1/L2
-		const float4 a = __ldcs(reinterpret_cast<const float4 *>(rays) + 2 * size_t(q.index));
-		const float4 b = __ldcs(reinterpret_cast<const float4 *>(rays) + 2 * size_t(q.index) + 1);
-		ready = setupRay<QUERY>(s, a, b, q, tree_space);
-		if(!ready)
-		{
-			TShadowState none;
-			none.depth = 0;
-			writeResult<QUERY>(out, q, false, none); // missed the tree bound
-		}
-	}
-	const unsigned m_ready = __ballot_sync(kFullMask, ready);
-	if(ready)
-	{
-		float *e = sh_queue + __popc(m_ready & ((1u << lane) - 1u));
-		e[0 * 32] = q.ox; e[1 * 32] = q.oy; e[2 * 32] = q.oz;
-		e[3 * 32] = q.dx; e[4 * 32] = q.dy; e[5 * 32] = q.dz;
-		e[6 * 32] = q.ix; e[7 * 32] = q.iy; e[8 * 32] = q.iz;
-		e[9 * 32] = q.t_min; e[10 * 32] = q.t_max; e[11 * 32] = q.seg_lo; e[12 * 32] = q.seg_hi;
-		e[13 * 32] = __uint_as_float(q.index);
-	}
-	__syncwarp();
-	return uint32_t(__popc(m_ready));
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulkCopyToShared(void *dst, const void *src, uint32_t bytes, uint32_t mbar)
+{
+	// the buffer was last touched by ordinary shared-memory loads: order them before the async-proxy write
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(uint32_t(__cvta_generic_to_shared(dst))), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ bool mbarTryWait(uint32_t mbar, uint32_t parity)
+{
+	uint32_t done;
+	asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+	return done != 0u;
 }
 
 // The traversal proper.  Called by every thread of the block; warps are independent of each other (no block-level
@@ -477,15 +506,19 @@ __device__ __noinline__ uint32_t setupPass(const SceneView &s, const b200rt_ray 
 // static pool in a cursor-less launch (ignored when `cursor` is given).
 // SPHERES: the scene holds sphere records (b200rt_add_spheres).  A compile-time switch, so that scenes of polygons only -- the
 // BASELINE workloads -- do not pay for the flag test and the extra code in the leaf loop (measured: 3 % on S1M-hf).
-template <int QUERY, bool SPHERES>
+// QUEUED: `rays` is the queue setupKernel wrote (n = its number of regions), sh_queue / sh_mbar the warp's staging buffer and
+// mbarrier; otherwise `rays` are the batch's ray records and idle lanes set their rays up themselves.
+template <int QUERY, bool SPHERES, bool QUEUED = false>
 __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray *__restrict__ rays, uint32_t n, typename OutType<QUERY>::type *__restrict__ out,
-                                           uint32_t *__restrict__ cursor, int max_depth, bool tree_space, uint2 (*sh_stack)[kBlock], float2 (*sh_axis)[kBlock], uint32_t static_base, float4 (*sh_leaf)[kBlock] = nullptr, float *sh_queue = nullptr)
+                                           uint32_t *__restrict__ cursor, int max_depth, bool tree_space, uint2 (*sh_stack)[kBlock], float2 (*sh_axis)[kBlock], uint32_t static_base, float4 (*sh_leaf)[kBlock] = nullptr, float *sh_queue = nullptr, uint64_t *sh_mbar = nullptr)
 {
 	const unsigned tid = threadIdx.x;
 	const unsigned lane = tid & 31u;
 	const unsigned lanes_below = (1u << lane) - 1u;
 	// the thread's column of the ring; r.sp and floor count in bytes of it (kRingStride per entry), which saves the shifts
 	char *const ring = reinterpret_cast<char *>(&sh_stack[0][tid]);
+	const uint32_t axis_base = uint32_t(__cvta_generic_to_shared(&sh_axis[0][tid])); (void)axis_base;
+	const uint32_t ring_addr = uint32_t(__cvta_generic_to_shared(ring)); (void)ring_addr; // RING_OR: the slot bits of this address are zero
 	RayState r;
 	TShadowState ts;
 	ts.depth = 0;
@@ -496,7 +529,22 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 	uint32_t pool_next = 0u, pool_end = 0u; // warp-uniform
 	bool exhausted = false;                 // warp-uniform
 	bool first_pool = true;                 // warp-uniform
-	uint32_t q_count = 0u;                  // warp-uniform: ready rays in the warp's queue (SETUP_QUEUE)
+	// two-pass batches (QUEUED), all warp-uniform and packed to spare registers: q_count = ready rays left in the staging buffer;
+	// q_group = the group being consumed (region * 8 + group within it), kNoGroup between regions; q_next = the region the cursor
+	// has already handed to this warp for later (valid in lane 0); q_flags = bulk copy in flight | its mbarrier phase | queue drained
+	constexpr uint32_t kNoGroup = 0xFFFFFFFFu, kInFlight = 1u, kParity = 2u, kDrained = 4u, kRegionEnd = 8u, kGroupsPerRegion = uint32_t(kRegionRays / 32);
+	uint32_t q_count = 0u, q_group = kNoGroup, q_next = 0u, q_flags = 0u;
+	constexpr bool kQueueTma = B200RT_QUEUE_TMA != 0;
+	const uint32_t mbar_addr = (QUEUED && kQueueTma) ? uint32_t(__cvta_generic_to_shared(sh_mbar)) : 0u;
+	if(QUEUED)
+	{
+		if(lane == 0u)
+		{
+			if(kQueueTma) mbarInit(mbar_addr, 1u);
+			q_next = atomicAdd(cursor, 1u);
+		}
+		__syncwarp();
+	}
 
 	// Exact kd-restart.  `target` is the leaf the ray has just left (ring empty, older entries lost).  The tree is stored
 	// depth first (left child = node + 1, the right subtree starts at `right`), so "target < right" tells which child holds
@@ -526,7 +574,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 			const bool target_near = ((target < right) != negative);
 			if(target_near)
 			{
-				const float limit = (QUERY == kClosest) ? fminf(hi, r.t_max) : hi;
+				const float limit = (QUERY == kClosest) ? fminf(hi, B200RT_TDONE ? r.t_done : r.t_max) : hi;
 				if(!(t_plane > limit)) // (t_plane < interval start cannot be: the first descent would have taken the far child only)
 				{
 					*reinterpret_cast<uint2 *>(ring + (r.sp & kRingMask)) = make_uint2(far, __float_as_uint(hi));
@@ -551,7 +599,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 	// (accelerator_kdtree_common.h:232); otherwise continue with the nearest postponed subtree, or replay the descent
 	// when ring entries were lost.  Returns true when the ray has ended.
 	auto popNode = [&]() -> bool {
-		if(QUERY == kClosest && r.best_prim != B200RT_MISS && r.t_max <= r.seg_hi) return true;
+		if(QUERY == kClosest && closestDone(r)) return true;
 		if(r.sp > floor)
 		{
 			r.sp -= kRingStride;
@@ -568,12 +616,147 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 
 	for(;;)
 	{
-#if B200RT_SETUP_QUEUE
-		// ---------------- ray setup (converged) and hand-out ----------------
 		const unsigned idle = __ballot_sync(kFullMask, !alive);
-		if(__popc(idle) >= kTake)
+		if(QUEUED)
 		{
-			if(q_count == 0u && !exhausted)
+			// ---------------- hand-out of set-up rays from the warp's staging buffer; TMA refill ----------------
+			if(kQueueTma && __popc(idle) >= kTake)
+			{
+				if(q_count == 0u && (q_flags & kInFlight))
+				{
+					// has the group landed?  (non-blocking: the warp goes on with its live rays otherwise)
+					if(mbarTryWait(mbar_addr, (q_flags & kParity) ? 1u : 0u))
+					{
+						q_flags ^= (kInFlight | kParity);
+						const bool valid = __float_as_uint(sh_queue[13 * 32 + lane]) != B200RT_MISS;
+						q_count = uint32_t(__popc(__ballot_sync(kFullMask, valid)));
+						// a group that is not full ends its region; so does the eighth group
+						q_group = (q_count < 32u || (q_group & (kGroupsPerRegion - 1u)) == kGroupsPerRegion - 1u) ? kNoGroup : q_group + 1u;
+					}
+				}
+				if(q_count != 0u)
+				{
+					const uint32_t rank = __popc(idle & lanes_below);
+					if(!alive && rank < q_count)
+					{
+						const float *e = sh_queue + (q_count - 1u - rank);
+						r.ox = e[0 * 32]; r.oy = e[1 * 32]; r.oz = e[2 * 32];
+						r.dx = e[3 * 32]; r.dy = e[4 * 32]; r.dz = e[5 * 32];
+						r.t_min = e[9 * 32]; r.t_max = e[10 * 32]; r.seg_lo = e[11 * 32]; r.seg_hi = e[12 * 32];
+						r.index = __float_as_uint(e[13 * 32]);
+						r.best_u = 0.f; r.best_v = 0.f; r.best_prim = B200RT_MISS;
+						r.t_done = __int_as_float(0x7f800000);
+						r.node = 0u;
+						r.sp = 0;
+						ts.depth = 0;
+						floor = 0;
+						alive = true;
+						sh_axis[0][tid] = make_float2(r.ox, e[6 * 32]);
+						sh_axis[1][tid] = make_float2(r.oy, e[7 * 32]);
+						sh_axis[2][tid] = make_float2(r.oz, e[8 * 32]);
+						if(__builtin_expect(r.dx == 0.f || r.dy == 0.f || r.dz == 0.f, 0))
+						{
+							// axis-parallel ray: traversal copy of the origin one ulp lower on the zero-direction axes (floatBelow)
+							if(r.dx == 0.f) sh_axis[0][tid].x = floatBelow(r.ox);
+							if(r.dy == 0.f) sh_axis[1][tid].x = floatBelow(r.oy);
+							if(r.dz == 0.f) sh_axis[2][tid].x = floatBelow(r.oz);
+						}
+						sh_axis[3][tid] = make_float2(r.seg_lo, r.seg_hi); // where the ray enters and leaves the tree bound (read by replayTo); a leaf's "axis" 3 also reads this row, value unused
+					}
+					q_count -= min(q_count, uint32_t(__popc(idle)));
+				}
+				if(q_count == 0u && (q_flags & (kInFlight | kDrained)) == 0u)
+				{
+					// the buffer is free: fetch the next group now, it lands while the warp traverses
+					if(q_group == kNoGroup)
+					{
+						// next region of the queue: the cursor was advanced one region ahead, so its answer has long arrived
+						const uint32_t region = __shfl_sync(kFullMask, q_next, 0);
+						if(region >= n) q_flags |= kDrained;
+						else
+						{
+							q_group = region * kGroupsPerRegion;
+							if(lane == 0u) q_next = atomicAdd(cursor, 1u);
+						}
+					}
+					if(!(q_flags & kDrained))
+					{
+						__syncwarp(); // every lane has read its entry of the previous group
+						if(lane == 0u) bulkCopyToShared(sh_queue, reinterpret_cast<const float *>(rays) + size_t(q_group) * kGroupFloats, uint32_t(kGroupBytes), mbar_addr);
+						q_flags |= kInFlight;
+					}
+				}
+			}
+					else if(__popc(idle) >= kTake)
+			{
+				// ---------------- hand-out of set-up rays straight from the queue (HBM / L2) ----------------
+				const float *gq = reinterpret_cast<const float *>(rays) + size_t(q_group) * kGroupFloats; // the group being consumed
+				if(q_count == 0u && !(q_flags & kDrained))
+				{
+					// next group: the one after this in the region, or the first of the region the cursor handed out ahead of time
+					if(q_group == kNoGroup || (q_flags & kRegionEnd))
+					{
+						const uint32_t region = __shfl_sync(kFullMask, q_next, 0);
+						q_flags &= ~kRegionEnd;
+						if(region >= n) q_flags |= kDrained;
+						else
+						{
+							q_group = region * kGroupsPerRegion;
+							if(lane == 0u) q_next = atomicAdd(cursor, 1u);
+						}
+					}
+					else ++q_group;
+					if(!(q_flags & kDrained))
+					{
+						gq = reinterpret_cast<const float *>(rays) + size_t(q_group) * kGroupFloats;
+						const bool valid = __float_as_uint(__ldcs(gq + 13 * 32 + lane)) != B200RT_MISS;
+						q_count = uint32_t(__popc(__ballot_sync(kFullMask, valid)));
+						// a group that is not full ends its region; so does the eighth group
+						if(q_count < 32u || (q_group & (kGroupsPerRegion - 1u)) == kGroupsPerRegion - 1u) q_flags |= kRegionEnd;
+						else if(lane < uint32_t(kQueueFields)) prefetchL2(gq + kGroupFloats + lane * 32u); // the following group, one 128-byte row per lane
+					}
+				}
+				if(q_count != 0u)
+				{
+					const uint32_t rank = __popc(idle & lanes_below);
+					if(!alive && rank < q_count)
+					{
+						const float *e = gq + (q_count - 1u - rank);
+						r.ox = __ldcs(e + 0 * 32); r.oy = __ldcs(e + 1 * 32); r.oz = __ldcs(e + 2 * 32);
+						r.dx = __ldcs(e + 3 * 32); r.dy = __ldcs(e + 4 * 32); r.dz = __ldcs(e + 5 * 32);
+						const float ix = __ldcs(e + 6 * 32), iy = __ldcs(e + 7 * 32), iz = __ldcs(e + 8 * 32);
+						r.t_min = __ldcs(e + 9 * 32); r.t_max = __ldcs(e + 10 * 32); r.seg_lo = __ldcs(e + 11 * 32); r.seg_hi = __ldcs(e + 12 * 32);
+						r.index = __float_as_uint(__ldcs(e + 13 * 32));
+						r.best_u = 0.f; r.best_v = 0.f; r.best_prim = B200RT_MISS;
+						r.t_done = __int_as_float(0x7f800000);
+						r.node = 0u;
+						r.sp = 0;
+						ts.depth = 0;
+						floor = 0;
+						alive = true;
+						sh_axis[0][tid] = make_float2(r.ox, ix);
+						sh_axis[1][tid] = make_float2(r.oy, iy);
+						sh_axis[2][tid] = make_float2(r.oz, iz);
+						if(__builtin_expect(r.dx == 0.f || r.dy == 0.f || r.dz == 0.f, 0))
+						{
+							// axis-parallel ray: traversal copy of the origin one ulp lower on the zero-direction axes (floatBelow)
+							if(r.dx == 0.f) sh_axis[0][tid].x = floatBelow(r.ox);
+							if(r.dy == 0.f) sh_axis[1][tid].x = floatBelow(r.oy);
+							if(r.dz == 0.f) sh_axis[2][tid].x = floatBelow(r.oz);
+						}
+						sh_axis[3][tid] = make_float2(r.seg_lo, r.seg_hi); // where the ray enters and leaves the tree bound (read by replayTo); a leaf's "axis" 3 also reads this row, value unused
+					}
+					q_count -= min(q_count, uint32_t(__popc(idle)));
+				}
+			}
+		}
+		else
+		{
+			// ---------------- refill idle lanes ----------------
+			// One pass per round: every idle lane takes the next ray of the warp's pool.  Rays that miss the tree bound
+			// are answered on the spot and leave their lane idle until the next round (looping here until every lane
+			// holds a live ray ran the ~160-instruction setup with only a few lanes active).
+			if(!exhausted && (__popc(idle) >= kRefill))
 			{
 				if(pool_next == pool_end)
 				{
@@ -591,118 +774,51 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 						pool_next = base;
 						const uint32_t pool = (cursor != nullptr) ? uint32_t(kPoolRays) : 32u;
 						pool_end = (n - base < pool) ? n : base + pool;
+#if B200RT_POOL_PREFETCH
+						// the pool is 8 KB of rays that will be read 8..32 rays at a time over the next few thousand cycles: pull it from HBM into L2 now
+						for(uint32_t line = lane; line * 4u < pool_end - base; line += 32u) prefetchL2(rays + base + line * 4u);
+#endif
 					}
 				}
 				if(!exhausted)
 				{
-					// all 32 lanes set up the next 32 rays of the pool, whatever their own ray is doing
-					const uint32_t avail = min(32u, pool_end - pool_next);
-					q_count = setupPass<QUERY>(s, rays, pool_next, avail, out, tree_space, sh_queue);
-					pool_next += avail;
-				}
-			}
-			if(q_count != 0u)
-			{
-				const uint32_t rank = __popc(idle & lanes_below);
-				if(!alive && rank < q_count)
-				{
-					const float *e = sh_queue + (q_count - 1u - rank);
-					r.ox = e[0 * 32]; r.oy = e[1 * 32]; r.oz = e[2 * 32];
-					r.dx = e[3 * 32]; r.dy = e[4 * 32]; r.dz = e[5 * 32];
-					r.ix = e[6 * 32]; r.iy = e[7 * 32]; r.iz = e[8 * 32];
-					r.t_min = e[9 * 32]; r.t_max = e[10 * 32]; r.seg_lo = e[11 * 32]; r.seg_hi = e[12 * 32];
-					r.index = __float_as_uint(e[13 * 32]);
-					r.best_u = 0.f; r.best_v = 0.f; r.best_prim = B200RT_MISS;
-					r.node = 0u;
-					r.sp = 0;
-					ts.depth = 0;
-					floor = 0;
-					alive = true;
-					sh_axis[0][tid] = make_float2(r.ox, r.ix);
-					sh_axis[1][tid] = make_float2(r.oy, r.iy);
-					sh_axis[2][tid] = make_float2(r.oz, r.iz);
-					if(__builtin_expect(r.dx == 0.f || r.dy == 0.f || r.dz == 0.f, 0))
+					const uint32_t avail = pool_end - pool_next;
+					const uint32_t rank = __popc(idle & lanes_below);
+					if(!alive && rank < avail)
 					{
-						// axis-parallel ray: traversal copy of the origin one ulp lower on the zero-direction axes (floatBelow)
-						if(r.dx == 0.f) sh_axis[0][tid].x = floatBelow(r.ox);
-						if(r.dy == 0.f) sh_axis[1][tid].x = floatBelow(r.oy);
-						if(r.dz == 0.f) sh_axis[2][tid].x = floatBelow(r.oz);
-					}
-					sh_axis[3][tid] = make_float2(r.seg_lo, r.seg_hi); // where the ray enters and leaves the tree bound (read by replayTo); a leaf's "axis" 3 also reads this row, value unused
-				}
-				q_count -= min(q_count, uint32_t(__popc(idle)));
-				__syncwarp();
-			}
-		}
-#else
-		// ---------------- refill idle lanes ----------------
-		// One pass per round: every idle lane takes the next ray of the warp's pool.  Rays that miss the tree bound
-		// are answered on the spot and leave their lane idle until the next round (looping here until every lane
-		// holds a live ray ran the ~160-instruction setup with only a few lanes active).
-		const unsigned idle = __ballot_sync(kFullMask, !alive);
-		if(!exhausted && (__popc(idle) >= kRefill))
-		{
-			if(pool_next == pool_end)
-			{
-				uint32_t base = n;
-				if(cursor != nullptr)
-				{
-					if(lane == 0u) base = atomicAdd(cursor, uint32_t(kPoolRays));
-					base = __shfl_sync(kFullMask, base, 0);
-				}
-				else if(first_pool) base = static_base; // cursor-less launch: the warp owns rays [static_base, static_base + 32)
-				first_pool = false;
-				if(base >= n) exhausted = true;
-				else
-				{
-					pool_next = base;
-					const uint32_t pool = (cursor != nullptr) ? uint32_t(kPoolRays) : 32u;
-					pool_end = (n - base < pool) ? n : base + pool;
-#if B200RT_POOL_PREFETCH
-					// the pool is 8 KB of rays that will be read 8..32 rays at a time over the next few thousand cycles: pull it from HBM into L2 now
-					for(uint32_t line = lane; line * 4u < pool_end - base; line += 32u) prefetchL2(rays + base + line * 4u);
-#endif
-				}
-			}
-			if(!exhausted)
-			{
-				const uint32_t avail = pool_end - pool_next;
-				const uint32_t rank = __popc(idle & lanes_below);
-				if(!alive && rank < avail)
-				{
-					r.index = pool_next + rank;
+						r.index = pool_next + rank;
 #if B200RT_STREAM_IO
-					// rays are read once: do not let them displace tree nodes from L1/L2
-					const float4 a = __ldcs(reinterpret_cast<const float4 *>(rays) + 2 * size_t(r.index));
-					const float4 b = __ldcs(reinterpret_cast<const float4 *>(rays) + 2 * size_t(r.index) + 1);
+						// rays are read once: do not let them displace tree nodes from L1/L2
+						const float4 a = __ldcs(reinterpret_cast<const float4 *>(rays) + 2 * size_t(r.index));
+						const float4 b = __ldcs(reinterpret_cast<const float4 *>(rays) + 2 * size_t(r.index) + 1);
 #else
-					const float4 a = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * size_t(r.index));
-					const float4 b = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * size_t(r.index) + 1);
+						const float4 a = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * size_t(r.index));
+						const float4 b = __ldg(reinterpret_cast<const float4 *>(rays) + 2 * size_t(r.index) + 1);
 #endif
-					ts.depth = 0;
-					floor = 0;
-					alive = setupRay<QUERY>(s, a, b, r, tree_space);
-					sh_axis[0][tid] = make_float2(r.ox, r.ix);
-					sh_axis[1][tid] = make_float2(r.oy, r.iy);
-					sh_axis[2][tid] = make_float2(r.oz, r.iz);
-					if(__builtin_expect(r.dx == 0.f || r.dy == 0.f || r.dz == 0.f, 0))
-					{
-						// axis-parallel ray: traversal copy of the origin one ulp lower on the zero-direction axes (floatBelow)
-						if(r.dx == 0.f) sh_axis[0][tid].x = floatBelow(r.ox);
-						if(r.dy == 0.f) sh_axis[1][tid].x = floatBelow(r.oy);
-						if(r.dz == 0.f) sh_axis[2][tid].x = floatBelow(r.oz);
+						ts.depth = 0;
+						floor = 0;
+						alive = setupRay<QUERY>(s, a, b, r, tree_space);
+						sh_axis[0][tid] = make_float2(r.ox, r.ix);
+						sh_axis[1][tid] = make_float2(r.oy, r.iy);
+						sh_axis[2][tid] = make_float2(r.oz, r.iz);
+						if(__builtin_expect(r.dx == 0.f || r.dy == 0.f || r.dz == 0.f, 0))
+						{
+							// axis-parallel ray: traversal copy of the origin one ulp lower on the zero-direction axes (floatBelow)
+							if(r.dx == 0.f) sh_axis[0][tid].x = floatBelow(r.ox);
+							if(r.dy == 0.f) sh_axis[1][tid].x = floatBelow(r.oy);
+							if(r.dz == 0.f) sh_axis[2][tid].x = floatBelow(r.oz);
+						}
+						sh_axis[3][tid] = make_float2(r.seg_lo, r.seg_hi); // where the ray enters and leaves the tree bound (read by replayTo); a leaf's "axis" 3 also reads this row, value unused
+						if(!alive) writeResult<QUERY>(out, r, false, ts); // missed the tree bound
 					}
-					sh_axis[3][tid] = make_float2(r.seg_lo, r.seg_hi); // where the ray enters and leaves the tree bound (read by replayTo); a leaf's "axis" 3 also reads this row, value unused
-					if(!alive) writeResult<QUERY>(out, r, false, ts); // missed the tree bound
+					pool_next += min(avail, uint32_t(__popc(idle)));
 				}
-				pool_next += min(avail, uint32_t(__popc(idle)));
 			}
 		}
-#endif
 		const unsigned m_alive = __ballot_sync(kFullMask, alive);
 		if(m_alive == 0u)
 		{
-			if(exhausted && q_count == 0u) break;
+			if(QUEUED ? (q_count == 0u && (q_flags & (kInFlight | kDrained)) == kDrained) : exhausted) break;
 			continue;
 		}
 		const unsigned m_pending = __ballot_sync(kFullMask, pending);
@@ -715,6 +831,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 			if(pending)
 			{
 				const float4 *rec = s.tris + leaf_first;
+				const float lox = r.ox, loy = r.oy, loz = r.oz, ldx = r.dx, ldy = r.dy, ldz = r.dz;
 #if B200RT_LEAF_PREFETCH == 2
 				cpAsyncWaitAll();
 				float4 q0 = sh_leaf[0][tid], q1 = sh_leaf[1][tid], q2 = sh_leaf[2][tid];
@@ -726,8 +843,8 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					const uint32_t flags = __float_as_uint(q1.w);
 					const bool quad = (flags & kFlagQuad) != 0u;
 					float u, v, t;
-					if(SPHERES && (flags & kFlagSphere)) { t = sphereIntersect(q0, q1.x, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz); u = 0.f; v = 0.f; }
-					else t = polyIntersect(q0, q1, q2, rec + 3, quad, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, u, v);
+					if(SPHERES && (flags & kFlagSphere)) { t = sphereIntersect(q0, q1.x, lox, loy, loz, ldx, ldy, ldz); u = 0.f; v = 0.f; }
+					else t = polyIntersect(q0, q1, q2, rec + 3, quad, lox, loy, loz, ldx, ldy, ldz, u, v);
 					rec += quad ? 4 : 3;
 					--leaf_count;
 					// accept rules, accelerator.h:125-127 / :137-139 / :150-154
@@ -736,7 +853,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					{
 						const uint32_t prim = __float_as_uint(q0.w);
 						r.best_u = u; r.best_v = v; r.best_prim = prim;
-						if(QUERY == kClosest) r.t_max = t;
+						if(QUERY == kClosest) { r.t_max = t; r.t_done = t; }
 						else if(QUERY == kShadow) { hit = true; leaf_count = 0u; }
 						else
 						{
@@ -787,7 +904,14 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					const uint32_t payload = nd.y >> 2; // interior: right child, leaf: primitive count
 					const bool is_leaf = (axis == 3u);
 					const float split = __uint_as_float(nd.x);
+#if B200RT_AXIS_MAD
+					uint32_t row_addr;
+					asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(row_addr) : "r"(axis), "r"(uint32_t(kBlock * sizeof(float2))), "r"(axis_base));
+					float2 oi;
+					asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(oi.x), "=f"(oi.y) : "r"(row_addr));
+#else
 					const float2 oi = sh_axis[axis][tid]; // row 3 (read at leaves) holds the tree interval: the value is not used there
+#endif
 					const float o = oi.x, inv = oi.y;
 					const float t_plane = (split - o) * inv;
 					// near / far child without a predicate: m = all ones for a negative direction component
@@ -795,20 +919,29 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					const uint32_t left = r.node + 1u;
 					const uint32_t swap = (left ^ payload) & m;
 					const uint32_t near = left ^ swap, far = payload ^ swap;
-					const float limit = (QUERY == kClosest) ? fminf(r.seg_hi, r.t_max) : r.seg_hi;
+					const float limit = (QUERY == kClosest) ? fminf(r.seg_hi, B200RT_TDONE ? r.t_done : r.t_max) : r.seg_hi;
 					const bool far_only = t_plane < r.seg_lo;
 					const bool both = !is_leaf && !(t_plane > limit) && !far_only;
 					// top of the ring (read before this step's speculative store; different slot)
+#if B200RT_RING_OR
+					uint2 popped;
+					asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(popped.x), "=r"(popped.y) : "r"(ring_addr | (uint32_t(r.sp - kRingStride) & uint32_t(kRingMask))));
+#else
 					const uint2 popped = *reinterpret_cast<const uint2 *>(ring + ((r.sp - kRingStride) & kRingMask));
+#endif
 					const uint32_t pop_node = popped.x;
 					const float pop_far = __uint_as_float(popped.y);
 					if(!is_leaf)
 					{
+#if B200RT_RING_OR
+						asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ring_addr | (uint32_t(r.sp) & uint32_t(kRingMask))), "r"(far), "r"(__float_as_uint(r.seg_hi)) : "memory");
+#else
 						*reinterpret_cast<uint2 *>(ring + (r.sp & kRingMask)) = make_uint2(far, __float_as_uint(r.seg_hi));
+#endif
 						floor = max(floor, r.sp + (1 - kShortStack) * kRingStride); // the store has clobbered the oldest slot of a full ring, pushed or not
 					}
 					// closest: once the best hit is not beyond the end of this leaf nothing nearer can follow (accelerator_kdtree_common.h:232)
-					const bool closest_done = (QUERY == kClosest) && r.best_prim != B200RT_MISS && r.t_max <= r.seg_hi;
+					const bool closest_done = (QUERY == kClosest) && closestDone(r);
 					const bool do_pop = nd.y == 3u && !closest_done && r.sp > floor; // an empty leaf (count 0, axis bits 3) with something to pop
 					leaf_count = payload;
 					leaf_first = nd.x;
@@ -841,7 +974,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 				}
 				else
 				{
-					const bool closest_done = (QUERY == kClosest) && r.best_prim != B200RT_MISS && r.t_max <= r.seg_hi;
+					const bool closest_done = (QUERY == kClosest) && closestDone(r);
 					if(closest_done || floor == 0) finished = true;
 					else need_replay = true; // ring entries were overwritten: exact kd-restart behind the leaf just left
 				}
@@ -862,24 +995,76 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 }
 
 
-template <int QUERY, bool SPHERES>
+template <int QUERY, bool SPHERES, bool QUEUED = false>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(const __grid_constant__ SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
                                                                  typename OutType<QUERY>::type *__restrict__ out, uint32_t *__restrict__ cursor, int max_depth, bool tree_space)
 {
-	__shared__ uint2 sh_stack[kShortStack][kBlock]; // x = node index, y = float bits of the far end of its interval
+	__shared__ __align__(kShortStack * kBlock * 8) uint2 sh_stack[kShortStack][kBlock]; // x = node index, y = float bits of the far end of its interval; aligned to its size (RING_OR)
 	__shared__ float2 sh_axis[4][kBlock];          // rows 0-2: (origin, inverse direction) of the lane's ray per axis; row 3: the interval inside the tree bound
 #if B200RT_LEAF_PREFETCH == 2
 	__shared__ float4 sh_leaf[3][kBlock];          // the first record of the leaf a lane has stopped at, staged by cp.async
 #else
 	float4 (*sh_leaf)[kBlock] = nullptr;
 #endif
-#if B200RT_SETUP_QUEUE
-	__shared__ float sh_queue[kBlock / 32][kQueueFields][32]; // per warp: up to 32 set-up rays waiting for a lane, [field][entry]
-	float *queue = &sh_queue[threadIdx.x >> 5][0][0];
-#else
-	float *queue = nullptr;
-#endif
-	traceWarps<QUERY, SPHERES>(s, rays, n, out, cursor, max_depth, tree_space, sh_stack, sh_axis, (blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5)) * 32u, sh_leaf, queue);
+	// two-pass batches: per warp one group of set-up rays ([field][entry], the target of the bulk copies) and its mbarrier
+	constexpr bool kStaged = QUEUED && B200RT_QUEUE_TMA != 0;
+	__shared__ __align__(128) float sh_queue[kStaged ? kBlock / 32 : 1][kStaged ? kGroupFloats : 4];
+	__shared__ uint64_t sh_mbar[kStaged ? kBlock / 32 : 1];
+	const unsigned w = threadIdx.x >> 5;
+	traceWarps<QUERY, SPHERES, QUEUED>(s, rays, n, out, cursor, max_depth, tree_space, sh_stack, sh_axis, (blockIdx.x * uint32_t(kBlock / 32) + w) * 32u, sh_leaf,
+	                                   kStaged ? &sh_queue[w][0] : nullptr, kStaged ? &sh_mbar[w] : nullptr);
+}
+
+// First pass of a two-pass batch: every lane sets up one ray per trip, fully converged.  Rays that miss the tree bound are
+// answered here; the others go, compacted, into their 256-ray region of the queue (see kQueueFields).  One warp per region,
+// no atomics: a region's entries are in batch order, which keeps the second pass deterministic in what it reads.
+template <int QUERY>
+__global__ void __launch_bounds__(256) setupKernel(const __grid_constant__ SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
+                                                   typename OutType<QUERY>::type *__restrict__ out, float *__restrict__ queue, bool tree_space)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	const uint32_t n_regions = (n + uint32_t(kRegionRays) - 1u) / uint32_t(kRegionRays);
+	const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+	for(uint32_t region = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); region < n_regions; region += warps)
+	{
+		float *const base = queue + size_t(region) * kRegionFloats;
+		uint32_t count = 0u; // warp-uniform: entries written so far
+#pragma unroll 2
+		for(uint32_t trip = 0; trip < uint32_t(kRegionRays / 32); ++trip)
+		{
+			const uint32_t index = region * uint32_t(kRegionRays) + trip * 32u + lane;
+			bool ready = false;
+			RayState q;
+			if(index < n)
+			{
+				q.index = index;
+				// rays are read once: do not let them displace the scene from L2
+				const float4 a = __ldcs(reinterpret_cast<const float4 *>(rays) + 2 * size_t(index));
+				const float4 b = __ldcs(reinterpret_cast<const float4 *>(rays) + 2 * size_t(index) + 1);
+				ready = setupRay<QUERY>(s, a, b, q, tree_space);
+				if(!ready)
+				{
+					TShadowState none;
+					none.depth = 0;
+					writeResult<QUERY>(out, q, false, none);
+				}
+			}
+			const unsigned m_ready = __ballot_sync(kFullMask, ready);
+			if(ready)
+			{
+				const uint32_t slot = count + uint32_t(__popc(m_ready & ((1u << lane) - 1u)));
+				float *e = base + (slot >> 5) * uint32_t(kGroupFloats) + (slot & 31u);
+				e[0 * 32] = q.ox; e[1 * 32] = q.oy; e[2 * 32] = q.oz;
+				e[3 * 32] = q.dx; e[4 * 32] = q.dy; e[5 * 32] = q.dz;
+				e[6 * 32] = q.ix; e[7 * 32] = q.iy; e[8 * 32] = q.iz;
+				e[9 * 32] = q.t_min; e[10 * 32] = q.t_max; e[11 * 32] = q.seg_lo; e[12 * 32] = q.seg_hi;
+				e[13 * 32] = __uint_as_float(q.index);
+			}
+			count += uint32_t(__popc(m_ready));
+		}
+		// end marker: the unused entries of the first group that is not full
+		if(count < uint32_t(kRegionRays) && lane >= (count & 31u)) base[(count >> 5) * uint32_t(kGroupFloats) + 13u * 32u + lane] = __uint_as_float(B200RT_MISS);
+	}
 }
 
 // One launch for the closest, shadow and transparent-shadow rays of one flush of the renderer's ray queue
@@ -895,24 +1080,18 @@ struct MixedBatch
 template <bool SPHERES>
 __global__ void __launch_bounds__(kBlock, 4) traceMixedKernel(const __grid_constant__ SceneView s, MixedBatch b, int max_depth, bool tree_space)
 {
-	__shared__ uint2 sh_stack[kShortStack][kBlock];
+	__shared__ __align__(kShortStack * kBlock * 8) uint2 sh_stack[kShortStack][kBlock];
 	__shared__ float2 sh_axis[4][kBlock];
 #if B200RT_LEAF_PREFETCH == 2
 	__shared__ float4 sh_leaf[3][kBlock];
 #else
 	float4 (*sh_leaf)[kBlock] = nullptr;
 #endif
-#if B200RT_SETUP_QUEUE
-	__shared__ float sh_queue[kBlock / 32][kQueueFields][32];
-	float *queue = &sh_queue[threadIdx.x >> 5][0][0];
-#else
-	float *queue = nullptr;
-#endif
 	const uint32_t warp = blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5);
 	const uint32_t w0 = (b.n[0] + 31u) / 32u, w1 = (b.n[1] + 31u) / 32u;
-	if(warp < w0) traceWarps<kClosest, SPHERES>(s, b.rays[0], b.n[0], static_cast<b200rt_hit *>(b.out[0]), nullptr, 0, tree_space, sh_stack, sh_axis, warp * 32u, sh_leaf, queue);
-	else if(warp < w0 + w1) traceWarps<kShadow, SPHERES>(s, b.rays[1], b.n[1], static_cast<uint32_t *>(b.out[1]), nullptr, 0, tree_space, sh_stack, sh_axis, (warp - w0) * 32u, sh_leaf, queue);
-	else traceWarps<kTShadow, SPHERES>(s, b.rays[2], b.n[2], static_cast<b200rt_tshadow *>(b.out[2]), nullptr, max_depth, tree_space, sh_stack, sh_axis, (warp - w0 - w1) * 32u, sh_leaf, queue);
+	if(warp < w0) traceWarps<kClosest, SPHERES>(s, b.rays[0], b.n[0], static_cast<b200rt_hit *>(b.out[0]), nullptr, 0, tree_space, sh_stack, sh_axis, warp * 32u, sh_leaf);
+	else if(warp < w0 + w1) traceWarps<kShadow, SPHERES>(s, b.rays[1], b.n[1], static_cast<uint32_t *>(b.out[1]), nullptr, 0, tree_space, sh_stack, sh_axis, (warp - w0) * 32u, sh_leaf);
+	else traceWarps<kTShadow, SPHERES>(s, b.rays[2], b.n[2], static_cast<b200rt_tshadow *>(b.out[2]), nullptr, max_depth, tree_space, sh_stack, sh_axis, (warp - w0 - w1) * 32u, sh_leaf);
 }
 
 } // namespace b200rt

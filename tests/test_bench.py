@@ -62,7 +62,7 @@ def test_product_arm_line_on_the_gpu(built):
     rec = json.loads(lines[0])
     assert BASE_KEYS <= set(rec) and "impl" not in rec
     assert rec["n_gpus"] == 1 and rec["scaling"] == "weak" and rec["dtype"] == "f32" and rec["vs_baseline"] is None
-    assert rec["gpu_launches"] == 2 * rec["steps"], "one closest and one shadow launch per step"
+    assert rec["gpu_launches"] == 4 * rec["steps"], "a setup pass and a queue-fed traversal launch per query per step"
     roof = rec["roofline"]
     assert roof["kernel"] == "b200rt::traceKernel<0,false>"
     assert roof["bound"] in ("hbm", "issue") and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9

@@ -521,7 +521,15 @@ def test_same_tree_exactness(built, name):
                    spheres=bool(is_sphere.any()))
     same = prim == ref["prim"]
     assert np.array_equal(h["t"][same], ref["t"][same]) and np.array_equal(h["u"][same], ref["u"][same]) and np.array_equal(h["v"][same], ref["v"][same])
-    assert n_bad == 0, f"{n_bad} rays differ in hit/miss or t on the same tree ({n_diff} id mismatches)"
+    if n_bad:
+        # Where the kernel and the reference traversal disagree on the SAME tree beyond an exact-t tie, the kernel must be the one
+        # that is right: its answer has to be what a brute-force test of every primitive gives.  (Seen on cube_grid_far only: the
+        # reference's stored entry/exit points lose a 1-ulp slab at coordinates of 300, the kernel's t-intervals do not; the
+        # unmodified reference shows the same leaks on its own tree, tests/test_oracle.py::test_reference_itself_is_not_exact_on_cube_grid_far.)
+        bad = np.flatnonzero((prim != ref["prim"]) & ((h["t"] != ref["t"]) | ((prim >= 0) != (ref["prim"] >= 0))))
+        brute = o.brute_closest(closest[bad], threads=NCPU)
+        assert np.array_equal(prim[bad], brute["prim"]) and np.array_equal(h["t"][bad], brute["t"]), f"{n_bad} rays differ from the reference traversal on the same tree and from brute force"
+        assert n_bad <= 2.5e-4 * closest.shape[0] and name == "cube_grid_far", (name, n_bad)
     assert agree >= (0.995 if "cube" in name else 0.99999), (agree, n_diff)
     assert np.array_equal(sh, rs)
     s.close()
