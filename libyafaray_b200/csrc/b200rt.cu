@@ -320,7 +320,7 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, La
 constexpr uint32_t kCursorRing = 4096;
 constexpr size_t kMaxRaysPerLaunch = size_t(1) << 30;
 constexpr size_t kTwoPassRays = size_t(1) << 15;        // batches from this size on take the two-pass path (setup pass + queue-fed traversal)
-constexpr size_t kMaxRaysPerTwoPass = size_t(1) << 26;  // 64 Mi rays = 3.5 GiB of queue scratch at most per launch pair
+constexpr size_t kMaxRaysPerTwoPass = size_t(1) << 26;  // 64 Mi rays = 4 GiB of queue scratch at most per launch pair
 
 int checkDeviceCall(const b200rt_scene *s, const void *rays, size_t n, const void *out)
 {
@@ -356,13 +356,13 @@ int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b2
 			const uint32_t count = uint32_t(std::min(kMaxRaysPerTwoPass, n - begin));
 			const uint32_t n_regions = (count + uint32_t(b200rt::kRegionRays) - 1u) / uint32_t(b200rt::kRegionRays);
 			float *queue = nullptr;
-			CUDA_TRY(cudaMallocAsync(&queue, size_t(n_regions) * b200rt::kRegionFloats * sizeof(float), stream));
+			CUDA_TRY(cudaMallocAsync(&queue, b200rt::queueBytes(n_regions), stream));
 			uint32_t *cursor = s->d_cursors + (s->next_cursor.fetch_add(1) % kCursorRing);
 			cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(uint32_t), stream);
 			if(e == cudaSuccess)
 			{
 				const unsigned setup_grid = std::max(1u, std::min((n_regions + 7u) / 8u, unsigned(s->setup_blocks)));
-				b200rt::setupKernel<Q><<<setup_grid, 256, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, queue, tree_space);
+				b200rt::setupKernel<Q><<<setup_grid, b200rt::kSetupBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, queue, tree_space);
 				++g_launches;
 				const unsigned wanted = unsigned((size_t(n_regions) + b200rt::kBlock / 32 - 1) / (b200rt::kBlock / 32));
 				const unsigned grid = std::max(1u, std::min(wanted, unsigned(s->resident_blocks_queued[Q])));
@@ -416,7 +416,7 @@ int queryResidency(b200rt_scene *s)
 	if(rc == B200RT_OK && Q == b200rt::kClosest)
 	{
 		int per_sm = 0, sms = 0;
-		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b200rt::setupKernel<b200rt::kClosest>, 256, 0));
+		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b200rt::setupKernel<b200rt::kClosest>, b200rt::kSetupBlock, 0));
 		CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
 		s->setup_blocks = std::max(1, per_sm) * std::max(1, sms);
 	}

@@ -224,29 +224,21 @@ __device__ __forceinline__ float sphereIntersect(const float4 q0, float radius, 
 //   LEAF_PREFETCH 2: cp.async (LDGSTS) of that record into the lane's shared-memory staging slot; the leaf phase reads it from there
 //   FAR_PREFETCH  1: prefetch.global.L1 of the postponed far child when it is pushed
 //   POOL_PREFETCH 1: prefetch.global.L2 of the whole 256-ray pool when the warp takes it from the cursor
-// Two-pass batches (setupKernel feeding traceKernel<.., QUEUED>): ray setup -- ~170 instructions with three IEEE divisions,
-// executed by ~10 of 32 lanes when idle lanes did it inside the traversal loop -- runs as its own fully converged,
-// bandwidth-bound pass that answers the rays missing the tree bound (41 % of the BASELINE closest rays) on the spot and writes
-// the others, set up, to a queue in HBM: 256-ray regions of 32-entry groups laid out [field][entry].  The traversal kernel's
-// warps pull whole groups into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier; SASS UBLKCP / SYNCS), issued
-// as soon as the previous group has been handed out, and idle lanes take a ready ray every round.  An in-kernel variant of the
-// same idea (a converged setup pass inside the traversal loop) executed 10 % fewer instructions at 18.8 instead of 16.0 lanes
-// but needed 72 registers; held to the 56 of 9 blocks/SM its spills (47 M local accesses per launch, 22 % L1 hits) made it 13 %
-// slower (profiles/r3d_*).  tools/simt_model.cc is the cost model both were designed with.  TWO_PASS 0 keeps large batches on
-// the single-kernel path (rays set up by idle lanes), which small batches and the renderer's mixed-kind flushes always use.
+// Two-pass batches (setupKernel feeding traceKernel<.., QUEUED>).  Ray setup -- ~170 instructions with three IEEE divisions,
+// executed by ~10 of 32 lanes when idle lanes do it inside the traversal loop -- runs as its own fully converged pass that
+// streams the ray records through shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier; SASS UBLKCP / SYNCS, the next
+// 32 rays in flight while the current 32 are set up), answers the rays that miss the tree bound (41 % of the BASELINE closest
+// rays) on the spot and writes the others, set up, to a queue in HBM: 64-byte entries, compacted per 256-ray region.  In the
+// traversal pass idle lanes then take a ready entry (four 16-byte loads) instead of setting a ray up.  History of the idea
+// (profiles/r3d_*, r3e_*, r3f_*; tools/simt_model.cc is the cost model): a converged setup pass INSIDE the traversal loop
+// executed 10 % fewer instructions at 18.8 instead of 16.0 lanes but needed 72 registers -- held to 56 its spills made it 13 %
+// slower; staging the queue in shared memory by bulk copies (7 KB per block) moved the SM to the 196 KB carve-out and left 32 KB
+// of L1 -- 33 % instead of 54 % hits on node loads; reading a [field][entry] queue directly re-fetched every sector several times
+// (4.5 GB of DRAM reads per launch instead of 1.6).  TWO_PASS 0 keeps large batches on the single-kernel path, which small
+// batches and the renderer's mixed-kind flushes always use.
 #ifndef B200RT_TWO_PASS
 #define B200RT_TWO_PASS 1
 #endif
-// QUEUE_TMA 1: groups are staged in shared memory by bulk copies as described; 7 KB more shared memory per block moved the SM to
-// the 196 KB carve-out and left 32 KB of L1: 33 % instead of 54 % L1 hits on node loads, 2.67 ms for the traversal pass although it
-// executed 18 % fewer instructions (profiles/r3e_*).  QUEUE_TMA 0: lanes read their entry straight from the queue in HBM / L2
-// (coalesced, the next group prefetched into L2), shared memory stays at 12 KB per block.
-#ifndef B200RT_QUEUE_TMA
-#define B200RT_QUEUE_TMA 0
-#endif
-// TDONE 1: the descent reads one register, t_done = +inf until a hit is accepted and the hit's t from then on, instead of
-// (best_prim, t_max): "closest so far ends the ray" and the near/far limit become one compare and one min (same decisions: without
-// a hit seg_hi never exceeds the ray's t_max).  AXIS_MAD 1: the address of the per-axis row as one multiply-add.
 #ifndef B200RT_TDONE
 #define B200RT_TDONE 0
 #endif
@@ -275,19 +267,17 @@ static constexpr int kBlock = B200RT_BLOCK;
 static constexpr int kPoolRays = B200RT_POOL;       // rays taken from the global cursor per atomicAdd
 static constexpr int kRefill = B200RT_REFILL;       // idle lanes that trigger a refill (single-kernel path)
 #ifndef B200RT_TAKE
-#define B200RT_TAKE 1
+#define B200RT_TAKE 4
 #endif
-static constexpr int kTake = B200RT_TAKE;           // idle lanes that trigger a hand-out from the ready queue (two-pass batches)
-// Ray queue between the two passes.  A REGION holds the rays of 256 consecutive batch indices that cross the tree bound, compacted,
-// in up to 8 GROUPS of 32 entries; a group is kQueueFields rows of 32 floats ([field][entry], 1792 bytes = one bulk copy):
-// rows 0-2 origin, 3-5 direction, 6-8 traversal 1/direction, 9 t_min, 10 t_max, 11-12 interval inside the tree bound, 13 ray index.
-// Entries past a region's last ray carry index B200RT_MISS in row 13 of the first group that is not full (that is how the
-// traversal pass learns a region's size without a second array).
-static constexpr int kQueueFields = 14;
+static constexpr int kTake = B200RT_TAKE;           // idle lanes that trigger a hand-out from the ray queue (two-pass batches)
+// Ray queue between the two passes: per REGION (the rays of 256 consecutive batch indices) up to 256 ENTRIES of 16 floats, the rays
+// that cross the tree bound in batch order:  ox oy oz dx | dy dz 1/dx 1/dy | 1/dz t_min t_max seg_lo | seg_hi index - -
+// (traversal inverse direction; [seg_lo, seg_hi] = the ray's interval inside the tree bound), followed by one uint32 per region,
+// its number of entries.  Scratch bytes for a batch: see queueBytes().
 static constexpr int kRegionRays = 256;
-static constexpr int kGroupFloats = kQueueFields * 32;
-static constexpr int kGroupBytes = kGroupFloats * 4;
-static constexpr int kRegionFloats = (kRegionRays / 32) * kGroupFloats;
+static constexpr int kEntryFloats = 16;
+static constexpr int kRegionFloats = kRegionRays * kEntryFloats;
+__host__ __device__ inline size_t queueBytes(uint32_t n_regions) { return size_t(n_regions) * (kRegionFloats * sizeof(float) + sizeof(uint32_t)); }
 static constexpr int kLeafBatch = B200RT_LEAF_BATCH; // lanes holding a leaf that trigger the leaf phase
 static constexpr int kUnroll = B200RT_UNROLL;       // unroll factor of the descent loop
 static constexpr int kSteps = B200RT_STEPS;         // node steps per lane between two warp votes
@@ -494,6 +484,15 @@ __device__ __forceinline__ void bulkCopyToShared(void *dst, const void *src, uin
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 	             ::"r"(uint32_t(__cvta_generic_to_shared(dst))), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
+// shared -> global: the block of entries a warp has staged in shared memory leaves as ONE bulk store
+__device__ __forceinline__ void bulkStoreFromShared(void *dst, const void *src, uint32_t bytes)
+{
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the staging writes were ordinary shared-memory stores
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(uint32_t(__cvta_generic_to_shared(src))), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulkStoreWaitRead() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulkStoreWaitAll() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ bool mbarTryWait(uint32_t mbar, uint32_t parity)
 {
 	uint32_t done;
@@ -506,11 +505,11 @@ __device__ __forceinline__ bool mbarTryWait(uint32_t mbar, uint32_t parity)
 // static pool in a cursor-less launch (ignored when `cursor` is given).
 // SPHERES: the scene holds sphere records (b200rt_add_spheres).  A compile-time switch, so that scenes of polygons only -- the
 // BASELINE workloads -- do not pay for the flag test and the extra code in the leaf loop (measured: 3 % on S1M-hf).
-// QUEUED: `rays` is the queue setupKernel wrote (n = its number of regions), sh_queue / sh_mbar the warp's staging buffer and
-// mbarrier; otherwise `rays` are the batch's ray records and idle lanes set their rays up themselves.
+// QUEUED: `rays` is the queue setupKernel wrote and n its number of regions; otherwise `rays` are the batch's ray records and idle
+// lanes set their rays up themselves.
 template <int QUERY, bool SPHERES, bool QUEUED = false>
 __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray *__restrict__ rays, uint32_t n, typename OutType<QUERY>::type *__restrict__ out,
-                                           uint32_t *__restrict__ cursor, int max_depth, bool tree_space, uint2 (*sh_stack)[kBlock], float2 (*sh_axis)[kBlock], uint32_t static_base, float4 (*sh_leaf)[kBlock] = nullptr, float *sh_queue = nullptr, uint64_t *sh_mbar = nullptr)
+                                           uint32_t *__restrict__ cursor, int max_depth, bool tree_space, uint2 (*sh_stack)[kBlock], float2 (*sh_axis)[kBlock], uint32_t static_base, float4 (*sh_leaf)[kBlock] = nullptr)
 {
 	const unsigned tid = threadIdx.x;
 	const unsigned lane = tid & 31u;
@@ -529,21 +528,14 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 	uint32_t pool_next = 0u, pool_end = 0u; // warp-uniform
 	bool exhausted = false;                 // warp-uniform
 	bool first_pool = true;                 // warp-uniform
-	// two-pass batches (QUEUED), all warp-uniform and packed to spare registers: q_count = ready rays left in the staging buffer;
-	// q_group = the group being consumed (region * 8 + group within it), kNoGroup between regions; q_next = the region the cursor
-	// has already handed to this warp for later (valid in lane 0); q_flags = bulk copy in flight | its mbarrier phase | queue drained
-	constexpr uint32_t kNoGroup = 0xFFFFFFFFu, kInFlight = 1u, kParity = 2u, kDrained = 4u, kRegionEnd = 8u, kGroupsPerRegion = uint32_t(kRegionRays / 32);
-	uint32_t q_count = 0u, q_group = kNoGroup, q_next = 0u, q_flags = 0u;
-	constexpr bool kQueueTma = B200RT_QUEUE_TMA != 0;
-	const uint32_t mbar_addr = (QUEUED && kQueueTma) ? uint32_t(__cvta_generic_to_shared(sh_mbar)) : 0u;
-	if(QUEUED)
+	// two-pass batches (QUEUED): pool_next / pool_end count queue entries of the region being consumed; q_next is the region the
+	// cursor has already handed to this warp for later and q_next_count its size, both valid in lane 0 and fetched one region
+	// ahead so that neither the atomic nor the load is waited for
+	uint32_t q_next = 0u, q_next_count = 0u;
+	if(QUEUED && lane == 0u)
 	{
-		if(lane == 0u)
-		{
-			if(kQueueTma) mbarInit(mbar_addr, 1u);
-			q_next = atomicAdd(cursor, 1u);
-		}
-		__syncwarp();
+		q_next = atomicAdd(cursor, 1u);
+		if(q_next < n) q_next_count = __ldg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const float *>(rays) + size_t(n) * kRegionFloats) + q_next);
 	}
 
 	// Exact kd-restart.  `target` is the leaf the ray has just left (ring empty, older entries lost).  The tree is stored
@@ -619,31 +611,41 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 		const unsigned idle = __ballot_sync(kFullMask, !alive);
 		if(QUEUED)
 		{
-			// ---------------- hand-out of set-up rays from the warp's staging buffer; TMA refill ----------------
-			if(kQueueTma && __popc(idle) >= kTake)
+			// ---------------- hand-out of set-up rays from the queue ----------------
+			if(!exhausted && __popc(idle) >= kTake)
 			{
-				if(q_count == 0u && (q_flags & kInFlight))
+				if(pool_next == pool_end)
 				{
-					// has the group landed?  (non-blocking: the warp goes on with its live rays otherwise)
-					if(mbarTryWait(mbar_addr, (q_flags & kParity) ? 1u : 0u))
+					// next region (possibly empty: all of its rays missed the bound -- the next round moves on)
+					const uint32_t region = __shfl_sync(kFullMask, q_next, 0);
+					const uint32_t count = __shfl_sync(kFullMask, q_next_count, 0);
+					if(region >= n) exhausted = true;
+					else
 					{
-						q_flags ^= (kInFlight | kParity);
-						const bool valid = __float_as_uint(sh_queue[13 * 32 + lane]) != B200RT_MISS;
-						q_count = uint32_t(__popc(__ballot_sync(kFullMask, valid)));
-						// a group that is not full ends its region; so does the eighth group
-						q_group = (q_count < 32u || (q_group & (kGroupsPerRegion - 1u)) == kGroupsPerRegion - 1u) ? kNoGroup : q_group + 1u;
+						pool_next = region * uint32_t(kRegionRays);
+						pool_end = pool_next + count;
+#if B200RT_POOL_PREFETCH
+						// the region's entries (64 bytes each) will be read a few at a time over the next rounds: pull them into L2 now
+						for(uint32_t line = lane; line * 2u < count; line += 32u) prefetchL2(reinterpret_cast<const float *>(rays) + (size_t(pool_next) + line * 2u) * kEntryFloats);
+#endif
+						if(lane == 0u)
+						{
+							q_next = atomicAdd(cursor, 1u);
+							if(q_next < n) q_next_count = __ldg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const float *>(rays) + size_t(n) * kRegionFloats) + q_next);
+						}
 					}
 				}
-				if(q_count != 0u)
+				if(pool_next != pool_end)
 				{
+					const uint32_t avail = pool_end - pool_next;
 					const uint32_t rank = __popc(idle & lanes_below);
-					if(!alive && rank < q_count)
+					if(!alive && rank < avail)
 					{
-						const float *e = sh_queue + (q_count - 1u - rank);
-						r.ox = e[0 * 32]; r.oy = e[1 * 32]; r.oz = e[2 * 32];
-						r.dx = e[3 * 32]; r.dy = e[4 * 32]; r.dz = e[5 * 32];
-						r.t_min = e[9 * 32]; r.t_max = e[10 * 32]; r.seg_lo = e[11 * 32]; r.seg_hi = e[12 * 32];
-						r.index = __float_as_uint(e[13 * 32]);
+						const float4 *e = reinterpret_cast<const float4 *>(rays) + size_t(pool_next + rank) * (kEntryFloats / 4);
+						const float4 e0 = __ldcs(e), e1 = __ldcs(e + 1), e2 = __ldcs(e + 2), e3 = __ldcs(e + 3);
+						r.ox = e0.x; r.oy = e0.y; r.oz = e0.z; r.dx = e0.w; r.dy = e1.x; r.dz = e1.y;
+						r.t_min = e2.y; r.t_max = e2.z; r.seg_lo = e2.w; r.seg_hi = e3.x;
+						r.index = __float_as_uint(e3.y);
 						r.best_u = 0.f; r.best_v = 0.f; r.best_prim = B200RT_MISS;
 						r.t_done = __int_as_float(0x7f800000);
 						r.node = 0u;
@@ -651,9 +653,9 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 						ts.depth = 0;
 						floor = 0;
 						alive = true;
-						sh_axis[0][tid] = make_float2(r.ox, e[6 * 32]);
-						sh_axis[1][tid] = make_float2(r.oy, e[7 * 32]);
-						sh_axis[2][tid] = make_float2(r.oz, e[8 * 32]);
+						sh_axis[0][tid] = make_float2(r.ox, e1.z);
+						sh_axis[1][tid] = make_float2(r.oy, e1.w);
+						sh_axis[2][tid] = make_float2(r.oz, e2.x);
 						if(__builtin_expect(r.dx == 0.f || r.dy == 0.f || r.dz == 0.f, 0))
 						{
 							// axis-parallel ray: traversal copy of the origin one ulp lower on the zero-direction axes (floatBelow)
@@ -663,90 +665,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 						}
 						sh_axis[3][tid] = make_float2(r.seg_lo, r.seg_hi); // where the ray enters and leaves the tree bound (read by replayTo); a leaf's "axis" 3 also reads this row, value unused
 					}
-					q_count -= min(q_count, uint32_t(__popc(idle)));
-				}
-				if(q_count == 0u && (q_flags & (kInFlight | kDrained)) == 0u)
-				{
-					// the buffer is free: fetch the next group now, it lands while the warp traverses
-					if(q_group == kNoGroup)
-					{
-						// next region of the queue: the cursor was advanced one region ahead, so its answer has long arrived
-						const uint32_t region = __shfl_sync(kFullMask, q_next, 0);
-						if(region >= n) q_flags |= kDrained;
-						else
-						{
-							q_group = region * kGroupsPerRegion;
-							if(lane == 0u) q_next = atomicAdd(cursor, 1u);
-						}
-					}
-					if(!(q_flags & kDrained))
-					{
-						__syncwarp(); // every lane has read its entry of the previous group
-						if(lane == 0u) bulkCopyToShared(sh_queue, reinterpret_cast<const float *>(rays) + size_t(q_group) * kGroupFloats, uint32_t(kGroupBytes), mbar_addr);
-						q_flags |= kInFlight;
-					}
-				}
-			}
-					else if(__popc(idle) >= kTake)
-			{
-				// ---------------- hand-out of set-up rays straight from the queue (HBM / L2) ----------------
-				const float *gq = reinterpret_cast<const float *>(rays) + size_t(q_group) * kGroupFloats; // the group being consumed
-				if(q_count == 0u && !(q_flags & kDrained))
-				{
-					// next group: the one after this in the region, or the first of the region the cursor handed out ahead of time
-					if(q_group == kNoGroup || (q_flags & kRegionEnd))
-					{
-						const uint32_t region = __shfl_sync(kFullMask, q_next, 0);
-						q_flags &= ~kRegionEnd;
-						if(region >= n) q_flags |= kDrained;
-						else
-						{
-							q_group = region * kGroupsPerRegion;
-							if(lane == 0u) q_next = atomicAdd(cursor, 1u);
-						}
-					}
-					else ++q_group;
-					if(!(q_flags & kDrained))
-					{
-						gq = reinterpret_cast<const float *>(rays) + size_t(q_group) * kGroupFloats;
-						const bool valid = __float_as_uint(__ldcs(gq + 13 * 32 + lane)) != B200RT_MISS;
-						q_count = uint32_t(__popc(__ballot_sync(kFullMask, valid)));
-						// a group that is not full ends its region; so does the eighth group
-						if(q_count < 32u || (q_group & (kGroupsPerRegion - 1u)) == kGroupsPerRegion - 1u) q_flags |= kRegionEnd;
-						else if(lane < uint32_t(kQueueFields)) prefetchL2(gq + kGroupFloats + lane * 32u); // the following group, one 128-byte row per lane
-					}
-				}
-				if(q_count != 0u)
-				{
-					const uint32_t rank = __popc(idle & lanes_below);
-					if(!alive && rank < q_count)
-					{
-						const float *e = gq + (q_count - 1u - rank);
-						r.ox = __ldcs(e + 0 * 32); r.oy = __ldcs(e + 1 * 32); r.oz = __ldcs(e + 2 * 32);
-						r.dx = __ldcs(e + 3 * 32); r.dy = __ldcs(e + 4 * 32); r.dz = __ldcs(e + 5 * 32);
-						const float ix = __ldcs(e + 6 * 32), iy = __ldcs(e + 7 * 32), iz = __ldcs(e + 8 * 32);
-						r.t_min = __ldcs(e + 9 * 32); r.t_max = __ldcs(e + 10 * 32); r.seg_lo = __ldcs(e + 11 * 32); r.seg_hi = __ldcs(e + 12 * 32);
-						r.index = __float_as_uint(__ldcs(e + 13 * 32));
-						r.best_u = 0.f; r.best_v = 0.f; r.best_prim = B200RT_MISS;
-						r.t_done = __int_as_float(0x7f800000);
-						r.node = 0u;
-						r.sp = 0;
-						ts.depth = 0;
-						floor = 0;
-						alive = true;
-						sh_axis[0][tid] = make_float2(r.ox, ix);
-						sh_axis[1][tid] = make_float2(r.oy, iy);
-						sh_axis[2][tid] = make_float2(r.oz, iz);
-						if(__builtin_expect(r.dx == 0.f || r.dy == 0.f || r.dz == 0.f, 0))
-						{
-							// axis-parallel ray: traversal copy of the origin one ulp lower on the zero-direction axes (floatBelow)
-							if(r.dx == 0.f) sh_axis[0][tid].x = floatBelow(r.ox);
-							if(r.dy == 0.f) sh_axis[1][tid].x = floatBelow(r.oy);
-							if(r.dz == 0.f) sh_axis[2][tid].x = floatBelow(r.oz);
-						}
-						sh_axis[3][tid] = make_float2(r.seg_lo, r.seg_hi); // where the ray enters and leaves the tree bound (read by replayTo); a leaf's "axis" 3 also reads this row, value unused
-					}
-					q_count -= min(q_count, uint32_t(__popc(idle)));
+					pool_next += min(avail, uint32_t(__popc(idle)));
 				}
 			}
 		}
@@ -818,7 +737,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 		const unsigned m_alive = __ballot_sync(kFullMask, alive);
 		if(m_alive == 0u)
 		{
-			if(QUEUED ? (q_count == 0u && (q_flags & (kInFlight | kDrained)) == kDrained) : exhausted) break;
+			if(exhausted) break;
 			continue;
 		}
 		const unsigned m_pending = __ballot_sync(kFullMask, pending);
@@ -1006,41 +925,66 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(const __grid_c
 #else
 	float4 (*sh_leaf)[kBlock] = nullptr;
 #endif
-	// two-pass batches: per warp one group of set-up rays ([field][entry], the target of the bulk copies) and its mbarrier
-	constexpr bool kStaged = QUEUED && B200RT_QUEUE_TMA != 0;
-	__shared__ __align__(128) float sh_queue[kStaged ? kBlock / 32 : 1][kStaged ? kGroupFloats : 4];
-	__shared__ uint64_t sh_mbar[kStaged ? kBlock / 32 : 1];
-	const unsigned w = threadIdx.x >> 5;
-	traceWarps<QUERY, SPHERES, QUEUED>(s, rays, n, out, cursor, max_depth, tree_space, sh_stack, sh_axis, (blockIdx.x * uint32_t(kBlock / 32) + w) * 32u, sh_leaf,
-	                                   kStaged ? &sh_queue[w][0] : nullptr, kStaged ? &sh_mbar[w] : nullptr);
+	traceWarps<QUERY, SPHERES, QUEUED>(s, rays, n, out, cursor, max_depth, tree_space, sh_stack, sh_axis, (blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5)) * 32u, sh_leaf);
 }
 
-// First pass of a two-pass batch: every lane sets up one ray per trip, fully converged.  Rays that miss the tree bound are
-// answered here; the others go, compacted, into their 256-ray region of the queue (see kQueueFields).  One warp per region,
-// no atomics: a region's entries are in batch order, which keeps the second pass deterministic in what it reads.
+// First pass of a two-pass batch.  One warp per 256-ray region, eight trips of 32 rays: the ray records of trip t + 1 are already
+// on their way into the warp's other shared-memory buffer (one 1 KB bulk copy, completion on an mbarrier) while every lane sets
+// up its ray of trip t, fully converged.  Rays that miss the tree bound are answered here; the others are appended, in batch
+// order, to the region's entries of the queue (see kEntryFloats); the region's count goes to the array behind the entries.
+static constexpr int kSetupBlock = 256;
+#ifndef B200RT_SETUP_STAGES
+#define B200RT_SETUP_STAGES 2
+#endif
+static constexpr int kSetupStages = B200RT_SETUP_STAGES; // 1 KB buffers per warp: bulk copies in flight ahead of the trip being set up
+static_assert((kSetupStages & (kSetupStages - 1)) == 0 && kSetupStages >= 2 && kSetupStages <= 8, "stages: a power of two, 2..8");
 template <int QUERY>
-__global__ void __launch_bounds__(256) setupKernel(const __grid_constant__ SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
-                                                   typename OutType<QUERY>::type *__restrict__ out, float *__restrict__ queue, bool tree_space)
+__global__ void __launch_bounds__(kSetupBlock) setupKernel(const __grid_constant__ SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
+                                                           typename OutType<QUERY>::type *__restrict__ out, float *__restrict__ queue, bool tree_space)
 {
-	const unsigned lane = threadIdx.x & 31u;
+	__shared__ __align__(128) float4 sh_rays[kSetupBlock / 32][kSetupStages][64]; // per warp a ring of buffers of 32 ray records
+	__shared__ __align__(128) float4 sh_out[kSetupBlock / 32][32 * (kEntryFloats / 4)]; // per warp the entries of one trip, compacted, before their bulk store
+	__shared__ uint64_t sh_mbar[kSetupBlock / 32][kSetupStages];
+	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
 	const uint32_t n_regions = (n + uint32_t(kRegionRays) - 1u) / uint32_t(kRegionRays);
-	const uint32_t warps = gridDim.x * (blockDim.x >> 5);
-	for(uint32_t region = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); region < n_regions; region += warps)
+	uint32_t *const counts = reinterpret_cast<uint32_t *>(queue + size_t(n_regions) * kRegionFloats);
+	const uint32_t mbar0 = uint32_t(__cvta_generic_to_shared(&sh_mbar[w][0]));
+	if(lane == 0u)
+		for(int k = 0; k < kSetupStages; ++k) mbarInit(mbar0 + 8u * k, 1u);
+	__syncwarp();
+	uint32_t parity = 0u; // bit b: phase of buffer b's mbarrier
+	const uint32_t warps = gridDim.x * uint32_t(kSetupBlock / 32);
+	for(uint32_t region = blockIdx.x * uint32_t(kSetupBlock / 32) + w; region < n_regions; region += warps)
 	{
-		float *const base = queue + size_t(region) * kRegionFloats;
+		const uint32_t first = region * uint32_t(kRegionRays);
+		const uint32_t n_rays = min(uint32_t(kRegionRays), n - first);
+		const uint32_t trips = (n_rays + 31u) / 32u;
+		float4 *const entries = reinterpret_cast<float4 *>(queue + size_t(region) * kRegionFloats);
+		auto fetch = [&](uint32_t trip) {
+			const uint32_t buf = trip & uint32_t(kSetupStages - 1);
+			bulkCopyToShared(&sh_rays[w][buf][0], rays + first + trip * 32u, min(32u, n_rays - trip * 32u) * uint32_t(sizeof(b200rt_ray)), mbar0 + 8u * buf);
+		};
+		__syncwarp(); // every buffer has been read (previous region)
+		if(lane == 0u)
+			for(uint32_t t = 0; t < uint32_t(kSetupStages - 1) && t < trips; ++t) fetch(t);
 		uint32_t count = 0u; // warp-uniform: entries written so far
-#pragma unroll 2
-		for(uint32_t trip = 0; trip < uint32_t(kRegionRays / 32); ++trip)
+		for(uint32_t trip = 0; trip < trips; ++trip)
 		{
-			const uint32_t index = region * uint32_t(kRegionRays) + trip * 32u + lane;
+			const uint32_t buf = trip & uint32_t(kSetupStages - 1);
+			if(trip + uint32_t(kSetupStages - 1) < trips)
+			{
+				__syncwarp(); // the buffer being refilled was read in the previous trip
+				if(lane == 0u) fetch(trip + uint32_t(kSetupStages - 1));
+			}
+			while(!mbarTryWait(mbar0 + 8u * buf, (parity >> buf) & 1u)) {}
+			parity ^= 1u << buf;
+			const uint32_t k = trip * 32u + lane;
 			bool ready = false;
 			RayState q;
-			if(index < n)
+			if(k < n_rays)
 			{
-				q.index = index;
-				// rays are read once: do not let them displace the scene from L2
-				const float4 a = __ldcs(reinterpret_cast<const float4 *>(rays) + 2 * size_t(index));
-				const float4 b = __ldcs(reinterpret_cast<const float4 *>(rays) + 2 * size_t(index) + 1);
+				q.index = first + k;
+				const float4 a = sh_rays[w][buf][2 * lane], b = sh_rays[w][buf][2 * lane + 1];
 				ready = setupRay<QUERY>(s, a, b, q, tree_space);
 				if(!ready)
 				{
@@ -1050,21 +994,24 @@ __global__ void __launch_bounds__(256) setupKernel(const __grid_constant__ Scene
 				}
 			}
 			const unsigned m_ready = __ballot_sync(kFullMask, ready);
+			if(lane == 0u) bulkStoreWaitRead(); // the previous trip's bulk store has read the staging buffer
+			__syncwarp();
 			if(ready)
 			{
-				const uint32_t slot = count + uint32_t(__popc(m_ready & ((1u << lane) - 1u)));
-				float *e = base + (slot >> 5) * uint32_t(kGroupFloats) + (slot & 31u);
-				e[0 * 32] = q.ox; e[1 * 32] = q.oy; e[2 * 32] = q.oz;
-				e[3 * 32] = q.dx; e[4 * 32] = q.dy; e[5 * 32] = q.dz;
-				e[6 * 32] = q.ix; e[7 * 32] = q.iy; e[8 * 32] = q.iz;
-				e[9 * 32] = q.t_min; e[10 * 32] = q.t_max; e[11 * 32] = q.seg_lo; e[12 * 32] = q.seg_hi;
-				e[13 * 32] = __uint_as_float(q.index);
+				float4 *e = &sh_out[w][uint32_t(__popc(m_ready & ((1u << lane) - 1u))) * (kEntryFloats / 4)];
+				e[0] = make_float4(q.ox, q.oy, q.oz, q.dx);
+				e[1] = make_float4(q.dy, q.dz, q.ix, q.iy);
+				e[2] = make_float4(q.iz, q.t_min, q.t_max, q.seg_lo);
+				e[3] = make_float4(q.seg_hi, __uint_as_float(q.index), 0.f, 0.f);
 			}
-			count += uint32_t(__popc(m_ready));
+			__syncwarp();
+			const uint32_t n_ready = uint32_t(__popc(m_ready));
+			if(lane == 0u && n_ready != 0u) bulkStoreFromShared(entries + size_t(count) * (kEntryFloats / 4), &sh_out[w][0], n_ready * uint32_t(kEntryFloats * 4));
+			count += n_ready;
 		}
-		// end marker: the unused entries of the first group that is not full
-		if(count < uint32_t(kRegionRays) && lane >= (count & 31u)) base[(count >> 5) * uint32_t(kGroupFloats) + 13u * 32u + lane] = __uint_as_float(B200RT_MISS);
+		if(lane == 0u) counts[region] = count;
 	}
+	if(lane == 0u) bulkStoreWaitAll(); // the last bulk stores must have left before the block's shared memory goes away
 }
 
 // One launch for the closest, shadow and transparent-shadow rays of one flush of the renderer's ray queue

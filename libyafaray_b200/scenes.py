@@ -286,3 +286,92 @@ def cube_grid(n_per_axis: int = 9, scale: float = 0.06, distance: float = 0.35, 
         xyz = np.concatenate([xyz, np.array([[-e, -e, z], [e, -e, z], [e, e, z], [-e, e, z]], dtype=np.float32)])
         idx = np.concatenate([idx, np.array([[base_v, base_v + 1, base_v + 2, base_v + 3]], dtype=np.uint32)])
     return _finish(xyz, idx)
+
+
+# ----------------------------------------------------------------------------------------------- motion blur
+
+def _offset_faces(idx, off):
+    out = idx.astype(np.int64).copy()
+    tri = out[:, 3] == int(TRI)
+    out[:, :3] += off
+    out[~tri, 3] += off
+    return out
+
+
+def _rigid(angle, axis, translate, scale=1.0):
+    """4x4 row-major obj_to_world: rotation about `axis` by `angle` (Rodrigues), uniform scale, translation."""
+    a = np.asarray(axis, np.float64)
+    a = a / np.linalg.norm(a)
+    k = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    r = np.eye(3) + np.sin(angle) * k + (1 - np.cos(angle)) * (k @ k)
+    m = np.eye(4)
+    m[:3, :3] = scale * r
+    m[:3, 3] = translate
+    return m
+
+
+def motion_scene(n_static: int = 3000, n_bezier: int = 2000, n_moving: int = 1500, seed: int = 3):
+    """Static geometry + one Bezier motion-blur mesh + two moving instances.
+
+    Returns (xyz, idx, flags, motion) in the conventions of this module, face rows in the order the reference numbers its
+    primitives: objects first (static mesh, then the motion-blur mesh), instance primitives last.  motion = dict(
+      kind        u8 [n_faces]        0 static, 1 face of the Bezier motion-blur mesh, 2 face of a moving instance
+      xyz1, xyz2  f32 [n_verts, 3]    Bezier control positions of time steps 1 and 2 (step 0 is xyz), as a motion-blur MeshObject stores
+                                      them -- it replaces the mid-time position p1 by the control point 2 p1 - (p0 + p2) / 2 when it is
+                                      initialised (src/geometry/object/object_mesh.cc:268-277), which the accelerator then reads
+      xyz1_user   f32 [n_verts, 3]    the mid-time positions themselves (what a client passes to yafaray_addVertexTimeStep)
+      face_times  f32 [n_faces, 2]    time range (start, end) of the face's mesh / instance; (0, 0) for static faces
+      face_matrix u32 [n_faces]       kind 2: index of the instance
+      matrices    f32 [n_inst, 3, 16] row-major obj_to_world at the three time steps)
+    For kind 2 faces xyz holds the BASE object's vertices; the world position is matrix(t) * vertex."""
+    rng = np.random.RandomState(seed)
+    sx, si, sf = objects(n_static, seed=seed, n_spheres=10)
+    bx, bi, bf = objects(n_bezier, seed=seed + 1, n_spheres=6)
+    bx = (bx * np.float32(0.6) + np.array([0.2, 0.2, 0.3], np.float32)).astype(np.float32)
+    # the Bezier control positions: a drift plus a bend that differs per vertex, so that faces really deform
+    drift1 = np.array([0.05, -0.03, 0.04]); drift2 = np.array([0.12, 0.02, -0.05])
+    wob = rng.normal(scale=0.01, size=bx.shape)
+    bx1 = (bx + drift1 + wob).astype(np.float32)
+    bx2 = (bx + drift2 - 0.5 * wob + 0.05 * np.sin(6.0 * bx[:, [1, 2, 0]])).astype(np.float32)
+    meshes = []
+    for k in range(2):
+        mx, mi, mf = objects(max(64, n_moving // 2), seed=seed + 2 + k, n_spheres=4)
+        meshes.append(((mx * np.float32(0.35)).astype(np.float32), mi, mf))
+    n_s, n_b = sx.shape[0], bx.shape[0]
+    xyz = [sx, bx]; xyz1 = [sx, bx1]; xyz2 = [sx, bx2]
+    idx = [si.astype(np.int64), _offset_faces(bi, n_s)]
+    flags = [sf, bf]
+    kind = [np.zeros(si.shape[0], np.uint8), np.ones(bi.shape[0], np.uint8)]
+    times = [np.zeros((si.shape[0], 2), np.float32), np.tile(np.array([[0.1, 0.9]], np.float32), (bi.shape[0], 1))]
+    fmat = [np.zeros(si.shape[0], np.uint32), np.zeros(bi.shape[0], np.uint32)]
+    mats = []
+    off = n_s + n_b
+    ranges = [(0.0, 1.0), (0.25, 0.75)]
+    for k, (mx, mi, mf) in enumerate(meshes):
+        xyz.append(mx); xyz1.append(mx); xyz2.append(mx)
+        idx.append(_offset_faces(mi, off)); off += mx.shape[0]
+        flags.append(mf)
+        kind.append(np.full(mi.shape[0], 2, np.uint8))
+        times.append(np.tile(np.array([ranges[k]], np.float32), (mi.shape[0], 1)))
+        fmat.append(np.full(mi.shape[0], k, np.uint32))
+        base = np.array([0.1 + 0.5 * k, 0.55 - 0.4 * k, 0.3 + 0.2 * k])
+        mats.append(np.stack([_rigid(0.0 + 0.3 * k, (0, 0, 1), base).reshape(16),
+                              _rigid(0.4 + 0.3 * k, (0.2, 0.1, 1), base + np.array([0.08, 0.05, 0.06]), 1.1).reshape(16),
+                              _rigid(0.9 + 0.3 * k, (0.3, -0.2, 1), base + np.array([0.1, 0.15, -0.04]), 0.9).reshape(16)]))
+    x, i, f = _finish(np.concatenate(xyz), np.concatenate(idx), np.concatenate(flags))
+    user1 = np.ascontiguousarray(np.concatenate(xyz1), np.float32)
+    last = np.ascontiguousarray(np.concatenate(xyz2), np.float32)
+    control = (np.float32(2) * user1 - (x + last) / np.float32(2)).astype(np.float32)  # math::bezierFindControlPoint, float arithmetic
+    motion = dict(kind=np.concatenate(kind), xyz1=control, xyz1_user=user1, xyz2=np.ascontiguousarray(np.concatenate(xyz2), np.float32),
+                  face_times=np.ascontiguousarray(np.concatenate(times), np.float32), face_matrix=np.concatenate(fmat),
+                  matrices=np.ascontiguousarray(np.stack(mats), np.float32))
+    return x, i, f, motion
+
+
+def ray_times(n: int, seed: int = 1):
+    """Ray::time_ values (include/geometry/ray.h:49): uniform in [0, 1] with the range ends and a few out-of-range values mixed in."""
+    rng = np.random.RandomState(seed)
+    t = rng.random_sample(n).astype(np.float32)
+    special = np.array([0.0, 1.0, 0.1, 0.9, 0.25, 0.75, 0.5, -0.5, 1.5], np.float32)
+    t[:: max(1, n // 200)] = special[np.arange(len(t[:: max(1, n // 200)])) % len(special)]
+    return t

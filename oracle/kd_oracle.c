@@ -154,7 +154,71 @@ float kdo_sphere_intersect(const float center[3], float radius, const float from
 	return sol;
 }
 
-static inline float primIntersect(const kdo_mesh *m, uint32_t prim, const float from[3], const float dir[3], float *u, float *v)
+/* math::bezierCalculateFactors of the ray time mapped into [start, end] by math::lerpSegment(time, 0, start, 1, end)
+ * (include/math/interpolation.h:50-93).  Returns 0 / 2 when the time lies at or outside the start / end of the range (time step 0 /
+ * 2 is then used as is), 1 when f[] holds the three factors. */
+static inline int bezierAtTime(float time, float start, float end, float f[3])
+{
+	if(time <= start) return 0;
+	if(time >= end) return 2;
+	/* lerpSegment: x == x_1 and x == x_2 were handled above; x_1 == x_2 cannot be (start < time < end) */
+	const float diff_x = end - start, diff_a = time - start;
+	const float x = 0.f + ((diff_a / diff_x) * (1.f - 0.f));
+	const float xr = 1.f - x;
+	f[0] = xr * xr;
+	f[1] = 2.f * x * xr;
+	f[2] = x * x;
+	return 1;
+}
+
+/* SquareMatrix * Point, include/geometry/matrix.h:131-144: aux = 0; aux += m[i][j] * v[j] (j = 0..2); aux += m[i][3]. */
+static inline void matPoint(const float *m, const float v[3], float o[3])
+{
+	for(int i = 0; i < 3; ++i)
+	{
+		float aux = 0.f;
+		for(int j = 0; j < 3; ++j) aux += m[4 * i + j] * v[j];
+		aux += m[4 * i + 3];
+		o[i] = aux;
+	}
+}
+
+/* Vertices of face `prim` at ray time `time` into vtx[4][3]; returns the vertex count. */
+static inline int faceVerticesAtTime(const kdo_mesh *m, uint32_t prim, float time, float vtx[4][3])
+{
+	const uint32_t *i = m->idx + 4 * (size_t) prim;
+	const int nv = (i[3] == 0xFFFFFFFFu) ? 3 : 4;
+	const kdo_motion *mo = m->motion;
+	const int kind = (mo && mo->kind) ? mo->kind[prim] : 0;
+	if(kind == 1)
+	{
+		float f[3];
+		const int where = bezierAtTime(time, mo->face_times[2 * (size_t) prim], mo->face_times[2 * (size_t) prim + 1], f);
+		for(int k = 0; k < nv; ++k)
+		{
+			const float *p0 = m->xyz + 3 * (size_t) i[k], *p1 = mo->xyz1 + 3 * (size_t) i[k], *p2 = mo->xyz2 + 3 * (size_t) i[k];
+			for(int a = 0; a < 3; ++a)
+				/* bezierInterpolate: y[0] * f[0] + y[1] * f[1] + y[2] * f[2], left to right (interpolation.h:83-86) */
+				vtx[k][a] = (where == 0) ? p0[a] : (where == 2) ? p2[a] : (f[0] * p0[a] + f[1] * p1[a]) + f[2] * p2[a];
+		}
+	}
+	else if(kind == 2)
+	{
+		const float *mats = mo->matrices + 48 * (size_t) mo->face_matrix[prim];
+		float f[3], mt[16];
+		const int where = bezierAtTime(time, mo->face_times[2 * (size_t) prim], mo->face_times[2 * (size_t) prim + 1], f);
+		const float *use = (where == 0) ? mats : (where == 2) ? mats + 32 : mt;
+		if(where == 1)
+			for(int e = 0; e < 16; ++e) mt[e] = (f[0] * mats[e] + f[1] * mats[16 + e]) + f[2] * mats[32 + e]; /* matrix.h:96-113 */
+		for(int k = 0; k < nv; ++k) matPoint(use, m->xyz + 3 * (size_t) i[k], vtx[k]);
+	}
+	else
+		for(int k = 0; k < nv; ++k)
+			for(int a = 0; a < 3; ++a) vtx[k][a] = m->xyz[3 * (size_t) i[k] + a];
+	return nv;
+}
+
+static inline float primIntersect(const kdo_mesh *m, uint32_t prim, const float from[3], const float dir[3], float time, float *u, float *v)
 {
 	const uint32_t *i = m->idx + 4 * (size_t) prim;
 	if(i[2] == KDO_SPHERE)
@@ -162,6 +226,12 @@ static inline float primIntersect(const kdo_mesh *m, uint32_t prim, const float 
 		*u = 0.f;
 		*v = 0.f;
 		return kdo_sphere_intersect(m->xyz + 3 * (size_t) i[0], m->xyz[3 * (size_t) i[1]], from, dir);
+	}
+	if(m->motion && m->motion->kind && m->motion->kind[prim])
+	{
+		float vtx[4][3];
+		const int nv = faceVerticesAtTime(m, prim, time, vtx);
+		return kdo_poly_intersect(vtx[0], vtx[1], vtx[2], nv == 4 ? vtx[3] : NULL, nv, from, dir, u, v);
 	}
 	const int nv = (i[3] == 0xFFFFFFFFu) ? 3 : 4;
 	return kdo_poly_intersect(m->xyz + 3 * (size_t) i[0], m->xyz + 3 * (size_t) i[1], m->xyz + 3 * (size_t) i[2],
@@ -202,10 +272,10 @@ static int tstateInsert(tstate *ts, uint32_t prim)
 
 /* include/accelerator/accelerator.h:122-169: the three accept rules.  Return 1 = "stop traversal". */
 static inline int primitiveIntersection(int query, idata *d, tstate *ts, const kdo_mesh *m, uint32_t prim,
-                                        const float from[3], const float dir[3], float t_min, float t_max)
+                                        const float from[3], const float dir[3], float t_min, float t_max, float time)
 {
 	float u, v;
-	const float t_hit = primIntersect(m, prim, from, dir, &u, &v);
+	const float t_hit = primIntersect(m, prim, from, dir, time, &u, &v);
 	if(t_hit <= 0.f || t_hit < t_min || t_hit >= t_max) return 0;
 	const uint8_t fl = m->flags ? m->flags[prim] : (uint8_t) (F_VISIBLE | F_SHADOW);
 	if(query == Q_NEAREST) { if(!(fl & F_VISIBLE)) return 0; }
@@ -239,7 +309,7 @@ typedef struct
  * Returns 1 when the query reports a hit (IntersectData::isHit(), t_hit > 0 after the query's own
  * post-processing), fills d. */
 static int kdIntersect(int query, const kdo_mesh *m, const kdo_tree *tree, const float from[3], const float dir[3],
-                       float ray_tmin, float t_max, idata *d, tstate *ts, kdo_counters *cnt)
+                       float ray_tmin, float t_max, float time, idata *d, tstate *ts, kdo_counters *cnt)
 {
 	d->t_hit = 0.f; d->u = 0.f; d->v = 0.f; d->t_max = 0.f; d->prim = -1;
 	float enter, leave;
@@ -301,7 +371,7 @@ static int kdIntersect(int query, const kdo_mesh *m, const kdo_tree *tree, const
 		for(uint32_t i = 0; i < n_prims; ++i)
 		{
 			const float tm = (query == Q_NEAREST) ? d->t_max : t_max;
-			if(primitiveIntersection(query, d, ts, m, refs[i], from, dir, t_min, tm)) return 1;
+			if(primitiveIntersection(query, d, ts, m, refs[i], from, dir, t_min, tm, time)) return 1;
 		}
 		if(query == Q_NEAREST && d->t_hit > 0.f && d->t_max <= stack[exit_id].t) return 1;
 		entry_id = exit_id;
@@ -329,6 +399,7 @@ typedef struct job
 	const kdo_tree *tree;
 	const float *bound6;
 	const float *rays;
+	const float *times; /* NULL = time 0 for every ray */
 	size_t n;
 	float *out_t, *out_u, *out_v;
 	int32_t *out_prim;
@@ -347,7 +418,7 @@ static void closestOne(job *j, size_t i, kdo_counters *local)
 	const float *r = j->rays + 8 * i;
 	const float t_max = (r[7] >= 0.f) ? r[7] : FLT_MAX; /* accelerator.h:91 */
 	idata d;
-	const int hit = kdIntersect(Q_NEAREST, j->mesh, j->tree, r, r + 4, r[3], t_max, &d, NULL, j->want_counters ? local : NULL);
+	const int hit = kdIntersect(Q_NEAREST, j->mesh, j->tree, r, r + 4, r[3], t_max, j->times ? j->times[i] : 0.f, &d, NULL, j->want_counters ? local : NULL);
 	if(hit && d.prim >= 0) { j->out_t[i] = d.t_max; j->out_u[i] = d.u; j->out_v[i] = d.v; j->out_prim[i] = d.prim; }
 	else { j->out_t[i] = 0.f; j->out_u[i] = 0.f; j->out_v[i] = 0.f; j->out_prim[i] = -1; }
 }
@@ -358,7 +429,7 @@ static void shadowOne(job *j, size_t i, kdo_counters *local)
 	float sfrom[3];
 	const float t_max = wrapperTmaxShadow(r, sfrom);
 	idata d;
-	const int hit = kdIntersect(Q_SHADOW, j->mesh, j->tree, sfrom, r + 4, r[3], t_max, &d, NULL, j->want_counters ? local : NULL);
+	const int hit = kdIntersect(Q_SHADOW, j->mesh, j->tree, sfrom, r + 4, r[3], t_max, j->times ? j->times[i] : 0.f, &d, NULL, j->want_counters ? local : NULL);
 	j->out_shadowed[i] = (uint8_t) (hit ? 1 : 0);
 	if(j->out_prim) j->out_prim[i] = hit ? d.prim : -1;
 }
@@ -371,7 +442,7 @@ static void tshadowOne(job *j, size_t i)
 	idata d;
 	tstate ts;
 	ts.depth = 0; ts.max_depth = j->max_depth; ts.n_filtered = 0; ts.cap = 64; ts.filtered = ts.small;
-	const int hit = kdIntersect(Q_TSHADOW, j->mesh, j->tree, sfrom, r + 4, r[3], t_max, &d, &ts, NULL);
+	const int hit = kdIntersect(Q_TSHADOW, j->mesh, j->tree, sfrom, r + 4, r[3], t_max, j->times ? j->times[i] : 0.f, &d, &ts, NULL);
 	j->out_shadowed[i] = (uint8_t) (hit ? 1 : 0);
 	if(j->out_n_transparent) j->out_n_transparent[i] = ts.depth;
 	if(j->out_list)
@@ -390,7 +461,7 @@ static void bruteOne(job *j, size_t i)
 	const float t_min = (r[3] < bias) ? bias : r[3];
 	idata d;
 	d.t_hit = 0.f; d.t_max = t_max; d.prim = -1; d.u = d.v = 0.f;
-	for(size_t p = 0; p < j->mesh->n_faces; ++p) primitiveIntersection(Q_NEAREST, &d, NULL, j->mesh, (uint32_t) p, r, r + 4, t_min, d.t_max);
+	for(size_t p = 0; p < j->mesh->n_faces; ++p) primitiveIntersection(Q_NEAREST, &d, NULL, j->mesh, (uint32_t) p, r, r + 4, t_min, d.t_max, j->times ? j->times[i] : 0.f);
 	if(d.t_hit > 0.f) { j->out_t[i] = d.t_max; j->out_u[i] = d.u; j->out_v[i] = d.v; j->out_prim[i] = d.prim; }
 }
 
@@ -482,6 +553,46 @@ void kdo_brute_closest(const kdo_mesh *mesh, const float bound6[6], const float 
 	runJob(&j, n_threads, NULL);
 }
 
+void kdo_trace_closest_timed(const kdo_mesh *mesh, const kdo_tree *tree, const float *rays, const float *times, size_t n,
+                             float *out_t, float *out_u, float *out_v, int32_t *out_prim, int n_threads)
+{
+	job j;
+	memset(&j, 0, sizeof(j));
+	j.query = Q_NEAREST; j.mesh = mesh; j.tree = tree; j.rays = rays; j.times = times; j.n = n;
+	j.out_t = out_t; j.out_u = out_u; j.out_v = out_v; j.out_prim = out_prim;
+	runJob(&j, n_threads, NULL);
+}
+
+void kdo_trace_shadow_timed(const kdo_mesh *mesh, const kdo_tree *tree, const float *rays, const float *times, size_t n,
+                            uint8_t *out_shadowed, int32_t *out_prim, int n_threads)
+{
+	job j;
+	memset(&j, 0, sizeof(j));
+	j.query = Q_SHADOW; j.mesh = mesh; j.tree = tree; j.rays = rays; j.times = times; j.n = n;
+	j.out_shadowed = out_shadowed; j.out_prim = out_prim;
+	runJob(&j, n_threads, NULL);
+}
+
+void kdo_trace_tshadow_timed(const kdo_mesh *mesh, const kdo_tree *tree, const float *rays, const float *times, size_t n, int max_depth,
+                             uint8_t *out_shadowed, int32_t *out_n_transparent, int32_t *out_list, int max_list, int n_threads)
+{
+	job j;
+	memset(&j, 0, sizeof(j));
+	j.query = Q_TSHADOW; j.mesh = mesh; j.tree = tree; j.rays = rays; j.times = times; j.n = n; j.max_depth = max_depth;
+	j.out_shadowed = out_shadowed; j.out_n_transparent = out_n_transparent; j.out_list = out_list; j.max_list = max_list;
+	runJob(&j, n_threads, NULL);
+}
+
+void kdo_brute_closest_timed(const kdo_mesh *mesh, const float bound6[6], const float *rays, const float *times, size_t n,
+                             float *out_t, float *out_u, float *out_v, int32_t *out_prim, int n_threads)
+{
+	job j;
+	memset(&j, 0, sizeof(j));
+	j.query = 3; j.mesh = mesh; j.bound6 = bound6; j.rays = rays; j.times = times; j.n = n;
+	j.out_t = out_t; j.out_u = out_u; j.out_v = out_v; j.out_prim = out_prim;
+	runJob(&j, n_threads, NULL);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Tree bound, src/accelerator/accelerator_kdtree_original.cc:88-103 (+ FacePrimitive::getBound =
  * min/max over the face's vertices). */
@@ -500,6 +611,32 @@ static void primBound(const kdo_mesh *m, size_t f, float lo[3], float hi[3])
 		return;
 	}
 	const int nv = (i[3] == 0xFFFFFFFFu) ? 3 : 4;
+	const kdo_motion *mo = m->motion;
+	const int kind = (mo && mo->kind) ? mo->kind[f] : 0;
+	if(kind)
+	{
+		/* FacePrimitive::getBoundTimeSteps (primitive_face.h:155-170): min/max over the vertices of all three time steps;
+		 * PrimitiveInstance::getBound (primitive_instance.h:119-128): the union of the base face's bound under each matrix */
+		int first = 1;
+		for(int step = 0; step < 3; ++step)
+			for(int k = 0; k < nv; ++k)
+			{
+				float p[3];
+				if(kind == 1)
+				{
+					const float *src = (step == 0 ? m->xyz : step == 1 ? mo->xyz1 : mo->xyz2) + 3 * (size_t) i[k];
+					p[0] = src[0]; p[1] = src[1]; p[2] = src[2];
+				}
+				else matPoint(mo->matrices + 48 * (size_t) mo->face_matrix[f] + 16 * step, m->xyz + 3 * (size_t) i[k], p);
+				for(int a = 0; a < 3; ++a)
+				{
+					if(first || p[a] < lo[a]) lo[a] = p[a];
+					if(first || p[a] > hi[a]) hi[a] = p[a];
+				}
+				first = 0;
+			}
+		return;
+	}
 	for(int a = 0; a < 3; ++a) lo[a] = hi[a] = m->xyz[3 * (size_t) i[0] + a];
 	for(int k = 1; k < nv; ++k)
 		for(int a = 0; a < 3; ++a)

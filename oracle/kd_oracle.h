@@ -29,6 +29,24 @@ extern "C" {
 /* A face with idx[4f+2] == KDO_SPHERE is a sphere (SpherePrimitive, src/geometry/primitive/primitive_sphere.cc):
  * vertex idx[4f+0] is its centre, the x component of vertex idx[4f+1] its radius, idx[4f+3] = 0xFFFFFFFF. */
 #define KDO_SPHERE 0xFFFFFFFEu
+/* Motion blur, per face (NULL = static scene).  kind 1 = face of a Bezier motion-blur mesh: its vertices exist at three time
+ * steps (step 0 in kdo_mesh.xyz, steps 1 and 2 in xyz1 / xyz2, same indices) and the shape at ray time t is built from
+ * vertices interpolated with the quadratic Bezier factors of t mapped into the mesh's time range
+ * (include/geometry/primitive/primitive_polygon.h:238-257, primitive_face.h:86-98, include/math/interpolation.h:50-93).
+ * kind 2 = face of a MOVING instance (three obj_to_world matrices): vertices = M(t) * vertex with M(t) interpolated the same way,
+ * element by element (include/geometry/instance.h:72-90, primitive_instance.h:83-86, include/geometry/matrix.h:96-144).
+ * face_times: 2 floats per face, the time range (the mesh's / the instance's); face_matrix: per face the index of its instance in
+ * `matrices` (3 x 16 floats per instance, row major).  A primitive's bound covers all three time steps / matrices
+ * (primitive_face.h:155-170, primitive_instance.h:119-128). */
+typedef struct kdo_motion
+{
+	const uint8_t *kind;
+	const float *xyz1, *xyz2;
+	const float *face_times;
+	const uint32_t *face_matrix;
+	const float *matrices;
+} kdo_motion;
+
 typedef struct kdo_mesh
 {
 	const float *xyz;
@@ -36,6 +54,7 @@ typedef struct kdo_mesh
 	const uint32_t *idx;
 	size_t n_faces;
 	const uint8_t *flags;
+	const kdo_motion *motion; /* NULL = every face static */
 } kdo_mesh;
 
 /* kd-tree in the reference's own node encoding (accelerator_kdtree_original.h:106-125):
@@ -86,6 +105,16 @@ void kdo_trace_shadow(const kdo_mesh *mesh, const kdo_tree *tree, const float *r
 void kdo_trace_tshadow(const kdo_mesh *mesh, const kdo_tree *tree, const float *rays, size_t n, int max_depth,
                        uint8_t *out_shadowed, int32_t *out_n_transparent, int32_t *out_list, int max_list,
                        int n_threads);
+
+/* The same three queries with a ray time per ray (Ray::time_, include/geometry/ray.h:49); times == NULL means time 0. */
+void kdo_trace_closest_timed(const kdo_mesh *mesh, const kdo_tree *tree, const float *rays, const float *times, size_t n,
+                             float *out_t, float *out_u, float *out_v, int32_t *out_prim, int n_threads);
+void kdo_trace_shadow_timed(const kdo_mesh *mesh, const kdo_tree *tree, const float *rays, const float *times, size_t n,
+                            uint8_t *out_shadowed, int32_t *out_prim, int n_threads);
+void kdo_trace_tshadow_timed(const kdo_mesh *mesh, const kdo_tree *tree, const float *rays, const float *times, size_t n, int max_depth,
+                             uint8_t *out_shadowed, int32_t *out_n_transparent, int32_t *out_list, int max_list, int n_threads);
+void kdo_brute_closest_timed(const kdo_mesh *mesh, const float bound6[6], const float *rays, const float *times, size_t n,
+                             float *out_t, float *out_u, float *out_v, int32_t *out_prim, int n_threads);
 
 /* Tree-free ground truth for small scenes: test every primitive in index order with the same accept
  * rules; the first primitive reaching the minimum t wins. */

@@ -15,8 +15,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkdoracle.so")
 
 
+class _Motion(C.Structure):
+    _fields_ = [("kind", C.c_void_p), ("xyz1", C.c_void_p), ("xyz2", C.c_void_p), ("face_times", C.c_void_p), ("face_matrix", C.c_void_p),
+                ("matrices", C.c_void_p)]
+
+
 class _Mesh(C.Structure):
-    _fields_ = [("xyz", C.c_void_p), ("n_verts", C.c_size_t), ("idx", C.c_void_p), ("n_faces", C.c_size_t), ("flags", C.c_void_p)]
+    _fields_ = [("xyz", C.c_void_p), ("n_verts", C.c_size_t), ("idx", C.c_void_p), ("n_faces", C.c_size_t), ("flags", C.c_void_p),
+                ("motion", C.c_void_p)]
 
 
 class _Tree(C.Structure):
@@ -65,6 +71,10 @@ def lib():
         L.kdo_trace_shadow.argtypes = [P, P, P, C.c_size_t, P, P, C.c_int, P]
         L.kdo_trace_tshadow.argtypes = [P, P, P, C.c_size_t, C.c_int, P, P, P, C.c_int, C.c_int]
         L.kdo_brute_closest.argtypes = [P, P, P, C.c_size_t, P, P, P, P, C.c_int]
+        L.kdo_trace_closest_timed.argtypes = [P, P, P, P, C.c_size_t, P, P, P, P, C.c_int]
+        L.kdo_trace_shadow_timed.argtypes = [P, P, P, P, C.c_size_t, P, P, C.c_int]
+        L.kdo_trace_tshadow_timed.argtypes = [P, P, P, P, C.c_size_t, C.c_int, P, P, P, C.c_int, C.c_int]
+        L.kdo_brute_closest_timed.argtypes = [P, P, P, P, C.c_size_t, P, P, P, P, C.c_int]
         L.kdo_poly_intersect.restype = C.c_float
         L.kdo_poly_intersect.argtypes = [P, P, P, P, C.c_int, P, P, P, P]
         L.kdo_bound_cross.restype = C.c_int
@@ -81,13 +91,22 @@ class Oracle:
     """The restated queries over one mesh, on either its own small SAH tree or a tree exported from the
     unmodified reference (oracle.yref.RefScene.export_tree()), which reproduces the reference's ties too."""
 
-    def __init__(self, xyz, idx, flags=None, *, tree=None, bound=None, max_leaf=2, max_depth=0):
+    def __init__(self, xyz, idx, flags=None, *, tree=None, bound=None, max_leaf=2, max_depth=0, motion=None):
+        """motion (optional): dict(kind u8[n_faces] 0 static / 1 Bezier face / 2 face of a moving instance, xyz1, xyz2 f32[n_verts, 3],
+        face_times f32[n_faces, 2], face_matrix u32[n_faces], matrices f32[n_instances, 3, 16]) -- libyafaray_b200/scenes.py::motion_scene."""
         L = lib()
         self.xyz = np.ascontiguousarray(xyz, dtype=np.float32)
         self.idx = np.ascontiguousarray(idx, dtype=np.uint32)
         n_faces = self.idx.shape[0]
         self.flags = np.full(n_faces, 3, np.uint8) if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
-        self.mesh = _Mesh(_p(self.xyz), self.xyz.shape[0], _p(self.idx), n_faces, _p(self.flags))
+        self._motion = None
+        if motion is not None:
+            self._mo = dict(kind=np.ascontiguousarray(motion["kind"], np.uint8), xyz1=np.ascontiguousarray(motion["xyz1"], np.float32),
+                            xyz2=np.ascontiguousarray(motion["xyz2"], np.float32), face_times=np.ascontiguousarray(motion["face_times"], np.float32),
+                            face_matrix=np.ascontiguousarray(motion["face_matrix"], np.uint32), matrices=np.ascontiguousarray(motion["matrices"], np.float32))
+            self._motion = _Motion(*[_p(self._mo[k]) for k in ("kind", "xyz1", "xyz2", "face_times", "face_matrix", "matrices")])
+        self.mesh = _Mesh(_p(self.xyz), self.xyz.shape[0], _p(self.idx), n_faces, _p(self.flags),
+                          C.cast(C.pointer(self._motion), C.c_void_p) if self._motion is not None else None)
         self.tree = _Tree()
         self._built = None
         if tree is None:
@@ -127,38 +146,54 @@ class Oracle:
     def bound(self):
         return np.array(list(self.tree.bound), dtype=np.float32)
 
-    def trace_closest(self, rays, threads=1, counters=False):
+    def trace_closest(self, rays, threads=1, counters=False, times=None):
         rays = np.ascontiguousarray(rays, dtype=np.float32)
         n = rays.shape[0]
         t = np.zeros(n, np.float32); u = np.zeros(n, np.float32); v = np.zeros(n, np.float32)
         prim = np.zeros(n, np.int32)
+        if times is not None:
+            times = np.ascontiguousarray(times, np.float32)
+            lib().kdo_trace_closest_timed(C.byref(self.mesh), C.byref(self.tree), _p(rays), _p(times), n, _p(t), _p(u), _p(v), _p(prim), threads)
+            return dict(t=t, u=u, v=v, prim=prim, counters=None)
         cnt = Counters() if counters else None
         lib().kdo_trace_closest(C.byref(self.mesh), C.byref(self.tree), _p(rays), n, _p(t), _p(u), _p(v), _p(prim), threads,
                                 C.byref(cnt) if counters else None)
         return dict(t=t, u=u, v=v, prim=prim, counters=cnt)
 
-    def trace_shadow(self, rays, threads=1, counters=False):
+    def trace_shadow(self, rays, threads=1, counters=False, times=None):
         rays = np.ascontiguousarray(rays, dtype=np.float32)
         n = rays.shape[0]
         sh = np.zeros(n, np.uint8); prim = np.zeros(n, np.int32)
+        if times is not None:
+            times = np.ascontiguousarray(times, np.float32)
+            lib().kdo_trace_shadow_timed(C.byref(self.mesh), C.byref(self.tree), _p(rays), _p(times), n, _p(sh), _p(prim), threads)
+            return dict(shadowed=sh, prim=prim, counters=None)
         cnt = Counters() if counters else None
         lib().kdo_trace_shadow(C.byref(self.mesh), C.byref(self.tree), _p(rays), n, _p(sh), _p(prim), threads,
                                C.byref(cnt) if counters else None)
         return dict(shadowed=sh, prim=prim, counters=cnt)
 
-    def trace_tshadow(self, rays, max_depth, threads=1, max_list=8):
+    def trace_tshadow(self, rays, max_depth, threads=1, max_list=8, times=None):
         rays = np.ascontiguousarray(rays, dtype=np.float32)
         n = rays.shape[0]
         sh = np.zeros(n, np.uint8); nt = np.zeros(n, np.int32); lst = np.zeros((n, max_list), np.int32)
+        if times is not None:
+            times = np.ascontiguousarray(times, np.float32)
+            lib().kdo_trace_tshadow_timed(C.byref(self.mesh), C.byref(self.tree), _p(rays), _p(times), n, int(max_depth), _p(sh), _p(nt), _p(lst), max_list, threads)
+            return dict(shadowed=sh, n_transparent=nt, list=lst)
         lib().kdo_trace_tshadow(C.byref(self.mesh), C.byref(self.tree), _p(rays), n, int(max_depth), _p(sh), _p(nt), _p(lst), max_list, threads)
         return dict(shadowed=sh, n_transparent=nt, list=lst)
 
-    def brute_closest(self, rays, threads=1):
+    def brute_closest(self, rays, threads=1, times=None):
         rays = np.ascontiguousarray(rays, dtype=np.float32)
         n = rays.shape[0]
         t = np.zeros(n, np.float32); u = np.zeros(n, np.float32); v = np.zeros(n, np.float32)
         prim = np.zeros(n, np.int32)
         b = self.bound()
+        if times is not None:
+            times = np.ascontiguousarray(times, np.float32)
+            lib().kdo_brute_closest_timed(C.byref(self.mesh), _p(b), _p(rays), _p(times), n, _p(t), _p(u), _p(v), _p(prim), threads)
+            return dict(t=t, u=u, v=v, prim=prim)
         lib().kdo_brute_closest(C.byref(self.mesh), _p(b), _p(rays), n, _p(t), _p(u), _p(v), _p(prim), threads)
         return dict(t=t, u=u, v=v, prim=prim)
 

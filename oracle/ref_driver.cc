@@ -23,6 +23,8 @@
 #include "accelerator/accelerator_kdtree_original.h"
 #include "geometry/object/object.h"
 #include "geometry/primitive/primitive.h"
+#include "geometry/primitive/primitive_instance.h"
+#include "geometry/instance.h"
 #include "geometry/ray.h"
 #include "common/items.h"
 
@@ -49,6 +51,7 @@ struct RefScene
 	std::unordered_map<const yafaray::Primitive *, int32_t> prim_index;
 	const yafaray::Accelerator *accel = nullptr;
 	double build_seconds = 0.0;
+	const float *times = nullptr; // Ray::time_ of the rays of the following trace calls (yref_set_times); nullptr = 0
 };
 
 void loggerSink(yafaray_LogLevel, size_t, const char *, const char *, void *) {}
@@ -73,9 +76,9 @@ void parallelFor(size_t n, int n_threads, F &&f)
 	for(auto &th : pool) th.join();
 }
 
-inline yafaray::Ray makeRay(const float *r)
+inline yafaray::Ray makeRay(const float *r, float time = 0.f)
 {
-	return yafaray::Ray{yafaray::Point3f{{r[0], r[1], r[2]}}, yafaray::Vec3f{{r[4], r[5], r[6]}}, /*time*/ 0.f, /*tmin*/ r[3], /*tmax*/ r[7]};
+	return yafaray::Ray{yafaray::Point3f{{r[0], r[1], r[2]}}, yafaray::Vec3f{{r[4], r[5], r[6]}}, time, /*tmin*/ r[3], /*tmax*/ r[7]};
 }
 
 } // namespace
@@ -155,6 +158,59 @@ int yref_add_mesh(void *h, const float *xyz, size_t n_verts, const uint32_t *idx
 	return static_cast<int>(object_id);
 }
 
+/* Mesh with motion blur and / or to be used as the base of instances.  xyz1 / xyz2 non-NULL: a Bezier motion-blur mesh
+ * ("motion_blur_bezier", three time steps given with yafaray_addVertexTimeStep, include/public_api/yafaray_c_api.h:214) over
+ * [time_start, time_end].  is_base != 0: "is_base_object", the object itself is not rendered (src/scene/scene.cc:324), only its
+ * instances are.  Returns the object id. */
+int yref_add_mesh_ex(void *h, const float *xyz, const float *xyz1, const float *xyz2, size_t n_verts, const uint32_t *idx, size_t n_faces,
+                     const int32_t *face_material, const char *object_visibility, int is_base, float time_start, float time_end)
+{
+	auto *s = static_cast<RefScene *>(h);
+	if(s->material_ids.empty()) return -1;
+	const bool bezier = xyz1 && xyz2;
+	yafaray_ParamMap *pm = yafaray_createParamMap();
+	yafaray_setParamMapString(pm, "type", "mesh");
+	yafaray_setParamMapInt(pm, "num_vertices", static_cast<int>(n_verts));
+	yafaray_setParamMapInt(pm, "num_faces", static_cast<int>(n_faces));
+	yafaray_setParamMapString(pm, "visibility", object_visibility ? object_visibility : "normal");
+	yafaray_setParamMapBool(pm, "is_base_object", is_base ? YAFARAY_BOOL_TRUE : YAFARAY_BOOL_FALSE);
+	if(bezier)
+	{
+		yafaray_setParamMapBool(pm, "motion_blur_bezier", YAFARAY_BOOL_TRUE);
+		yafaray_setParamMapFloat(pm, "time_range_start", time_start);
+		yafaray_setParamMapFloat(pm, "time_range_end", time_end);
+	}
+	size_t object_id = 0;
+	const std::string name = "oracle_mesh_" + std::to_string(s->n_objects++);
+	const yafaray_ResultFlags res = yafaray_createObject(s->scene, &object_id, name.c_str(), pm);
+	yafaray_destroyParamMap(pm);
+	if(res & YAFARAY_RESULT_ERROR_WHILE_CREATING) return -2;
+	const float *steps[3] = {xyz, xyz1, xyz2};
+	for(int step = 0; step < (bezier ? 3 : 1); ++step)
+		for(size_t v = 0; v < n_verts; ++v) yafaray_addVertexTimeStep(s->scene, object_id, steps[step][3 * v], steps[step][3 * v + 1], steps[step][3 * v + 2], static_cast<unsigned char>(step));
+	for(size_t f = 0; f < n_faces; ++f)
+	{
+		const size_t mat = s->material_ids[face_material ? face_material[f] : 0];
+		const uint32_t *i = idx + 4 * f;
+		if(i[3] == 0xFFFFFFFFu) yafaray_addTriangle(s->scene, object_id, i[0], i[1], i[2], mat);
+		else yafaray_addQuad(s->scene, object_id, i[0], i[1], i[2], i[3], mat);
+	}
+	yafaray_initObject(s->scene, object_id, s->material_ids[0]);
+	return static_cast<int>(object_id);
+}
+
+/* One instance of object `object_id` with n_matrices obj_to_world matrices (16 doubles each, row major) at the given times:
+ * 1 matrix = static instance, 3 = moving instance (Instance::hasMotionBlur, include/geometry/instance.h:48). */
+int yref_add_instance(void *h, int object_id, const double *matrices, const float *times, int n_matrices)
+{
+	auto *s = static_cast<RefScene *>(h);
+	const size_t instance_id = yafaray_createInstance(s->scene);
+	if(!yafaray_addInstanceObject(s->scene, instance_id, static_cast<size_t>(object_id))) return -1;
+	for(int k = 0; k < n_matrices; ++k)
+		if(!yafaray_addInstanceMatrixArray(s->scene, instance_id, matrices + 16 * k, times[k])) return -2;
+	return static_cast<int>(instance_id);
+}
+
 /* One "sphere" object (Object::factory -> SpherePrimitive, src/geometry/object/object.cc:80-90,
  * src/geometry/primitive/primitive_sphere.cc).  material: index returned by yref_add_material. */
 int yref_add_sphere(void *h, float cx, float cy, float cz, float radius, int material, const char *object_visibility)
@@ -198,7 +254,7 @@ int yref_build(void *h, const char *accel_type, int depth, int max_leaf_size, fl
 	auto *scene = reinterpret_cast<yafaray::Scene *>(s->scene);
 	s->accel = scene->getAccelerator();
 	if(!s->accel) return -2;
-	// identical gathering order to Scene::preprocess (src/scene/scene.cc:320-326); the driver adds no instances
+	// identical gathering order to Scene::preprocess (src/scene/scene.cc:320-341): objects, then instances
 	s->prims.clear();
 	s->prim_index.clear();
 	for(const auto &[object, object_name, object_enabled] : scene->getObjects())
@@ -207,9 +263,18 @@ int yref_build(void *h, const char *accel_type, int depth, int max_leaf_size, fl
 		const auto object_primitives{object->getPrimitives()};
 		s->prims.insert(s->prims.end(), object_primitives.begin(), object_primitives.end());
 	}
+	for(const auto &instance : scene->instances_)
+	{
+		if(!instance) continue;
+		const auto instance_primitives{instance->getPrimitives()};
+		s->prims.insert(s->prims.end(), instance_primitives.begin(), instance_primitives.end());
+	}
 	for(size_t i = 0; i < s->prims.size(); ++i) s->prim_index[s->prims[i]] = static_cast<int32_t>(i);
 	return 0;
 }
+
+/* Ray::time_ (include/geometry/ray.h:49) of the rays of the following trace calls, one float per ray; NULL = time 0. */
+void yref_set_times(void *h, const float *times) { static_cast<RefScene *>(h)->times = times; }
 
 double yref_build_seconds(void *h) { return static_cast<RefScene *>(h)->build_seconds; }
 size_t yref_num_prims(void *h) { return static_cast<RefScene *>(h)->prims.size(); }
@@ -228,7 +293,7 @@ double yref_trace_closest(void *h, const float *rays, size_t n, float *out_t, fl
 	parallelFor(n, n_threads, [&](size_t b, size_t e) {
 		for(size_t i = b; i < e; ++i)
 		{
-			const yafaray::Ray ray{makeRay(rays + 8 * i)};
+			const yafaray::Ray ray{makeRay(rays + 8 * i, s->times ? s->times[i] : 0.f)};
 			const float t_max = (ray.tmax_ >= 0.f) ? ray.tmax_ : std::numeric_limits<float>::max(); // accelerator.h:91
 			const yafaray::IntersectData d{s->accel->intersect(ray, t_max)};
 			if(d.isHit() && d.primitive_)
@@ -250,7 +315,7 @@ double yref_trace_shadow(void *h, const float *rays, size_t n, uint8_t *out_shad
 	parallelFor(n, n_threads, [&](size_t b, size_t e) {
 		for(size_t i = b; i < e; ++i)
 		{
-			const auto [shadowed, prim] = s->accel->isShadowed(makeRay(rays + 8 * i));
+			const auto [shadowed, prim] = s->accel->isShadowed(makeRay(rays + 8 * i, s->times ? s->times[i] : 0.f));
 			out_shadowed[i] = shadowed ? 1 : 0;
 			if(out_prim) out_prim[i] = (shadowed && prim) ? s->prim_index.at(prim) : -1;
 		}
@@ -266,7 +331,7 @@ double yref_trace_tshadow(void *h, const float *rays, size_t n, int max_depth, u
 	parallelFor(n, n_threads, [&](size_t b, size_t e) {
 		for(size_t i = b; i < e; ++i)
 		{
-			const auto [shadowed, color, prim] = s->accel->isShadowedTransparentShadow(makeRay(rays + 8 * i), max_depth, nullptr);
+			const auto [shadowed, color, prim] = s->accel->isShadowedTransparentShadow(makeRay(rays + 8 * i, s->times ? s->times[i] : 0.f), max_depth, nullptr);
 			out_shadowed[i] = shadowed ? 1 : 0;
 			out_rgb[3 * i] = color.r_; out_rgb[3 * i + 1] = color.g_; out_rgb[3 * i + 2] = color.b_;
 		}

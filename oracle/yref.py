@@ -32,6 +32,9 @@ def lib():
         L.yref_scene_destroy.argtypes = [C.c_void_p]
         L.yref_add_material.argtypes = [C.c_void_p, C.c_char_p, C.c_float]
         L.yref_add_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_char_p]
+        L.yref_add_mesh_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_char_p, C.c_int, C.c_float, C.c_float]
+        L.yref_add_instance.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.yref_set_times.argtypes = [C.c_void_p, C.c_void_p]
         L.yref_add_sphere.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_char_p]
         L.yref_add_sphere.restype = C.c_int
         L.yref_build.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_float, C.c_float]
@@ -67,7 +70,7 @@ class RefScene:
     """
 
     def __init__(self, xyz, idx, flags=None, *, accel_type=None, depth=-1, max_leaf_size=-1, cost_ratio=-1.0,
-                 empty_bonus=-1.0, transparency=0.5, verbose=False):
+                 empty_bonus=-1.0, transparency=0.5, verbose=False, motion=None):
         L = lib()
         xyz = np.ascontiguousarray(xyz, dtype=np.float32)
         idx = np.ascontiguousarray(idx, dtype=np.uint32)
@@ -91,9 +94,43 @@ class RefScene:
         n_mesh = int(n_faces - is_sphere.sum())
         if is_sphere[:n_mesh].any():
             raise ValueError("sphere faces must follow all mesh faces")
-        if n_mesh and L.yref_add_mesh(self.h, _p(xyz), xyz.shape[0], _p(np.ascontiguousarray(idx[:n_mesh])), n_mesh, _p(np.ascontiguousarray(face_mat[:n_mesh])), b"normal") < 0:
+        if motion is not None:
+            # Motion blur (libyafaray_b200/scenes.py::motion_scene): runs of static faces become plain meshes, runs of Bezier faces with
+            # one time range become motion-blur meshes, runs of faces of one moving instance become a base object plus an instance
+            # with three matrices.  The reference lists all object primitives before the instance primitives
+            # (src/scene/scene.cc:320-341), so the instance faces must be the last ones for face ids to equal array rows.
+            kind = np.ascontiguousarray(motion["kind"], np.uint8)
+            # the client passes the mid-time POSITIONS; the mesh turns them into the control points motion["xyz1"] holds
+            xyz1 = np.ascontiguousarray(motion["xyz1_user"], np.float32); xyz2 = np.ascontiguousarray(motion["xyz2"], np.float32)
+            ft = np.asarray(motion["face_times"], np.float32); fm = np.asarray(motion["face_matrix"], np.uint32)
+            mats = np.asarray(motion["matrices"], np.float64)
+            if is_sphere.any():
+                raise ValueError("motion scenes with spheres are not built by this driver")
+            seen_instance = False
+            f = 0
+            while f < n_faces:
+                e = f
+                while e < n_faces and kind[e] == kind[f] and np.array_equal(ft[e], ft[f]) and (kind[f] != 2 or fm[e] == fm[f]):
+                    e += 1
+                sub_idx = np.ascontiguousarray(idx[f:e]); sub_mat = np.ascontiguousarray(face_mat[f:e])
+                if kind[f] == 2:
+                    seen_instance = True
+                    oid = L.yref_add_mesh_ex(self.h, _p(xyz), None, None, xyz.shape[0], _p(sub_idx), e - f, _p(sub_mat), b"normal", 1, 0.0, 0.0)
+                    m3 = np.ascontiguousarray(mats[fm[f]].reshape(3, 16))
+                    tt = np.array([ft[f, 0], 0.5 * (float(ft[f, 0]) + float(ft[f, 1])), ft[f, 1]], np.float32)
+                    if oid < 0 or L.yref_add_instance(self.h, oid, _p(m3), _p(tt), 3) < 0:
+                        raise RuntimeError("reference refused the moving instance")
+                else:
+                    if seen_instance:
+                        raise ValueError("faces of moving instances must follow all other faces")
+                    bez = kind[f] == 1
+                    if L.yref_add_mesh_ex(self.h, _p(xyz), _p(xyz1) if bez else None, _p(xyz2) if bez else None, xyz.shape[0], _p(sub_idx), e - f,
+                                          _p(sub_mat), b"normal", 0, float(ft[f, 0]), float(ft[f, 1])) < 0:
+                        raise RuntimeError("reference refused the mesh")
+                f = e
+        elif n_mesh and L.yref_add_mesh(self.h, _p(xyz), xyz.shape[0], _p(np.ascontiguousarray(idx[:n_mesh])), n_mesh, _p(np.ascontiguousarray(face_mat[:n_mesh])), b"normal") < 0:
             raise RuntimeError("reference refused the mesh")
-        for f in range(n_mesh, n_faces):
+        for f in (range(n_mesh, n_faces) if motion is None else ()):
             c = xyz[idx[f, 0]]
             if L.yref_add_sphere(self.h, float(c[0]), float(c[1]), float(c[2]), float(xyz[idx[f, 1], 0]), int(face_mat[f]), b"normal") < 0:
                 raise RuntimeError("reference refused the sphere")
@@ -119,23 +156,35 @@ class RefScene:
         lib().yref_get_bound(self.h, _p(b))
         return b
 
-    def trace_closest(self, rays, threads=0):
+    def _set_times(self, times, n):
+        if times is None:
+            lib().yref_set_times(self.h, None)
+            return None
+        t = np.ascontiguousarray(times, np.float32)
+        assert t.shape[0] == n
+        lib().yref_set_times(self.h, _p(t))
+        return t
+
+    def trace_closest(self, rays, threads=0, times=None):
         rays = np.ascontiguousarray(rays, dtype=np.float32)
+        _keep = self._set_times(times, rays.shape[0])
         n = rays.shape[0]
         t = np.zeros(n, np.float32); u = np.zeros(n, np.float32); v = np.zeros(n, np.float32)
         prim = np.zeros(n, np.int32)
         secs = lib().yref_trace_closest(self.h, _p(rays), n, _p(t), _p(u), _p(v), _p(prim), threads)
         return dict(t=t, u=u, v=v, prim=prim, seconds=secs)
 
-    def trace_shadow(self, rays, threads=0):
+    def trace_shadow(self, rays, threads=0, times=None):
         rays = np.ascontiguousarray(rays, dtype=np.float32)
+        _keep = self._set_times(times, rays.shape[0])
         n = rays.shape[0]
         sh = np.zeros(n, np.uint8); prim = np.zeros(n, np.int32)
         secs = lib().yref_trace_shadow(self.h, _p(rays), n, _p(sh), _p(prim), threads)
         return dict(shadowed=sh, prim=prim, seconds=secs)
 
-    def trace_tshadow(self, rays, max_depth, threads=0):
+    def trace_tshadow(self, rays, max_depth, threads=0, times=None):
         rays = np.ascontiguousarray(rays, dtype=np.float32)
+        _keep = self._set_times(times, rays.shape[0])
         n = rays.shape[0]
         sh = np.zeros(n, np.uint8); rgb = np.zeros((n, 3), np.float32)
         secs = lib().yref_trace_tshadow(self.h, _p(rays), n, int(max_depth), _p(sh), _p(rgb), threads)
