@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B200RT_VERSION 2
+#define B200RT_VERSION 3
 #define B200RT_MISS 0xFFFFFFFFu
 
 enum
@@ -110,6 +110,7 @@ typedef struct b200rt_stats
 	double build_seconds, upload_seconds;
 	uint64_t device_bytes;
 	uint64_t n_spheres;
+	uint64_t n_bezier_faces, n_moving_faces;
 } b200rt_stats;
 
 typedef struct b200rt_scene b200rt_scene;
@@ -134,6 +135,25 @@ int b200rt_add_mesh(b200rt_scene *scene, const float *xyz, size_t n_verts, const
  * reference.  An instance of a sphere is the same sphere: the reference ignores the instance matrix for spheres
  * (primitive_sphere.cc:104-122), so upload it unchanged. */
 int b200rt_add_spheres(b200rt_scene *scene, const float *center_radius, size_t n_spheres, const uint8_t *flags);
+
+/* ---- motion blur (Ray::time_, include/geometry/ray.h:49).  Rays keep their 32-byte record: the timed queries below take the ray
+ * times in a parallel float array.  Faces added here take the next face ids like any other face.
+ *
+ * Bezier motion-blur mesh (MeshObject with "motion_blur_bezier", three time steps): at ray time t a face is the polygon of its
+ * vertices interpolated with the quadratic Bezier factors of t mapped into [time_start, time_end]; at or outside the ends of the
+ * range time step 0 / 2 is used as is (include/geometry/primitive/primitive_polygon.h:238-257, primitive_face.h:86-98,
+ * include/math/interpolation.h:50-93).  xyz0 / xyz1 / xyz2 are the three time steps AS THE MESH STORES THEM, i.e. xyz1 holds the
+ * Bezier control points MeshObject::convertToBezierControlPoints has put there (src/geometry/object/object_mesh.cc:268-277) --
+ * what FacePrimitive::getVertex(v, 1) returns.  A face's bound covers all three steps (primitive_face.h:155-170). */
+int b200rt_add_mesh_bezier(b200rt_scene *scene, const float *xyz0, const float *xyz1, const float *xyz2, size_t n_verts, const uint32_t *idx, size_t n_faces,
+                           const uint8_t *flags, float time_start, float time_end);
+/* Faces of a MOVING instance (Instance with three obj_to_world matrices, include/geometry/instance.h:48,72-90): at ray time t
+ * the face's vertices are matrix(t) * vertex, matrix(t) interpolated element by element with the same Bezier factors
+ * (primitive_instance.h:83-86, include/geometry/matrix.h:96-144).  xyz = the base object's vertices; matrices = 3 x 16 floats,
+ * row major, at time_start, mid-time and time_end.  A face's bound is the union of its bounds under the three matrices
+ * (primitive_instance.h:119-128). */
+int b200rt_add_mesh_moving(b200rt_scene *scene, const float *xyz, size_t n_verts, const uint32_t *idx, size_t n_faces, const uint8_t *flags,
+                           const float matrices[48], float time_start, float time_end);
 
 /* Build the kd-tree on the host, flatten it and upload it.  Must precede any trace call; calling it
  * again after more b200rt_add_mesh calls rebuilds. */
@@ -181,6 +201,10 @@ enum
 };
 int b200rt_trace(b200rt_scene *scene, int query, unsigned flags, const b200rt_ray *rays, size_t n, void *out, int max_depth);
 int b200rt_trace_device(b200rt_scene *scene, int query, unsigned flags, const b200rt_ray *d_rays, size_t n, void *d_out, int max_depth, void *stream);
+/* The same with one ray time per ray (Ray::time_); times == NULL means time 0 for every ray, which is what the untimed entry
+ * points trace with.  Static faces and spheres ignore the time. */
+int b200rt_trace_timed(b200rt_scene *scene, int query, unsigned flags, const b200rt_ray *rays, const float *times, size_t n, void *out, int max_depth);
+int b200rt_trace_timed_device(b200rt_scene *scene, int query, unsigned flags, const b200rt_ray *d_rays, const float *d_times, size_t n, void *d_out, int max_depth, void *stream);
 
 /* Several host-buffer batches in one call -- what one flush of the renderer's wavefront ray queue holds (closest,
  * shadow and transparent-shadow rays of the pixels in flight on one render thread; Accelerator::intersect / isShadowed /
@@ -197,6 +221,7 @@ typedef struct b200rt_job
 	size_t n;
 	void *out;
 	int max_depth;      /* transparent shadows only */
+	const float *times; /* one ray time per ray (same memory kind as rays), or NULL = time 0 */
 } b200rt_job;
 int b200rt_trace_jobs(const b200rt_job *jobs, size_t n_jobs);
 /* The same in two halves, so that a render thread can shade one group of pixels while the rays of another group are

@@ -5,6 +5,7 @@
 #include "kd_kernels.cuh"
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -38,6 +39,7 @@ int fail(int code, const std::string &msg)
 
 constexpr uint32_t kTriangle = 0xFFFFFFFFu;
 constexpr uint32_t kSphere = 0xFFFFFFFEu; // idx[2] of a sphere face (kd_build.h)
+constexpr uint32_t kBox = 0xFFFFFFFDu;    // idx[2] of a motion-blur face: the builder only sees its bound (kd_build.h)
 // staging granularity of the host-buffer queries and chunks in flight per call; the environment overrides are tuning aids
 // (tools/gpu_e2e_sweep.sh), read once.  Defaults from the measured sweep (profiles/r1m_e2e_sweep.txt): 16 MiB x 6 in flight.
 size_t chunkBytes()
@@ -59,7 +61,8 @@ struct Lane
 	cudaStream_t stream = nullptr;
 	cudaEvent_t done = nullptr;
 	void *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
-	size_t in_cap = 0, out_cap = 0;
+	float *d_times = nullptr; // ray times of the chunk (timed queries), in_cap / sizeof(b200rt_ray) floats
+	size_t in_cap = 0, out_cap = 0, times_cap = 0;
 	// pending copy-out of the previous chunk this lane carried
 	void *pending_dst = nullptr;
 	size_t pending_bytes = 0;
@@ -71,6 +74,7 @@ struct Lane
 		if(h_out) cudaFreeHost(h_out);
 		if(d_in) cudaFree(d_in);
 		if(d_out) cudaFree(d_out);
+		if(d_times) cudaFree(d_times);
 		if(done) cudaEventDestroy(done);
 		if(stream) cudaStreamDestroy(stream);
 	}
@@ -88,7 +92,15 @@ struct b200rt_scene
 	std::vector<uint8_t> flags;
 	// built state
 	bool built = false;
-	bool has_spheres = false;               // selects the kernel variant with the sphere branch
+	bool has_spheres = false;               // selects the kernel variant with the branches for spheres and motion-blur faces
+	// motion blur: kind per face (0 static or sphere, 1 Bezier face, 2 face of a moving instance) and, for kinds 1 and 2, the record
+	// the flattener emits (b200rt_add_mesh_bezier / _moving); the builder sees such a face as a box (kBox) over its bound
+	struct MotionFace { uint32_t nv; float v[3][4][3]; float t0, t1; uint32_t matrix; };
+	std::vector<uint8_t> kind;
+	std::vector<int32_t> motion_of_face;
+	std::vector<MotionFace> motion;
+	std::vector<std::array<float, 50>> matrices; // per moving instance: 3 x 16 floats row major, then time_start, time_end
+	float4 *d_inst = nullptr;
 	b200rt::HostTree tree;
 	std::vector<uint32_t> record_of_ref; // float4 offset of every leaf reference's record (for flag updates)
 	uint2 *d_nodes = nullptr;
@@ -111,6 +123,7 @@ struct b200rt_scene
 		free_lanes.clear();
 		if(d_nodes) cudaFree(d_nodes);
 		if(d_tris) cudaFree(d_tris);
+		if(d_inst) cudaFree(d_inst);
 		if(d_cursors) cudaFree(d_cursors);
 	}
 };
@@ -154,6 +167,18 @@ int ensureLane(Lane &l, size_t in_bytes, size_t out_bytes, bool need_h_in, bool 
 	return B200RT_OK;
 }
 
+// device buffer for the ray times of one chunk (timed queries only)
+int ensureLaneTimes(Lane &l, size_t n_rays)
+{
+	if(l.times_cap >= n_rays) return B200RT_OK;
+	if(l.d_times) cudaFree(l.d_times);
+	l.d_times = nullptr;
+	l.times_cap = 0;
+	CUDA_TRY(cudaMalloc(&l.d_times, n_rays * sizeof(float)));
+	l.times_cap = n_rays;
+	return B200RT_OK;
+}
+
 // Staging copy between a caller's pageable buffer and a pinned lane buffer.  One thread moves ~10 GB/s, a fifth of what the
 // copy engine then needs; chunks of 4 MiB and more are split over a few short-lived threads (the caller's thread takes a share).
 // Measured (tools/e2e_pageable.py, profiles/r2i_pageable.jsonl): 213 Mrays/s with the caller's thread alone, 549 with 5 helpers;
@@ -189,8 +214,9 @@ bool isPinned(const void *p)
 	return a.type == cudaMemoryTypeHost;
 }
 
+// `times` (optional) = one ray time per ray, in host memory like the rays; it travels to the device with them.
 template <typename Out, typename LaunchFn>
-int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, LaunchFn launch, bool known_pinned = false)
+int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, const float *times, size_t n, Out *out, LaunchFn launch, bool known_pinned = false)
 {
 	if(!s || (!rays && n) || (!out && n)) return fail(B200RT_E_INVALID, "null argument");
 	if(!s->built) return fail(B200RT_E_INVALID, "scene not built: call b200rt_build first");
@@ -198,7 +224,8 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, La
 	CUDA_TRY(cudaSetDevice(s->device));
 	// a batch of one is the per-ray compatibility path (stack variables of the caller): not worth the pointer query
 	const bool in_pinned = known_pinned || (n > 1 && isPinned(rays)), out_pinned = known_pinned || (n > 1 && isPinned(out));
-	if(in_pinned && out_pinned && n <= kDirectRays)
+	const bool times_pinned = !times || known_pinned || (n > 1 && isPinned(times));
+	if(in_pinned && out_pinned && times_pinned && n <= kDirectRays)
 	{
 		// Batches in pinned memory (the wavefront ray queue of the renderer, integration/src/render): the kernel
 		// reads the rays and writes the results across PCIe itself -- one cursor reset, one launch and one stream
@@ -215,7 +242,7 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, La
 			const cudaError_t e = cudaStreamCreateWithFlags(&lane->stream, cudaStreamNonBlocking);
 			if(e != cudaSuccess) rc = fail(B200RT_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
 		}
-		if(rc == B200RT_OK) rc = launch(rays, n, out, lane->stream, true);
+		if(rc == B200RT_OK) rc = launch(rays, times, n, out, lane->stream, true);
 		if(rc == B200RT_OK)
 		{
 			const cudaError_t e = cudaStreamSynchronize(lane->stream);
@@ -237,10 +264,16 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, La
 		}
 		if(!lane) lane = std::make_unique<Lane>();
 		int rc = ensureLane(*lane, kSmallBatchRays * sizeof(b200rt_ray), kSmallBatchRays * sizeof(Out), true, true);
+		if(rc == B200RT_OK && times) rc = ensureLaneTimes(*lane, kSmallBatchRays);
+		if(rc == B200RT_OK && times)
+		{
+			const cudaError_t e = cudaMemcpyAsync(lane->d_times, times, n * sizeof(float), cudaMemcpyHostToDevice, lane->stream);
+			if(e != cudaSuccess) rc = fail(B200RT_E_CUDA, std::string("small-batch times: ") + cudaGetErrorString(e));
+		}
 		if(rc == B200RT_OK)
 		{
 			std::memcpy(lane->h_in, rays, n * sizeof(b200rt_ray));
-			rc = launch(static_cast<const b200rt_ray *>(lane->h_in), n, static_cast<Out *>(lane->h_out), lane->stream, /*cursorless*/ true);
+			rc = launch(static_cast<const b200rt_ray *>(lane->h_in), times ? lane->d_times : nullptr, n, static_cast<Out *>(lane->h_out), lane->stream, /*cursorless*/ true);
 			if(rc == B200RT_OK)
 			{
 				const cudaError_t e = cudaStreamSynchronize(lane->stream);
@@ -284,6 +317,7 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, La
 	{
 		l->pending_dst = nullptr;
 		rc = ensureLane(*l, rays_this * sizeof(b200rt_ray), rays_this * sizeof(Out), !in_pinned, !out_pinned);
+		if(rc == B200RT_OK && times) rc = ensureLaneTimes(*l, rays_this);
 		if(rc != B200RT_OK) { give_back(); return rc; }
 	}
 	for(size_t c = 0; c < n_chunks && rc == B200RT_OK; ++c)
@@ -295,9 +329,10 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, size_t n, Out *out, La
 		const void *src = rays + begin;
 		if(!in_pinned) { stagingCopy(l.h_in, src, count * sizeof(b200rt_ray)); src = l.h_in; }
 		cudaError_t e = cudaMemcpyAsync(l.d_in, src, count * sizeof(b200rt_ray), cudaMemcpyHostToDevice, l.stream);
+		if(e == cudaSuccess && times) e = cudaMemcpyAsync(l.d_times, times + begin, count * sizeof(float), cudaMemcpyHostToDevice, l.stream);
 		if(e == cudaSuccess)
 		{
-			rc = launch(static_cast<const b200rt_ray *>(l.d_in), count, static_cast<Out *>(l.d_out), l.stream, false);
+			rc = launch(static_cast<const b200rt_ray *>(l.d_in), times ? l.d_times : nullptr, count, static_cast<Out *>(l.d_out), l.stream, false);
 			if(rc != B200RT_OK) break;
 		}
 		if(e == cudaSuccess) e = cudaMemcpyAsync(out_pinned ? static_cast<void *>(out + begin) : l.h_out, l.d_out, count * sizeof(Out), cudaMemcpyDeviceToHost, l.stream);
@@ -332,14 +367,15 @@ int checkDeviceCall(const b200rt_scene *s, const void *rays, size_t n, const voi
 // Enqueue traceKernel<Q> over n rays on `stream`: a persistent grid (at most one resident wave) whose warps
 // pull rays from a cursor that is zeroed on the same stream just before the launch.
 template <int Q>
-int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b200rt::OutType<Q>::type *d_out, cudaStream_t stream, int max_depth, unsigned flags = 0u, bool cursorless = false)
+int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b200rt::OutType<Q>::type *d_out, cudaStream_t stream, int max_depth, unsigned flags = 0u, bool cursorless = false,
+                const float *d_times = nullptr)
 {
 	if(cursorless)
 	{
 		// small batch (n <= kDirectRays): no ray cursor, so nothing to reset before the launch; warp w owns rays [32 w, 32 w + 32)
 		const unsigned grid = unsigned((n + b200rt::kBlock - 1) / b200rt::kBlock);
-		if(s->has_spheres) b200rt::traceKernel<Q, true><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays, uint32_t(n), d_out, nullptr, max_depth, (flags & B200RT_RAYS_TREE_SPACE) != 0u);
-		else b200rt::traceKernel<Q, false><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays, uint32_t(n), d_out, nullptr, max_depth, (flags & B200RT_RAYS_TREE_SPACE) != 0u);
+		if(s->has_spheres) b200rt::traceKernel<Q, true><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays, uint32_t(n), d_out, nullptr, max_depth, (flags & B200RT_RAYS_TREE_SPACE) != 0u, d_times);
+		else b200rt::traceKernel<Q, false><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays, uint32_t(n), d_out, nullptr, max_depth, (flags & B200RT_RAYS_TREE_SPACE) != 0u, d_times);
 		++g_launches;
 		CUDA_TRY(cudaGetLastError());
 		return B200RT_OK;
@@ -362,13 +398,13 @@ int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b2
 			if(e == cudaSuccess)
 			{
 				const unsigned setup_grid = std::max(1u, std::min((n_regions + 7u) / 8u, unsigned(s->setup_blocks)));
-				b200rt::setupKernel<Q><<<setup_grid, b200rt::kSetupBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, queue, tree_space);
+				b200rt::setupKernel<Q><<<setup_grid, b200rt::kSetupBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, queue, tree_space, d_times ? d_times + begin : nullptr);
 				++g_launches;
 				const unsigned wanted = unsigned((size_t(n_regions) + b200rt::kBlock / 32 - 1) / (b200rt::kBlock / 32));
 				const unsigned grid = std::max(1u, std::min(wanted, unsigned(s->resident_blocks_queued[Q])));
 				const b200rt_ray *as_rays = reinterpret_cast<const b200rt_ray *>(queue);
-				if(s->has_spheres) b200rt::traceKernel<Q, true, true><<<grid, b200rt::kBlock, 0, stream>>>(s->view, as_rays, n_regions, d_out + begin, cursor, max_depth, tree_space);
-				else b200rt::traceKernel<Q, false, true><<<grid, b200rt::kBlock, 0, stream>>>(s->view, as_rays, n_regions, d_out + begin, cursor, max_depth, tree_space);
+				if(s->has_spheres) b200rt::traceKernel<Q, true, true><<<grid, b200rt::kBlock, 0, stream>>>(s->view, as_rays, n_regions, d_out + begin, cursor, max_depth, tree_space, nullptr);
+				else b200rt::traceKernel<Q, false, true><<<grid, b200rt::kBlock, 0, stream>>>(s->view, as_rays, n_regions, d_out + begin, cursor, max_depth, tree_space, nullptr);
 				++g_launches;
 				e = cudaGetLastError();
 			}
@@ -386,8 +422,8 @@ int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b2
 		CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), stream));
 		const unsigned wanted = unsigned((size_t(count) + b200rt::kBlock - 1) / b200rt::kBlock);
 		const unsigned grid = std::max(1u, std::min(wanted, unsigned(s->resident_blocks[Q])));
-		if(s->has_spheres) b200rt::traceKernel<Q, true><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, cursor, max_depth, tree_space);
-		else b200rt::traceKernel<Q, false><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, cursor, max_depth, tree_space);
+		if(s->has_spheres) b200rt::traceKernel<Q, true><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, cursor, max_depth, tree_space, d_times ? d_times + begin : nullptr);
+		else b200rt::traceKernel<Q, false><<<grid, b200rt::kBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, cursor, max_depth, tree_space, d_times ? d_times + begin : nullptr);
 		++g_launches;
 		CUDA_TRY(cudaGetLastError());
 	}
@@ -505,10 +541,110 @@ int b200rt_add_mesh(b200rt_scene *s, const float *xyz, size_t n_verts, const uin
 			}
 		if(flags) s->flags.insert(s->flags.end(), flags, flags + n_faces);
 		else s->flags.insert(s->flags.end(), n_faces, uint8_t(B200RT_FACE_VISIBLE | B200RT_FACE_CASTS_SHADOWS));
+		s->kind.resize(s->flags.size(), uint8_t(0));
+		s->motion_of_face.resize(s->flags.size(), -1);
 	}
 	catch(const std::bad_alloc &) { return fail(B200RT_E_MEMORY, "out of host memory"); }
 	s->built = false;
 	return B200RT_OK;
+}
+
+namespace {
+
+// SquareMatrix * Point (include/geometry/matrix.h:131-144): aux = 0; aux += m[i][j] * v[j], j = 0..2; aux += m[i][3] -- float
+// operations in this order (part of a primitive's bound, hence of the tree bound and the ray bias)
+void matPoint(const float *m, const float *v, float *o)
+{
+	for(int i = 0; i < 3; ++i)
+	{
+		volatile float aux = 0.f;
+		for(int j = 0; j < 3; ++j) { volatile float prod = m[4 * i + j] * v[j]; aux = aux + prod; }
+		aux = aux + m[4 * i + 3];
+		o[i] = aux;
+	}
+}
+
+// Faces of a motion-blur mesh / moving instance: the builder gets one box face per face (two corner vertices appended to the
+// scene's vertex array), the flattener the MotionFace record.  steps: the vertex arrays of the three time steps (Bezier) or
+// {xyz, nullptr, nullptr} with `matrix` >= 0 (moving instance).
+int addMotionFaces(b200rt_scene *s, const float *const steps[3], size_t n_verts, const uint32_t *idx, size_t n_faces, const uint8_t *flags, float t0, float t1, int matrix)
+{
+	if(s->idx.size() / 4 + n_faces >= (size_t(1) << 30)) return fail(B200RT_E_INVALID, "too many faces");
+	if(s->xyz.size() / 3 + 2 * n_faces >= size_t(kBox)) return fail(B200RT_E_INVALID, "too many vertices");
+	for(size_t f = 0; f < n_faces; ++f)
+		for(int k = 0; k < 4; ++k)
+		{
+			const uint32_t v = idx[4 * f + k];
+			if(k == 3 && v == kTriangle) continue;
+			if(v >= n_verts) return fail(B200RT_E_INVALID, "face " + std::to_string(f) + " references vertex " + std::to_string(v) + " >= n_verts");
+		}
+	try
+	{
+		for(size_t f = 0; f < n_faces; ++f)
+		{
+			b200rt_scene::MotionFace mf{};
+			mf.nv = (idx[4 * f + 3] == kTriangle) ? 3u : 4u;
+			mf.t0 = t0; mf.t1 = t1;
+			mf.matrix = matrix >= 0 ? uint32_t(matrix) : 0u;
+			float lo[3], hi[3];
+			bool first = true;
+			for(int step = 0; step < 3; ++step)
+				for(uint32_t k = 0; k < mf.nv; ++k)
+				{
+					float p[3];
+					if(matrix >= 0)
+					{
+						const float *base = steps[0] + 3 * size_t(idx[4 * f + k]);
+						if(step == 0) for(int a = 0; a < 3; ++a) mf.v[0][k][a] = base[a];
+						matPoint(s->matrices[size_t(matrix)].data() + 16 * step, base, p); // PrimitiveInstance::getBound, primitive_instance.h:119-128
+					}
+					else
+					{
+						const float *src = steps[step] + 3 * size_t(idx[4 * f + k]);
+						for(int a = 0; a < 3; ++a) { mf.v[step][k][a] = src[a]; p[a] = src[a]; } // FacePrimitive::getBoundTimeSteps, primitive_face.h:155-170
+					}
+					for(int a = 0; a < 3; ++a)
+					{
+						if(first || p[a] < lo[a]) lo[a] = p[a];
+						if(first || p[a] > hi[a]) hi[a] = p[a];
+					}
+					first = false;
+				}
+			const uint32_t corner = uint32_t(s->xyz.size() / 3);
+			s->xyz.insert(s->xyz.end(), {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]});
+			s->idx.insert(s->idx.end(), {corner, corner + 1u, kBox, kTriangle});
+			s->flags.push_back(flags ? flags[f] : uint8_t(B200RT_FACE_VISIBLE | B200RT_FACE_CASTS_SHADOWS));
+			s->kind.push_back(matrix >= 0 ? uint8_t(2) : uint8_t(1));
+			s->motion_of_face.push_back(int32_t(s->motion.size()));
+			s->motion.push_back(mf);
+		}
+	}
+	catch(const std::bad_alloc &) { return fail(B200RT_E_MEMORY, "out of host memory"); }
+	s->built = false;
+	return B200RT_OK;
+}
+
+} // namespace
+
+int b200rt_add_mesh_bezier(b200rt_scene *s, const float *xyz0, const float *xyz1, const float *xyz2, size_t n_verts, const uint32_t *idx, size_t n_faces,
+                           const uint8_t *flags, float time_start, float time_end)
+{
+	if(!s || ((!xyz0 || !xyz1 || !xyz2) && n_verts) || (!idx && n_faces)) return fail(B200RT_E_INVALID, "null argument");
+	const float *const steps[3] = {xyz0, xyz1, xyz2};
+	return addMotionFaces(s, steps, n_verts, idx, n_faces, flags, time_start, time_end, -1);
+}
+
+int b200rt_add_mesh_moving(b200rt_scene *s, const float *xyz, size_t n_verts, const uint32_t *idx, size_t n_faces, const uint8_t *flags,
+                           const float matrices[48], float time_start, float time_end)
+{
+	if(!s || (!xyz && n_verts) || (!idx && n_faces) || !matrices) return fail(B200RT_E_INVALID, "null argument");
+	std::array<float, 50> m{};
+	std::copy(matrices, matrices + 48, m.begin());
+	m[48] = time_start; m[49] = time_end;
+	try { s->matrices.push_back(m); }
+	catch(const std::bad_alloc &) { return fail(B200RT_E_MEMORY, "out of host memory"); }
+	const float *const steps[3] = {xyz, nullptr, nullptr};
+	return addMotionFaces(s, steps, n_verts, idx, n_faces, flags, time_start, time_end, int(s->matrices.size()) - 1);
 }
 
 int b200rt_add_spheres(b200rt_scene *s, const float *center_radius, size_t n_spheres, const uint8_t *flags)
@@ -528,6 +664,8 @@ int b200rt_add_spheres(b200rt_scene *s, const float *center_radius, size_t n_sph
 		}
 		if(flags) s->flags.insert(s->flags.end(), flags, flags + n_spheres);
 		else s->flags.insert(s->flags.end(), n_spheres, uint8_t(B200RT_FACE_VISIBLE | B200RT_FACE_CASTS_SHADOWS));
+		s->kind.resize(s->flags.size(), uint8_t(0));
+		s->motion_of_face.resize(s->flags.size(), -1);
 	}
 	catch(const std::bad_alloc &) { return fail(B200RT_E_MEMORY, "out of host memory"); }
 	s->built = false;
@@ -552,8 +690,12 @@ int b200rt_build(b200rt_scene *s)
 		s->record_of_ref.assign(tree.leaf_refs.size(), 0u);
 		tris.reserve(tree.leaf_refs.size() * 3 + 4);
 		nodes.resize(tree.nodes.size());
-		uint64_t n_tri = 0, n_quad = 0, n_sphere = 0;
-		for(size_t f = 0; f < n_faces; ++f) (s->idx[4 * f + 2] == kSphere ? n_sphere : s->idx[4 * f + 3] == kTriangle ? n_tri : n_quad)++;
+		uint64_t n_tri = 0, n_quad = 0, n_sphere = 0, n_bezier = 0, n_moving = 0;
+		for(size_t f = 0; f < n_faces; ++f)
+		{
+			if(s->kind[f]) { (s->kind[f] == 1 ? n_bezier : n_moving)++; (s->motion[size_t(s->motion_of_face[f])].nv == 3u ? n_tri : n_quad)++; }
+			else (s->idx[4 * f + 2] == kSphere ? n_sphere : s->idx[4 * f + 3] == kTriangle ? n_tri : n_quad)++;
+		}
 		for(size_t i = 0; i < tree.nodes.size(); ++i)
 		{
 			const b200rt::HostNode hn = tree.nodes[i];
@@ -564,6 +706,27 @@ int b200rt_build(b200rt_scene *s)
 			{
 				const uint32_t face = tree.leaf_refs[hn.a + k];
 				const uint32_t *id = s->idx.data() + 4 * size_t(face);
+				if(s->kind[face])
+				{
+					// motion-blur face (record layouts: kd_kernels.cuh, kFlagBezier / kFlagMoving)
+					const b200rt_scene::MotionFace &mf = s->motion[size_t(s->motion_of_face[face])];
+					const bool bezier = s->kind[face] == 1;
+					s->record_of_ref[hn.a + k] = uint32_t(tris.size());
+					uint32_t fl = (s->flags[face] & 7u) | (bezier ? b200rt::kFlagBezier : b200rt::kFlagMoving);
+					if(mf.nv == 4u) fl |= b200rt::kFlagQuad;
+					const uint32_t inst_offset = mf.matrix * 10u;
+					for(int step = 0; step < (bezier ? 3 : 1); ++step)
+						for(uint32_t v = 0; v < mf.nv; ++v)
+						{
+							float4 q = make_float4(mf.v[step][v][0], mf.v[step][v][1], mf.v[step][v][2], 0.f);
+							if(step == 0 && v == 0) std::memcpy(&q.w, &face, 4);
+							else if(step == 0 && v == 1) std::memcpy(&q.w, &fl, 4);
+							else if(step == 0 && v == 2) { if(bezier) q.w = mf.t0; else std::memcpy(&q.w, &inst_offset, 4); }
+							else if(step == 1 && v == 0) q.w = mf.t1;
+							tris.push_back(q);
+						}
+					continue;
+				}
 				const bool quad = id[3] != kTriangle;
 				const float *v0 = s->xyz.data() + 3 * size_t(id[0]);
 				s->record_of_ref[hn.a + k] = uint32_t(tris.size());
@@ -599,13 +762,15 @@ int b200rt_build(b200rt_scene *s)
 			}
 		}
 		if(tris.size() >= (size_t(1) << 32)) return fail(B200RT_E_INVALID, "leaf stream exceeds 2^32 records");
-		tris.push_back(make_float4(0.f, 0.f, 0.f, 0.f)); // a quad's 4th record may be prefetched one past a triangle
+		for(int pad = 0; pad < 4; ++pad) tris.push_back(make_float4(0.f, 0.f, 0.f, 0.f)); // records are read up to four vectors ahead of their kind test
 		s->stats = b200rt_stats{};
 		s->stats.n_faces = n_faces;
 		s->stats.n_triangles = n_tri;
 		s->stats.n_quads = n_quad;
 		s->stats.n_spheres = n_sphere;
-		s->has_spheres = n_sphere != 0;
+		s->stats.n_bezier_faces = n_bezier;
+		s->stats.n_moving_faces = n_moving;
+		s->has_spheres = n_sphere != 0 || n_bezier != 0 || n_moving != 0; // the kernel variant with the other primitive kinds
 		s->stats.n_nodes = tree.nodes.size();
 		s->stats.n_interior = tree.n_interior;
 		s->stats.n_leaves = tree.n_leaves;
@@ -625,6 +790,20 @@ int b200rt_build(b200rt_scene *s)
 	CUDA_TRY(cudaMalloc(&s->d_tris, tris.size() * sizeof(float4)));
 	CUDA_TRY(cudaMemcpy(s->d_nodes, nodes.data(), nodes.size() * sizeof(uint2), cudaMemcpyHostToDevice));
 	CUDA_TRY(cudaMemcpy(s->d_tris, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
+	if(s->d_inst) { cudaFree(s->d_inst); s->d_inst = nullptr; }
+	if(!s->matrices.empty())
+	{
+		// per moving instance: rows 0-2 of its three matrices, then (time_start, time_end, -, -)
+		std::vector<float4> inst;
+		for(const auto &m : s->matrices)
+		{
+			for(int step = 0; step < 3; ++step)
+				for(int i = 0; i < 3; ++i) inst.push_back(make_float4(m[16 * step + 4 * i], m[16 * step + 4 * i + 1], m[16 * step + 4 * i + 2], m[16 * step + 4 * i + 3]));
+			inst.push_back(make_float4(m[48], m[49], 0.f, 0.f));
+		}
+		CUDA_TRY(cudaMalloc(&s->d_inst, inst.size() * sizeof(float4)));
+		CUDA_TRY(cudaMemcpy(s->d_inst, inst.data(), inst.size() * sizeof(float4), cudaMemcpyHostToDevice));
+	}
 	// one resident wave of the kernel variant THIS build launches (a rebuild after b200rt_add_spheres switches variants); the
 	// cursors are allocated only once the occupancy queries have succeeded, so a failed query is retried by the next build
 	{
@@ -637,6 +816,7 @@ int b200rt_build(b200rt_scene *s)
 	s->n_tri_vec4 = tris.size();
 	s->view.nodes = s->d_nodes;
 	s->view.tris = s->d_tris;
+	s->view.inst = s->d_inst;
 	std::memcpy(s->view.bound, s->tree.bound, sizeof(s->view.bound));
 	s->stats.device_bytes = nodes.size() * sizeof(uint2) + tris.size() * sizeof(float4);
 	s->stats.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
@@ -674,8 +854,16 @@ int b200rt_update_face_flags(b200rt_scene *s, const uint8_t *flags, size_t n_fac
 	{
 		const uint32_t face = s->tree.leaf_refs[r];
 		uint32_t fl = s->flags[face] & 7u;
-		if(s->idx[4 * size_t(face) + 3] != kTriangle) fl |= b200rt::kFlagQuad;
-		if(s->idx[4 * size_t(face) + 2] == kSphere) fl |= b200rt::kFlagSphere;
+		if(s->kind[face])
+		{
+			fl |= (s->kind[face] == 1) ? b200rt::kFlagBezier : b200rt::kFlagMoving;
+			if(s->motion[size_t(s->motion_of_face[face])].nv == 4u) fl |= b200rt::kFlagQuad;
+		}
+		else
+		{
+			if(s->idx[4 * size_t(face) + 3] != kTriangle) fl |= b200rt::kFlagQuad;
+			if(s->idx[4 * size_t(face) + 2] == kSphere) fl |= b200rt::kFlagSphere;
+		}
 		std::memcpy(&tris[size_t(s->record_of_ref[r]) + 1].w, &fl, 4);
 	}
 	CUDA_TRY(cudaMemcpy(s->d_tris, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
@@ -709,31 +897,8 @@ int b200rt_trace_tshadow_device(b200rt_scene *s, const b200rt_ray *d_rays, size_
 	return launchTrace<b200rt::kTShadow>(s, d_rays, n, d_out, static_cast<cudaStream_t>(stream), max_depth);
 }
 
-// ---- host-buffer queries ----------------------------------------------------------------------
-int b200rt_trace_closest(b200rt_scene *s, const b200rt_ray *rays, size_t n, b200rt_hit *out)
-{
-	return tracedStaged(s, rays, n, out, [&](const b200rt_ray *d_rays, size_t count, b200rt_hit *d_out, cudaStream_t st, bool small) {
-		return launchTrace<b200rt::kClosest>(s, d_rays, count, d_out, st, 0, 0u, small);
-	});
-}
-
-int b200rt_trace_shadow(b200rt_scene *s, const b200rt_ray *rays, size_t n, uint32_t *out)
-{
-	return tracedStaged(s, rays, n, out, [&](const b200rt_ray *d_rays, size_t count, uint32_t *d_out, cudaStream_t st, bool small) {
-		return launchTrace<b200rt::kShadow>(s, d_rays, count, d_out, st, 0, 0u, small);
-	});
-}
-
-int b200rt_trace_tshadow(b200rt_scene *s, const b200rt_ray *rays, size_t n, int max_depth, b200rt_tshadow *out)
-{
-	if(max_depth < 0 || max_depth > B200RT_TSHADOW_MAX) return fail(B200RT_E_INVALID, "max_depth must be in [0, B200RT_TSHADOW_MAX]");
-	return tracedStaged(s, rays, n, out, [&](const b200rt_ray *d_rays, size_t count, b200rt_tshadow *d_out, cudaStream_t st, bool small) {
-		return launchTrace<b200rt::kTShadow>(s, d_rays, count, d_out, st, max_depth, 0u, small);
-	});
-}
-
-// ---- generic entry points (query kind + flags) ------------------------------------------------
-int b200rt_trace_device(b200rt_scene *s, int query, unsigned flags, const b200rt_ray *d_rays, size_t n, void *d_out, int max_depth, void *stream)
+// ---- generic entry points (query kind + flags [+ ray times]); everything else forwards here ------------------------
+int b200rt_trace_timed_device(b200rt_scene *s, int query, unsigned flags, const b200rt_ray *d_rays, const float *d_times, size_t n, void *d_out, int max_depth, void *stream)
 {
 	const int rc = checkDeviceCall(s, d_rays, n, d_out);
 	if(rc != B200RT_OK) return rc;
@@ -743,33 +908,49 @@ int b200rt_trace_device(b200rt_scene *s, int query, unsigned flags, const b200rt
 	cudaStream_t st = static_cast<cudaStream_t>(stream);
 	switch(query)
 	{
-		case B200RT_QUERY_CLOSEST: return launchTrace<b200rt::kClosest>(s, d_rays, n, static_cast<b200rt_hit *>(d_out), st, 0, flags);
-		case B200RT_QUERY_SHADOW: return launchTrace<b200rt::kShadow>(s, d_rays, n, static_cast<uint32_t *>(d_out), st, 0, flags);
-		case B200RT_QUERY_TSHADOW: return launchTrace<b200rt::kTShadow>(s, d_rays, n, static_cast<b200rt_tshadow *>(d_out), st, max_depth, flags);
+		case B200RT_QUERY_CLOSEST: return launchTrace<b200rt::kClosest>(s, d_rays, n, static_cast<b200rt_hit *>(d_out), st, 0, flags, false, d_times);
+		case B200RT_QUERY_SHADOW: return launchTrace<b200rt::kShadow>(s, d_rays, n, static_cast<uint32_t *>(d_out), st, 0, flags, false, d_times);
+		case B200RT_QUERY_TSHADOW: return launchTrace<b200rt::kTShadow>(s, d_rays, n, static_cast<b200rt_tshadow *>(d_out), st, max_depth, flags, false, d_times);
+		default: return fail(B200RT_E_INVALID, "unknown query kind");
+	}
+}
+
+int b200rt_trace_device(b200rt_scene *s, int query, unsigned flags, const b200rt_ray *d_rays, size_t n, void *d_out, int max_depth, void *stream)
+{
+	return b200rt_trace_timed_device(s, query, flags, d_rays, nullptr, n, d_out, max_depth, stream);
+}
+
+int b200rt_trace_timed(b200rt_scene *s, int query, unsigned flags, const b200rt_ray *rays, const float *times, size_t n, void *out, int max_depth)
+{
+	const bool known_pinned = (flags & B200RT_BUFFERS_PINNED) != 0u;
+	switch(query)
+	{
+		case B200RT_QUERY_CLOSEST:
+			return tracedStaged(s, rays, times, n, static_cast<b200rt_hit *>(out), [&](const b200rt_ray *d_rays, const float *d_times, size_t count, b200rt_hit *d_out, cudaStream_t st, bool small) {
+				return launchTrace<b200rt::kClosest>(s, d_rays, count, d_out, st, 0, flags, small, d_times);
+			}, known_pinned);
+		case B200RT_QUERY_SHADOW:
+			return tracedStaged(s, rays, times, n, static_cast<uint32_t *>(out), [&](const b200rt_ray *d_rays, const float *d_times, size_t count, uint32_t *d_out, cudaStream_t st, bool small) {
+				return launchTrace<b200rt::kShadow>(s, d_rays, count, d_out, st, 0, flags, small, d_times);
+			}, known_pinned);
+		case B200RT_QUERY_TSHADOW:
+			if(max_depth < 0 || max_depth > B200RT_TSHADOW_MAX) return fail(B200RT_E_INVALID, "max_depth must be in [0, B200RT_TSHADOW_MAX]");
+			return tracedStaged(s, rays, times, n, static_cast<b200rt_tshadow *>(out), [&](const b200rt_ray *d_rays, const float *d_times, size_t count, b200rt_tshadow *d_out, cudaStream_t st, bool small) {
+				return launchTrace<b200rt::kTShadow>(s, d_rays, count, d_out, st, max_depth, flags, small, d_times);
+			}, known_pinned);
 		default: return fail(B200RT_E_INVALID, "unknown query kind");
 	}
 }
 
 int b200rt_trace(b200rt_scene *s, int query, unsigned flags, const b200rt_ray *rays, size_t n, void *out, int max_depth)
 {
-	switch(query)
-	{
-		case B200RT_QUERY_CLOSEST:
-			return tracedStaged(s, rays, n, static_cast<b200rt_hit *>(out), [&](const b200rt_ray *d_rays, size_t count, b200rt_hit *d_out, cudaStream_t st, bool small) {
-				return launchTrace<b200rt::kClosest>(s, d_rays, count, d_out, st, 0, flags, small);
-			});
-		case B200RT_QUERY_SHADOW:
-			return tracedStaged(s, rays, n, static_cast<uint32_t *>(out), [&](const b200rt_ray *d_rays, size_t count, uint32_t *d_out, cudaStream_t st, bool small) {
-				return launchTrace<b200rt::kShadow>(s, d_rays, count, d_out, st, 0, flags, small);
-			});
-		case B200RT_QUERY_TSHADOW:
-			if(max_depth < 0 || max_depth > B200RT_TSHADOW_MAX) return fail(B200RT_E_INVALID, "max_depth must be in [0, B200RT_TSHADOW_MAX]");
-			return tracedStaged(s, rays, n, static_cast<b200rt_tshadow *>(out), [&](const b200rt_ray *d_rays, size_t count, b200rt_tshadow *d_out, cudaStream_t st, bool small) {
-				return launchTrace<b200rt::kTShadow>(s, d_rays, count, d_out, st, max_depth, flags, small);
-			});
-		default: return fail(B200RT_E_INVALID, "unknown query kind");
-	}
+	return b200rt_trace_timed(s, query, flags, rays, nullptr, n, out, max_depth);
 }
+
+// ---- host-buffer queries ----------------------------------------------------------------------
+int b200rt_trace_closest(b200rt_scene *s, const b200rt_ray *rays, size_t n, b200rt_hit *out) { return b200rt_trace_timed(s, B200RT_QUERY_CLOSEST, 0u, rays, nullptr, n, out, 0); }
+int b200rt_trace_shadow(b200rt_scene *s, const b200rt_ray *rays, size_t n, uint32_t *out) { return b200rt_trace_timed(s, B200RT_QUERY_SHADOW, 0u, rays, nullptr, n, out, 0); }
+int b200rt_trace_tshadow(b200rt_scene *s, const b200rt_ray *rays, size_t n, int max_depth, b200rt_tshadow *out) { return b200rt_trace_timed(s, B200RT_QUERY_TSHADOW, 0u, rays, nullptr, n, out, max_depth); }
 
 int b200rt_trace_jobs_begin(const b200rt_job *jobs, size_t n_jobs, b200rt_flight **out_flight)
 {
@@ -815,6 +996,7 @@ int b200rt_trace_jobs_begin(const b200rt_job *jobs, size_t n_jobs, b200rt_flight
 				batch.rays[k] = bundle.job[k]->rays;
 				batch.out[k] = bundle.job[k]->out;
 				batch.n[k] = uint32_t(bundle.job[k]->n);
+				batch.times[k] = bundle.job[k]->times;
 				warps += (bundle.job[k]->n + 31) / 32;
 			}
 			const unsigned grid = unsigned((warps + b200rt::kBlock / 32 - 1) / (b200rt::kBlock / 32));
@@ -835,7 +1017,7 @@ int b200rt_trace_jobs_begin(const b200rt_job *jobs, size_t n_jobs, b200rt_flight
 		if(rc == B200RT_OK && (job.query < B200RT_QUERY_CLOSEST || job.query > B200RT_QUERY_TSHADOW)) rc = fail(B200RT_E_INVALID, "unknown query kind");
 		if(rc == B200RT_OK && job.query == B200RT_QUERY_TSHADOW && (job.max_depth < 0 || job.max_depth > B200RT_TSHADOW_MAX)) rc = fail(B200RT_E_INVALID, "max_depth must be in [0, B200RT_TSHADOW_MAX]");
 		if(rc != B200RT_OK) { flight->note(rc); continue; }
-		const bool pinned = (job.flags & B200RT_BUFFERS_PINNED) != 0u || (isPinned(job.rays) && isPinned(job.out));
+		const bool pinned = (job.flags & B200RT_BUFFERS_PINNED) != 0u || (isPinned(job.rays) && isPinned(job.out) && (!job.times || isPinned(job.times)));
 		if(!pinned || job.n > kDirectRays) { staged.push_back(j); continue; }
 		const unsigned tree_space = job.flags & B200RT_RAYS_TREE_SPACE;
 		Bundle *home = nullptr;
@@ -851,7 +1033,7 @@ int b200rt_trace_jobs_begin(const b200rt_job *jobs, size_t n_jobs, b200rt_flight
 	for(const Bundle &bundle : bundles) launchBundle(bundle);
 	for(size_t j : staged)
 	{
-		const int rc = b200rt_trace(jobs[j].scene, jobs[j].query, jobs[j].flags, jobs[j].rays, jobs[j].n, jobs[j].out, jobs[j].max_depth);
+		const int rc = b200rt_trace_timed(jobs[j].scene, jobs[j].query, jobs[j].flags & ~unsigned(B200RT_BUFFERS_PINNED), jobs[j].rays, jobs[j].times, jobs[j].n, jobs[j].out, jobs[j].max_depth);
 		if(rc != B200RT_OK) flight->note(rc);
 	}
 	*out_flight = flight;
@@ -935,7 +1117,7 @@ int b200rt_host_tree_build(const float *xyz, size_t n_verts, const uint32_t *idx
 		{
 			const uint32_t v = idx[4 * f + k];
 			if(k == 3 && v == kTriangle) continue;
-			if(k == 2 && v == kSphere && idx[4 * f + 3] == kTriangle) continue; // sphere face (kd_build.h)
+			if(k == 2 && (v == kSphere || v == kBox) && idx[4 * f + 3] == kTriangle) continue; // sphere / box face (kd_build.h)
 			if(v >= n_verts) return fail(B200RT_E_INVALID, "face references a vertex >= n_verts");
 		}
 	try

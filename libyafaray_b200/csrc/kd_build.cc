@@ -25,6 +25,7 @@ constexpr size_t kClipThreshold = 64;
 constexpr size_t kSpawnThreshold = 40000; // references; below this a subtree is built serially
 constexpr uint32_t kTriangle = 0xFFFFFFFFu;
 constexpr uint32_t kSphere = 0xFFFFFFFEu; // idx[2] of a sphere "face": vertex idx[0] = centre, x of vertex idx[1] = radius (kd_build.h)
+constexpr uint32_t kBox = 0xFFFFFFFDu;    // idx[2] of a box "face" (a primitive the builder only knows the bound of): vertices idx[0], idx[1] = lo, hi corner
 
 void faceBound(const MeshView &mesh, size_t f, float lo[3], float hi[3]);
 
@@ -228,9 +229,9 @@ inline float roundUp(double x) { float f = float(x); return (double(f) < x) ? st
 bool clipRef(const Context &c, uint32_t prim, const Box &box, Ref &out)
 {
 	const uint32_t *id = c.mesh.idx + 4 * size_t(prim);
-	if(id[2] == kSphere)
+	if(id[2] == kSphere || id[2] == kBox)
 	{
-		// no clipping for spheres (SpherePrimitive has no clippingSupport() either): the padded bound cut to the box
+		// no clipping for spheres and motion-blur primitives (no clippingSupport() in the reference either): the bound cut to the box
 		out.prim = prim;
 		faceBound(c.mesh, prim, out.lo, out.hi);
 		for(int k = 0; k < 3; ++k)
@@ -392,6 +393,11 @@ void faceBound(const MeshView &mesh, size_t f, float lo[3], float hi[3])
 			lo[k] = a;
 			hi[k] = g;
 		}
+		return;
+	}
+	if(id[2] == kBox)
+	{
+		for(int k = 0; k < 3; ++k) { lo[k] = mesh.xyz[3 * size_t(id[0]) + k]; hi[k] = mesh.xyz[3 * size_t(id[1]) + k]; }
 		return;
 	}
 	const int nv = (id[3] == kTriangle) ? 3 : 4;

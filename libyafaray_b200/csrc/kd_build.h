@@ -42,6 +42,8 @@ struct HostTree
 
 // Flat mesh view shared by builder and flattener.  idx: 4 per face, idx[3] == 0xFFFFFFFF => triangle.
 // A face with idx[2] == 0xFFFFFFFE is a sphere: vertex idx[0] is its centre, the x of vertex idx[1] its radius.
+// A face with idx[2] == 0xFFFFFFFD is a box: vertices idx[0] / idx[1] are the corners of the primitive's bound (motion-blur
+// primitives: the builder sees the union of their bounds over the time steps and never clips them).
 struct MeshView
 {
 	const float *xyz;

@@ -35,12 +35,19 @@ struct SceneView
 	const uint2 *nodes;
 	const float4 *tris;
 	float bound[6];
+	const float4 *inst; // moving instances: per instance 10 float4 = three obj_to_world matrices (rows 0-2 of each) + (time_start, time_end, -, -)
 };
 
 enum Query { kClosest = 0, kShadow = 1, kTShadow = 2 };
 
 static constexpr uint32_t kFlagQuad = 8u;
 static constexpr uint32_t kFlagSphere = 16u;
+// Motion blur (scenes built with b200rt_add_mesh_bezier / _moving; kernels of the SPHERES = "other primitive kinds" variant):
+//   Bezier face, nv vertices: 3 nv float4 = the vertices at time steps 0, 1, 2; w of the first four: face id, flags, time_start,
+//     - (quads); w of the first vertex of step 1: time_end.  (Static records hold v0 and EDGES; these hold vertices.)
+//   face of a moving instance: nv float4 = the base vertices; w: face id, flags, float4 index of the instance in SceneView::inst, -
+static constexpr uint32_t kFlagBezier = 32u;
+static constexpr uint32_t kFlagMoving = 64u;
 
 __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz)
 {
@@ -88,8 +95,10 @@ __device__ __forceinline__ bool boundCross(const float *b, float ox, float oy, f
 }
 
 // shape_polygon.h:126-176 on a record of the leaf stream.  Returns t (0 = miss) and uv.
-__device__ __forceinline__ float polyIntersect(const float4 q0, const float4 q1, const float4 q2, const float4 *q3_ptr, bool quad,
-                                               float ox, float oy, float oz, float dx, float dy, float dz, float &out_u, float &out_v)
+// `edge3` returns the quad's third edge (only called when the second triangle of a quad has to be tested).
+template <typename Edge3>
+__device__ __forceinline__ float polyIntersectWith(const float4 q0, const float4 q1, const float4 q2, Edge3 edge3, bool quad,
+                                                   float ox, float oy, float oz, float dx, float dy, float dz, float &out_u, float &out_v)
 {
 	B200RT_CROSS(px, py, pz, dx, dy, dz, q2.x, q2.y, q2.z)            // pvec_2 = dir ^ edge_2
 	const float det = dot3(q1.x, q1.y, q1.z, px, py, pz);             // edge_1 * pvec_2
@@ -115,7 +124,7 @@ __device__ __forceinline__ float polyIntersect(const float4 q0, const float4 q1,
 		}
 		else if(quad)
 		{
-			const float4 q3 = __ldg(q3_ptr);
+			const float4 q3 = edge3();
 			B200RT_CROSS(p3x, p3y, p3z, dx, dy, dz, q3.x, q3.y, q3.z)  // pvec_3 = dir ^ edge_3
 			const float det2 = dot3(q2.x, q2.y, q2.z, p3x, p3y, p3z);  // edge_2 * pvec_3
 			if(det2 != 0.f)
@@ -143,6 +152,93 @@ __device__ __forceinline__ float polyIntersect(const float4 q0, const float4 q1,
 	out_u = 0.f;
 	out_v = 0.f;
 	return 0.f;
+}
+
+__device__ __forceinline__ float polyIntersect(const float4 q0, const float4 q1, const float4 q2, const float4 *q3_ptr, bool quad,
+                                               float ox, float oy, float oz, float dx, float dy, float dz, float &out_u, float &out_v)
+{
+	return polyIntersectWith(q0, q1, q2, [&]() { return __ldg(q3_ptr); }, quad, ox, oy, oz, dx, dy, dz, out_u, out_v);
+}
+
+// Quadratic Bezier factors of a ray time inside (start, end): math::lerpSegment(time, 0, start, 1, end) then
+// math::bezierCalculateFactors (include/math/interpolation.h:50-93).  Returns 0 / 2 when the time is at or outside the start /
+// end of the range -- time step 0 / 2 is then used as it is (primitive_polygon.h:245-248, instance.h:78-80) -- else 1.
+__device__ __forceinline__ int bezierFactors(float time, float start, float end, float &f0, float &f1, float &f2)
+{
+	if(time <= start) return 0;
+	if(time >= end) return 2;
+	const float x = __fadd_rn(0.f, __fmul_rn(__fdiv_rn(__fsub_rn(time, start), __fsub_rn(end, start)), __fsub_rn(1.f, 0.f)));
+	const float xr = __fsub_rn(1.f, x);
+	f0 = __fmul_rn(xr, xr);
+	f1 = __fmul_rn(__fmul_rn(2.f, x), xr);
+	f2 = __fmul_rn(x, x);
+	return 1;
+}
+
+// math::bezierInterpolate (interpolation.h:83-86): y0 * f0 + y1 * f1 + y2 * f2, left to right, every product and sum rounded
+__device__ __forceinline__ float bezier3(int where, float y0, float y1, float y2, float f0, float f1, float f2)
+{
+	return where == 0 ? y0 : where == 2 ? y2 : __fadd_rn(__fadd_rn(__fmul_rn(y0, f0), __fmul_rn(y1, f1)), __fmul_rn(y2, f2));
+}
+
+// A motion-blur face at the ray's time (records: kFlagBezier / kFlagMoving above).  The vertices are rebuilt with the reference's
+// operations (FacePrimitive::getVertex with Bezier factors, primitive_face.h:86-90; SquareMatrix * Point, matrix.h:131-144, on the
+// interpolated instance matrix, instance.h:82-85), the edges are the test's own subtractions (shape_polygon.h:130-131,150).
+// `rec` is advanced past the record.
+__device__ __forceinline__ float motionIntersect(const SceneView &s, const float4 *&rec, const float4 q0, const float4 q1, const float4 q2, uint32_t flags, bool quad, float time,
+                                                 float ox, float oy, float oz, float dx, float dy, float dz, float &u, float &v)
+{
+	const int nv = quad ? 4 : 3;
+	float4 p[4];
+	p[0] = q0; p[1] = q1; p[2] = q2;
+	if(quad) p[3] = __ldg(rec + 3);
+	float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+	if(flags & kFlagBezier)
+	{
+		const float4 first1 = __ldg(rec + nv);
+		const int where = bezierFactors(time, q2.w, first1.w, f0, f1, f2);
+		for(int k = 0; k < nv; ++k)
+		{
+			const float4 a = (k == 0) ? first1 : __ldg(rec + nv + k), b = __ldg(rec + 2 * nv + k);
+			p[k].x = bezier3(where, p[k].x, a.x, b.x, f0, f1, f2);
+			p[k].y = bezier3(where, p[k].y, a.y, b.y, f0, f1, f2);
+			p[k].z = bezier3(where, p[k].z, a.z, b.z, f0, f1, f2);
+		}
+		rec += 3 * nv;
+	}
+	else
+	{
+		const float4 *m = s.inst + __float_as_uint(q2.w);
+		const float4 range = __ldg(m + 9);
+		const int where = bezierFactors(time, range.x, range.y, f0, f1, f2);
+		float4 row[3];
+		for(int i = 0; i < 3; ++i)
+		{
+			const float4 a = __ldg(m + i), b = __ldg(m + 3 + i), c = __ldg(m + 6 + i);
+			row[i].x = bezier3(where, a.x, b.x, c.x, f0, f1, f2);
+			row[i].y = bezier3(where, a.y, b.y, c.y, f0, f1, f2);
+			row[i].z = bezier3(where, a.z, b.z, c.z, f0, f1, f2);
+			row[i].w = bezier3(where, a.w, b.w, c.w, f0, f1, f2);
+		}
+		for(int k = 0; k < nv; ++k)
+		{
+			const float vx = p[k].x, vy = p[k].y, vz = p[k].z;
+			float o[3];
+			for(int i = 0; i < 3; ++i)
+			{
+				float aux = __fadd_rn(0.f, __fmul_rn(row[i].x, vx));
+				aux = __fadd_rn(aux, __fmul_rn(row[i].y, vy));
+				aux = __fadd_rn(aux, __fmul_rn(row[i].z, vz));
+				o[i] = __fadd_rn(aux, row[i].w);
+			}
+			p[k].x = o[0]; p[k].y = o[1]; p[k].z = o[2];
+		}
+		rec += nv;
+	}
+	const float4 e1 = make_float4(__fsub_rn(p[1].x, p[0].x), __fsub_rn(p[1].y, p[0].y), __fsub_rn(p[1].z, p[0].z), 0.f);
+	const float4 e2 = make_float4(__fsub_rn(p[2].x, p[0].x), __fsub_rn(p[2].y, p[0].y), __fsub_rn(p[2].z, p[0].z), 0.f);
+	const float4 e3 = quad ? make_float4(__fsub_rn(p[3].x, p[0].x), __fsub_rn(p[3].y, p[0].y), __fsub_rn(p[3].z, p[0].z), 0.f) : e2;
+	return polyIntersectWith(p[0], e1, e2, [&]() { return e3; }, quad, ox, oy, oz, dx, dy, dz, u, v);
 }
 
 // SpherePrimitive::intersect, src/geometry/primitive/primitive_sphere.cc:83-102, on a sphere record (q0 = centre, q1.x =
@@ -272,7 +368,8 @@ static constexpr int kRefill = B200RT_REFILL;       // idle lanes that trigger a
 static constexpr int kTake = B200RT_TAKE;           // idle lanes that trigger a hand-out from the ray queue (two-pass batches)
 // Ray queue between the two passes: per REGION (the rays of 256 consecutive batch indices) up to 256 ENTRIES of 16 floats, the rays
 // that cross the tree bound in batch order:  ox oy oz dx | dy dz 1/dx 1/dy | 1/dz t_min t_max seg_lo | seg_hi index - -
-// (traversal inverse direction; [seg_lo, seg_hi] = the ray's interval inside the tree bound), followed by one uint32 per region,
+// (traversal inverse direction; [seg_lo, seg_hi] = the ray's interval inside the tree bound; the 15th float is the ray time),
+// followed by one uint32 per region,
 // its number of entries.  Scratch bytes for a batch: see queueBytes().
 static constexpr int kRegionRays = 256;
 static constexpr int kEntryFloats = 16;
@@ -296,6 +393,7 @@ struct RayState
 	uint32_t best_prim;
 	uint32_t node;
 	uint32_t index;               // ray index in the batch
+	float time;                   // Ray::time_ (motion blur; read by the SPHERES kernel variants only)
 	int sp;                       // ring depth in bytes (kRingStride per entry)
 };
 
@@ -509,7 +607,8 @@ __device__ __forceinline__ bool mbarTryWait(uint32_t mbar, uint32_t parity)
 // lanes set their rays up themselves.
 template <int QUERY, bool SPHERES, bool QUEUED = false>
 __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray *__restrict__ rays, uint32_t n, typename OutType<QUERY>::type *__restrict__ out,
-                                           uint32_t *__restrict__ cursor, int max_depth, bool tree_space, uint2 (*sh_stack)[kBlock], float2 (*sh_axis)[kBlock], uint32_t static_base, float4 (*sh_leaf)[kBlock] = nullptr)
+                                           uint32_t *__restrict__ cursor, int max_depth, bool tree_space, uint2 (*sh_stack)[kBlock], float2 (*sh_axis)[kBlock], uint32_t static_base, float4 (*sh_leaf)[kBlock] = nullptr,
+                                           const float *__restrict__ times = nullptr)
 {
 	const unsigned tid = threadIdx.x;
 	const unsigned lane = tid & 31u;
@@ -646,6 +745,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 						r.ox = e0.x; r.oy = e0.y; r.oz = e0.z; r.dx = e0.w; r.dy = e1.x; r.dz = e1.y;
 						r.t_min = e2.y; r.t_max = e2.z; r.seg_lo = e2.w; r.seg_hi = e3.x;
 						r.index = __float_as_uint(e3.y);
+						if(SPHERES) r.time = e3.z;
 						r.best_u = 0.f; r.best_v = 0.f; r.best_prim = B200RT_MISS;
 						r.t_done = __int_as_float(0x7f800000);
 						r.node = 0u;
@@ -706,6 +806,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					if(!alive && rank < avail)
 					{
 						r.index = pool_next + rank;
+						if(SPHERES) r.time = times ? __ldg(times + r.index) : 0.f;
 #if B200RT_STREAM_IO
 						// rays are read once: do not let them displace tree nodes from L1/L2
 						const float4 a = __ldcs(reinterpret_cast<const float4 *>(rays) + 2 * size_t(r.index));
@@ -762,9 +863,9 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					const uint32_t flags = __float_as_uint(q1.w);
 					const bool quad = (flags & kFlagQuad) != 0u;
 					float u, v, t;
-					if(SPHERES && (flags & kFlagSphere)) { t = sphereIntersect(q0, q1.x, lox, loy, loz, ldx, ldy, ldz); u = 0.f; v = 0.f; }
-					else t = polyIntersect(q0, q1, q2, rec + 3, quad, lox, loy, loz, ldx, ldy, ldz, u, v);
-					rec += quad ? 4 : 3;
+					if(SPHERES && (flags & kFlagSphere)) { t = sphereIntersect(q0, q1.x, lox, loy, loz, ldx, ldy, ldz); u = 0.f; v = 0.f; rec += 3; }
+					else if(SPHERES && (flags & (kFlagBezier | kFlagMoving))) t = motionIntersect(s, rec, q0, q1, q2, flags, quad, r.time, lox, loy, loz, ldx, ldy, ldz, u, v);
+					else { t = polyIntersect(q0, q1, q2, rec + 3, quad, lox, loy, loz, ldx, ldy, ldz, u, v); rec += quad ? 4 : 3; }
 					--leaf_count;
 					// accept rules, accelerator.h:125-127 / :137-139 / :150-154
 					const uint32_t need = (QUERY == kClosest) ? uint32_t(B200RT_FACE_VISIBLE) : uint32_t(B200RT_FACE_CASTS_SHADOWS);
@@ -916,7 +1017,8 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 
 template <int QUERY, bool SPHERES, bool QUEUED = false>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(const __grid_constant__ SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
-                                                                 typename OutType<QUERY>::type *__restrict__ out, uint32_t *__restrict__ cursor, int max_depth, bool tree_space)
+                                                                 typename OutType<QUERY>::type *__restrict__ out, uint32_t *__restrict__ cursor, int max_depth, bool tree_space,
+                                                                 const float *__restrict__ times)
 {
 	__shared__ __align__(kShortStack * kBlock * 8) uint2 sh_stack[kShortStack][kBlock]; // x = node index, y = float bits of the far end of its interval; aligned to its size (RING_OR)
 	__shared__ float2 sh_axis[4][kBlock];          // rows 0-2: (origin, inverse direction) of the lane's ray per axis; row 3: the interval inside the tree bound
@@ -925,7 +1027,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(const __grid_c
 #else
 	float4 (*sh_leaf)[kBlock] = nullptr;
 #endif
-	traceWarps<QUERY, SPHERES, QUEUED>(s, rays, n, out, cursor, max_depth, tree_space, sh_stack, sh_axis, (blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5)) * 32u, sh_leaf);
+	traceWarps<QUERY, SPHERES, QUEUED>(s, rays, n, out, cursor, max_depth, tree_space, sh_stack, sh_axis, (blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5)) * 32u, sh_leaf, times);
 }
 
 // First pass of a two-pass batch.  One warp per 256-ray region, eight trips of 32 rays: the ray records of trip t + 1 are already
@@ -940,7 +1042,7 @@ static constexpr int kSetupStages = B200RT_SETUP_STAGES; // 1 KB buffers per war
 static_assert((kSetupStages & (kSetupStages - 1)) == 0 && kSetupStages >= 2 && kSetupStages <= 8, "stages: a power of two, 2..8");
 template <int QUERY>
 __global__ void __launch_bounds__(kSetupBlock) setupKernel(const __grid_constant__ SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
-                                                           typename OutType<QUERY>::type *__restrict__ out, float *__restrict__ queue, bool tree_space)
+                                                           typename OutType<QUERY>::type *__restrict__ out, float *__restrict__ queue, bool tree_space, const float *__restrict__ times)
 {
 	__shared__ __align__(128) float4 sh_rays[kSetupBlock / 32][kSetupStages][64]; // per warp a ring of buffers of 32 ray records
 	__shared__ __align__(128) float4 sh_out[kSetupBlock / 32][32 * (kEntryFloats / 4)]; // per warp the entries of one trip, compacted, before their bulk store
@@ -1002,7 +1104,7 @@ __global__ void __launch_bounds__(kSetupBlock) setupKernel(const __grid_constant
 				e[0] = make_float4(q.ox, q.oy, q.oz, q.dx);
 				e[1] = make_float4(q.dy, q.dz, q.ix, q.iy);
 				e[2] = make_float4(q.iz, q.t_min, q.t_max, q.seg_lo);
-				e[3] = make_float4(q.seg_hi, __uint_as_float(q.index), 0.f, 0.f);
+				e[3] = make_float4(q.seg_hi, __uint_as_float(q.index), times ? __ldg(times + q.index) : 0.f, 0.f);
 			}
 			__syncwarp();
 			const uint32_t n_ready = uint32_t(__popc(m_ready));
@@ -1022,6 +1124,7 @@ struct MixedBatch
 	const b200rt_ray *rays[3];
 	void *out[3];
 	uint32_t n[3];
+	const float *times[3]; // ray times per kind, nullptr = 0
 };
 
 template <bool SPHERES>
@@ -1036,9 +1139,9 @@ __global__ void __launch_bounds__(kBlock, 4) traceMixedKernel(const __grid_const
 #endif
 	const uint32_t warp = blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5);
 	const uint32_t w0 = (b.n[0] + 31u) / 32u, w1 = (b.n[1] + 31u) / 32u;
-	if(warp < w0) traceWarps<kClosest, SPHERES>(s, b.rays[0], b.n[0], static_cast<b200rt_hit *>(b.out[0]), nullptr, 0, tree_space, sh_stack, sh_axis, warp * 32u, sh_leaf);
-	else if(warp < w0 + w1) traceWarps<kShadow, SPHERES>(s, b.rays[1], b.n[1], static_cast<uint32_t *>(b.out[1]), nullptr, 0, tree_space, sh_stack, sh_axis, (warp - w0) * 32u, sh_leaf);
-	else traceWarps<kTShadow, SPHERES>(s, b.rays[2], b.n[2], static_cast<b200rt_tshadow *>(b.out[2]), nullptr, max_depth, tree_space, sh_stack, sh_axis, (warp - w0 - w1) * 32u, sh_leaf);
+	if(warp < w0) traceWarps<kClosest, SPHERES>(s, b.rays[0], b.n[0], static_cast<b200rt_hit *>(b.out[0]), nullptr, 0, tree_space, sh_stack, sh_axis, warp * 32u, sh_leaf, b.times[0]);
+	else if(warp < w0 + w1) traceWarps<kShadow, SPHERES>(s, b.rays[1], b.n[1], static_cast<uint32_t *>(b.out[1]), nullptr, 0, tree_space, sh_stack, sh_axis, (warp - w0) * 32u, sh_leaf, b.times[1]);
+	else traceWarps<kTShadow, SPHERES>(s, b.rays[2], b.n[2], static_cast<b200rt_tshadow *>(b.out[2]), nullptr, max_depth, tree_space, sh_stack, sh_axis, (warp - w0 - w1) * 32u, sh_leaf, b.times[2]);
 }
 
 } // namespace b200rt

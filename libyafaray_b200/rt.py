@@ -35,7 +35,7 @@ class Stats(C.Structure):
                 ("n_nodes", C.c_uint64), ("n_interior", C.c_uint64), ("n_leaves", C.c_uint64), ("n_empty_leaves", C.c_uint64),
                 ("n_leaf_refs", C.c_uint64), ("max_depth", C.c_uint32), ("max_leaf_prims", C.c_uint32),
                 ("build_seconds", C.c_double), ("upload_seconds", C.c_double), ("device_bytes", C.c_uint64),
-                ("n_spheres", C.c_uint64)]
+                ("n_spheres", C.c_uint64), ("n_bezier_faces", C.c_uint64), ("n_moving_faces", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -43,7 +43,8 @@ class Stats(C.Structure):
 
 class Job(C.Structure):
     """b200rt_job (include/b200rt.h)."""
-    _fields_ = [("scene", C.c_void_p), ("query", C.c_int), ("flags", C.c_uint), ("rays", C.c_void_p), ("n", C.c_size_t), ("out", C.c_void_p), ("max_depth", C.c_int)]
+    _fields_ = [("scene", C.c_void_p), ("query", C.c_int), ("flags", C.c_uint), ("rays", C.c_void_p), ("n", C.c_size_t), ("out", C.c_void_p), ("max_depth", C.c_int),
+                ("times", C.c_void_p)]
 
 
 class B200RTError(RuntimeError):
@@ -57,7 +58,7 @@ SYMBOLS = [
     "b200rt_device_count", "b200rt_create", "b200rt_destroy", "b200rt_add_mesh", "b200rt_add_spheres", "b200rt_build", "b200rt_get_bound",
     "b200rt_get_stats", "b200rt_update_face_flags", "b200rt_trace_closest", "b200rt_trace_shadow", "b200rt_trace_tshadow",
     "b200rt_trace_closest_device", "b200rt_trace_shadow_device", "b200rt_trace_tshadow_device", "b200rt_trace",
-    "b200rt_trace_device", "b200rt_trace_jobs", "b200rt_trace_jobs_begin", "b200rt_trace_jobs_end", "b200rt_host_alloc",
+    "b200rt_trace_device", "b200rt_trace_timed", "b200rt_trace_timed_device", "b200rt_add_mesh_bezier", "b200rt_add_mesh_moving", "b200rt_trace_jobs", "b200rt_trace_jobs_begin", "b200rt_trace_jobs_end", "b200rt_host_alloc",
     "b200rt_host_free", "b200rt_host_tree_build", "b200rt_host_tree_sizes", "b200rt_host_tree_export",
     "b200rt_host_tree_destroy", "b200rt_launch_count", "b200rt_last_error", "b200rt_version",
 ]
@@ -91,6 +92,10 @@ def lib():
         L.b200rt_trace_tshadow_device.argtypes = [P, P, Z, C.c_int, P, P]
         L.b200rt_trace.argtypes = [P, C.c_int, C.c_uint, P, Z, P, C.c_int]
         L.b200rt_trace_device.argtypes = [P, C.c_int, C.c_uint, P, Z, P, C.c_int, P]
+        L.b200rt_trace_timed.argtypes = [P, C.c_int, C.c_uint, P, P, Z, P, C.c_int]
+        L.b200rt_trace_timed_device.argtypes = [P, C.c_int, C.c_uint, P, P, Z, P, C.c_int, P]
+        L.b200rt_add_mesh_bezier.argtypes = [P, P, P, P, Z, P, Z, P, C.c_float, C.c_float]
+        L.b200rt_add_mesh_moving.argtypes = [P, P, Z, P, Z, P, P, C.c_float, C.c_float]
         L.b200rt_trace_jobs.argtypes = [P, Z]
         L.b200rt_trace_jobs_begin.argtypes = [P, Z, P]
         L.b200rt_trace_jobs_end.argtypes = [P]
@@ -208,6 +213,24 @@ class Scene:
         _check(lib().b200rt_add_spheres(self._h, _p(cr), cr.shape[0], _p(flags)))
         self.n_faces += cr.shape[0]
 
+    def add_mesh_bezier(self, xyz0, xyz1, xyz2, idx, flags=None, time_range=(0.0, 1.0)):
+        """Faces of a Bezier motion-blur mesh: the vertex arrays of its three time steps as the mesh stores them (b200rt_add_mesh_bezier)."""
+        steps = [np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 3) for x in (xyz0, xyz1, xyz2)]
+        idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1, 4)
+        flags = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
+        _check(lib().b200rt_add_mesh_bezier(self._h, _p(steps[0]), _p(steps[1]), _p(steps[2]), steps[0].shape[0], _p(idx), idx.shape[0], _p(flags),
+                                            float(time_range[0]), float(time_range[1])))
+        self.n_faces += idx.shape[0]
+
+    def add_mesh_moving(self, xyz, idx, matrices, flags=None, time_range=(0.0, 1.0)):
+        """Faces of a moving instance: base vertices + three row-major 4x4 obj_to_world matrices (b200rt_add_mesh_moving)."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1, 4)
+        m = np.ascontiguousarray(matrices, dtype=np.float32).reshape(48)
+        flags = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
+        _check(lib().b200rt_add_mesh_moving(self._h, _p(xyz), xyz.shape[0], _p(idx), idx.shape[0], _p(flags), _p(m), float(time_range[0]), float(time_range[1])))
+        self.n_faces += idx.shape[0]
+
     def build(self):
         _check(lib().b200rt_build(self._h))
 
@@ -247,12 +270,19 @@ class Scene:
         _check(lib().b200rt_trace_tshadow(self._h, _p(r), r.shape[0], int(max_depth), _p(out)))
         return out
 
-    def trace(self, query, rays, flags=0, max_depth=0, out=None) -> np.ndarray:
-        """Generic entry point: query = QUERY_CLOSEST / QUERY_SHADOW / QUERY_TSHADOW, flags = RAYS_TREE_SPACE or 0."""
+    def trace(self, query, rays, flags=0, max_depth=0, out=None, times=None) -> np.ndarray:
+        """Generic entry point: query = QUERY_CLOSEST / QUERY_SHADOW / QUERY_TSHADOW, flags = RAYS_TREE_SPACE or 0; times = one ray
+        time per ray (b200rt_trace_timed) or None."""
         r = as_rays(rays)
         if out is None:
             out = np.empty(r.shape[0], {QUERY_CLOSEST: HIT_DTYPE, QUERY_SHADOW: np.uint32, QUERY_TSHADOW: TSHADOW_DTYPE}.get(int(query), TSHADOW_DTYPE))
-        _check(lib().b200rt_trace(self._h, int(query), int(flags), _p(r), r.shape[0], _p(out), int(max_depth)))
+        if times is not None:
+            times = np.ascontiguousarray(times, dtype=np.float32)
+            if times.shape[0] != r.shape[0]:
+                raise ValueError("one time per ray")
+            _check(lib().b200rt_trace_timed(self._h, int(query), int(flags), _p(r), _p(times), r.shape[0], _p(out), int(max_depth)))
+        else:
+            _check(lib().b200rt_trace(self._h, int(query), int(flags), _p(r), r.shape[0], _p(out), int(max_depth)))
         return out
 
     # ---- device-buffer queries (raw device pointers, e.g. torch.Tensor.data_ptr()) ----
@@ -270,8 +300,10 @@ def trace_jobs(jobs, split=False):
     """b200rt_trace_jobs over a list of (scene, query, flags, rays[n,8] float32, out array, max_depth); split=True goes through
     the _begin / _end pair.  The arrays must stay alive (and, for the in-place path, be PinnedBuffer arrays)."""
     arr = (Job * len(jobs))()
-    for k, (scene, query, flags, rays, out, max_depth) in enumerate(jobs):
-        arr[k] = Job(scene._h, int(query), int(flags), rays.ctypes.data, rays.shape[0], out.ctypes.data, int(max_depth))
+    for k, job in enumerate(jobs):
+        scene, query, flags, rays, out, max_depth = job[:6]
+        times = job[6] if len(job) > 6 else None
+        arr[k] = Job(scene._h, int(query), int(flags), rays.ctypes.data, rays.shape[0], out.ctypes.data, int(max_depth), times.ctypes.data if times is not None else None)
     if not split:
         _check(lib().b200rt_trace_jobs(arr, len(jobs)))
         return

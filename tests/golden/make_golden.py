@@ -57,5 +57,36 @@ def main():
               f"{shadow_rays.shape[0]} shadow rays ({s['shadowed'].mean():.2f} shadowed, tshadow {t['shadowed'].mean():.2f})")
 
 
+def main_motion():
+    """tests/golden/motion/motion.npz: static geometry + a Bezier motion-blur mesh + two moving instances (scenes.motion_scene),
+    timed rays, and what the unmodified reference returned for them -- plus its kd-tree and bound."""
+    os.makedirs(os.path.join(HERE, "motion"), exist_ok=True)
+    xyz, idx, _, mo = scenes.motion_scene(n_static=1500, n_bezier=1200, n_moving=900, seed=5)
+    flags = flag_mix(idx.shape[0], seed=41)
+    ref = yref.RefScene(xyz, idx, flags, motion=mo)
+    bound = ref.bound()
+    closest_rays, shadow_rays = ray_zoo(bound, n=6000, seed=43)
+    ct, st = scenes.ray_times(closest_rays.shape[0], 44), scenes.ray_times(shadow_rays.shape[0], 45)
+    c = ref.trace_closest(closest_rays, threads=1, times=ct)
+    s = ref.trace_shadow(shadow_rays, threads=1, times=st)
+    t = ref.trace_tshadow(shadow_rays, TSHADOW_DEPTH, threads=1, times=st)
+    tree = ref.export_tree()
+    np.savez_compressed(
+        os.path.join(HERE, "motion", "motion.npz"),
+        xyz=xyz, idx=idx, flags=flags, bound=bound, **{"motion_" + k: v for k, v in mo.items()},
+        closest_rays=closest_rays, closest_times=ct, closest_t=c["t"], closest_u=c["u"], closest_v=c["v"], closest_prim=c["prim"],
+        shadow_rays=shadow_rays, shadow_times=st, shadow_shadowed=s["shadowed"], shadow_prim=s["prim"],
+        tshadow_depth=np.int32(TSHADOW_DEPTH), tshadow_shadowed=t["shadowed"], tshadow_rgb=t["rgb"],
+        tree_split=tree["split"], tree_flags=tree["flags"], tree_first_ref=tree["first_ref"], tree_refs=tree["refs"],
+    )
+    hit = c["prim"] >= 0
+    print(f"motion: {idx.shape[0]} faces (kinds {np.bincount(mo['kind']).tolist()}), {closest_rays.shape[0]} closest rays ({hit.mean():.2f} hit, "
+          f"kinds hit {np.bincount(mo['kind'][c['prim'][hit]]).tolist()}), {shadow_rays.shape[0]} shadow rays ({s['shadowed'].mean():.2f} shadowed)")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "motion":
+        main_motion()
+    else:
+        main()
+        main_motion()

@@ -170,3 +170,24 @@ def cube_grid_far():
     """The thin-slab cube grid moved to coordinates of 300 (ulp 3e-5): 1-ulp slabs AND a coarse float grid."""
     x, i, f = scenes.cube_grid(5)
     return (x + np.array([300.0, 300.0, 300.0], np.float32)).astype(np.float32), i, f
+
+
+def make_rt_motion_scene(rt, xyz, idx, flags, motion, params=None, device=0):
+    """rt.Scene of a scenes.motion_scene(): runs of faces of one kind / time range / instance go to add_mesh, add_mesh_bezier and
+    add_mesh_moving in face order, so that face ids equal array rows (as oracle.yref.RefScene builds the reference's scene)."""
+    s = rt.Scene(device, params)
+    kind, ft, fm = motion["kind"], motion["face_times"], motion["face_matrix"]
+    n, f = idx.shape[0], 0
+    while f < n:
+        e = f
+        while e < n and kind[e] == kind[f] and np.array_equal(ft[e], ft[f]) and (kind[f] != 2 or fm[e] == fm[f]):
+            e += 1
+        if kind[f] == 0:
+            s.add_mesh(xyz, idx[f:e], flags[f:e])
+        elif kind[f] == 1:
+            s.add_mesh_bezier(xyz, motion["xyz1"], motion["xyz2"], idx[f:e], flags[f:e], (float(ft[f, 0]), float(ft[f, 1])))
+        else:
+            s.add_mesh_moving(xyz, idx[f:e], motion["matrices"][fm[f]], flags[f:e], (float(ft[f, 0]), float(ft[f, 1])))
+        f = e
+    s.build()
+    return s

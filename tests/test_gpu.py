@@ -575,3 +575,79 @@ def test_soup_1m_sample_against_oracle_and_live_reference(built):
         helpers.check_closest_parity(helpers.prim_signed(h["prim"][:200000]), h["t"][:200000], h["u"][:200000], h["v"][:200000], r)
         ref.close()
     s.close()
+
+
+# ---------------------------------------------------------------------------------------------- motion blur
+MOTION_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "motion", "motion.npz")
+
+
+def test_motion_blur_golden_vectors(built):
+    """Bezier motion-blur faces + faces of moving instances + static faces at per-ray times, against what the unmodified reference
+    returned (tests/golden/motion/motion.npz): ids up to ties, t/u/v bit-identical, shadow and transparent-shadow booleans."""
+    g = np.load(MOTION_GOLDEN)
+    mo = {k[len("motion_"):]: g[k] for k in g.files if k.startswith("motion_")}
+    s = helpers.make_rt_motion_scene(rt, g["xyz"], g["idx"], g["flags"], mo)
+    st = s.stats()
+    assert st["n_bezier_faces"] == int((mo["kind"] == 1).sum()) and st["n_moving_faces"] == int((mo["kind"] == 2).sum())
+    assert np.array_equal(s.bound(), g["bound"])
+    h = s.trace(rt.QUERY_CLOSEST, g["closest_rays"], times=g["closest_times"])
+    ref = dict(prim=g["closest_prim"], t=g["closest_t"], u=g["closest_u"], v=g["closest_v"])
+    helpers.check_closest_parity(helpers.prim_signed(h["prim"]), h["t"], h["u"], h["v"], ref)
+    sh = s.trace(rt.QUERY_SHADOW, g["shadow_rays"], times=g["shadow_times"])
+    assert np.array_equal((sh != rt.MISS).astype(np.uint8), g["shadow_shadowed"])
+    ts = s.trace(rt.QUERY_TSHADOW, g["shadow_rays"], max_depth=int(g["tshadow_depth"]), times=g["shadow_times"])
+    assert np.array_equal(ts["shadowed"].astype(np.uint8), g["tshadow_shadowed"])
+    # without times every ray is traced at time 0 (what the untimed entry points do)
+    h0 = s.trace_closest(g["closest_rays"])
+    assert h0.tobytes() == s.trace(rt.QUERY_CLOSEST, g["closest_rays"], times=np.zeros_like(g["closest_times"])).tobytes()
+    assert h0.tobytes() != h.tobytes()
+    s.close()
+
+
+def test_motion_blur_against_oracle_and_live_reference(built):
+    """A larger moving scene; batches big enough for the two-pass path (the ray time travels through the ray queue), the
+    device entry point, and a jobs bundle with times."""
+    import torch
+    xyz, idx, _, mo = scenes.motion_scene(n_static=30000, n_bezier=20000, n_moving=12000, seed=21)
+    flags = helpers.flag_mix(idx.shape[0], seed=22)
+    s = helpers.make_rt_motion_scene(rt, xyz, idx, flags, mo)
+    o = kdo.Oracle(xyz, idx, flags, motion=mo)
+    assert np.array_equal(s.bound(), o.bound())
+    b = s.bound()
+    rays = scenes.rays_incoherent(300000, seed=23, lo=b[:3], hi=b[3:])
+    times = scenes.ray_times(rays.shape[0], 24)
+    h = s.trace(rt.QUERY_CLOSEST, rays, times=times)
+    prim = helpers.prim_signed(h["prim"])
+    ref = o.trace_closest(rays, threads=NCPU, times=times)
+    helpers.check_closest_parity(prim, h["t"], h["u"], h["v"], ref)
+    hit = prim >= 0
+    assert set(np.unique(mo["kind"][prim[hit]])) == {0, 1, 2}
+    srays = scenes.rays_shadow(300000, seed=25, lo=b[:3], hi=b[3:], t_max=0.4)
+    sh = s.trace(rt.QUERY_SHADOW, srays, times=times)
+    assert np.array_equal((sh != rt.MISS).astype(np.uint8), o.trace_shadow(srays, threads=NCPU, times=times)["shadowed"])
+    if yref.available():
+        live = yref.RefScene(xyz, idx, flags, motion=mo)
+        assert np.array_equal(s.bound(), live.bound())
+        helpers.check_closest_parity(prim, h["t"], h["u"], h["v"], live.trace_closest(rays, threads=NCPU, times=times))
+        assert np.array_equal((sh != rt.MISS).astype(np.uint8), live.trace_shadow(srays, threads=NCPU, times=times)["shadowed"])
+        live.close()
+    # small batches take the single-kernel path: same bytes as the slice of the big batch
+    assert s.trace(rt.QUERY_CLOSEST, rays[:1000], times=times[:1000]).tobytes() == h[:1000].tobytes()
+    # device entry point
+    d_r, d_t = torch.from_numpy(rays).cuda(), torch.from_numpy(times).cuda()
+    d_o = torch.empty((rays.shape[0], 4), dtype=torch.float32, device="cuda")
+    rt._check(rt.lib().b200rt_trace_timed_device(s._h, rt.QUERY_CLOSEST, 0, d_r.data_ptr(), d_t.data_ptr(), rays.shape[0], d_o.data_ptr(), 0, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert d_o.cpu().numpy().tobytes() == h.tobytes()
+    # a flush of the renderer's queue with ray times (pinned, in place, mixed kinds)
+    n = 3000
+    pr = rt.PinnedBuffer((n, 8), np.float32); pr.array[:] = rays[:n]
+    ps = rt.PinnedBuffer((n, 8), np.float32); ps.array[:] = srays[:n]
+    pt = rt.PinnedBuffer((n,), np.float32); pt.array[:] = times[:n]
+    oc = rt.PinnedBuffer((n,), rt.HIT_DTYPE); os_ = rt.PinnedBuffer((n,), np.uint32)
+    fl = rt.BUFFERS_PINNED
+    rt.trace_jobs([(s, rt.QUERY_CLOSEST, fl, pr.array, oc.array, 0, pt.array), (s, rt.QUERY_SHADOW, fl, ps.array, os_.array, 0, pt.array)])
+    assert oc.array.tobytes() == h[:n].tobytes() and np.array_equal(os_.array, sh[:n])
+    for buf in (pr, ps, pt, oc, os_):
+        buf.free()
+    s.close()

@@ -23,15 +23,15 @@ def test_library_exports_every_declared_symbol(built):
     L = rt.lib()
     for name in sorted(declared):
         assert hasattr(L, name), f"libb200rt.so does not export {name}"
-    assert L.b200rt_version() == 2
+    assert L.b200rt_version() == 3
 
 
 def test_struct_sizes_match_header():
     assert rt.RAY_DTYPE.itemsize == 32 and rt.HIT_DTYPE.itemsize == 16 and rt.TSHADOW_DTYPE.itemsize == 16 + 16 * rt.TSHADOW_MAX
     assert C.sizeof(rt.BuildParams) == 32
-    # b200rt_stats: 8 uint64 counters, 2 uint32, 2 doubles, device_bytes, n_spheres (include/b200rt.h)
-    assert C.sizeof(rt.Stats) == 8 * 8 + 2 * 4 + 2 * 8 + 8 + 8
-    assert C.sizeof(rt.Job) == 8 + 4 + 4 + 8 + 8 + 8 + 8  # b200rt_job with its tail padding
+    # b200rt_stats: 8 uint64 counters, 2 uint32, 2 doubles, device_bytes, n_spheres, n_bezier_faces, n_moving_faces (include/b200rt.h)
+    assert C.sizeof(rt.Stats) == 8 * 8 + 2 * 4 + 2 * 8 + 8 + 8 + 16
+    assert C.sizeof(rt.Job) == 8 + 4 + 4 + 8 + 8 + 8 + 8 + 8  # b200rt_job: max_depth is padded to 8 bytes before the times pointer
 
 
 def test_no_silent_cpu_fallback(built):

@@ -184,3 +184,58 @@ def test_reference_itself_is_not_exact_on_cube_grid_far(built):
         total_bad += n_bad
     assert total_bad > 0, "the reference agreed with brute force everywhere: tighten test_adversarial_scenes[cube_grid_far]"
     ref.close()
+
+
+# ---------------------------------------------------------------------------------------------- motion blur
+MOTION_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "motion", "motion.npz")
+
+
+def _golden_motion(g):
+    return {k[len("motion_"):]: g[k] for k in g.files if k.startswith("motion_")}
+
+
+def test_oracle_motion_blur_bit_exact_on_reference_tree(built):
+    """Bezier motion-blur faces and faces of moving instances at per-ray times: the restated vertex interpolation (Bezier factors,
+    interpolated instance matrix, matrix * point) + polygon test on the reference's own tree == the unmodified reference, bit
+    for bit (golden vector generated by tests/golden/make_golden.py motion)."""
+    g = np.load(MOTION_GOLDEN)
+    mo = _golden_motion(g)
+    o = kdo.Oracle(g["xyz"], g["idx"], g["flags"], tree=_golden_tree(g), motion=mo)
+    assert np.array_equal(o.bound(), g["bound"])  # the tree bound covers every time step / matrix
+    c = o.trace_closest(g["closest_rays"], times=g["closest_times"])
+    assert np.array_equal(c["prim"], g["closest_prim"])
+    for k in ("t", "u", "v"):
+        assert np.array_equal(c[k], g["closest_" + k]), k
+    hit = g["closest_prim"] >= 0
+    assert set(np.unique(mo["kind"][g["closest_prim"][hit]])) == {0, 1, 2}, "the golden rays must hit all three kinds of faces"
+    s = o.trace_shadow(g["shadow_rays"], times=g["shadow_times"])
+    assert np.array_equal(s["shadowed"], g["shadow_shadowed"]) and np.array_equal(s["prim"], g["shadow_prim"])
+    t = o.trace_tshadow(g["shadow_rays"], int(g["tshadow_depth"]), times=g["shadow_times"])
+    assert np.array_equal(t["shadowed"], g["tshadow_shadowed"])
+    # time matters: the same rays at time 0 give other answers
+    c0 = o.trace_closest(g["closest_rays"], times=np.zeros_like(g["closest_times"]))
+    assert (c0["prim"] != c["prim"]).mean() > 0.01
+
+
+@pytest.mark.skipif(not yref.available(), reason="oracle/_ref/libyafref.so was not built")
+def test_oracle_motion_blur_vs_live_reference(built):
+    xyz, idx, flags, mo = scenes.motion_scene(seed=11)
+    flags = helpers.flag_mix(idx.shape[0], seed=12)
+    ref = yref.RefScene(xyz, idx, flags, motion=mo)
+    o = kdo.Oracle(xyz, idx, flags, tree=ref.export_tree(), motion=mo)
+    assert np.array_equal(o.bound(), ref.bound())
+    b = ref.bound()
+    ncpu = os.cpu_count() or 1
+    rays = scenes.rays_incoherent(100000, seed=13, lo=b[:3], hi=b[3:])
+    times = scenes.ray_times(rays.shape[0], 14)
+    r, c = ref.trace_closest(rays, threads=ncpu, times=times), o.trace_closest(rays, threads=ncpu, times=times)
+    assert np.array_equal(c["prim"], r["prim"]) and np.array_equal(c["t"], r["t"]) and np.array_equal(c["u"], r["u"]) and np.array_equal(c["v"], r["v"])
+    srays = scenes.rays_shadow(100000, seed=15, lo=b[:3], hi=b[3:], t_max=0.4)
+    assert np.array_equal(o.trace_shadow(srays, threads=ncpu, times=times)["shadowed"], ref.trace_shadow(srays, threads=ncpu, times=times)["shadowed"])
+    assert np.array_equal(o.trace_tshadow(srays, 2, threads=ncpu, times=times)["shadowed"], ref.trace_tshadow(srays, 2, threads=ncpu, times=times)["shadowed"])
+    # the oracle's own tree (boxes over all time steps) gives the same answers up to ties
+    own = kdo.Oracle(xyz, idx, flags, motion=mo)
+    assert np.array_equal(own.bound(), ref.bound())
+    c2 = own.trace_closest(rays, threads=ncpu, times=times)
+    helpers.check_closest_parity(c2["prim"], c2["t"], c2["u"], c2["v"], r)
+    ref.close()
