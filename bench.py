@@ -43,7 +43,9 @@ TSHADOW_DEPTH = 4
 # a capture of an older kernel is reported as stale (traffic = null) instead of silently going out of date.
 COUNTERS_JSON = os.path.join(ROOT, "profiles", "kernel_counters.json")
 KERNEL_SOURCES = [os.path.join(ROOT, "libyafaray_b200", "csrc", f) for f in ("kd_kernels.cuh",)]
-KERNEL_NAMES = {"closest": "b200rt::traceKernel<0,false>", "shadow": "b200rt::traceKernel<1,false>", "tshadow": "b200rt::traceKernel<2,false>"}
+# batches of 32 Ki rays and more run as two passes: setupKernel<Q> (ray setup, bound misses answered) + traceKernel<Q,false,true> (queue-fed traversal)
+KERNEL_NAMES = {"closest": "b200rt::setupKernel<0> + b200rt::traceKernel<0,false,true>", "shadow": "b200rt::setupKernel<1> + b200rt::traceKernel<1,false,true>",
+                "tshadow": "b200rt::setupKernel<2> + b200rt::traceKernel<2,false,true>"}
 SMS, SCHEDULERS_PER_SM = 148, 4
 
 
@@ -448,6 +450,12 @@ def run_b200(args):
         counters, counters_note = load_counters(args.workload)
         full_size = n == (1 << 24) and (args.workload != "s1m" or args.cells == 707)
         cc = (counters or {}).get("closest") if full_size else None
+        if cc and "setup" in cc:
+            # two-pass batch: closest_ms spans the setup pass and the traversal pass, so do the counters
+            cc = dict(cc)
+            for k in ("dram_bytes", "warp_inst", "l2_sector_bytes"):
+                cc[k] = cc[k] + cc["setup"][k]
+            cc["lanes_per_inst"] = None
         # HBM bound: algorithmic bytes of one closest launch / its measured duration
         algo = ALGO_BYTES.get(args.workload)
         hbm = None

@@ -58,9 +58,9 @@ class RayQueue final
 
 		/*! To be called on a fiber: park one ray and return its answer once the batch it joined has been traced.
 		 *  Rays are as the Accelerator virtuals receive them (B200RT_RAYS_TREE_SPACE). */
-		b200rt_hit closest(b200rt_scene *scene, const b200rt_ray &ray);
-		uint32_t shadow(b200rt_scene *scene, const b200rt_ray &ray);
-		const b200rt_tshadow &transparentShadow(b200rt_scene *scene, const b200rt_ray &ray, int max_depth);
+		b200rt_hit closest(b200rt_scene *scene, const b200rt_ray &ray, float time);
+		uint32_t shadow(b200rt_scene *scene, const b200rt_ray &ray, float time);
+		const b200rt_tshadow &transparentShadow(b200rt_scene *scene, const b200rt_ray &ray, float time, int max_depth);
 
 		/*! Runs `body` once on every fiber (started one after the other; a fiber whose body returns without ever
 		 *  having parked a ray tells the queue that no work is left, and no further fiber is started), then keeps
@@ -91,11 +91,13 @@ class RayQueue final
 			uint32_t capacity = 0;
 			std::vector<Fiber *> fibers, parked;
 			b200rt_ray *rays[3] = {nullptr, nullptr, nullptr};
+			float *times[3] = {nullptr, nullptr, nullptr}; //!< Ray::time_ of the parked rays (motion blur)
 			void *outs[3] = {nullptr, nullptr, nullptr};   //!< b200rt_hit[], uint32_t[], b200rt_tshadow[]
 			std::vector<Request> requests[3];
 			uint32_t count[3] = {0, 0, 0};
 			// a flight whose rays of one kind belong to different scenes or shadow depths is traced from sorted copies (rare)
 			b200rt_ray *sorted_rays[3] = {nullptr, nullptr, nullptr};
+			float *sorted_times[3] = {nullptr, nullptr, nullptr};
 			void *sorted_out[3] = {nullptr, nullptr, nullptr};
 			std::vector<uint32_t> order[3];
 			bool mixed[3] = {false, false, false};
@@ -103,7 +105,7 @@ class RayQueue final
 			b200rt_flight *flight = nullptr;
 			bool flying = false;
 		};
-		void park(int kind, b200rt_scene *scene, const b200rt_ray &ray, int max_depth);
+		void park(int kind, b200rt_scene *scene, const b200rt_ray &ray, float time, int max_depth);
 		void submit(Group &group);
 		void land(Group &group);
 		void resume(Fiber &fiber);

@@ -11,6 +11,7 @@
  *     i:key=value       extra integer integrator parameters (e.g. i:AO_samples=32 i:bounces=5)
  *     b:key=0|1         extra boolean integrator parameters (e.g. b:do_AO=1)
  *     f:key=value       extra float integrator parameters (e.g. f:AO_distance=2.5)
+ *     b:key=value       extra boolean integrator parameters (e.g. b:time_forced=1 f:time_forced_value=0.4)
  *     tile_shard=i/n    multi-GPU rendering: render only share i of n of the frame's tiles (render/tile_shard_b200.h); sets the
  *                       b200-kdtree parameters tile_shard_index / tile_shard_count, or B200_TILE_SHARD for the stock accelerators
  *     instances=n       n static instances (rotation about z + translation) of one box standing on the field; every third one
@@ -158,6 +159,75 @@ int main(int argc, char **argv)
 		}
 	}
 
+	/* motion blur: motion=n adds n boxes that deform over the frame (Bezier motion-blur meshes, three time steps)
+	 * and n moving instances (three matrices) of one pillar that is itself not rendered ("is_base_object") */
+	int n_motion = 0;
+	for(int a = 9; a < argc; ++a) if(strncmp(argv[a], "motion=", 7) == 0) n_motion = atoi(argv[a] + 7);
+	for(int k = 0; k < n_motion; ++k)
+	{
+		char name[32];
+		snprintf(name, sizeof name, "blur%02d", k);
+		const double cx = scale * (0.2 + 0.6 * lcg()), cy = scale * (0.2 + 0.6 * lcg()), s = scale * 0.03, h = scale * 0.2;
+		size_t blur_id = 0, blur_material = 0;
+		yafaray_clearParamMap(pm);
+		yafaray_setParamMapInt(pm, "num_faces", 6);
+		yafaray_setParamMapInt(pm, "num_vertices", 8);
+		yafaray_setParamMapString(pm, "type", "mesh");
+		yafaray_setParamMapBool(pm, "motion_blur_bezier", YAFARAY_BOOL_TRUE);
+		yafaray_setParamMapFloat(pm, "time_range_start", 0.f);
+		yafaray_setParamMapFloat(pm, "time_range_end", 1.f);
+		yafaray_createObject(scene, &blur_id, name, pm);
+		for(int step = 0; step < 3; ++step)
+		{
+			/* the box slides along x, rises and twists a little: every vertex has its own path */
+			const double dx = 0.06 * scale * step, dz = 0.03 * scale * step * (2 - step), tw = 0.25 * step;
+			for(int v = 0; v < 8; ++v)
+			{
+				const double x = (v & 4) ? s : -s, y = (v & 2) ? s : -s, z = (v & 1) ? h : -0.6;
+				yafaray_addVertexTimeStep(scene, blur_id, cx + dx + x * cos(tw) - y * sin(tw), cy + x * sin(tw) + y * cos(tw), z + ((v & 1) ? dz : 0.), (unsigned char) step);
+			}
+		}
+		yafaray_getMaterialId(scene, &blur_material, "boxes");
+		yafaray_addQuad(scene, blur_id, 2, 0, 1, 3, blur_material);
+		yafaray_addQuad(scene, blur_id, 3, 7, 6, 2, blur_material);
+		yafaray_addQuad(scene, blur_id, 7, 5, 4, 6, blur_material);
+		yafaray_addQuad(scene, blur_id, 0, 4, 5, 1, blur_material);
+		yafaray_addQuad(scene, blur_id, 0, 2, 6, 4, blur_material);
+		yafaray_addQuad(scene, blur_id, 5, 7, 3, 1, blur_material);
+		yafaray_initObject(scene, blur_id, blur_material);
+	}
+	if(n_motion > 0)
+	{
+		const double s = 0.02 * scale;
+		size_t base_id = 0, base_material = 0;
+		yafaray_clearParamMap(pm);
+		yafaray_setParamMapInt(pm, "num_faces", 6);
+		yafaray_setParamMapInt(pm, "num_vertices", 8);
+		yafaray_setParamMapString(pm, "type", "mesh");
+		yafaray_setParamMapBool(pm, "is_base_object", YAFARAY_BOOL_TRUE);
+		yafaray_createObject(scene, &base_id, "moving_base", pm);
+		for(int v = 0; v < 8; ++v) yafaray_addVertex(scene, base_id, (v & 4) ? s : -s, (v & 2) ? s : -s, (v & 1) ? 0.18 * scale : -0.6);
+		yafaray_getMaterialId(scene, &base_material, "boxes");
+		yafaray_addQuad(scene, base_id, 2, 0, 1, 3, base_material);
+		yafaray_addQuad(scene, base_id, 3, 7, 6, 2, base_material);
+		yafaray_addQuad(scene, base_id, 7, 5, 4, 6, base_material);
+		yafaray_addQuad(scene, base_id, 0, 4, 5, 1, base_material);
+		yafaray_addQuad(scene, base_id, 0, 2, 6, 4, base_material);
+		yafaray_addQuad(scene, base_id, 5, 7, 3, 1, base_material);
+		yafaray_initObject(scene, base_id, base_material);
+		for(int k = 0; k < n_motion; ++k)
+		{
+			const double px = scale * (0.15 + 0.7 * lcg()), py = scale * (0.15 + 0.7 * lcg());
+			const size_t instance = yafaray_createInstance(scene);
+			yafaray_addInstanceObject(scene, instance, base_id);
+			for(int step = 0; step < 3; ++step)
+			{
+				const double ang = 0.5 * step + k, c = cos(ang), sn = sin(ang), tx = px + 0.05 * scale * step, ty = py - 0.03 * scale * step * step;
+				yafaray_addInstanceMatrix(scene, instance, c, -sn, 0., tx, sn, c, 0., ty, 0., 0., 1. + 0.1 * step, 0., 0., 0., 0., 1., 0.5f * step);
+			}
+		}
+	}
+
 	/* spheres: objects of type "sphere", src/geometry/object/object.cc:80-90 */
 	int n_spheres = 0;
 	for(int a = 9; a < argc; ++a) if(strncmp(argv[a], "spheres=", 8) == 0) n_spheres = atoi(argv[a] + 8);
@@ -208,7 +278,7 @@ int main(int argc, char **argv)
 		memcpy(key, argv[a], (size_t) (eq - argv[a]));
 		key[eq - argv[a]] = 0;
 		if(strcmp(key, "film_save") == 0) { film_save = eq + 1; continue; }
-		if(strcmp(key, "instances") == 0 || strcmp(key, "spheres") == 0 || strcmp(key, "rerender_hidden") == 0) continue; /* handled elsewhere */
+		if(strcmp(key, "instances") == 0 || strcmp(key, "spheres") == 0 || strcmp(key, "motion") == 0 || strcmp(key, "rerender_hidden") == 0) continue; /* handled elsewhere */
 		if(strcmp(key, "tile_shard") == 0)
 		{
 			int shard_index = 0, shard_count = 1;
@@ -250,6 +320,7 @@ int main(int argc, char **argv)
 		if(argv[a][0] == 'i') yafaray_setParamMapInt(pm, key, atoi(eq + 1));
 		else if(argv[a][0] == 'b') yafaray_setParamMapBool(pm, key, atoi(eq + 1) ? YAFARAY_BOOL_TRUE : YAFARAY_BOOL_FALSE);
 		else if(argv[a][0] == 'f') yafaray_setParamMapFloat(pm, key, (float) atof(eq + 1));
+		else if(argv[a][0] == 'b') yafaray_setParamMapBool(pm, key, atoi(eq + 1) ? YAFARAY_BOOL_TRUE : YAFARAY_BOOL_FALSE);
 	}
 	yafaray_SurfaceIntegrator *surface_integrator = yafaray_createSurfaceIntegrator(logger, "surface integrator", pm);
 
@@ -316,7 +387,7 @@ int main(int argc, char **argv)
 	}
 	printf("RENDER_BENCH {\"accelerator\": \"%s\", \"integrator\": \"%s\", \"triangles\": %d, \"width\": %d, \"height\": %d, \"aa_samples\": %d, \"threads\": %d, "
 	       "\"scene_seconds\": %.3f, \"preprocess_seconds\": %.3f, \"render_seconds\": %.3f}\n",
-	       accel, integrator, 2 * cells * cells + 72 + (n_instances > 0 ? 6 * (n_instances + 1) : 0) + n_spheres, width, height, aa_samples, threads, t_built - t_scene, t_pre - t_built, t_render1 - t_render0);
+	       accel, integrator, 2 * cells * cells + 72 + (n_instances > 0 ? 6 * (n_instances + 1) : 0) + n_spheres + 12 * n_motion, width, height, aa_samples, threads, t_built - t_scene, t_pre - t_built, t_render1 - t_render0);
 	yafaray_destroyRenderControl(render_control);
 	yafaray_destroyRenderMonitor(render_monitor);
 	yafaray_destroyFilm(film);

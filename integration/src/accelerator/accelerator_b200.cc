@@ -6,6 +6,7 @@
 #include "accelerator/accelerator_b200.h"
 #include "b200rt.h"
 #include "common/logger.h"
+#include "geometry/object/object_mesh.h"
 #include "geometry/primitive/primitive_face.h"
 #include "geometry/primitive/primitive_instance.h"
 #include "geometry/primitive/primitive_sphere.h"
@@ -152,6 +153,28 @@ AcceleratorB200::AcceleratorB200(Logger &logger, ParamResult &param_result, cons
 		idx.clear();
 		flags.clear();
 	}};
+	// faces of one motion-blur mesh / moving instance gathered so far (b200rt_add_mesh_bezier / _moving)
+	std::vector<float> mxyz[3];
+	std::vector<uint32_t> midx;
+	std::vector<uint8_t> mflags;
+	const void *motion_key{nullptr}, *motion_transform{nullptr};
+	bool motion_bezier{false};
+	float motion_t0{0.f}, motion_t1{0.f}, motion_matrices[48];
+	const auto instanceKey{[](const Primitive *p) -> const void * {
+		const auto *instance_primitive{dynamic_cast<const PrimitiveInstance *>(p)};
+		return instance_primitive ? static_cast<const void *>(&instance_primitive->getBaseInstance()) : nullptr;
+	}};
+	const auto flush_motion{[&]() {
+		if(rc == B200RT_OK && !mflags.empty())
+		{
+			if(motion_bezier) rc = b200rt_add_mesh_bezier(scene, mxyz[0].data(), mxyz[1].data(), mxyz[2].data(), mxyz[0].size() / 3, midx.data(), midx.size() / 4, mflags.data(), motion_t0, motion_t1);
+			else rc = b200rt_add_mesh_moving(scene, mxyz[0].data(), mxyz[0].size() / 3, midx.data(), midx.size() / 4, mflags.data(), motion_matrices, motion_t0, motion_t1);
+		}
+		for(auto &v : mxyz) v.clear();
+		midx.clear();
+		mflags.clear();
+		motion_key = nullptr;
+	}};
 	const bool verify_extraction{std::getenv("B200_VERIFY_EXTRACTION") != nullptr};
 	size_t verify_tests{0}, verify_hits{0}, verify_mismatches{0};
 	for(const Primitive *primitive : primitives_)
@@ -169,12 +192,15 @@ AcceleratorB200::AcceleratorB200(Logger &logger, ParamResult &param_result, cons
 		const Primitive *base{primitive};
 		Matrix4f obj_to_world{1.f};
 		bool transformed{false}, moving{false};
+		int levels{0};
+		const Instance *moving_instance{nullptr};
 		while(const auto *instance_primitive{dynamic_cast<const PrimitiveInstance *>(base)})
 		{
 			const Instance &instance{instance_primitive->getBaseInstance()};
-			moving = moving || instance.hasMotionBlur();
+			if(instance.hasMotionBlur()) { moving = true; moving_instance = &instance; }
 			obj_to_world = transformed ? obj_to_world * instance.getObjToWorldMatrix(0) : instance.getObjToWorldMatrix(0);
 			transformed = true;
+			++levels;
 			base = &instance_primitive->getBasePrimitive();
 		}
 		if(const auto *sphere{dynamic_cast<const SpherePrimitive *>(base)})
@@ -186,6 +212,7 @@ AcceleratorB200::AcceleratorB200(Logger &logger, ParamResult &param_result, cons
 			const ParamMap sphere_params{sphere->getAsParamMap(false)};
 			sphere_params.getParam("center", center);
 			sphere_params.getParam("radius", radius);
+			flush_motion();
 			flush_mesh();
 			if(rc == B200RT_OK)
 			{
@@ -198,12 +225,63 @@ AcceleratorB200::AcceleratorB200(Logger &logger, ParamResult &param_result, cons
 		}
 		const auto *face{dynamic_cast<const FacePrimitive *>(base)};
 		const int n_vertices{face ? face->numVertices() : 0};
-		if(!face || moving || face->hasMotionBlur() || (n_vertices != 3 && n_vertices != 4))
+		// Motion blur: a face of a Bezier motion-blur mesh (directly or under static instances) and a static face
+		// directly under ONE moving instance go to the GPU with their three time steps / matrices (b200rt_add_mesh_bezier / _moving).
+		// Not carried: moving instances of motion-blur meshes and nested instances with a moving level (the reference multiplies
+		// per-ray matrices there, primitive_instance.h:88-91).
+		const bool bezier{face && face->hasMotionBlur() && !moving};
+		const bool moving_face{face && moving && !face->hasMotionBlur() && levels == 1};
+		if(!face || (moving && !moving_face) || (n_vertices != 3 && n_vertices != 4))
 		{
-			logger_.logError(getClassName(), ": primitive kind not supported by the b200-kdtree accelerator (static triangle and quad mesh faces, spheres and static instances of them are); no accelerator created");
+			logger_.logError(getClassName(), ": primitive kind not supported by the b200-kdtree accelerator (triangle and quad mesh faces -- static, Bezier motion blur, or under one moving instance --, spheres and static instances of them are); no accelerator created");
 			if(scene) b200rt_destroy(scene);
 			return;
 		}
+		if(bezier || moving_face)
+		{
+			// consecutive faces of one motion-blur mesh / one moving instance travel in one call (one matrix table entry per instance)
+			const void *key{bezier ? reinterpret_cast<const void *>(face->getObjectHandle()) : static_cast<const void *>(moving_instance)};
+			if(motion_key != key || motion_transform != (transformed ? instanceKey(primitive) : nullptr)) flush_motion();
+			flush_mesh();
+			motion_key = key;
+			motion_transform = transformed ? instanceKey(primitive) : nullptr;
+			motion_bezier = bezier;
+			const uint8_t motion_flags{faceFlags(primitive)};
+			face_flags_.push_back(motion_flags);
+			mflags.push_back(motion_flags);
+			const uint32_t first{static_cast<uint32_t>(mxyz[0].size() / 3)};
+			for(int v = 0; v < 4; ++v) midx.push_back(v < n_vertices ? first + static_cast<uint32_t>(v) : 0xFFFFFFFFu);
+			if(bezier)
+			{
+				// the mesh's three time steps as FacePrimitive::getVertex returns them (time step 1 already holds the Bezier control
+				// points, object_mesh.cc:268-277); FacePrimitive::getObjectHandle() is the address of the face's MeshObject
+				const auto *mesh{reinterpret_cast<const MeshObject *>(face->getObjectHandle())};
+				motion_t0 = mesh->getTimeRangeStart(); motion_t1 = mesh->getTimeRangeEnd();
+				for(unsigned char step = 0; step < 3; ++step)
+					for(int v = 0; v < n_vertices; ++v)
+					{
+						const Point3f p{transformed ? face->getVertex(v, step, obj_to_world) : face->getVertex(v, step)};
+						mxyz[step].push_back(p[Axis::X]); mxyz[step].push_back(p[Axis::Y]); mxyz[step].push_back(p[Axis::Z]);
+					}
+			}
+			else
+			{
+				motion_t0 = moving_instance->getTimeRangeStart(); motion_t1 = moving_instance->getTimeRangeEnd();
+				for(int v = 0; v < n_vertices; ++v)
+				{
+					const Point3f p{face->getVertex(v, 0)};
+					mxyz[0].push_back(p[Axis::X]); mxyz[0].push_back(p[Axis::Y]); mxyz[0].push_back(p[Axis::Z]);
+				}
+				for(unsigned char step = 0; step < 3; ++step)
+				{
+					const Matrix4f &m{moving_instance->getObjToWorldMatrix(step)};
+					for(int i = 0; i < 4; ++i)
+						for(int j = 0; j < 4; ++j) motion_matrices[16 * step + 4 * i + j] = m[i][j];
+				}
+			}
+			continue;
+		}
+		flush_motion();
 		const uint32_t first_vertex{static_cast<uint32_t>(xyz.size() / 3)};
 		for(int v = 0; v < n_vertices; ++v)
 		{
@@ -236,6 +314,7 @@ AcceleratorB200::AcceleratorB200(Logger &logger, ParamResult &param_result, cons
 		}
 	}
 	if(verify_extraction) logger_.logInfo(getClassName(), ": extraction check: ", verify_tests, " test rays, ", verify_hits, " hits, ", verify_mismatches, " differ from Primitive::intersect");
+	flush_motion();
 	flush_mesh();
 	if(dump) std::fflush(dump);
 	if(rc == B200RT_OK) rc = b200rt_build(scene);
@@ -273,8 +352,8 @@ IntersectData AcceleratorB200::intersect(const Ray &ray, float t_max) const
 	IntersectData data;
 	data.t_max_ = t_max;
 	if(!scene_) return data;
-	if(b200::RayQueue *queue{b200::RayQueue::current()}) hit = queue->closest(scene_, r); //on a fiber: joins the thread's next batch
-	else if(++wf_per_ray_calls_, b200rt_trace(scene_, B200RT_QUERY_CLOSEST, B200RT_RAYS_TREE_SPACE, &r, 1, &hit, 0) != B200RT_OK) return data;
+	if(b200::RayQueue *queue{b200::RayQueue::current()}) hit = queue->closest(scene_, r, ray.time_); //on a fiber: joins the thread's next batch
+	else if(++wf_per_ray_calls_, b200rt_trace_timed(scene_, B200RT_QUERY_CLOSEST, B200RT_RAYS_TREE_SPACE, &r, &ray.time_, 1, &hit, 0) != B200RT_OK) return data;
 	if(hit.prim == B200RT_MISS) return data;
 	data.t_hit_ = hit.t;
 	data.t_max_ = hit.t;
@@ -289,8 +368,8 @@ IntersectData AcceleratorB200::intersectShadow(const Ray &ray, float t_max) cons
 	uint32_t occluder = B200RT_MISS;
 	IntersectData data;
 	if(!scene_) return data;
-	if(b200::RayQueue *queue{b200::RayQueue::current()}) occluder = queue->shadow(scene_, r);
-	else if(++wf_per_ray_calls_, b200rt_trace(scene_, B200RT_QUERY_SHADOW, B200RT_RAYS_TREE_SPACE, &r, 1, &occluder, 0) != B200RT_OK) return data;
+	if(b200::RayQueue *queue{b200::RayQueue::current()}) occluder = queue->shadow(scene_, r, ray.time_);
+	else if(++wf_per_ray_calls_, b200rt_trace_timed(scene_, B200RT_QUERY_SHADOW, B200RT_RAYS_TREE_SPACE, &r, &ray.time_, 1, &occluder, 0) != B200RT_OK) return data;
 	if(occluder == B200RT_MISS) return data;
 	data.t_hit_ = 1.f; //any value > 0: callers only use isHit() and primitive_ (accelerator.h:110)
 	data.primitive_ = primitives_[occluder];
@@ -304,8 +383,8 @@ IntersectData AcceleratorB200::intersectTransparentShadow(const Ray &ray, int ma
 	IntersectData data;
 	max_depth = clampShadowDepth(max_depth);
 	if(!scene_) return data;
-	if(b200::RayQueue *queue{b200::RayQueue::current()}) res = queue->transparentShadow(scene_, r, max_depth);
-	else if(++wf_per_ray_calls_, b200rt_trace(scene_, B200RT_QUERY_TSHADOW, B200RT_RAYS_TREE_SPACE, &r, 1, &res, max_depth) != B200RT_OK) return data;
+	if(b200::RayQueue *queue{b200::RayQueue::current()}) res = queue->transparentShadow(scene_, r, ray.time_, max_depth);
+	else if(++wf_per_ray_calls_, b200rt_trace_timed(scene_, B200RT_QUERY_TSHADOW, B200RT_RAYS_TREE_SPACE, &r, &ray.time_, 1, &res, max_depth) != B200RT_OK) return data;
 	if(res.shadowed)
 	{
 		data.t_hit_ = 1.f;

@@ -109,7 +109,7 @@ RayQueue::RayQueue(int n_fibers, int n_groups, size_t stack_bytes) : n_fibers_{s
 	const size_t per_group = (fibers_per_group + 3) & ~size_t(3);
 	// one pinned slab for the rays and answers of all groups (a pinned allocation costs the driver a fraction of a millisecond and
 	// sixteen render threads create their queues at the same moment)
-	const size_t per_slot = 3 * sizeof(b200rt_ray) + kOutSize[0] + kOutSize[1] + kOutSize[2];
+	const size_t per_slot = 3 * sizeof(b200rt_ray) + kOutSize[0] + kOutSize[1] + kOutSize[2] + 3 * sizeof(float); // rays, answers, ray times
 	slab_ = static_cast<char *>(pinned(size_t(n_groups) * per_group * per_slot + 64, error_));
 	char *cursor = slab_;
 	for(size_t g = 0; g < groups_.size(); ++g)
@@ -132,6 +132,11 @@ RayQueue::RayQueue(int n_fibers, int n_groups, size_t stack_bytes) : n_fibers_{s
 			group.outs[kind] = cursor;
 			cursor += per_group * kOutSize[kind];
 		}
+		for(int kind = 0; kind < 3 && slab_; ++kind) // Ray::time_ of every parked ray (motion blur), 4-byte values: 16-byte aligned too
+		{
+			group.times[kind] = reinterpret_cast<float *>(cursor);
+			cursor += per_group * sizeof(float);
+		}
 		for(auto &r : group.requests) r.resize(group.capacity);
 	}
 	resuming_.reserve(per_group);
@@ -145,6 +150,7 @@ RayQueue::~RayQueue()
 		for(int kind = 0; kind < 3; ++kind)
 		{
 			b200rt_host_free(group.sorted_rays[kind]);
+			b200rt_host_free(group.sorted_times[kind]);
 			b200rt_host_free(group.sorted_out[kind]);
 		}
 	}
@@ -177,12 +183,13 @@ void RayQueue::resume(Fiber &fiber)
 	running_ = nullptr;
 }
 
-void RayQueue::park(int kind, b200rt_scene *scene, const b200rt_ray &ray, int max_depth)
+void RayQueue::park(int kind, b200rt_scene *scene, const b200rt_ray &ray, float time, int max_depth)
 {
 	Fiber *self = running_;
 	Group &group = *self->group;
 	const uint32_t slot = group.count[kind]++;
 	group.rays[kind][slot] = ray;
+	group.times[kind][slot] = time;
 	group.requests[kind][slot] = {scene, max_depth};
 	self->slot = slot;
 	group.parked.push_back(self);
@@ -190,21 +197,21 @@ void RayQueue::park(int kind, b200rt_scene *scene, const b200rt_ray &ray, int ma
 	B200_SWITCH(&self->sp, scheduler_sp_); // back in run(); returns here once the group's flight has landed
 }
 
-b200rt_hit RayQueue::closest(b200rt_scene *scene, const b200rt_ray &ray)
+b200rt_hit RayQueue::closest(b200rt_scene *scene, const b200rt_ray &ray, float time)
 {
-	park(B200RT_QUERY_CLOSEST, scene, ray, 0);
+	park(B200RT_QUERY_CLOSEST, scene, ray, time, 0);
 	return static_cast<const b200rt_hit *>(running_->group->outs[B200RT_QUERY_CLOSEST])[running_->slot];
 }
 
-uint32_t RayQueue::shadow(b200rt_scene *scene, const b200rt_ray &ray)
+uint32_t RayQueue::shadow(b200rt_scene *scene, const b200rt_ray &ray, float time)
 {
-	park(B200RT_QUERY_SHADOW, scene, ray, 0);
+	park(B200RT_QUERY_SHADOW, scene, ray, time, 0);
 	return static_cast<const uint32_t *>(running_->group->outs[B200RT_QUERY_SHADOW])[running_->slot];
 }
 
-const b200rt_tshadow &RayQueue::transparentShadow(b200rt_scene *scene, const b200rt_ray &ray, int max_depth)
+const b200rt_tshadow &RayQueue::transparentShadow(b200rt_scene *scene, const b200rt_ray &ray, float time, int max_depth)
 {
-	park(B200RT_QUERY_TSHADOW, scene, ray, max_depth);
+	park(B200RT_QUERY_TSHADOW, scene, ray, time, max_depth);
 	return static_cast<const b200rt_tshadow *>(running_->group->outs[B200RT_QUERY_TSHADOW])[running_->slot];
 }
 
@@ -230,13 +237,14 @@ void RayQueue::submit(Group &group)
 		for(uint32_t i = 1; i < n && uniform; ++i) uniform = req[i].scene == req[0].scene && req[i].max_depth == req[0].max_depth;
 		if(uniform)
 		{
-			jobs[n_jobs++] = {req[0].scene, kind, flags, group.rays[kind], n, group.outs[kind], req[0].max_depth};
+			jobs[n_jobs++] = {req[0].scene, kind, flags, group.rays[kind], n, group.outs[kind], req[0].max_depth, group.times[kind]};
 			continue;
 		}
 		// several scenes / shadow depths: one job per (scene, depth), rays gathered into the pinned scratch of the kind
 		if(!group.sorted_rays[kind])
 		{
 			group.sorted_rays[kind] = static_cast<b200rt_ray *>(pinned(size_t(group.capacity) * sizeof(b200rt_ray), error_));
+			group.sorted_times[kind] = static_cast<float *>(pinned(size_t(group.capacity) * sizeof(float), error_));
 			group.sorted_out[kind] = pinned(size_t(group.capacity) * kOutSize[kind], error_);
 		}
 		std::vector<uint32_t> &order = group.order[kind];
@@ -245,7 +253,7 @@ void RayQueue::submit(Group &group)
 		std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return req[a].scene != req[b].scene ? req[a].scene < req[b].scene : req[a].max_depth < req[b].max_depth; });
 		size_t pairs = 1;
 		for(uint32_t i = 1; i < n; ++i) pairs += (req[order[i]].scene != req[order[i - 1]].scene || req[order[i]].max_depth != req[order[i - 1]].max_depth) ? 1 : 0;
-		if(!group.sorted_rays[kind] || !group.sorted_out[kind] || pairs > kMaxGroupsPerKind)
+		if(!group.sorted_rays[kind] || !group.sorted_out[kind] || !group.sorted_times[kind] || pairs > kMaxGroupsPerKind)
 		{
 			// no CPU path: these rays read as misses / unshadowed, and the render reports the error
 			if(error_.empty()) error_ = "more distinct (scene, shadow depth) pairs in one flight than the ray queue supports";
@@ -254,13 +262,13 @@ void RayQueue::submit(Group &group)
 			continue;
 		}
 		group.mixed[kind] = true;
-		for(uint32_t i = 0; i < n; ++i) group.sorted_rays[kind][i] = group.rays[kind][order[i]];
+		for(uint32_t i = 0; i < n; ++i) { group.sorted_rays[kind][i] = group.rays[kind][order[i]]; group.sorted_times[kind][i] = group.times[kind][order[i]]; }
 		for(uint32_t first = 0; first < n;)
 		{
 			uint32_t last = first + 1;
 			const Request &key = req[order[first]];
 			while(last < n && req[order[last]].scene == key.scene && req[order[last]].max_depth == key.max_depth) ++last;
-			jobs[n_jobs++] = {key.scene, kind, flags, group.sorted_rays[kind] + first, last - first, static_cast<char *>(group.sorted_out[kind]) + size_t(first) * kOutSize[kind], key.max_depth};
+			jobs[n_jobs++] = {key.scene, kind, flags, group.sorted_rays[kind] + first, last - first, static_cast<char *>(group.sorted_out[kind]) + size_t(first) * kOutSize[kind], key.max_depth, group.sorted_times[kind] + first};
 			first = last;
 		}
 	}

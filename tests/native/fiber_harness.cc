@@ -74,7 +74,7 @@ static double shade(RayQueue &q, b200rt_scene *scene_a, b200rt_scene *scene_b, i
 	b200rt_scene *scene = (job % 7 == 0) ? scene_b : scene_a;
 	const b200rt_ray ray{x, float(job), float(depth), 0.f, 0.f, 0.f, 1.f, float(depth)};
 	const long double keep = std::sqrt(static_cast<long double>(job) + 2.0L); // x87 state across the switch
-	const b200rt_hit h = q.closest(scene, ray);
+	const b200rt_hit h = q.closest(scene, ray, 0.f);
 	CHECK(h.t == x * 2.f + 1.f);
 	CHECK(h.u == float(job) && h.v == float(depth));
 	CHECK(h.prim == uint32_t(reinterpret_cast<uintptr_t>(scene)) + uint32_t(depth));
@@ -82,7 +82,7 @@ static double shade(RayQueue &q, b200rt_scene *scene_a, b200rt_scene *scene_b, i
 	double sum = h.t;
 	if(job % 3 == 0)
 	{
-		const uint32_t occ = q.shadow(scene, ray);
+		const uint32_t occ = q.shadow(scene, ray, 0.f);
 		CHECK(occ == uint32_t(reinterpret_cast<uintptr_t>(scene)) * 1000u + uint32_t(x));
 		sum += occ;
 	}

@@ -85,25 +85,35 @@ def to_json(workload, path):
     w = rec["workloads"].setdefault(workload, {})
     for r in rows[2:]:
         d = dict(zip(hdr, r))
-        m = re.search(r"traceKernel<\(int\)(\d)", d.get("Kernel Name", ""))
-        if not m or kinds[m.group(1)] in w:
-            continue  # the first launch of each kind
+        name = d.get("Kernel Name", "")
+        m = re.search(r"(traceKernel|setupKernel)<(?:\(int\))?(\d)", name)
+        if not m:
+            continue
+        kind, is_setup = kinds[m.group(2)], m.group(1) == "setupKernel"
+        if (is_setup and "setup" in w.get(kind, {})) or (not is_setup and "kernel" in w.get(kind, {})):
+            continue  # the first launch of each kernel
         f = lambda k: float(d[k].replace(",", "")) if d.get(k) not in (None, "") else None
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
         u = dict(zip(hdr, rows[1]))
         dram = sum(f(k) * scale[u[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
         t_unit = {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}[u["gpu__time_duration.sum"]]
-        w[kinds[m.group(1)]] = {
+        entry = {
             "kernel": d["Kernel Name"].split("(")[0].replace("void ", ""), "capture": os.path.basename(path),
             "duration_ms_under_ncu": f("gpu__time_duration.sum") * t_unit, "dram_bytes": dram,
             "dram_bytes_read": f("dram__bytes_read.sum") * scale[u["dram__bytes_read.sum"]],
             "warp_inst": f("smsp__inst_executed.sum"), "lanes_per_inst": f("smsp__thread_inst_executed_per_inst_executed.ratio"),
             "issue_active_pct": f("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-            "l2_sector_bytes": 32.0 * ((f("lts__t_sectors_op_read.sum") or 0.0) + (f("lts__t_sectors_op_write.sum") or 0.0)),
+            "l2_sector_bytes": 32.0 * (f("lts__t_sectors.sum") or ((f("lts__t_sectors_op_read.sum") or 0.0) + (f("lts__t_sectors_op_write.sum") or 0.0))),
             "l1_hit_pct": f("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": f("lts__t_sector_hit_rate.pct"),
             "long_scoreboard_per_issue": f("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
             "registers": f("launch__registers_per_thread"),
         }
+        # a two-pass batch is setupKernel<Q> + traceKernel<Q, ., true>: the traversal pass is the entry, the setup pass hangs below it
+        if is_setup:
+            w.setdefault(kind, {})["setup"] = entry
+        else:
+            entry.update({k: v for k, v in w.get(kind, {}).items() if k == "setup"})
+            w[kind] = entry
     json.dump(rec, open(dest, "w"), indent=1, sort_keys=True)
     print(json.dumps(rec["workloads"][workload], indent=1))
 
