@@ -143,6 +143,31 @@ class ClockSampler:
         self.stop_flag = True
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank (and the pinned host buffers it allocates from here on, first touch) to the NUMA node its GPU hangs off:
+    at N = 8 every rank streams 1.3 GiB per step through the host's memory controllers, and a buffer on the other socket
+    crosses the inter-socket link on its way to the PCIe root complex.  Returns a description for the bench line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        node = int(open(path + "/numa_node").read())
+        if node < 0:
+            return {"numa_node": None, "note": "the platform reports no NUMA node for this GPU"}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus_bound": len(allowed)}
+    except Exception as e:  # not fatal: the run goes on unbound
+        return {"numa_node": None, "note": f"not bound ({e.__class__.__name__})"}
+
+
 # ------------------------------------------------------------------------------------------ workload
 LIGHT = np.array([0.5, 0.5, 3.0])  # rcoh: the point light the shadow rays aim at
 
@@ -319,6 +344,8 @@ def run_b200(args):
     if not torch.cuda.is_available() or rt.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device -- libb200rt has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    # only when several ranks share the host: at N = 1 the cpu_baseline leg below wants every core of the box
+    affinity = bind_to_gpu_numa_node(local) if world > 1 else {"numa_node": None, "note": "single rank: not bound"}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -500,6 +527,7 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "wall_ms_per_step": (w1 - w0) * 1e3 / args.steps,
+            "host_affinity": affinity,
         }
         if tshadow:
             line["tshadow"] = tshadow

@@ -206,6 +206,14 @@ int b200rt_trace_device(b200rt_scene *scene, int query, unsigned flags, const b2
 int b200rt_trace_timed(b200rt_scene *scene, int query, unsigned flags, const b200rt_ray *rays, const float *times, size_t n, void *out, int max_depth);
 int b200rt_trace_timed_device(b200rt_scene *scene, int query, unsigned flags, const b200rt_ray *d_rays, const float *d_times, size_t n, void *d_out, int max_depth, void *stream);
 
+/* Transparent shadows through more than B200RT_TSHADOW_MAX distinct transparent casters (an integrator "shadow_depth" above 8;
+ * the reference has no limit, include/accelerator/accelerator.h:147-169).  The result record of ray i starts at byte
+ * i * (16 + 16 * capacity) of `out`: the first 16 bytes are the first four fields of b200rt_tshadow, then `capacity` b200rt_hit
+ * entries of which the first n_transparent are written.  max_depth <= capacity <= 4096; n <= 2^26 rays per call.  `times` may
+ * be NULL.  The host variant copies rays and results through device memory it allocates for the call. */
+int b200rt_trace_tshadow_deep(b200rt_scene *scene, unsigned flags, const b200rt_ray *rays, const float *times, size_t n, int max_depth, int capacity, void *out);
+int b200rt_trace_tshadow_deep_device(b200rt_scene *scene, unsigned flags, const b200rt_ray *d_rays, const float *d_times, size_t n, int max_depth, int capacity, void *d_out, void *stream);
+
 /* Several host-buffer batches in one call -- what one flush of the renderer's wavefront ray queue holds (closest,
  * shadow and transparent-shadow rays of the pixels in flight on one render thread; Accelerator::intersect / isShadowed /
  * isShadowedTransparentShadow call sites of integrator_montecarlo.cc:148,240,362, integrator_path_tracer.cc:145,210,251).

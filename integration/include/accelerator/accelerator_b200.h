@@ -34,15 +34,10 @@ class AcceleratorB200 final : public Accelerator
 		~AcceleratorB200() override;
 		bool ok() const { return scene_ != nullptr; }
 
-		/* Batched entry points (north-star (c)): n rays per call, one kernel launch per chunk.
-		 * intersectBatch is Accelerator::intersect(ray, camera) without the getSurface() step: out[i].isHit(),
-		 * t_hit_/t_max_, uv_ and primitive_ are filled exactly as the per-ray query fills them. */
-		bool intersectBatch(const Ray *rays, size_t n, IntersectData *out) const;
-		/* isShadowedBatch is Accelerator::isShadowed(ray): shadowed[i] and (optionally) the occluder. */
-		bool isShadowedBatch(const Ray *rays, size_t n, bool *shadowed, const Primitive **occluders) const;
-		/* isShadowedTransparentShadowBatch is Accelerator::isShadowedTransparentShadow(ray, max_depth, camera). */
-		bool isShadowedTransparentShadowBatch(const Ray *rays, size_t n, int max_depth, const Camera *camera, bool *shadowed, Rgb *colors, const Primitive **occluders) const;
-
+		/* The batched entry of north-star (c) is the wavefront ray queue below: every Accelerator::intersect / isShadowed /
+		 * isShadowedTransparentShadow call an integrator makes on a fiber joins the batch its render thread flushes through
+		 * b200rt_trace_jobs (one mixed-kind launch).  (Round 1 also had intersectBatch / isShadowedBatch methods nothing called;
+		 * they are gone.) */
 		/* Wavefront rendering (render/wavefront_b200.h): TiledIntegrator::renderWorkerWavefront runs the reference's
 		 * renderTile() on wavefrontFibers() fibers per render thread; the three per-ray virtuals below then park their ray
 		 * in the calling fiber's queue instead of launching a one-ray kernel.  0 fibers = the per-ray path only. */
@@ -57,7 +52,6 @@ class AcceleratorB200 final : public Accelerator
 		void releaseRayQueue(std::unique_ptr<b200::RayQueue> queue) const;
 		void addWavefrontStats(const b200::RayQueue::Stats &stats) const;
 		void logWavefrontStats() const; //!< one Info line with the totals since the last call, then resets them
-		int clampShadowDepth(int max_depth) const; //!< the depth the result record can express (warns once when it has to clamp)
 		void logQueueError(const std::string &what) const; //!< a ray queue could not run (photon_fibers_b200.h, integrator_tiled_b200.cc)
 		/*! The reference reads object / material visibility and transparency LIVE at every hit (accelerator.h:126-127,138-139,152-154),
 		 *  while the GPU scene bakes them per face; Scene::preprocess rebuilds the accelerator for OBJECTS / accelerator-parameter

@@ -22,6 +22,7 @@
 #include "accelerator/accelerator_b200.h"
 #include "render/wavefront_b200.h"
 #include <algorithm>
+#include <cstdlib>
 #include <functional>
 #include <thread>
 #include <vector>
@@ -39,7 +40,7 @@ class PhotonWorkers final
 			if(b200_) b200_->refreshFaceFlags(); //materials may have been replaced since the accelerator was built
 			if(b200_ && b200_->wavefrontFibers() > 0)
 			{
-				const int per_thread{std::clamp(n_photons / (os_threads_ * kMinPhotonsPerWorker), 1, b200_->wavefrontFibers())};
+				const int per_thread{std::clamp(n_photons / (os_threads_ * minPhotonsPerWorker()), 1, b200_->wavefrontFibers())};
 				fibers_per_thread_ = per_thread;
 				num_threads_ = os_threads_ * per_thread;
 			}
@@ -86,6 +87,12 @@ class PhotonWorkers final
 
 	private:
 		static constexpr int kMinPhotonsPerWorker = 16;
+		//! photons a logical worker shoots at least; B200_MIN_PHOTONS_PER_WORKER overrides it (tuning aid, profiles/r3l_*)
+		static int minPhotonsPerWorker()
+		{
+			static const int value{[] { const char *e{std::getenv("B200_MIN_PHOTONS_PER_WORKER")}; const int n{e ? std::atoi(e) : 0}; return n > 0 ? n : kMinPhotonsPerWorker; }()};
+			return value;
+		}
 		int &num_threads_;
 		const int os_threads_;
 		int fibers_per_thread_ = 1;

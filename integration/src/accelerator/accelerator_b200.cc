@@ -381,9 +381,20 @@ IntersectData AcceleratorB200::intersectTransparentShadow(const Ray &ray, int ma
 	const b200rt_ray r{toRay(ray, dist)};
 	b200rt_tshadow res{};
 	IntersectData data;
-	max_depth = clampShadowDepth(max_depth);
+	if(max_depth < 0) max_depth = 0; //behaves like 0 in the reference: "depth >= max_depth" holds for the first transparent caster (accelerator.h:161)
 	if(!scene_) return data;
-	if(b200::RayQueue *queue{b200::RayQueue::current()}) res = queue->transparentShadow(scene_, r, ray.time_, max_depth);
+	const b200rt_hit *casters{res.transparent};
+	std::vector<uint32_t> deep; //a shadow_depth above the 8 casters of b200rt_tshadow: a larger record, traced on its own
+	if(max_depth > B200RT_TSHADOW_MAX)
+	{
+		if(!depth_clamp_logged_.exchange(true)) logger_.logInfo(getClassName(), ": shadow_depth ", max_depth, " exceeds the ", B200RT_TSHADOW_MAX, " casters of a queued result record; such rays are traced one call each (b200rt_trace_tshadow_deep)");
+		deep.resize(4u + 4u * static_cast<size_t>(max_depth));
+		++wf_per_ray_calls_;
+		if(b200rt_trace_tshadow_deep(scene_, B200RT_RAYS_TREE_SPACE, &r, &ray.time_, 1, max_depth, max_depth, deep.data()) != B200RT_OK) return data;
+		res.shadowed = deep[0]; res.n_transparent = deep[1]; res.occluder = deep[2];
+		casters = reinterpret_cast<const b200rt_hit *>(deep.data() + 4);
+	}
+	else if(b200::RayQueue *queue{b200::RayQueue::current()}) res = queue->transparentShadow(scene_, r, ray.time_, max_depth);
 	else if(++wf_per_ray_calls_, b200rt_trace_timed(scene_, B200RT_QUERY_TSHADOW, B200RT_RAYS_TREE_SPACE, &r, &ray.time_, 1, &res, max_depth) != B200RT_OK) return data;
 	if(res.shadowed)
 	{
@@ -394,7 +405,7 @@ IntersectData AcceleratorB200::intersectTransparentShadow(const Ray &ray, int ma
 	// material evaluation stays on the host: colour = product of the transparencies of the distinct casters (accelerator.h:163-166)
 	for(uint32_t k = 0; k < res.n_transparent; ++k)
 	{
-		const b200rt_hit &h{res.transparent[k]};
+		const b200rt_hit &h{casters[k]};
 		const Primitive *primitive{primitives_[h.prim]};
 		const Point3f hit_point{ray.from_ + h.t * ray.dir_};
 		const auto sp{primitive->getSurface(nullptr, hit_point, ray.time_, {h.u, h.v}, camera)};
@@ -463,97 +474,9 @@ void AcceleratorB200::logWavefrontStats() const
 					" libb200rt calls (", batches ? (closest + shadow + tshadow) / batches : 0, " rays per batch), ", trace_s, " thread-seconds inside libb200rt of ", run_s, " thread-seconds in the render workers; per-ray calls outside fibers: ", per_ray);
 }
 
-int AcceleratorB200::clampShadowDepth(int max_depth) const
-{
-	// a negative depth behaves like 0 in the reference (accelerator.h:161: "depth >= max_depth" holds for the first transparent caster)
-	if(max_depth < 0) return 0;
-	if(max_depth > B200RT_TSHADOW_MAX)
-	{
-		// the result record lists at most B200RT_TSHADOW_MAX distinct transparent casters: a ray through more of them reads as
-		// shadowed here, while the reference lets up to shadow_depth of them through -- say so once instead of clamping silently
-		if(!depth_clamp_logged_.exchange(true))
-			logger_.logWarning(getClassName(), ": shadow_depth ", max_depth, " exceeds the ", B200RT_TSHADOW_MAX, " distinct transparent shadow casters one result record holds; rays through more than ", B200RT_TSHADOW_MAX, " of them are reported as shadowed");
-		return B200RT_TSHADOW_MAX;
-	}
-	return max_depth;
-}
-
 void AcceleratorB200::logQueueError(const std::string &what) const
 {
 	logger_.logError(getClassName(), ": wavefront ray queue failed (", what, "); the affected workers fall back to one-ray launches");
-}
-
-// ---- batched entry points ---------------------------------------------------------------------------------
-bool AcceleratorB200::intersectBatch(const Ray *rays, size_t n, IntersectData *out) const
-{
-	if(!scene_) return false;
-	std::vector<b200rt_ray> r(n);
-	std::vector<b200rt_hit> hits(n);
-	for(size_t i = 0; i < n; ++i) r[i] = toRay(rays[i], rays[i].tmax_); //tmax_ < 0 means unbounded, as accelerator.h:91
-	if(b200rt_trace_closest(scene_, r.data(), n, hits.data()) != B200RT_OK)
-	{
-		logger_.logError(getClassName(), ": intersectBatch failed: ", b200rt_last_error());
-		return false;
-	}
-	for(size_t i = 0; i < n; ++i)
-	{
-		out[i] = IntersectData{};
-		if(hits[i].prim == B200RT_MISS) continue;
-		out[i].t_hit_ = hits[i].t;
-		out[i].t_max_ = hits[i].t;
-		out[i].uv_ = {hits[i].u, hits[i].v};
-		out[i].primitive_ = primitives_[hits[i].prim];
-	}
-	return true;
-}
-
-bool AcceleratorB200::isShadowedBatch(const Ray *rays, size_t n, bool *shadowed, const Primitive **occluders) const
-{
-	if(!scene_) return false;
-	std::vector<b200rt_ray> r(n);
-	std::vector<uint32_t> occ(n);
-	for(size_t i = 0; i < n; ++i) r[i] = toRay(rays[i], rays[i].tmax_);
-	if(b200rt_trace_shadow(scene_, r.data(), n, occ.data()) != B200RT_OK)
-	{
-		logger_.logError(getClassName(), ": isShadowedBatch failed: ", b200rt_last_error());
-		return false;
-	}
-	for(size_t i = 0; i < n; ++i)
-	{
-		shadowed[i] = occ[i] != B200RT_MISS;
-		if(occluders) occluders[i] = shadowed[i] ? primitives_[occ[i]] : nullptr;
-	}
-	return true;
-}
-
-bool AcceleratorB200::isShadowedTransparentShadowBatch(const Ray *rays, size_t n, int max_depth, const Camera *camera, bool *shadowed, Rgb *colors, const Primitive **occluders) const
-{
-	if(!scene_) return false;
-	std::vector<b200rt_ray> r(n);
-	std::vector<b200rt_tshadow> res(n);
-	for(size_t i = 0; i < n; ++i) r[i] = toRay(rays[i], rays[i].tmax_);
-	max_depth = clampShadowDepth(max_depth);
-	if(b200rt_trace_tshadow(scene_, r.data(), n, max_depth, res.data()) != B200RT_OK)
-	{
-		logger_.logError(getClassName(), ": isShadowedTransparentShadowBatch failed: ", b200rt_last_error());
-		return false;
-	}
-	for(size_t i = 0; i < n; ++i)
-	{
-		shadowed[i] = res[i].shadowed != 0;
-		colors[i] = Rgb{1.f};
-		if(occluders) occluders[i] = shadowed[i] ? primitives_[res[i].occluder] : nullptr;
-		if(shadowed[i]) continue;
-		const Point3f from{rays[i].from_ + rays[i].dir_ * rays[i].tmin_}; //the wrapper's moved origin (accelerator.h:116)
-		for(uint32_t k = 0; k < res[i].n_transparent; ++k)
-		{
-			const b200rt_hit &h{res[i].transparent[k]};
-			const Primitive *primitive{primitives_[h.prim]};
-			const auto sp{primitive->getSurface(nullptr, from + h.t * rays[i].dir_, rays[i].time_, {h.u, h.v}, camera)};
-			if(sp) colors[i] *= sp->getTransparency(rays[i].dir_, camera);
-		}
-	}
-	return true;
 }
 
 } //namespace yafaray

@@ -470,7 +470,7 @@ int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b2
 			if(e == cudaSuccess)
 			{
 				const unsigned setup_grid = std::max(1u, std::min((n_regions + 7u) / 8u, unsigned(s->setup_blocks)));
-				b200rt::setupKernel<Q><<<setup_grid, b200rt::kSetupBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, queue, tree_space, d_times ? d_times + begin : nullptr);
+				b200rt::setupKernel<Q><<<setup_grid, b200rt::kSetupBlock, 0, stream>>>(s->view, d_rays + begin, count, d_out + begin, queue, tree_space, d_times ? d_times + begin : nullptr, max_depth);
 				++g_launches;
 				const unsigned wanted = unsigned((size_t(n_regions) + b200rt::kBlock / 32 - 1) / (b200rt::kBlock / 32));
 				const unsigned grid = std::max(1u, std::min(wanted, unsigned(s->resident_blocks_queued[Q])));
@@ -1024,6 +1024,44 @@ int b200rt_trace_closest(b200rt_scene *s, const b200rt_ray *rays, size_t n, b200
 int b200rt_trace_shadow(b200rt_scene *s, const b200rt_ray *rays, size_t n, uint32_t *out) { return b200rt_trace_timed(s, B200RT_QUERY_SHADOW, 0u, rays, nullptr, n, out, 0); }
 int b200rt_trace_tshadow(b200rt_scene *s, const b200rt_ray *rays, size_t n, int max_depth, b200rt_tshadow *out) { return b200rt_trace_timed(s, B200RT_QUERY_TSHADOW, 0u, rays, nullptr, n, out, max_depth); }
 
+int b200rt_trace_tshadow_deep_device(b200rt_scene *s, unsigned flags, const b200rt_ray *d_rays, const float *d_times, size_t n, int max_depth, int capacity, void *d_out, void *stream)
+{
+	const int rc = checkDeviceCall(s, d_rays, n, d_out);
+	if(rc != B200RT_OK) return rc;
+	if(max_depth < 0 || capacity < 1 || capacity > 4096 || max_depth > capacity) return fail(B200RT_E_INVALID, "need 0 <= max_depth <= capacity <= 4096");
+	if(n > kMaxRaysPerTwoPass) return fail(B200RT_E_INVALID, "at most 2^26 rays per deep transparent-shadow call");
+	if(n == 0) return B200RT_OK;
+	CUDA_TRY(cudaSetDevice(s->device));
+	// the kernels take the record capacity in the upper half of max_depth (kd_kernels.cuh, TShadowState); one launch (pair) covers n
+	return launchTrace<b200rt::kTShadow>(s, d_rays, n, static_cast<b200rt_tshadow *>(d_out), static_cast<cudaStream_t>(stream), max_depth | (capacity << 16), flags, false, d_times);
+}
+
+int b200rt_trace_tshadow_deep(b200rt_scene *s, unsigned flags, const b200rt_ray *rays, const float *times, size_t n, int max_depth, int capacity, void *out)
+{
+	if(!s || (!rays && n) || (!out && n)) return fail(B200RT_E_INVALID, "null argument");
+	if(!s->built) return fail(B200RT_E_INVALID, "scene not built: call b200rt_build first");
+	if(max_depth < 0 || capacity < 1 || capacity > 4096 || max_depth > capacity) return fail(B200RT_E_INVALID, "need 0 <= max_depth <= capacity <= 4096");
+	if(n > kMaxRaysPerTwoPass) return fail(B200RT_E_INVALID, "at most 2^26 rays per deep transparent-shadow call");
+	if(n == 0) return B200RT_OK;
+	CUDA_TRY(cudaSetDevice(s->device));
+	// a rare query (shadow_depth > 8): plain copies around one launch, no staging pipeline
+	const size_t record = 16u + 16u * size_t(capacity);
+	b200rt_ray *d_rays = nullptr;
+	float *d_times = nullptr;
+	void *d_out = nullptr;
+	cudaError_t e = cudaMalloc(&d_rays, n * sizeof(b200rt_ray));
+	if(e == cudaSuccess) e = cudaMalloc(&d_out, n * record);
+	if(e == cudaSuccess && times) e = cudaMalloc(&d_times, n * sizeof(float));
+	if(e == cudaSuccess) e = cudaMemcpy(d_rays, rays, n * sizeof(b200rt_ray), cudaMemcpyHostToDevice);
+	if(e == cudaSuccess && times) e = cudaMemcpy(d_times, times, n * sizeof(float), cudaMemcpyHostToDevice);
+	int rc = B200RT_OK;
+	if(e == cudaSuccess) rc = b200rt_trace_tshadow_deep_device(s, flags, d_rays, d_times, n, max_depth, capacity, d_out, nullptr);
+	if(e == cudaSuccess && rc == B200RT_OK) e = cudaMemcpy(out, d_out, n * record, cudaMemcpyDeviceToHost);
+	cudaFree(d_rays); cudaFree(d_times); cudaFree(d_out);
+	if(e != cudaSuccess) return fail(B200RT_E_CUDA, std::string("b200rt_trace_tshadow_deep: ") + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+	return rc;
+}
+
 int b200rt_trace_jobs_begin(const b200rt_job *jobs, size_t n_jobs, b200rt_flight **out_flight)
 {
 	if((!jobs && n_jobs) || !out_flight) return fail(B200RT_E_INVALID, "null argument");
@@ -1053,9 +1091,9 @@ int b200rt_trace_jobs_begin(const b200rt_job *jobs, size_t n_jobs, b200rt_flight
 			const b200rt_job &job = *(bundle.job[0] ? bundle.job[0] : bundle.job[1] ? bundle.job[1] : bundle.job[2]);
 			switch(job.query)
 			{
-				case B200RT_QUERY_CLOSEST: rc = launchTrace<b200rt::kClosest>(s, job.rays, job.n, static_cast<b200rt_hit *>(job.out), lane->stream, 0, job.flags, true); break;
-				case B200RT_QUERY_SHADOW: rc = launchTrace<b200rt::kShadow>(s, job.rays, job.n, static_cast<uint32_t *>(job.out), lane->stream, 0, job.flags, true); break;
-				default: rc = launchTrace<b200rt::kTShadow>(s, job.rays, job.n, static_cast<b200rt_tshadow *>(job.out), lane->stream, job.max_depth, job.flags, true); break;
+				case B200RT_QUERY_CLOSEST: rc = launchTrace<b200rt::kClosest>(s, job.rays, job.n, static_cast<b200rt_hit *>(job.out), lane->stream, 0, job.flags, true, job.times); break;
+				case B200RT_QUERY_SHADOW: rc = launchTrace<b200rt::kShadow>(s, job.rays, job.n, static_cast<uint32_t *>(job.out), lane->stream, 0, job.flags, true, job.times); break;
+				default: rc = launchTrace<b200rt::kTShadow>(s, job.rays, job.n, static_cast<b200rt_tshadow *>(job.out), lane->stream, job.max_depth, job.flags, true, job.times); break;
 			}
 		}
 		else if(rc == B200RT_OK)

@@ -471,11 +471,16 @@ __device__ __forceinline__ bool setupRay(const SceneView &s, const float4 a, con
 	return crossed;
 }
 
+// Transparent shadows: the distinct transparent casters a ray has met are written straight into its result record as they are
+// found (and read back from there for the "seen before?" test of accelerator.h:160), so the kernel keeps only their number --
+// no per-thread list in local memory, and no limit on the number but the record's capacity.  The kernels' max_depth parameter
+// carries that capacity in its upper half: max_depth | capacity << 16 (capacity 0 = the 8 entries of b200rt_tshadow).
 struct TShadowState
 {
 	int depth;
-	b200rt_hit list[B200RT_TSHADOW_MAX];
 };
+__device__ __forceinline__ int tsDepthLimit(int packed) { return packed & 0xFFFF; }
+__device__ __forceinline__ int tsCapacity(int packed) { return (packed >> 16) ? (packed >> 16) : B200RT_TSHADOW_MAX; }
 
 template <int QUERY> struct OutType;
 template <> struct OutType<kClosest> { using type = b200rt_hit; };
@@ -483,7 +488,7 @@ template <> struct OutType<kShadow> { using type = uint32_t; };
 template <> struct OutType<kTShadow> { using type = b200rt_tshadow; };
 
 template <int QUERY>
-__device__ __forceinline__ void writeResult(typename OutType<QUERY>::type *out, const RayState &r, bool hit, const TShadowState &ts)
+__device__ __forceinline__ void writeResult(typename OutType<QUERY>::type *out, const RayState &r, bool hit, const TShadowState &ts, int ts_capacity = B200RT_TSHADOW_MAX)
 {
 	if(QUERY == kClosest)
 	{
@@ -505,15 +510,11 @@ __device__ __forceinline__ void writeResult(typename OutType<QUERY>::type *out, 
 	}
 	else
 	{
-		uint4 *o = reinterpret_cast<uint4 *>(reinterpret_cast<b200rt_tshadow *>(out) + r.index);
+		// record = header + ts_capacity entries of 16 bytes; entries [0, depth) are in place already
+		uint4 *o = reinterpret_cast<uint4 *>(out) + size_t(r.index) * size_t(1 + ts_capacity);
 		o[0] = make_uint4(hit ? 1u : 0u, uint32_t(ts.depth), hit ? r.best_prim : B200RT_MISS, 0u); // setNoHit() clears primitive_
-#pragma unroll
-		for(int k = 0; k < B200RT_TSHADOW_MAX; ++k)
-		{
-			uint4 e = make_uint4(0u, 0u, 0u, B200RT_MISS);
-			if(k < ts.depth) e = make_uint4(__float_as_uint(ts.list[k].t), __float_as_uint(ts.list[k].u), __float_as_uint(ts.list[k].v), ts.list[k].prim);
-			o[1 + k] = e;
-		}
+		if(ts_capacity == B200RT_TSHADOW_MAX) // the fixed-size record of b200rt_tshadow is defined to its last byte; larger ones only up to n_transparent
+			for(int k = ts.depth; k < B200RT_TSHADOW_MAX; ++k) o[1 + k] = make_uint4(0u, 0u, 0u, B200RT_MISS);
 	}
 }
 
@@ -829,7 +830,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 							if(r.dz == 0.f) sh_axis[2][tid].x = floatBelow(r.oz);
 						}
 						sh_axis[3][tid] = make_float2(r.seg_lo, r.seg_hi); // where the ray enters and leaves the tree bound (read by replayTo); a leaf's "axis" 3 also reads this row, value unused
-						if(!alive) writeResult<QUERY>(out, r, false, ts); // missed the tree bound
+						if(!alive) writeResult<QUERY>(out, r, false, ts, tsCapacity(max_depth)); // missed the tree bound
 					}
 					pool_next += min(avail, uint32_t(__popc(idle)));
 				}
@@ -880,14 +881,15 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 							if(!(flags & B200RT_FACE_TRANSPARENT)) { hit = true; leaf_count = 0u; } // opaque caster
 							else
 							{
+								uint4 *list = reinterpret_cast<uint4 *>(out) + size_t(r.index) * size_t(1 + tsCapacity(max_depth)) + 1;
 								bool seen = false;
-								for(int k = 0; k < ts.depth; ++k) seen = seen || (ts.list[k].prim == prim);
+								for(int k = 0; k < ts.depth; ++k) seen = seen || (*reinterpret_cast<volatile uint32_t *>(&list[k].w) == prim);
 								if(!seen)
 								{
-									if(ts.depth >= max_depth) { hit = true; leaf_count = 0u; }
+									if(ts.depth >= tsDepthLimit(max_depth)) { hit = true; leaf_count = 0u; }
 									else
 									{
-										ts.list[ts.depth].t = t; ts.list[ts.depth].u = u; ts.list[ts.depth].v = v; ts.list[ts.depth].prim = prim;
+										list[ts.depth] = make_uint4(__float_as_uint(t), __float_as_uint(u), __float_as_uint(v), prim);
 										++ts.depth;
 									}
 								}
@@ -1008,7 +1010,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 		}
 		if(finished)
 		{
-			writeResult<QUERY>(out, r, (QUERY == kClosest) ? (r.best_prim != B200RT_MISS) : hit, ts);
+			writeResult<QUERY>(out, r, (QUERY == kClosest) ? (r.best_prim != B200RT_MISS) : hit, ts, tsCapacity(max_depth));
 			alive = false;
 		}
 	}
@@ -1042,7 +1044,7 @@ static constexpr int kSetupStages = B200RT_SETUP_STAGES; // 1 KB buffers per war
 static_assert((kSetupStages & (kSetupStages - 1)) == 0 && kSetupStages >= 2 && kSetupStages <= 8, "stages: a power of two, 2..8");
 template <int QUERY>
 __global__ void __launch_bounds__(kSetupBlock) setupKernel(const __grid_constant__ SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
-                                                           typename OutType<QUERY>::type *__restrict__ out, float *__restrict__ queue, bool tree_space, const float *__restrict__ times)
+                                                           typename OutType<QUERY>::type *__restrict__ out, float *__restrict__ queue, bool tree_space, const float *__restrict__ times, int max_depth)
 {
 	__shared__ __align__(128) float4 sh_rays[kSetupBlock / 32][kSetupStages][64]; // per warp a ring of buffers of 32 ray records
 	__shared__ __align__(128) float4 sh_out[kSetupBlock / 32][32 * (kEntryFloats / 4)]; // per warp the entries of one trip, compacted, before their bulk store
@@ -1092,7 +1094,7 @@ __global__ void __launch_bounds__(kSetupBlock) setupKernel(const __grid_constant
 				{
 					TShadowState none;
 					none.depth = 0;
-					writeResult<QUERY>(out, q, false, none);
+					writeResult<QUERY>(out, q, false, none, tsCapacity(max_depth));
 				}
 			}
 			const unsigned m_ready = __ballot_sync(kFullMask, ready);

@@ -58,7 +58,7 @@ SYMBOLS = [
     "b200rt_device_count", "b200rt_create", "b200rt_destroy", "b200rt_add_mesh", "b200rt_add_spheres", "b200rt_build", "b200rt_get_bound",
     "b200rt_get_stats", "b200rt_update_face_flags", "b200rt_trace_closest", "b200rt_trace_shadow", "b200rt_trace_tshadow",
     "b200rt_trace_closest_device", "b200rt_trace_shadow_device", "b200rt_trace_tshadow_device", "b200rt_trace",
-    "b200rt_trace_device", "b200rt_trace_timed", "b200rt_trace_timed_device", "b200rt_add_mesh_bezier", "b200rt_add_mesh_moving", "b200rt_trace_jobs", "b200rt_trace_jobs_begin", "b200rt_trace_jobs_end", "b200rt_host_alloc",
+    "b200rt_trace_device", "b200rt_trace_timed", "b200rt_trace_timed_device", "b200rt_add_mesh_bezier", "b200rt_add_mesh_moving", "b200rt_trace_tshadow_deep", "b200rt_trace_tshadow_deep_device", "b200rt_trace_jobs", "b200rt_trace_jobs_begin", "b200rt_trace_jobs_end", "b200rt_host_alloc",
     "b200rt_host_free", "b200rt_host_tree_build", "b200rt_host_tree_sizes", "b200rt_host_tree_export",
     "b200rt_host_tree_destroy", "b200rt_launch_count", "b200rt_last_error", "b200rt_version",
 ]
@@ -96,6 +96,8 @@ def lib():
         L.b200rt_trace_timed_device.argtypes = [P, C.c_int, C.c_uint, P, P, Z, P, C.c_int, P]
         L.b200rt_add_mesh_bezier.argtypes = [P, P, P, P, Z, P, Z, P, C.c_float, C.c_float]
         L.b200rt_add_mesh_moving.argtypes = [P, P, Z, P, Z, P, P, C.c_float, C.c_float]
+        L.b200rt_trace_tshadow_deep.argtypes = [P, C.c_uint, P, P, Z, C.c_int, C.c_int, P]
+        L.b200rt_trace_tshadow_deep_device.argtypes = [P, C.c_uint, P, P, Z, C.c_int, C.c_int, P, P]
         L.b200rt_trace_jobs.argtypes = [P, Z]
         L.b200rt_trace_jobs_begin.argtypes = [P, Z, P]
         L.b200rt_trace_jobs_end.argtypes = [P]
@@ -283,6 +285,18 @@ class Scene:
             _check(lib().b200rt_trace_timed(self._h, int(query), int(flags), _p(r), _p(times), r.shape[0], _p(out), int(max_depth)))
         else:
             _check(lib().b200rt_trace(self._h, int(query), int(flags), _p(r), r.shape[0], _p(out), int(max_depth)))
+        return out
+
+    def trace_tshadow_deep(self, rays, max_depth, capacity=None, flags=0, times=None) -> np.ndarray:
+        """Transparent shadows with more than TSHADOW_MAX distinct transparent casters (b200rt_trace_tshadow_deep): a structured array
+        with the fields of TSHADOW_DTYPE whose `transparent` list has `capacity` entries."""
+        r = as_rays(rays)
+        capacity = int(max_depth if capacity is None else capacity)
+        dt = np.dtype([("shadowed", np.uint32), ("n_transparent", np.uint32), ("occluder", np.uint32), ("pad_", np.uint32), ("transparent", HIT_DTYPE, capacity)])
+        out = np.zeros(r.shape[0], dt)
+        if times is not None:
+            times = np.ascontiguousarray(times, dtype=np.float32)
+        _check(lib().b200rt_trace_tshadow_deep(self._h, int(flags), _p(r), _p(times), r.shape[0], int(max_depth), capacity, _p(out)))
         return out
 
     # ---- device-buffer queries (raw device pointers, e.g. torch.Tensor.data_ptr()) ----

@@ -89,7 +89,7 @@ static double shade(RayQueue &q, b200rt_scene *scene_a, b200rt_scene *scene_b, i
 	if(job % 5 == 0)
 	{
 		const int md = 1 + job % 4;
-		const b200rt_tshadow &t = q.transparentShadow(scene, ray, md);
+		const b200rt_tshadow &t = q.transparentShadow(scene, ray, 0.f, md);
 		CHECK(t.n_transparent == uint32_t(md) && t.occluder == uint32_t(reinterpret_cast<uintptr_t>(scene)) && t.transparent[0].t == x);
 	}
 	if(job % 11 == 0 && depth == 2)

@@ -651,3 +651,45 @@ def test_motion_blur_against_oracle_and_live_reference(built):
     for buf in (pr, ps, pt, oc, os_):
         buf.free()
     s.close()
+
+
+def test_transparent_shadows_deeper_than_the_fixed_record(built):
+    """A "shadow_depth" above the 8 casters b200rt_tshadow holds (the reference has no limit, accelerator.h:147-169):
+    b200rt_trace_tshadow_deep with records of `capacity` casters, on 24 stacked transparent sheets over an opaque floor."""
+    n_sheets = 24
+    vs, fs = [], []
+    for k in range(n_sheets + 1):
+        z = 0.1 + 0.03 * k
+        off = 4 * k
+        vs.append(np.array([[0, 0, z], [1, 0, z], [1, 1, z], [0, 1, z]], np.float32) + np.float32(0.001 * k))
+        fs.append([off, off + 1, off + 2, off + 3])
+    xyz, idx = np.concatenate(vs), np.array(fs, np.uint32)
+    flags = np.full(idx.shape[0], scenes.F_NORMAL | scenes.F_TRANSPARENT, np.uint8)
+    flags[0] = scenes.F_NORMAL  # the lowest sheet is opaque
+    s = make_scene(xyz, idx, flags)
+    o = kdo.Oracle(xyz, idx, flags)
+    rng = np.random.default_rng(3)
+    n = 20000
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:2] = rng.random((n, 2)) * 0.8 + 0.1
+    rays[:, 2] = rng.random(n) * 1.2          # start between, above or below the sheets
+    rays[:, 3] = 0.0005
+    rays[:, 4:6] = rng.normal(scale=0.2, size=(n, 2))
+    rays[:, 6] = np.where(rng.random(n) < 0.5, -1.0, 1.0)
+    rays[:, 7] = -1.0
+    for depth in (3, 8, 12, 24, 40):
+        ref = o.trace_tshadow(rays, depth, threads=NCPU, max_list=max(depth, 1))
+        got = s.trace_tshadow_deep(rays, depth)
+        assert np.array_equal(got["shadowed"].astype(np.uint8), ref["shadowed"]), depth
+        lit = ref["shadowed"] == 0
+        assert np.array_equal(got["n_transparent"][lit].astype(np.int32), ref["n_transparent"][lit]), depth
+        a = np.sort(np.where(np.arange(max(depth, 1))[None, :] < got["n_transparent"][:, None], helpers.prim_signed(got["transparent"]["prim"]), -1), axis=1)
+        b = np.sort(ref["list"].astype(np.int64), axis=1)
+        assert np.array_equal(a[lit], b[lit]), depth
+        if depth <= rt.TSHADOW_MAX:  # the fixed-size record gives the same answers
+            fixed = s.trace_tshadow(rays, depth)
+            assert np.array_equal(fixed["shadowed"], got["shadowed"]) and np.array_equal(fixed["n_transparent"], got["n_transparent"])
+    assert (ref["n_transparent"][lit] > rt.TSHADOW_MAX).any(), "no ray passed more than 8 transparent sheets: the test would prove nothing"
+    with pytest.raises(rt.B200RTError):
+        s.trace_tshadow_deep(rays[:10], 9, capacity=8)
+    s.close()
