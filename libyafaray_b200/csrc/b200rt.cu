@@ -773,7 +773,18 @@ int b200rt_build(b200rt_scene *s)
 			const b200rt::HostNode hn = tree.nodes[i];
 			if((hn.b & 3u) != 3u) { nodes[i] = make_uint2(hn.a, hn.b); continue; }
 			const uint32_t count = hn.b >> 2;
-			nodes[i] = make_uint2(uint32_t(tris.size()), hn.b);
+			if(count >= b200rt::kLeafStride4) return fail(B200RT_E_INVALID, "a leaf holds 2^29 primitives or more");
+			// a leaf of static polygons with at least one quad stores all of its records in four float4 (kd_kernels.cuh, kLeafStride4)
+			bool stride4 = false, plain = true;
+			for(uint32_t k = 0; k < count; ++k)
+			{
+				const uint32_t face = tree.leaf_refs[hn.a + k];
+				const uint32_t *id = s->idx.data() + 4 * size_t(face);
+				if(s->kind[face] || id[2] == kSphere) plain = false;
+				else if(id[3] != kTriangle) stride4 = true;
+			}
+			stride4 = stride4 && plain && B200RT_COOP_LEAF != 0; // only the cooperative leaf phase needs the padding
+			nodes[i] = make_uint2(uint32_t(tris.size()), hn.b | (stride4 ? (b200rt::kLeafStride4 << 2) : 0u));
 			for(uint32_t k = 0; k < count; ++k)
 			{
 				const uint32_t face = tree.leaf_refs[hn.a + k];
@@ -831,6 +842,7 @@ int b200rt_build(b200rt_scene *s)
 					std::memcpy(&q.w, &w, 4);
 					tris.push_back(q);
 				}
+				if(stride4 && !quad) tris.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
 			}
 		}
 		if(tris.size() >= (size_t(1) << 32)) return fail(B200RT_E_INVALID, "leaf stream exceeds 2^32 records");

@@ -48,6 +48,12 @@ static constexpr uint32_t kFlagSphere = 16u;
 //   face of a moving instance: nv float4 = the base vertices; w: face id, flags, float4 index of the instance in SceneView::inst, -
 static constexpr uint32_t kFlagBezier = 32u;
 static constexpr uint32_t kFlagMoving = 64u;
+// Leaf nodes: y = (count << 2) | 3 with bit 31 (bit 29 of the count field) set when every record of the leaf is a static polygon
+// stored in FOUR float4 (a leaf with at least one quad pads its triangles), so that record k starts at first + 4 k; without the
+// bit the records of a polygon-only scene are triangles of three float4.  (Scenes with spheres / motion-blur faces are walked
+// record by record.)
+static constexpr uint32_t kLeafStride4 = 1u << 29;
+static constexpr uint32_t kLeafCountMask = kLeafStride4 - 1u;
 
 __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz)
 {
@@ -349,6 +355,19 @@ __device__ __forceinline__ float sphereIntersect(const float4 q0, float radius, 
 #ifndef B200RT_LEAF_PREFETCH
 #define B200RT_LEAF_PREFETCH 0
 #endif
+// COOP_LEAF 1: warp-cooperative leaf phase (closest and shadow queries of polygon-only scenes).  The (ray, record) pairs of all
+// lanes holding a leaf are laid out over the warp's 32 lanes -- an exclusive scan of the leaf sizes gives every pair a slot, the
+// owners publish (owner lane, record number) per slot through 128 bytes of shared memory, the slot's lane fetches the owner's
+// ray by shuffles and tests ONE record -- and each owner then takes, in leaf order, the nearest accepted candidate of its slots
+// (the same result as the sequential accept rule: the first record among those with the smallest t).  Needs a uniform record
+// stride per leaf (kLeafStride4, b200rt.cu flattening).  MEASURED DEAD END (profiles/r4a_knob_sweep.txt, r4b_coop_leaf_kernels.txt):
+// byte-identical results, 21.9 instead of 18.5 active lanes per instruction and the wait for leaf records down from 13.8 % to
+// 5.3 % of the warp time -- but the scan, the slot table, 13 shuffles and the gather loop cost ~240 instructions per leaf phase
+// (344 per phase against 312 for the 2.7 sequential passes they replace), and the longer live ranges spill ~15 registers across
+// every round of the outer loop (39 M local loads per launch instead of 1.8 M): closest 4655 instead of 5930 Mrays/s.  Off.
+#ifndef B200RT_COOP_LEAF
+#define B200RT_COOP_LEAF 0
+#endif
 #ifndef B200RT_FAR_PREFETCH
 #define B200RT_FAR_PREFETCH 0
 #endif
@@ -609,8 +628,9 @@ __device__ __forceinline__ bool mbarTryWait(uint32_t mbar, uint32_t parity)
 template <int QUERY, bool SPHERES, bool QUEUED = false>
 __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray *__restrict__ rays, uint32_t n, typename OutType<QUERY>::type *__restrict__ out,
                                            uint32_t *__restrict__ cursor, int max_depth, bool tree_space, uint2 (*sh_stack)[kBlock], float2 (*sh_axis)[kBlock], uint32_t static_base, float4 (*sh_leaf)[kBlock] = nullptr,
-                                           const float *__restrict__ times = nullptr)
+                                           const float *__restrict__ times = nullptr, uint32_t (*sh_task)[32] = nullptr)
 {
+	constexpr bool kCoopLeaf = B200RT_COOP_LEAF && !SPHERES && QUERY != kTShadow;
 	const unsigned tid = threadIdx.x;
 	const unsigned lane = tid & 31u;
 	const unsigned lanes_below = (1u << lane) - 1u;
@@ -849,9 +869,81 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 		if(__popc(m_pending) >= kLeafBatch || m_pending == m_alive)
 		{
 			// ---------------- leaf phase: every lane holding a leaf tests its primitives ----------------
-			if(pending)
+			if(kCoopLeaf)
+			{
+				// warp-cooperative (B200RT_COOP_LEAF): all 32 lanes take part, whatever their own state
+				const uint32_t w = tid >> 5;
+				const uint32_t c = pending ? (leaf_count & kLeafCountMask) : 0u;
+				uint32_t incl = c; // inclusive scan of the leaf sizes over the lanes
+#pragma unroll
+				for(int d = 1; d < 32; d <<= 1)
+				{
+					const uint32_t up = __shfl_up_sync(kFullMask, incl, d);
+					if(lane >= uint32_t(d)) incl += up;
+				}
+				const uint32_t start = incl - c, total = __shfl_sync(kFullMask, incl, 31);
+				const uint32_t my_stride = (leaf_count & kLeafStride4) ? 4u : 3u;
+				const uint32_t need = (QUERY == kClosest) ? uint32_t(B200RT_FACE_VISIBLE) : uint32_t(B200RT_FACE_CASTS_SHADOWS);
+				for(uint32_t base = 0u; base < total; base += 32u)
+				{
+					// the owners publish their pairs of this chunk: slot -> (owner lane, record number within the leaf)
+					const uint32_t own_lo = max(start, base), own_hi = min(start + c, base + 32u); // own slots of this chunk: [own_lo, own_hi), empty when own_lo >= own_hi
+					for(uint32_t slot = own_lo; slot < own_hi; ++slot) sh_task[w][slot - base] = lane | ((slot - start) << 5);
+					__syncwarp();
+					const uint32_t task = sh_task[w][lane];
+					const uint32_t owner = task & 31u, k = task >> 5;
+					const bool active = base + lane < total;
+					// the owner's ray and leaf (stale slots of the last chunk name some lane: harmless, their result is not used)
+					const float tox = __shfl_sync(kFullMask, r.ox, owner), toy = __shfl_sync(kFullMask, r.oy, owner), toz = __shfl_sync(kFullMask, r.oz, owner);
+					const float tdx = __shfl_sync(kFullMask, r.dx, owner), tdy = __shfl_sync(kFullMask, r.dy, owner), tdz = __shfl_sync(kFullMask, r.dz, owner);
+					const float t_lo = __shfl_sync(kFullMask, r.t_min, owner), t_hi = __shfl_sync(kFullMask, r.t_max, owner);
+					const uint32_t first = __shfl_sync(kFullMask, leaf_first, owner), stride = __shfl_sync(kFullMask, my_stride, owner);
+					float cand = __int_as_float(0x7f800000), cu = 0.f, cv = 0.f; // +inf = no acceptable hit in this slot
+					uint32_t cprim = B200RT_MISS;
+					if(active)
+					{
+						const float4 *rec = s.tris + first + k * stride;
+						const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+						const uint32_t flags = __float_as_uint(q1.w);
+						float u, v;
+						const float t = polyIntersect(q0, q1, q2, rec + 3, (flags & kFlagQuad) != 0u, tox, toy, toz, tdx, tdy, tdz, u, v);
+						// accept rules, accelerator.h:125-127 / :137-139
+						if(!(t <= 0.f || t < t_lo || t >= t_hi) && (flags & need)) { cand = t; cu = u; cv = v; cprim = __float_as_uint(q0.w); }
+					}
+					// every owner goes through its slots in leaf order: closest keeps the first of the nearest candidates (what the
+					// sequential rule "accept when t < t_max, then t_max = t" ends with), shadow the first candidate
+					const uint32_t n_own = (own_hi > own_lo) ? own_hi - own_lo : 0u;
+					const uint32_t n_most = __reduce_max_sync(kFullMask, n_own);
+					float best = (QUERY == kClosest) ? r.t_max : __int_as_float(0x7f800000);
+					uint32_t best_slot = 0u;
+					bool found = false;
+					for(uint32_t j = 0u; j < n_most; ++j)
+					{
+						const uint32_t src = (own_lo - base + j) & 31u;
+						const float tj = __shfl_sync(kFullMask, cand, src);
+						if(j < n_own && tj < best && !(QUERY == kShadow && found)) { best = tj; best_slot = src; found = true; }
+					}
+					const float bu = __shfl_sync(kFullMask, cu, best_slot), bv = __shfl_sync(kFullMask, cv, best_slot);
+					const uint32_t bprim = __shfl_sync(kFullMask, cprim, best_slot);
+					if(found && !hit) // (shadow: the occluder is the first candidate of the first chunk that has one)
+					{
+						r.best_u = bu; r.best_v = bv; r.best_prim = bprim;
+						if(QUERY == kClosest) { r.t_max = best; r.t_done = best; }
+						else hit = true;
+					}
+					__syncwarp(); // the slots are rewritten by the next chunk
+				}
+				if(pending)
+				{
+					pending = false;
+					finished = hit || popNode();
+				}
+			}
+			else if(pending)
 			{
 				const float4 *rec = s.tris + leaf_first;
+				const bool leaf_stride4 = (leaf_count & kLeafStride4) != 0u;
+				leaf_count &= kLeafCountMask;
 				const float lox = r.ox, loy = r.oy, loz = r.oz, ldx = r.dx, ldy = r.dy, ldz = r.dz;
 #if B200RT_LEAF_PREFETCH == 2
 				cpAsyncWaitAll();
@@ -866,7 +958,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					float u, v, t;
 					if(SPHERES && (flags & kFlagSphere)) { t = sphereIntersect(q0, q1.x, lox, loy, loz, ldx, ldy, ldz); u = 0.f; v = 0.f; rec += 3; }
 					else if(SPHERES && (flags & (kFlagBezier | kFlagMoving))) t = motionIntersect(s, rec, q0, q1, q2, flags, quad, r.time, lox, loy, loz, ldx, ldy, ldz, u, v);
-					else { t = polyIntersect(q0, q1, q2, rec + 3, quad, lox, loy, loz, ldx, ldy, ldz, u, v); rec += quad ? 4 : 3; }
+					else { t = polyIntersect(q0, q1, q2, rec + 3, quad, lox, loy, loz, ldx, ldy, ldz, u, v); rec += (quad || leaf_stride4) ? 4 : 3; }
 					--leaf_count;
 					// accept rules, accelerator.h:125-127 / :137-139 / :150-154
 					const uint32_t need = (QUERY == kClosest) ? uint32_t(B200RT_FACE_VISIBLE) : uint32_t(B200RT_FACE_CASTS_SHADOWS);
@@ -1029,7 +1121,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(const __grid_c
 #else
 	float4 (*sh_leaf)[kBlock] = nullptr;
 #endif
-	traceWarps<QUERY, SPHERES, QUEUED>(s, rays, n, out, cursor, max_depth, tree_space, sh_stack, sh_axis, (blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5)) * 32u, sh_leaf, times);
+	__shared__ uint32_t sh_task[kBlock / 32][32];   // cooperative leaf phase: slot -> (owner lane, record number)
+	traceWarps<QUERY, SPHERES, QUEUED>(s, rays, n, out, cursor, max_depth, tree_space, sh_stack, sh_axis, (blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5)) * 32u, sh_leaf, times, sh_task);
 }
 
 // First pass of a two-pass batch.  One warp per 256-ray region, eight trips of 32 rays: the ray records of trip t + 1 are already
@@ -1139,11 +1232,12 @@ __global__ void __launch_bounds__(kBlock, 4) traceMixedKernel(const __grid_const
 #else
 	float4 (*sh_leaf)[kBlock] = nullptr;
 #endif
+	__shared__ uint32_t sh_task[kBlock / 32][32];
 	const uint32_t warp = blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5);
 	const uint32_t w0 = (b.n[0] + 31u) / 32u, w1 = (b.n[1] + 31u) / 32u;
-	if(warp < w0) traceWarps<kClosest, SPHERES>(s, b.rays[0], b.n[0], static_cast<b200rt_hit *>(b.out[0]), nullptr, 0, tree_space, sh_stack, sh_axis, warp * 32u, sh_leaf, b.times[0]);
-	else if(warp < w0 + w1) traceWarps<kShadow, SPHERES>(s, b.rays[1], b.n[1], static_cast<uint32_t *>(b.out[1]), nullptr, 0, tree_space, sh_stack, sh_axis, (warp - w0) * 32u, sh_leaf, b.times[1]);
-	else traceWarps<kTShadow, SPHERES>(s, b.rays[2], b.n[2], static_cast<b200rt_tshadow *>(b.out[2]), nullptr, max_depth, tree_space, sh_stack, sh_axis, (warp - w0 - w1) * 32u, sh_leaf, b.times[2]);
+	if(warp < w0) traceWarps<kClosest, SPHERES>(s, b.rays[0], b.n[0], static_cast<b200rt_hit *>(b.out[0]), nullptr, 0, tree_space, sh_stack, sh_axis, warp * 32u, sh_leaf, b.times[0], sh_task);
+	else if(warp < w0 + w1) traceWarps<kShadow, SPHERES>(s, b.rays[1], b.n[1], static_cast<uint32_t *>(b.out[1]), nullptr, 0, tree_space, sh_stack, sh_axis, (warp - w0) * 32u, sh_leaf, b.times[1], sh_task);
+	else traceWarps<kTShadow, SPHERES>(s, b.rays[2], b.n[2], static_cast<b200rt_tshadow *>(b.out[2]), nullptr, max_depth, tree_space, sh_stack, sh_axis, (warp - w0 - w1) * 32u, sh_leaf, b.times[2], sh_task);
 }
 
 } // namespace b200rt
