@@ -21,6 +21,7 @@
 
 #include "accelerator/accelerator_b200.h"
 #include "render/wavefront_b200.h"
+#include "render/photon_mutex_b200.h"
 #include <algorithm>
 #include <cstdlib>
 #include <functional>
@@ -34,7 +35,7 @@ class PhotonWorkers final
 	public:
 		/*! num_threads: the integrator's num_threads_photons_ (raised here, restored by run() / the destructor);
 		 *  n_photons: how many photons this pass shoots (a logical worker gets at least kMinPhotonsPerWorker of them). */
-		PhotonWorkers(const Accelerator *accelerator, int &num_threads, int n_photons) : num_threads_{num_threads}, os_threads_{std::max(1, num_threads)}
+		PhotonWorkers(const Accelerator *accelerator, int &num_threads, int n_photons, PhotonMutex *per_photon_lock = nullptr) : num_threads_{num_threads}, os_threads_{std::max(1, num_threads)}, per_photon_lock_{per_photon_lock}
 		{
 			b200_ = dynamic_cast<const AcceleratorB200 *>(accelerator);
 			if(b200_) b200_->refreshFaceFlags(); //materials may have been replaced since the accelerator was built
@@ -64,6 +65,7 @@ class PhotonWorkers final
 			}
 			else
 			{
+				if(per_photon_lock_) per_photon_lock_->spin(true); //the workers arrive at it back to back (photon_mutex_b200.h)
 				for(int t = 0; t < os_threads_; ++t) threads.emplace_back([this, t, &worker]() {
 					std::unique_ptr<RayQueue> queue{b200_->acquireRayQueue()};
 					int next{t * fibers_per_thread_};
@@ -81,6 +83,7 @@ class PhotonWorkers final
 				});
 			}
 			for(auto &thread : threads) thread.join();
+			if(b200_ && per_photon_lock_) per_photon_lock_->spin(false);
 			if(b200_) b200_->logWavefrontStats();
 			restore();
 		}
@@ -97,6 +100,7 @@ class PhotonWorkers final
 		const int os_threads_;
 		int fibers_per_thread_ = 1;
 		const AcceleratorB200 *b200_ = nullptr;
+		PhotonMutex *const per_photon_lock_;
 };
 
 } //namespace yafaray::b200

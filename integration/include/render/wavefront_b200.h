@@ -73,7 +73,7 @@ class RayQueue final
 		struct Fiber
 		{
 			void *sp = nullptr;        //!< saved stack pointer while switched out
-			void *stack = nullptr;     //!< mapping base (guard page first)
+			void *stack = nullptr;     //!< lowest address of its stack (canary word first)
 			size_t stack_bytes = 0;
 			Group *group = nullptr;
 			uint32_t slot = 0;         //!< index of its parked ray within its group and query kind
@@ -110,12 +110,16 @@ class RayQueue final
 		void land(Group &group);
 		void resume(Fiber &fiber);
 		static void entry();
+		static void checkStack(const Fiber &fiber);
+		static constexpr uint64_t kStackCanary = 0xB200CA9A57ACC0DEull; //!< lowest word of every fiber stack
 
 		static thread_local RayQueue *current_;
 		const int n_fibers_;
 		std::vector<Fiber> fibers_;
 		std::vector<Group> groups_;
 		char *slab_ = nullptr;     //!< the pinned memory every group's ray / answer arrays are carved from
+		char *stacks_ = nullptr;   //!< one mapping: guard page, then the fibers' stacks
+		size_t stacks_bytes_ = 0;
 		Fiber *running_ = nullptr;
 		void *scheduler_sp_ = nullptr;
 		const std::function<void()> *body_ = nullptr;

@@ -23,8 +23,14 @@
  *     film_save=prefix  write the film's weighted sums as "<prefix> - node 0000.film" when the render ends (the reference's own
  *                       film_load_save_mode=save, src/render/imagefilm.cc:1099-1176); libyafaray_b200/film.py sums such films
  */
+#define _GNU_SOURCE
 #include "yafaray_c_api.h"
+#include <dlfcn.h>
 #include <math.h>
+#include <signal.h>
+#include <stdint.h>
+#include <sys/time.h>
+#include <ucontext.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -63,6 +69,58 @@ static size_t add_box(yafaray_Scene *scene, const char *name, double x0, double 
 	yafaray_initObject(scene, object_id, material_id);
 	yafaray_destroyParamMap(pm);
 	return object_id;
+}
+
+/* B200_PROF=1: a sampling profile of yafaray_render (SIGPROF on process CPU time, the interrupted program counter only -- the
+ * render threads run on fibers, which unwinders do not like).  Prints the hottest (module, offset) pairs; resolve them with
+ * addr2line / nm against the same binaries.  A diagnostic for "where does the CPU side of a b200-kdtree frame go". */
+#define PROF_MAX (1 << 20)
+static uintptr_t prof_pc[PROF_MAX];
+static volatile int prof_n = 0;
+static void prof_handler(int sig, siginfo_t *si, void *uc)
+{
+	(void) sig; (void) si;
+	const int i = __atomic_fetch_add(&prof_n, 1, __ATOMIC_RELAXED);
+	if(i < PROF_MAX) prof_pc[i] = (uintptr_t) ((ucontext_t *) uc)->uc_mcontext.gregs[REG_RIP];
+}
+static void prof_start(void)
+{
+	struct sigaction sa;
+	memset(&sa, 0, sizeof sa);
+	sa.sa_sigaction = prof_handler;
+	sa.sa_flags = SA_SIGINFO | SA_RESTART;
+	sigaction(SIGPROF, &sa, NULL);
+	const struct itimerval it = {{0, 200}, {0, 200}};
+	setitimer(ITIMER_PROF, &it, NULL);
+}
+static int prof_cmp(const void *a, const void *b) { const uintptr_t x = *(const uintptr_t *) a, y = *(const uintptr_t *) b; return x < y ? -1 : x > y; }
+static void prof_stop(void)
+{
+	const struct itimerval off = {{0, 0}, {0, 0}};
+	setitimer(ITIMER_PROF, &off, NULL);
+	int n = prof_n < PROF_MAX ? prof_n : PROF_MAX;
+	/* per function (dladdr symbol, else module + 256-byte bucket) */
+	for(int i = 0; i < n; ++i)
+	{
+		Dl_info info;
+		if(dladdr((void *) prof_pc[i], &info) && info.dli_saddr) prof_pc[i] = (uintptr_t) info.dli_saddr;
+		else prof_pc[i] &= ~(uintptr_t) 255;
+	}
+	qsort(prof_pc, (size_t) n, sizeof(uintptr_t), prof_cmp);
+	printf("PROF %d samples\n", n);
+	for(int i = 0; i < n;)
+	{
+		int j = i;
+		while(j < n && prof_pc[j] == prof_pc[i]) ++j;
+		if((j - i) * 400 >= n) /* at least 0.25 % */
+		{
+			Dl_info info;
+			memset(&info, 0, sizeof info);
+			dladdr((void *) prof_pc[i], &info);
+			printf("PROF %6.2f%% %s +0x%lx %s\n", 100.0 * (j - i) / n, info.dli_fname ? info.dli_fname : "?", (unsigned long) (prof_pc[i] - (uintptr_t) info.dli_fbase), info.dli_sname ? info.dli_sname : "");
+		}
+		i = j;
+	}
 }
 
 int main(int argc, char **argv)
@@ -365,9 +423,12 @@ int main(int argc, char **argv)
 	yafaray_preprocessScene(scene, render_control, flags);
 	const double t_pre = now();
 	yafaray_preprocessSurfaceIntegrator(render_monitor, surface_integrator, render_control, scene);
+	const int profile = getenv("B200_PROF") != NULL;
+	if(profile) prof_start();
 	const double t_render0 = now();
 	yafaray_render(render_control, render_monitor, surface_integrator, film);
 	double t_render1 = now();
+	if(profile) prof_stop();
 	int rerender_hidden = 0;
 	for(int a = 9; a < argc; ++a) if(strncmp(argv[a], "rerender_hidden=", 16) == 0) rerender_hidden = atoi(argv[a] + 16);
 	if(rerender_hidden)

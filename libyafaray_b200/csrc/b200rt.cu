@@ -903,6 +903,41 @@ int b200rt_build(b200rt_scene *s)
 	s->view.inst = s->d_inst;
 	std::memcpy(s->view.bound, s->tree.bound, sizeof(s->view.bound));
 	s->stats.device_bytes = nodes.size() * sizeof(uint2) + tris.size() * sizeof(float4);
+	// Warm start for the renderer's ray queues (b200rt_trace_jobs_begin): their first flushes come from sixteen threads at once,
+	// and what a first use costs -- a stream per lane, the lazy load of a kernel, the growth of the device's local-memory pool for
+	// a kernel with a stack frame -- is serialised inside the driver while every render thread waits (measured on a one-frame SPPM
+	// render: 2.1 thread-seconds inside libb200rt during the first photon pass, 0.02 in the second; profiles/r4g_*).  So: one
+	// empty launch of each kernel a flush can use, and a stock of lanes with their streams, paid once here.
+	{
+		b200rt::MixedBatch none{};
+		cudaStream_t warm = nullptr;
+		CUDA_TRY(cudaStreamCreateWithFlags(&warm, cudaStreamNonBlocking));
+		if(s->has_spheres)
+		{
+			b200rt::traceMixedKernel<true><<<1, b200rt::kBlock, 0, warm>>>(s->view, none, 0, true);
+			b200rt::traceKernel<b200rt::kClosest, true><<<1, b200rt::kBlock, 0, warm>>>(s->view, nullptr, 0u, nullptr, nullptr, 0, true, nullptr);
+			b200rt::traceKernel<b200rt::kShadow, true><<<1, b200rt::kBlock, 0, warm>>>(s->view, nullptr, 0u, nullptr, nullptr, 0, true, nullptr);
+			b200rt::traceKernel<b200rt::kTShadow, true><<<1, b200rt::kBlock, 0, warm>>>(s->view, nullptr, 0u, nullptr, nullptr, 0, true, nullptr);
+		}
+		else
+		{
+			b200rt::traceMixedKernel<false><<<1, b200rt::kBlock, 0, warm>>>(s->view, none, 0, true);
+			b200rt::traceKernel<b200rt::kClosest, false><<<1, b200rt::kBlock, 0, warm>>>(s->view, nullptr, 0u, nullptr, nullptr, 0, true, nullptr);
+			b200rt::traceKernel<b200rt::kShadow, false><<<1, b200rt::kBlock, 0, warm>>>(s->view, nullptr, 0u, nullptr, nullptr, 0, true, nullptr);
+			b200rt::traceKernel<b200rt::kTShadow, false><<<1, b200rt::kBlock, 0, warm>>>(s->view, nullptr, 0u, nullptr, nullptr, 0, true, nullptr);
+		}
+		cudaError_t e = cudaStreamSynchronize(warm);
+		cudaStreamDestroy(warm);
+		if(e != cudaSuccess) return fail(B200RT_E_CUDA, std::string("warm-up launches: ") + cudaGetErrorString(e));
+		std::lock_guard<std::mutex> lock(s->lane_mutex);
+		const size_t stock = std::min<size_t>(64, 2 * std::max(1u, std::thread::hardware_concurrency()));
+		while(s->free_lanes.size() < stock)
+		{
+			auto lane = std::make_unique<Lane>();
+			if(cudaStreamCreateWithFlags(&lane->stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); break; }
+			s->free_lanes.push_back(std::move(lane));
+		}
+	}
 	s->stats.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
 	s->built = true;
 	return B200RT_OK;

@@ -326,6 +326,7 @@ __device__ __forceinline__ float sphereIntersect(const float4 q0, float radius, 
 //   LEAF_PREFETCH 2: cp.async (LDGSTS) of that record into the lane's shared-memory staging slot; the leaf phase reads it from there
 //   FAR_PREFETCH  1: prefetch.global.L1 of the postponed far child when it is pushed
 //   POOL_PREFETCH 1: prefetch.global.L2 of the whole 256-ray pool when the warp takes it from the cursor
+//   POOL_PREFETCH 2: (two-pass batches) prefetch.global.L1 of the next 32 queue entries right after a hand-out
 // Two-pass batches (setupKernel feeding traceKernel<.., QUEUED>).  Ray setup -- ~170 instructions with three IEEE divisions,
 // executed by ~10 of 32 lanes when idle lanes do it inside the traversal loop -- runs as its own fully converged pass that
 // streams the ray records through shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier; SASS UBLKCP / SYNCS, the next
@@ -579,6 +580,21 @@ __device__ __forceinline__ uint32_t selectu(bool p, uint32_t a, uint32_t b)
 	return r;
 }
 
+// LEAF_NOALLOC 1: leaf records (read once per test, 73 MB of them on the BASELINE scene) are loaded without allocating in L1, so
+// that they do not displace tree nodes there
+#ifndef B200RT_LEAF_NOALLOC
+#define B200RT_LEAF_NOALLOC 0
+#endif
+__device__ __forceinline__ float4 loadRecord(const float4 *p)
+{
+#if B200RT_LEAF_NOALLOC
+	float4 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+	return v;
+#else
+	return __ldg(p);
+#endif
+}
 __device__ __forceinline__ void prefetchL1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cpAsync16(void *smem, const void *gmem)
@@ -744,7 +760,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					{
 						pool_next = region * uint32_t(kRegionRays);
 						pool_end = pool_next + count;
-#if B200RT_POOL_PREFETCH
+#if B200RT_POOL_PREFETCH == 1
 						// the region's entries (64 bytes each) will be read a few at a time over the next rounds: pull them into L2 now
 						for(uint32_t line = lane; line * 2u < count; line += 32u) prefetchL2(reinterpret_cast<const float *>(rays) + (size_t(pool_next) + line * 2u) * kEntryFloats);
 #endif
@@ -787,6 +803,15 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 						sh_axis[3][tid] = make_float2(r.seg_lo, r.seg_hi); // where the ray enters and leaves the tree bound (read by replayTo); a leaf's "axis" 3 also reads this row, value unused
 					}
 					pool_next += min(avail, uint32_t(__popc(idle)));
+#if B200RT_POOL_PREFETCH == 2
+					// the entries the next hand-outs will take: on their way into L1 while this round's rays descend
+					if(pool_next + lane < pool_end)
+					{
+						const float4 *e = reinterpret_cast<const float4 *>(rays) + size_t(pool_next + lane) * (kEntryFloats / 4);
+						prefetchL1(e);
+						prefetchL1(e + 2);
+					}
+#endif
 				}
 			}
 		}
@@ -814,7 +839,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 						pool_next = base;
 						const uint32_t pool = (cursor != nullptr) ? uint32_t(kPoolRays) : 32u;
 						pool_end = (n - base < pool) ? n : base + pool;
-#if B200RT_POOL_PREFETCH
+#if B200RT_POOL_PREFETCH == 1
 						// the pool is 8 KB of rays that will be read 8..32 rays at a time over the next few thousand cycles: pull it from HBM into L2 now
 						for(uint32_t line = lane; line * 4u < pool_end - base; line += 32u) prefetchL2(rays + base + line * 4u);
 #endif
@@ -949,7 +974,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 				cpAsyncWaitAll();
 				float4 q0 = sh_leaf[0][tid], q1 = sh_leaf[1][tid], q2 = sh_leaf[2][tid];
 #else
-				float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+				float4 q0 = loadRecord(rec), q1 = loadRecord(rec + 1), q2 = loadRecord(rec + 2);
 #endif
 				for(;;)
 				{
@@ -989,7 +1014,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 						}
 					}
 					if(leaf_count == 0u) break;
-					q0 = __ldg(rec); q1 = __ldg(rec + 1); q2 = __ldg(rec + 2);
+					q0 = loadRecord(rec); q1 = loadRecord(rec + 1); q2 = loadRecord(rec + 2);
 				}
 				pending = false;
 				finished = hit || popNode();

@@ -15,7 +15,8 @@ timeout 900 ncu --set full --clock-control none --import-source on -k "regex:tra
     python bench.py --workload s10m --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-tshadow > gpurun_out/${tag}_s10m_ncu.log 2>&1
 for integ in SPPM photonmapping; do
   for mp in 16 64 256 1024; do
-    B200_MIN_PHOTONS_PER_WORKER=$mp timeout 300 python tools/render_compare.py --integrator $integ --width 960 --height 540 --aa 1 --fibers 512 --block 2 --skip-second-stock 2>> gpurun_out/${tag}_bench.err | sed "s/^{/{\"min_photons_per_worker\": $mp, /" >> gpurun_out/${tag}_render_photon.jsonl
+    extra="i:diffuse_photons=1000000 i:caustic_photons=200000 b:finalGather=0"; [ $integ = SPPM ] && extra="i:photons=500000 i:passNums=2"
+    B200_MIN_PHOTONS_PER_WORKER=$mp timeout 300 python tools/render_compare.py --integrator $integ --width 960 --height 540 --aa 1 --fibers 512 --block 2 --skip-second-stock --extra "$extra" 2>> gpurun_out/${tag}_bench.err | sed "s/^{/{\"min_photons_per_worker\": $mp, /" >> gpurun_out/${tag}_render_photon.jsonl
   done
 done
 cut -c1-400 gpurun_out/${tag}_render_photon.jsonl

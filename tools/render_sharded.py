@@ -90,6 +90,14 @@ def main():
     if args.accelerator == "b200-kdtree":
         extra.append(f"device={local}")
 
+    # the ranks build the SAME kd-tree on host cores they share: the first to take the cache lock builds it, the others read it
+    # (libyafaray_b200/csrc/b200rt.cu, "Tree cache")
+    cache_dir = ""
+    if world > 1 and args.accelerator == "b200-kdtree" and "B200RT_TREE_CACHE_DIR" not in os.environ:
+        cache_dir = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(), "b200rt_tree_cache_" + os.environ.get("MASTER_PORT", "0"))
+        os.makedirs(cache_dir, exist_ok=True)
+        os.environ["B200RT_TREE_CACHE_DIR"] = cache_dir
+
     with tempfile.TemporaryDirectory() as d:
         dist.barrier()
         w0 = time.perf_counter()
@@ -127,6 +135,9 @@ def main():
                 line["max_weight_difference"] = float(np.abs(total.weights - single.weights).max())
             print(json.dumps(line), flush=True)
         dist.barrier()
+    if cache_dir and rank == 0:
+        import shutil
+        shutil.rmtree(cache_dir, ignore_errors=True)
     dist.destroy_process_group()
 
 
