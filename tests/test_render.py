@@ -110,13 +110,15 @@ def test_reference_scene_renders_through_b200_accelerator(built, test, determini
 @needs_build("yafaray_test01")
 def test_b200_accelerator_fails_loudly_without_a_device(built):
     """CPU box: the patched reference selects b200-kdtree, libb200rt reports the missing device, the error is logged and
-    the scene renders no geometry -- there is no hidden CPU traversal."""
+    yafaray_render refuses to start (TiledIntegrator::render returns false) -- there is no hidden CPU traversal and no
+    silently empty frame."""
     from libyafaray_b200 import rt
     if rt.device_count() > 0:
         pytest.skip("a CUDA device is present")
     with tempfile.TemporaryDirectory() as d:
         log = render(os.path.join(BUILD, "yafaray_test01"), d, "b200-kdtree", {"B200_AA_PASSES": "1", "B200_DETERMINISTIC": "1"})
         assert "libb200rt failed" in log and "no usable accelerator" in log
+        assert "nothing is rendered" in log
 
 
 @needs_build("yafaray_test02")

@@ -28,3 +28,16 @@ def test_fiber_queue(harness, threads, fibers, jobs, depth, groups):
     assert p.returncode == 0 and p.stdout.startswith("ok "), p.stdout[-2000:]
     rays, batches, calls = map(int, p.stdout.split()[1:4])
     assert rays > jobs and batches > 0 and calls >= batches
+
+
+def test_photon_mutex_draws_each_tuple_once(tmp_path):
+    """b200::PhotonMutex, the lock around SppmIntegrator's shared Halton sequences (integrator_sppm.cc:395-400): as a std::mutex
+    and in spin mode (tuples drawn in batches per OS thread while a photon pass runs on fibers) every tuple comes from one step of
+    the four sequences and is handed out at most once."""
+    out = str(tmp_path / "photon_mutex_test")
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "integration", "include"),
+           os.path.join(ROOT, "tests", "native", "photon_mutex_test.cc"), "-o", out, "-lpthread"]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert p.returncode == 0, p.stdout
+    p = subprocess.run([out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert p.returncode == 0 and p.stdout.startswith("ok "), p.stdout

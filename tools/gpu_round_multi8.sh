@@ -14,7 +14,7 @@ timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --mas
     bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/${tag}_bench_n$n.json 2>> gpurun_out/${tag}.err; tail -c 900 gpurun_out/${tag}_bench_n$n.json
 # configs[2]: 64 spp path tracing, 1 M triangles, 1080p
 timeout 300 python tools/render_sharded.py --integrator pathtracing --width 1920 --height 1080 --aa 64 >> gpurun_out/${tag}_config2.jsonl 2>> gpurun_out/${tag}.err
-for k in 2 4 $n; do
+for k in $(echo 2 4 $n | tr " " "\n" | sort -nu); do
   [ $k -le $n ] && timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $k --master-addr 127.0.0.1 --master-port 2951$k \
       tools/render_sharded.py --integrator pathtracing --width 1920 --height 1080 --aa 64 >> gpurun_out/${tag}_config2.jsonl 2>> gpurun_out/${tag}.err
 done
