@@ -345,8 +345,11 @@ __device__ __forceinline__ float sphereIntersect(const float4 q0, float radius, 
 #ifndef B200RT_TDONE
 #define B200RT_TDONE 0
 #endif
+// AXIS_MAD 1: the address of the ray's (origin, inverse direction) row of the node's axis is one mad.lo + ld.shared instead of the
+// shift / mask / add the compiler makes of sh_axis[axis][tid]; with LEAF_PREFETCH 1 (below) +1.7-2 % on both passes, byte-identical
+// (profiles/r4j_knob_sweep.txt)
 #ifndef B200RT_AXIS_MAD
-#define B200RT_AXIS_MAD 0
+#define B200RT_AXIS_MAD 1
 #endif
 // RING_OR 1: the ring is aligned to its own size, so a slot's address is (column address | slot bits): one LOP3 instead of
 // LOP3 + IADD for the speculative store and for the read of the top entry.
@@ -354,7 +357,7 @@ __device__ __forceinline__ float sphereIntersect(const float4 q0, float radius, 
 #define B200RT_RING_OR 0
 #endif
 #ifndef B200RT_LEAF_PREFETCH
-#define B200RT_LEAF_PREFETCH 0
+#define B200RT_LEAF_PREFETCH 1
 #endif
 // COOP_LEAF 1: warp-cooperative leaf phase (closest and shadow queries of polygon-only scenes).  The (ray, record) pairs of all
 // lanes holding a leaf are laid out over the warp's 32 lanes -- an exclusive scan of the leaf sizes gives every pair a slot, the
