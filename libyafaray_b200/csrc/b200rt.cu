@@ -107,6 +107,8 @@ struct b200rt_scene
 	b200rt::HostTree tree;
 	std::vector<uint32_t> record_of_ref; // float4 offset of every leaf reference's record (for flag updates)
 	uint2 *d_nodes = nullptr;
+	uint4 *d_treelets = nullptr;            // B200RT_TREELET: two-level treelets of polygon-only scenes (kd_kernels.cuh, kEmptyRef)
+	uint2 *d_spill = nullptr;               // ... and the per-thread overflow area of the short stack
 	float4 *d_tris = nullptr;
 	size_t n_tri_vec4 = 0;
 	b200rt::SceneView view{};
@@ -116,6 +118,7 @@ struct b200rt_scene
 	std::atomic<uint32_t> next_cursor{0};
 	int resident_blocks[3] = {0, 0, 0};     // blocks of traceKernel<Q> that fit the whole device
 	int resident_blocks_queued[3] = {0, 0, 0}; // the same for the queue-fed variant of the two-pass path
+	int resident_blocks_treelet[3] = {0, 0, 0}; // ... and for its treelet variant
 	int setup_blocks = 0;                   // blocks of setupKernel for one resident wave
 	std::mutex lane_mutex;
 	std::vector<std::unique_ptr<Lane>> free_lanes;
@@ -125,6 +128,8 @@ struct b200rt_scene
 		cudaSetDevice(device);
 		free_lanes.clear();
 		if(d_nodes) cudaFree(d_nodes);
+		if(d_treelets) cudaFree(d_treelets);
+		if(d_spill) cudaFree(d_spill);
 		if(d_tris) cudaFree(d_tris);
 		if(d_inst) cudaFree(d_inst);
 		if(d_cursors) cudaFree(d_cursors);
@@ -476,6 +481,13 @@ int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b2
 				const unsigned grid = std::max(1u, std::min(wanted, unsigned(s->resident_blocks_queued[Q])));
 				const b200rt_ray *as_rays = reinterpret_cast<const b200rt_ray *>(queue);
 				if(s->has_spheres) b200rt::traceKernel<Q, true, true><<<grid, b200rt::kBlock, 0, stream>>>(s->view, as_rays, n_regions, d_out + begin, cursor, max_depth, tree_space, nullptr);
+#if B200RT_TREELET
+				else if(s->d_treelets && Q != b200rt::kTShadow)
+				{
+					const unsigned tgrid = std::max(1u, std::min(wanted, unsigned(s->resident_blocks_treelet[Q])));
+					b200rt::traceKernel<Q, false, true, true><<<tgrid, b200rt::kBlock, 0, stream>>>(s->view, as_rays, n_regions, d_out + begin, cursor, max_depth, tree_space, nullptr);
+				}
+#endif
 				else b200rt::traceKernel<Q, false, true><<<grid, b200rt::kBlock, 0, stream>>>(s->view, as_rays, n_regions, d_out + begin, cursor, max_depth, tree_space, nullptr);
 				++g_launches;
 				e = cudaGetLastError();
@@ -502,14 +514,14 @@ int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b2
 	return B200RT_OK;
 }
 
-template <int Q, bool SPHERES, bool QUEUED>
+template <int Q, bool SPHERES, bool QUEUED, bool TREELET = false>
 int queryResidencyOf(b200rt_scene *s, int &blocks)
 {
 	int per_sm = 0, sms = 0;
 #ifdef B200RT_CARVEOUT
-	CUDA_TRY(cudaFuncSetAttribute(b200rt::traceKernel<Q, SPHERES, QUEUED>, cudaFuncAttributePreferredSharedMemoryCarveout, B200RT_CARVEOUT));
+	CUDA_TRY(cudaFuncSetAttribute(b200rt::traceKernel<Q, SPHERES, QUEUED, TREELET>, cudaFuncAttributePreferredSharedMemoryCarveout, B200RT_CARVEOUT));
 #endif
-	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b200rt::traceKernel<Q, SPHERES, QUEUED>, b200rt::kBlock, 0));
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b200rt::traceKernel<Q, SPHERES, QUEUED, TREELET>, b200rt::kBlock, 0));
 	CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
 	blocks = std::max(1, per_sm) * std::max(1, sms);
 	return B200RT_OK;
@@ -753,6 +765,7 @@ int b200rt_build(b200rt_scene *s)
 	const auto t0 = std::chrono::steady_clock::now();
 	std::vector<uint2> nodes;
 	std::vector<float4> tris;
+	std::vector<uint4> treelets; // B200RT_TREELET
 	try
 	{
 		const b200rt::MeshView mesh{s->xyz.data(), s->xyz.size() / 3, s->idx.data(), n_faces};
@@ -846,6 +859,62 @@ int b200rt_build(b200rt_scene *s)
 			}
 		}
 		if(tris.size() >= (size_t(1) << 32)) return fail(B200RT_E_INVALID, "leaf stream exceeds 2^32 records");
+#if B200RT_TREELET
+		// Two-level treelets of a polygon-only scene (kd_kernels.cuh, kEmptyRef): every interior node whose parent is not in a
+		// treelet already becomes a treelet root; allocation in depth-first order, like the nodes.
+		treelets.clear();
+		if(n_sphere == 0 && n_bezier == 0 && n_moving == 0 && tris.size() < (size_t(1) << 31) - 4)
+		{
+			const auto is_interior = [&](uint32_t i) { return (tree.nodes[i].b & 3u) != 3u; };
+			const auto leaf_ref = [&](uint32_t i) -> uint32_t {
+				const uint32_t count = tree.nodes[i].b >> 2;
+				if(count == 0u) return b200rt::kEmptyRef;
+				const uint32_t first = nodes[i].x;
+				std::memcpy(&tris[size_t(first) + 2].w, &count, 4); // the count rides in q2.w of the leaf's first record
+				return b200rt::kLeafRef | first;
+			};
+			const float far_plane = FLT_MAX;
+			uint32_t far_bits;
+			std::memcpy(&far_bits, &far_plane, 4);
+			// work list of (node, slot to patch with the treelet's index); slot = index into `treelets` as uint32 words, or ~0 for the root
+			std::vector<std::pair<uint32_t, size_t>> todo;
+			if(is_interior(0u)) todo.push_back({0u, ~size_t(0)});
+			else
+			{
+				// a tree of one leaf: a treelet whose planes all lie beyond every interval and whose first slot is that leaf
+				treelets.push_back(make_uint4(far_bits, far_bits, far_bits, (3u << 2) | (3u << 10) | (3u << 18)));
+				treelets.push_back(make_uint4(leaf_ref(0u), b200rt::kEmptyRef, b200rt::kEmptyRef, b200rt::kEmptyRef));
+			}
+			while(!todo.empty())
+			{
+				const auto [node, slot] = todo.back();
+				todo.pop_back();
+				const uint32_t index = uint32_t(treelets.size() / 2);
+				if(slot != ~size_t(0)) reinterpret_cast<uint32_t *>(treelets.data())[slot] = index;
+				const uint32_t child[2] = {node + 1u, tree.nodes[node].b >> 2};
+				uint32_t split[2] = {far_bits, far_bits}, axis[2] = {3u, 3u}, ref[4] = {b200rt::kEmptyRef, b200rt::kEmptyRef, b200rt::kEmptyRef, b200rt::kEmptyRef};
+				uint32_t grand[4] = {0u, 0u, 0u, 0u}; // interior grandchildren still to become treelets (0 = none: node 0 is never a grandchild)
+				for(int c = 0; c < 2; ++c)
+				{
+					if(!is_interior(child[c])) { ref[2 * c] = leaf_ref(child[c]); continue; }
+					split[c] = tree.nodes[child[c]].a;
+					axis[c] = tree.nodes[child[c]].b & 3u;
+					const uint32_t g[2] = {child[c] + 1u, tree.nodes[child[c]].b >> 2};
+					for(int k = 0; k < 2; ++k)
+					{
+						if(is_interior(g[k])) grand[2 * c + k] = g[k];
+						else ref[2 * c + k] = leaf_ref(g[k]);
+					}
+				}
+				treelets.push_back(make_uint4(tree.nodes[node].a, split[0], split[1], ((tree.nodes[node].b & 3u) << 2) | (axis[0] << 10) | (axis[1] << 18)));
+				treelets.push_back(make_uint4(ref[0], ref[1], ref[2], ref[3]));
+				// depth-first order: the first grandchild's treelet follows its parent's directly (pushed last = popped first)
+				for(int k = 3; k >= 0; --k)
+					if(grand[k]) todo.push_back({grand[k], (size_t(index) * 2 + 1) * 4 + size_t(k)});
+			}
+			if(treelets.size() / 2 >= size_t(b200rt::kLeafRef)) treelets.clear();
+		}
+#endif
 		for(int pad = 0; pad < 4; ++pad) tris.push_back(make_float4(0.f, 0.f, 0.f, 0.f)); // records are read up to four vectors ahead of their kind test
 		s->stats = b200rt_stats{};
 		s->stats.n_faces = n_faces;
@@ -874,6 +943,12 @@ int b200rt_build(b200rt_scene *s)
 	CUDA_TRY(cudaMalloc(&s->d_tris, tris.size() * sizeof(float4)));
 	CUDA_TRY(cudaMemcpy(s->d_nodes, nodes.data(), nodes.size() * sizeof(uint2), cudaMemcpyHostToDevice));
 	CUDA_TRY(cudaMemcpy(s->d_tris, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
+	if(s->d_treelets) { cudaFree(s->d_treelets); s->d_treelets = nullptr; }
+	if(!treelets.empty())
+	{
+		CUDA_TRY(cudaMalloc(&s->d_treelets, treelets.size() * sizeof(uint4)));
+		CUDA_TRY(cudaMemcpy(s->d_treelets, treelets.data(), treelets.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+	}
 	if(s->d_inst) { cudaFree(s->d_inst); s->d_inst = nullptr; }
 	if(!s->matrices.empty())
 	{
@@ -901,6 +976,26 @@ int b200rt_build(b200rt_scene *s)
 	s->view.nodes = s->d_nodes;
 	s->view.tris = s->d_tris;
 	s->view.inst = s->d_inst;
+	s->view.treelets = s->d_treelets;
+	s->view.spill = nullptr;
+	s->view.spill_threads = 0u;
+#if B200RT_TREELET
+	if(s->d_treelets)
+	{
+		// overflow area of the short stacks: one column per thread of the largest resident grid, kMaxTreeDepth entries deep
+		int blocks_c = 0, blocks_s = 0;
+		int rc2 = queryResidencyOf<b200rt::kClosest, false, true, true>(s, blocks_c);
+		if(rc2 == B200RT_OK) rc2 = queryResidencyOf<b200rt::kShadow, false, true, true>(s, blocks_s);
+		if(rc2 != B200RT_OK) return rc2;
+		s->resident_blocks_treelet[b200rt::kClosest] = blocks_c;
+		s->resident_blocks_treelet[b200rt::kShadow] = blocks_s;
+		const size_t threads = size_t(std::max(blocks_c, blocks_s)) * b200rt::kBlock;
+		if(s->d_spill) { cudaFree(s->d_spill); s->d_spill = nullptr; }
+		CUDA_TRY(cudaMalloc(&s->d_spill, threads * 96 * sizeof(uint2))); // up to three postponed subtrees per treelet level: 1.5 x kMaxTreeDepth entries, less the 8 of the ring
+		s->view.spill = s->d_spill;
+		s->view.spill_threads = uint32_t(threads);
+	}
+#endif
 	std::memcpy(s->view.bound, s->tree.bound, sizeof(s->view.bound));
 	s->stats.device_bytes = nodes.size() * sizeof(uint2) + tris.size() * sizeof(float4);
 	// Warm start for the renderer's ray queues (b200rt_trace_jobs_begin): their first flushes come from sixteen threads at once,

@@ -36,6 +36,10 @@ struct SceneView
 	const float4 *tris;
 	float bound[6];
 	const float4 *inst; // moving instances: per instance 10 float4 = three obj_to_world matrices (rows 0-2 of each) + (time_start, time_end, -, -)
+	// two-level treelets (TREELET kernel variants, polygon-only scenes): 2 uint4 per treelet, see kEmptyRef below
+	const uint4 *treelets;
+	uint2 *spill;           // per-thread overflow of the short stack: entry e of global thread g at spill[e * spill_threads + g]
+	uint32_t spill_threads;
 };
 
 enum Query { kClosest = 0, kShadow = 1, kTShadow = 2 };
@@ -52,6 +56,15 @@ static constexpr uint32_t kFlagMoving = 64u;
 // stored in FOUR float4 (a leaf with at least one quad pads its triangles), so that record k starts at first + 4 k; without the
 // bit the records of a polygon-only scene are triangles of three float4.  (Scenes with spheres / motion-blur faces are walked
 // record by record.)
+// Treelets (B200RT_TREELET): an interior node together with its two children in one 32-byte sector, so that one dependent load
+// advances the ray TWO levels.  uint4 A = (split of the node, split of its left child, split of its right child, meta),
+// uint4 B = references to the four grandchildren (left-left, left-right, right-left, right-right).  meta: byte 0 / 1 / 2 = axis << 2
+// of the node / left child / right child; axis 3 = "this child is a leaf": its split is FLT_MAX (with row 3 of the axis table =
+// (0, 1) the plane then lies beyond every interval: near side only), its reference sits in the child's FIRST slot and the second
+// slot is kEmptyRef.  A reference is a treelet index, or kLeafRef | first float4 of a non-empty leaf's records (the count rides in
+// q2.w of the leaf's first record), or kEmptyRef for an empty leaf -- never visited, never pushed.
+static constexpr uint32_t kEmptyRef = 0xFFFFFFFFu;
+static constexpr uint32_t kLeafRef = 0x80000000u;
 static constexpr uint32_t kLeafStride4 = 1u << 29;
 static constexpr uint32_t kLeafCountMask = kLeafStride4 - 1u;
 
@@ -398,6 +411,18 @@ static constexpr int kRegionRays = 256;
 static constexpr int kEntryFloats = 16;
 static constexpr int kRegionFloats = kRegionRays * kEntryFloats;
 __host__ __device__ inline size_t queueBytes(uint32_t n_regions) { return size_t(n_regions) * (kRegionFloats * sizeof(float) + sizeof(uint32_t)); }
+// TREELET 1: batches of polygon-only scenes on the two-pass path are traversed over two-level treelets (kEmptyRef above)
+#ifndef B200RT_TREELET
+#define B200RT_TREELET 0
+#endif
+#ifndef B200RT_TREELET_STEPS
+#define B200RT_TREELET_STEPS 8
+#endif
+#ifndef B200RT_TREELET_UNROLL
+#define B200RT_TREELET_UNROLL 2
+#endif
+static constexpr int kTreeletSteps = B200RT_TREELET_STEPS;   // treelet steps (two levels each) per lane between two warp votes
+static constexpr int kTreeletUnroll = B200RT_TREELET_UNROLL;
 static constexpr int kLeafBatch = B200RT_LEAF_BATCH; // lanes holding a leaf that trigger the leaf phase
 static constexpr int kUnroll = B200RT_UNROLL;       // unroll factor of the descent loop
 static constexpr int kSteps = B200RT_STEPS;         // node steps per lane between two warp votes
@@ -644,7 +669,7 @@ __device__ __forceinline__ bool mbarTryWait(uint32_t mbar, uint32_t parity)
 // BASELINE workloads -- do not pay for the flag test and the extra code in the leaf loop (measured: 3 % on S1M-hf).
 // QUEUED: `rays` is the queue setupKernel wrote and n its number of regions; otherwise `rays` are the batch's ray records and idle
 // lanes set their rays up themselves.
-template <int QUERY, bool SPHERES, bool QUEUED = false>
+template <int QUERY, bool SPHERES, bool QUEUED = false, bool TREELET = false>
 __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray *__restrict__ rays, uint32_t n, typename OutType<QUERY>::type *__restrict__ out,
                                            uint32_t *__restrict__ cursor, int max_depth, bool tree_space, uint2 (*sh_stack)[kBlock], float2 (*sh_axis)[kBlock], uint32_t static_base, float4 (*sh_leaf)[kBlock] = nullptr,
                                            const float *__restrict__ times = nullptr, uint32_t (*sh_task)[32] = nullptr)
@@ -684,6 +709,18 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 	// then the next postponed subtree is popped.  Returns true when nothing is left.  Rare path (the ring holds the 7
 	// deepest entries), divergent on purpose.
 	bool need_replay = false;
+	// TREELET: the ring holds the entries [floor, sp) of the stack, the older ones [0, floor) were moved to global memory (spill)
+	// before they could be overwritten; an empty ring with floor > 0 continues there.  No replay in this variant.
+	const uint32_t gtid = blockIdx.x * uint32_t(kBlock) + tid; (void)gtid;
+	auto globalPop = [&]() -> bool {
+		floor -= kRingStride;
+		r.sp = floor;
+		const uint2 e = s.spill[size_t(floor / kRingStride) * s.spill_threads + gtid];
+		r.node = e.x;
+		r.seg_lo = r.seg_hi;
+		r.seg_hi = __uint_as_float(e.y);
+		return false;
+	};
 	auto replayTo = [&](const uint32_t target) -> bool {
 		r.sp = 0;
 		floor = 0;
@@ -803,7 +840,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 							if(r.dy == 0.f) sh_axis[1][tid].x = floatBelow(r.oy);
 							if(r.dz == 0.f) sh_axis[2][tid].x = floatBelow(r.oz);
 						}
-						sh_axis[3][tid] = make_float2(r.seg_lo, r.seg_hi); // where the ray enters and leaves the tree bound (read by replayTo); a leaf's "axis" 3 also reads this row, value unused
+						sh_axis[3][tid] = TREELET ? make_float2(0.f, 1.f) : make_float2(r.seg_lo, r.seg_hi); // where the ray enters and leaves the tree bound (read by replayTo); a leaf's "axis" 3 also reads this row, value unused.  TREELET: the "axis" of a child that is a leaf, (FLT_MAX - 0) * 1 puts its plane beyond every interval
 					}
 					pool_next += min(avail, uint32_t(__popc(idle)));
 #if B200RT_POOL_PREFETCH == 2
@@ -979,6 +1016,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 #else
 				float4 q0 = loadRecord(rec), q1 = loadRecord(rec + 1), q2 = loadRecord(rec + 2);
 #endif
+				if(TREELET) leaf_count = __float_as_uint(q2.w); // a leaf reference carries no count: it rides in the first record
 				for(;;)
 				{
 					const uint32_t flags = __float_as_uint(q1.w);
@@ -1029,7 +1067,90 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 			// Lanes that descend in this round; a lane drops out at a leaf it cannot pop past: a non-empty leaf, the end of its ray,
 			// or an empty ring with lost entries.  Which of the three is decided after the loop, from state the step left untouched.
 			const bool descending = alive && !pending;
-			bool go = descending;
+			bool go = descending && !(TREELET && (r.node & kLeafRef)); // TREELET: a popped reference may be a leaf: the lane stops at once and holds it
+			if constexpr(TREELET)
+			{
+				// One TREELET per step: the node's plane and both children's planes are known after ONE load, the ray's way through
+				// the two levels -- up to four grandchildren, front to back -- is worked out without divergent branches, the first
+				// one that is neither culled nor empty is entered, the others are postponed (last first), and a step that finds
+				// nothing to enter pops.  A reference with kLeafRef set ends the lane's descent (non-empty leaf).
+				static_assert(kBlock * sizeof(float2) == 1024, "meta bytes hold axis << 2: the byte, moved to bits 8..15, is the row offset");
+#pragma unroll kTreeletUnroll
+				for(int step = 0; step < kTreeletSteps; ++step)
+				{
+					if(!go) break;
+					// room for three pushes: the oldest ring entries move to global memory first (rare: 6 % of the rays ever get here)
+					if(__builtin_expect(r.sp - floor > (kShortStack - 3) * kRingStride, 0))
+					{
+#pragma unroll 1
+						while(r.sp - floor > (kShortStack - 3) * kRingStride)
+						{
+							s.spill[size_t(floor / kRingStride) * s.spill_threads + gtid] = *reinterpret_cast<const uint2 *>(ring + (floor & kRingMask));
+							floor += kRingStride;
+						}
+					}
+					const uint4 A = __ldg(s.treelets + 2 * size_t(r.node)), B = __ldg(s.treelets + 2 * size_t(r.node) + 1);
+					float2 oi0, oiL, oiR;
+					asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(oi0.x), "=f"(oi0.y) : "r"(axis_base + __byte_perm(A.w, 0u, 0x4404u)));
+					asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(oiL.x), "=f"(oiL.y) : "r"(axis_base + __byte_perm(A.w, 0u, 0x4414u)));
+					asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(oiR.x), "=f"(oiR.y) : "r"(axis_base + __byte_perm(A.w, 0u, 0x4424u)));
+					const float t0 = (__uint_as_float(A.x) - oi0.x) * oi0.y, tL = (__uint_as_float(A.y) - oiL.x) * oiL.y, tR = (__uint_as_float(A.z) - oiR.x) * oiR.y;
+					const bool n0 = __float_as_int(oi0.y) < 0;
+					// the child entered first (N) and the other one (F), and their children in the order the ray meets them
+					const float tN = n0 ? tR : tL, tF = n0 ? tL : tR;
+					const bool nN = __float_as_int(n0 ? oiR.y : oiL.y) < 0, nF = __float_as_int(n0 ? oiL.y : oiR.y) < 0;
+					const uint32_t cN0 = n0 ? B.z : B.x, cN1 = n0 ? B.w : B.y, cF0 = n0 ? B.x : B.z, cF1 = n0 ? B.y : B.w;
+					const uint32_t g0 = nN ? cN1 : cN0, g1 = nN ? cN0 : cN1, g2 = nF ? cF1 : cF0, g3 = nF ? cF0 : cF1;
+					// the same strict rule as the node step, twice: t_plane > limit -> near only, t_plane < start -> far only
+					const float limit = (QUERY == kClosest) ? fminf(r.seg_hi, r.t_max) : r.seg_hi;
+					const bool visN = !(t0 < r.seg_lo), visF = !(t0 > limit);
+					const float hiN = visF ? t0 : r.seg_hi, loF = visN ? t0 : r.seg_lo;
+					const float limN = (QUERY == kClosest) ? fminf(hiN, r.t_max) : hiN;
+					const bool w0 = visN && !(tN < r.seg_lo), w1 = visN && !(tN > limN), w2 = visF && !(tF < loF), w3 = visF && !(tF > limit);
+					const float h0 = w1 ? tN : hiN, h2 = w3 ? tF : r.seg_hi; // ends of the intervals of g0 and g2 (g1: hiN, g3: seg_hi)
+					const float l1 = w0 ? tN : r.seg_lo, l3 = w2 ? tF : loF;  // starts of g1 and g3 (g0: seg_lo, g2: loF)
+					const bool v0 = w0 && g0 != kEmptyRef, v1 = w1 && g1 != kEmptyRef, v2 = w2 && g2 != kEmptyRef, v3 = w3 && g3 != kEmptyRef;
+					// top of the ring, for the step that has nothing to enter
+					const uint2 popped = *reinterpret_cast<const uint2 *>(ring + ((r.sp - kRingStride) & kRingMask));
+					// postpone all but the first, the last one first
+					if(v3 && (v0 || v1 || v2)) { *reinterpret_cast<uint2 *>(ring + (r.sp & kRingMask)) = make_uint2(g3, __float_as_uint(r.seg_hi)); r.sp += kRingStride; }
+					if(v2 && (v0 || v1)) { *reinterpret_cast<uint2 *>(ring + (r.sp & kRingMask)) = make_uint2(g2, __float_as_uint(h2)); r.sp += kRingStride; }
+					if(v1 && v0) { *reinterpret_cast<uint2 *>(ring + (r.sp & kRingMask)) = make_uint2(g1, __float_as_uint(hiN)); r.sp += kRingStride; }
+					const bool any = v0 || v1 || v2 || v3;
+					const bool closest_done = (QUERY == kClosest) && closestDone(r);
+					const bool do_pop = !any && !closest_done && r.sp > floor;
+					const uint32_t next = v0 ? g0 : (v1 ? g1 : (v2 ? g2 : g3));
+					const float next_lo = v0 ? r.seg_lo : (v1 ? l1 : (v2 ? loF : l3));
+					const float next_hi = v0 ? h0 : (v1 ? hiN : (v2 ? h2 : r.seg_hi));
+					r.node = any ? next : selectu(do_pop, popped.x, r.node);
+					r.seg_lo = any ? next_lo : selectf(do_pop, r.seg_hi, r.seg_lo);
+					r.seg_hi = any ? next_hi : selectf(do_pop, __uint_as_float(popped.y), r.seg_hi);
+					if(do_pop) r.sp -= kRingStride;
+					go = (any || do_pop) && !(r.node & kLeafRef);
+				}
+				if(descending && !go)
+				{
+					if(r.node & kLeafRef)
+					{
+						pending = true;
+						leaf_first = r.node & ~kLeafRef;
+						leaf_count = 1u; // the real count is read with the first record
+#if B200RT_LEAF_PREFETCH == 1
+						prefetchL1(s.tris + leaf_first);
+						prefetchL1(s.tris + leaf_first + 2);
+#endif
+					}
+					else
+					{
+						// nothing to enter and nothing popped: the ray has ended, or its stack continues in global memory
+						const bool closest_done = (QUERY == kClosest) && closestDone(r);
+						if(closest_done || floor == 0) finished = true;
+						else need_replay = true;
+					}
+				}
+			}
+			else
+			{
 #pragma unroll kUnroll
 			for(int step = 0; step < kSteps; ++step)
 			{
@@ -1121,12 +1242,14 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 					else need_replay = true; // ring entries were overwritten: exact kd-restart behind the leaf just left
 				}
 			}
+			} // !TREELET
 		}
 
 		if(need_replay)
 		{
 			need_replay = false;
-			finished = replayTo(r.node);
+			if constexpr(TREELET) finished = globalPop();
+			else finished = replayTo(r.node);
 		}
 		if(finished)
 		{
@@ -1137,7 +1260,7 @@ __device__ __forceinline__ void traceWarps(const SceneView &s, const b200rt_ray 
 }
 
 
-template <int QUERY, bool SPHERES, bool QUEUED = false>
+template <int QUERY, bool SPHERES, bool QUEUED = false, bool TREELET = false>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(const __grid_constant__ SceneView s, const b200rt_ray *__restrict__ rays, uint32_t n,
                                                                  typename OutType<QUERY>::type *__restrict__ out, uint32_t *__restrict__ cursor, int max_depth, bool tree_space,
                                                                  const float *__restrict__ times)
@@ -1150,7 +1273,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) traceKernel(const __grid_c
 	float4 (*sh_leaf)[kBlock] = nullptr;
 #endif
 	__shared__ uint32_t sh_task[kBlock / 32][32];   // cooperative leaf phase: slot -> (owner lane, record number)
-	traceWarps<QUERY, SPHERES, QUEUED>(s, rays, n, out, cursor, max_depth, tree_space, sh_stack, sh_axis, (blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5)) * 32u, sh_leaf, times, sh_task);
+	traceWarps<QUERY, SPHERES, QUEUED, TREELET>(s, rays, n, out, cursor, max_depth, tree_space, sh_stack, sh_axis, (blockIdx.x * uint32_t(kBlock / 32) + (threadIdx.x >> 5)) * 32u, sh_leaf, times, sh_task);
 }
 
 // First pass of a two-pass batch.  One warp per 256-ray region, eight trips of 32 rays: the ray records of trip t + 1 are already
