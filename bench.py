@@ -44,8 +44,8 @@ TSHADOW_DEPTH = 4
 COUNTERS_JSON = os.path.join(ROOT, "profiles", "kernel_counters.json")
 KERNEL_SOURCES = [os.path.join(ROOT, "libyafaray_b200", "csrc", f) for f in ("kd_kernels.cuh",)]
 # batches of 32 Ki rays and more run as two passes: setupKernel<Q> (ray setup, bound misses answered) + traceKernel<Q,false,true> (queue-fed traversal)
-KERNEL_NAMES = {"closest": "b200rt::setupKernel<0> + b200rt::traceKernel<0,false,true>", "shadow": "b200rt::setupKernel<1> + b200rt::traceKernel<1,false,true>",
-                "tshadow": "b200rt::setupKernel<2> + b200rt::traceKernel<2,false,true>"}
+KERNEL_NAMES = {"closest": "b200rt::setupKernel<0> + b200rt::traceKernel<0,false,true,false>", "shadow": "b200rt::setupKernel<1> + b200rt::traceKernel<1,false,true,false>",
+                "tshadow": "b200rt::setupKernel<2> + b200rt::traceKernel<2,false,true,false>"}
 SMS, SCHEDULERS_PER_SM = 148, 4
 
 

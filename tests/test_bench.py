@@ -64,7 +64,7 @@ def test_product_arm_line_on_the_gpu(built):
     assert rec["n_gpus"] == 1 and rec["scaling"] == "weak" and rec["dtype"] == "f32" and rec["vs_baseline"] is None
     assert rec["gpu_launches"] == 4 * rec["steps"], "a setup pass and a queue-fed traversal launch per query per step"
     roof = rec["roofline"]
-    assert "traceKernel<0,false,true>" in roof["kernel"] and "setupKernel<0>" in roof["kernel"]
+    assert "traceKernel<0,false,true,false>" in roof["kernel"] and "setupKernel<0>" in roof["kernel"]
     assert roof["bound"] in ("hbm", "issue") and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
     assert roof["hbm"]["unit"] == "GB/s" and roof["hbm"]["peak"] > 1000 and abs(roof["hbm"]["frac"] - roof["hbm"]["achieved"] / roof["hbm"]["peak"]) < 1e-9
     assert roof["traffic"] is None, "a reduced-size run must not carry the full-size ncu traffic figure"
