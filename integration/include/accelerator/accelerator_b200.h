@@ -93,7 +93,7 @@ class AcceleratorB200 final : public Accelerator
 		mutable std::atomic<bool> depth_clamp_logged_{false};
 		mutable std::mutex queues_mutex_;
 		mutable std::vector<std::unique_ptr<b200::RayQueue>> idle_queues_;
-		mutable std::atomic<uint64_t> wf_rays_[3]{}, wf_batches_{0}, wf_calls_{0}, wf_switches_{0}, wf_trace_us_{0}, wf_run_us_{0}, wf_per_ray_calls_{0};
+		mutable std::atomic<uint64_t> wf_rays_[3]{}, wf_batches_{0}, wf_calls_{0}, wf_switches_{0}, wf_trace_us_{0}, wf_run_us_{0}, wf_per_ray_calls_{0}, wf_launches_seen_{0};
 };
 
 } //namespace yafaray

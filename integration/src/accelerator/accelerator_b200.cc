@@ -470,8 +470,12 @@ void AcceleratorB200::logWavefrontStats() const
 	const uint64_t batches{wf_batches_.exchange(0)}, calls{wf_calls_.exchange(0)}, per_ray{wf_per_ray_calls_.exchange(0)};
 	const double trace_s{static_cast<double>(wf_trace_us_.exchange(0)) * 1e-6}, run_s{static_cast<double>(wf_run_us_.exchange(0)) * 1e-6};
 	wf_switches_ = 0;
+	// kernel launches since the last line: the flush combiner of libb200rt merges the flushes of all render threads (process-wide counter)
+	const uint64_t launches_now{b200rt_launch_count()};
+	const uint64_t launches{launches_now - wf_launches_seen_.exchange(launches_now)};
 	logger_.logInfo(getClassName(), ": wavefront rays closest=", closest, " shadow=", shadow, " transparent-shadow=", tshadow, " in ", batches, " batches / ", calls,
-					" libb200rt calls (", batches ? (closest + shadow + tshadow) / batches : 0, " rays per batch), ", trace_s, " thread-seconds inside libb200rt of ", run_s, " thread-seconds in the render workers; per-ray calls outside fibers: ", per_ray);
+					" libb200rt calls (", batches ? (closest + shadow + tshadow) / batches : 0, " rays per batch), ", trace_s, " thread-seconds inside libb200rt of ", run_s, " thread-seconds in the render workers; per-ray calls outside fibers: ", per_ray,
+					"; kernel launches: ", launches, " (", launches ? (closest + shadow + tshadow) / launches : 0, " rays per launch)");
 }
 
 void AcceleratorB200::logQueueError(const std::string &what) const

@@ -368,7 +368,20 @@ bool RayQueue::run(const std::function<void()> &body)
 			land(group);
 			resuming_.swap(group.parked);
 			group.parked.clear();
-			for(Fiber *f : resuming_) resume(*f);
+			// A resumed fiber finds its stack frames and its answer cold (512 fibers per thread do not fit the core's caches, and the
+			// answers were written by the GPU): pull the next fiber's top frames and its answer slot in while this one shades.
+			for(size_t i = 0; i < resuming_.size(); ++i)
+			{
+				if(i + 1 < resuming_.size())
+				{
+					const Fiber *next = resuming_[i + 1];
+					const char *top = static_cast<const char *>(next->sp);
+					for(int line = 0; line < 8; ++line) __builtin_prefetch(top + 64 * line);
+					for(int kind = 0; kind < 3; ++kind)
+						if(next->slot < group.in_flight[kind]) __builtin_prefetch(static_cast<const char *>(group.outs[kind]) + size_t(next->slot) * kOutSize[kind]);
+				}
+				resume(*resuming_[i]);
+			}
 			if(!group.parked.empty()) submit(group);
 		}
 	}

@@ -3,6 +3,7 @@
 #include "../../include/b200rt.h"
 #include "kd_build.h"
 #include "kd_kernels.cuh"
+#include "kd_segments.cuh"
 
 #include <algorithm>
 #include <fcntl.h>
@@ -85,6 +86,42 @@ struct Lane
 
 } // namespace
 
+// ---- flush combiner (kd_segments.cuh) ----------------------------------------------------------------------------------
+// The in-place jobs of b200rt_trace_jobs_begin -- the flushes of the renderer's ray queues, a few hundred rays each, from sixteen
+// threads -- gather in the scene's pending list and leave in ONE launch: the thread whose job brings the list to
+// B200RT_COMBINE_RAYS rays launches it, and so does a thread that comes to b200rt_trace_jobs_end while its job is still waiting
+// (nobody waits for a timer, and no extra thread competes with the render threads for a core: a first version with a worker
+// thread and a 60 us window was starved by the sixteen busy render threads and DOUBLED the frame time, profiles/r4t_*).  A ticket
+// is what the flight keeps of such a job: `batch` is set once the launch that carries the job has been issued.
+namespace b200rt {
+struct CombinedBatch
+{
+	cudaEvent_t event = nullptr;
+	std::atomic<int> users{0};
+	int rc = B200RT_OK;
+	std::string error;
+};
+struct Ticket
+{
+	std::atomic<CombinedBatch *> batch{nullptr};
+};
+struct PendingJob
+{
+	b200rt_job job;
+	std::shared_ptr<Ticket> ticket;
+};
+struct Combiner
+{
+	std::mutex mutex;
+	std::vector<PendingJob> pending;      // guarded by `mutex`
+	size_t pending_rays = 0;
+	std::vector<cudaStream_t> streams;
+	std::atomic<size_t> next_stream{0};
+	std::vector<CombinedBatch *> free_batches; // guarded by `mutex`
+	std::atomic<uint64_t> launches{0}, jobs{0}, rays{0};
+};
+} // namespace b200rt
+
 struct b200rt_scene
 {
 	int device = 0;
@@ -122,10 +159,13 @@ struct b200rt_scene
 	int setup_blocks = 0;                   // blocks of setupKernel for one resident wave
 	std::mutex lane_mutex;
 	std::vector<std::unique_ptr<Lane>> free_lanes;
+	std::unique_ptr<b200rt::Combiner> combiner;     // made by b200rt_build unless B200RT_COMBINE=0
+	void stopCombiner();
 
 	~b200rt_scene()
 	{
 		cudaSetDevice(device);
+		stopCombiner();
 		free_lanes.clear();
 		if(d_nodes) cudaFree(d_nodes);
 		if(d_treelets) cudaFree(d_treelets);
@@ -141,6 +181,8 @@ struct b200rt_flight
 {
 	struct Entry { b200rt_scene *scene; std::unique_ptr<Lane> lane; };
 	std::vector<Entry> lanes;
+	struct Combined { b200rt_scene *scene; std::shared_ptr<b200rt::Ticket> ticket; };
+	std::vector<Combined> tickets; // jobs that travel with the scene's flush combiner
 	int first_error = B200RT_OK;
 	std::string error_text;
 	void note(int rc) { if(first_error == B200RT_OK) { first_error = rc; error_text = g_last_error; } }
@@ -544,6 +586,99 @@ int queryResidency(b200rt_scene *s)
 }
 
 } // namespace
+
+// ---- flush combiner: the worker thread of a scene ---------------------------------------------------------------------
+namespace {
+
+long envLong(const char *name, long fallback)
+{
+	const char *v = std::getenv(name);
+	return (v && *v) ? std::atol(v) : fallback;
+}
+// flushes are held back for at most this long, or until this many rays are pending (B200RT_COMBINE_WINDOW_US / _RAYS)
+size_t combineTargetRays() { static const size_t v = size_t(std::max(1l, envLong("B200RT_COMBINE_RAYS", 2048))); return v; }
+
+// One launch per group of up to kMaxSegments jobs with the same ray-space flag.  Called WITHOUT the combiner's mutex by the thread
+// that took `jobs` off the pending list.
+void launchCombined(b200rt_scene *s, std::vector<b200rt::PendingJob> &jobs)
+{
+	b200rt::Combiner &c = *s->combiner;
+	cudaSetDevice(s->device);
+	for(unsigned tree_space = 0u; tree_space < 2u; ++tree_space)
+	{
+		size_t j = 0;
+		while(j < jobs.size())
+		{
+			b200rt::SegmentTable table{};
+			b200rt::Ticket *riders[b200rt::kMaxSegments];
+			uint32_t warps = 0u;
+			size_t rays = 0;
+			for(; j < jobs.size() && table.n_segments < uint32_t(b200rt::kMaxSegments); ++j)
+			{
+				const b200rt_job &job = jobs[j].job;
+				if(((job.flags & B200RT_RAYS_TREE_SPACE) != 0u) != (tree_space != 0u)) continue;
+				riders[table.n_segments] = jobs[j].ticket.get();
+				b200rt::Segment &g = table.seg[table.n_segments++];
+				g.rays = job.rays; g.out = job.out; g.times = job.times; g.n = uint32_t(job.n);
+				g.first_warp = warps; g.query = job.query; g.max_depth = job.max_depth;
+				warps += uint32_t((job.n + 31) / 32);
+				rays += job.n;
+			}
+			if(table.n_segments == 0u) continue;
+			table.n_warps = warps;
+			b200rt::CombinedBatch *batch = nullptr;
+			{
+				std::lock_guard<std::mutex> lock(c.mutex);
+				if(!c.free_batches.empty()) { batch = c.free_batches.back(); c.free_batches.pop_back(); }
+			}
+			if(!batch) batch = new b200rt::CombinedBatch;
+			batch->rc = B200RT_OK;
+			batch->error.clear();
+			cudaError_t e = cudaSuccess;
+			if(!batch->event) e = cudaEventCreateWithFlags(&batch->event, cudaEventDisableTiming);
+			cudaStream_t stream = c.streams[c.next_stream.fetch_add(1) % c.streams.size()];
+			if(e == cudaSuccess)
+			{
+				const unsigned grid = (warps + b200rt::kBlock / 32 - 1) / (b200rt::kBlock / 32);
+				if(s->has_spheres) b200rt::traceSegmentsKernel<true><<<grid, b200rt::kBlock, 0, stream>>>(s->view, table, tree_space != 0u);
+				else b200rt::traceSegmentsKernel<false><<<grid, b200rt::kBlock, 0, stream>>>(s->view, table, tree_space != 0u);
+				++g_launches;
+				e = cudaGetLastError();
+			}
+			if(e == cudaSuccess) e = cudaEventRecord(batch->event, stream);
+			if(e != cudaSuccess) { batch->rc = B200RT_E_CUDA; batch->error = std::string("traceSegmentsKernel: ") + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")"; }
+			c.launches.fetch_add(1);
+			c.jobs.fetch_add(table.n_segments);
+			c.rays.fetch_add(rays);
+			batch->users.store(int(table.n_segments), std::memory_order_relaxed);
+			for(uint32_t k = 0; k < table.n_segments; ++k) riders[k]->batch.store(batch, std::memory_order_release);
+		}
+	}
+}
+
+// Take whatever is pending and launch it (the caller's own job included, if it is still there).
+void flushCombiner(b200rt_scene *s)
+{
+	b200rt::Combiner &c = *s->combiner;
+	std::vector<b200rt::PendingJob> taken;
+	{
+		std::lock_guard<std::mutex> lock(c.mutex);
+		taken.swap(c.pending);
+		c.pending_rays = 0;
+	}
+	if(!taken.empty()) launchCombined(s, taken);
+}
+
+} // namespace
+
+void b200rt_scene::stopCombiner()
+{
+	if(!combiner) return;
+	flushCombiner(this); // (jobs whose flights were never ended)
+	for(cudaStream_t st : combiner->streams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+	for(b200rt::CombinedBatch *b : combiner->free_batches) { if(b->event) cudaEventDestroy(b->event); delete b; }
+	combiner.reset();
+}
 
 extern "C" {
 
@@ -1010,6 +1145,7 @@ int b200rt_build(b200rt_scene *s)
 		if(s->has_spheres)
 		{
 			b200rt::traceMixedKernel<true><<<1, b200rt::kBlock, 0, warm>>>(s->view, none, 0, true);
+			b200rt::traceSegmentsKernel<true><<<1, b200rt::kBlock, 0, warm>>>(s->view, b200rt::SegmentTable{}, true);
 			b200rt::traceKernel<b200rt::kClosest, true><<<1, b200rt::kBlock, 0, warm>>>(s->view, nullptr, 0u, nullptr, nullptr, 0, true, nullptr);
 			b200rt::traceKernel<b200rt::kShadow, true><<<1, b200rt::kBlock, 0, warm>>>(s->view, nullptr, 0u, nullptr, nullptr, 0, true, nullptr);
 			b200rt::traceKernel<b200rt::kTShadow, true><<<1, b200rt::kBlock, 0, warm>>>(s->view, nullptr, 0u, nullptr, nullptr, 0, true, nullptr);
@@ -1017,6 +1153,7 @@ int b200rt_build(b200rt_scene *s)
 		else
 		{
 			b200rt::traceMixedKernel<false><<<1, b200rt::kBlock, 0, warm>>>(s->view, none, 0, true);
+			b200rt::traceSegmentsKernel<false><<<1, b200rt::kBlock, 0, warm>>>(s->view, b200rt::SegmentTable{}, true);
 			b200rt::traceKernel<b200rt::kClosest, false><<<1, b200rt::kBlock, 0, warm>>>(s->view, nullptr, 0u, nullptr, nullptr, 0, true, nullptr);
 			b200rt::traceKernel<b200rt::kShadow, false><<<1, b200rt::kBlock, 0, warm>>>(s->view, nullptr, 0u, nullptr, nullptr, 0, true, nullptr);
 			b200rt::traceKernel<b200rt::kTShadow, false><<<1, b200rt::kBlock, 0, warm>>>(s->view, nullptr, 0u, nullptr, nullptr, 0, true, nullptr);
@@ -1032,6 +1169,22 @@ int b200rt_build(b200rt_scene *s)
 			if(cudaStreamCreateWithFlags(&lane->stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); break; }
 			s->free_lanes.push_back(std::move(lane));
 		}
+	}
+	// the flush combiner (kd_segments.cuh): the in-place jobs of b200rt_trace_jobs_begin -- the flushes of the renderer's sixteen ray
+	// queues -- leave in shared launches
+	// OFF unless B200RT_COMBINE=1: measured on path-traced and direct-lighting frames it reaches 2-4 k rays per launch and 8-16 x fewer
+	// launches, and the frames get SLOWER (2.9 s -> 3.0 / 3.9 / 4.8 s at 1024 / 2048 / 4096 rays per launch): a render thread wants a
+	// flush back within the ~180 us it takes to shade its other fiber group, and waiting for company spends that (profiles/r4u_*).
+	if(!s->combiner && envLong("B200RT_COMBINE", 0) != 0)
+	{
+		auto combiner = std::make_unique<b200rt::Combiner>();
+		for(int k = 0; k < 4; ++k)
+		{
+			cudaStream_t st = nullptr;
+			CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+			combiner->streams.push_back(st);
+		}
+		s->combiner = std::move(combiner);
 	}
 	s->stats.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
 	s->built = true;
@@ -1271,6 +1424,22 @@ int b200rt_trace_jobs_begin(const b200rt_job *jobs, size_t n_jobs, b200rt_flight
 		if(rc != B200RT_OK) { flight->note(rc); continue; }
 		const bool pinned = (job.flags & B200RT_BUFFERS_PINNED) != 0u || (isPinned(job.rays) && isPinned(job.out) && (!job.times || isPinned(job.times)));
 		if(!pinned || job.n > kDirectRays) { staged.push_back(j); continue; }
+		if(job.scene->combiner)
+		{
+			// rides with the flushes of the other render threads (flush combiner); b200rt_trace_jobs_end waits for its launch
+			b200rt::Combiner &c = *job.scene->combiner;
+			auto ticket = std::make_shared<b200rt::Ticket>();
+			bool full = false;
+			{
+				std::lock_guard<std::mutex> lock(c.mutex);
+				c.pending.push_back(b200rt::PendingJob{job, ticket});
+				c.pending_rays += job.n;
+				full = c.pending_rays >= combineTargetRays() || c.pending.size() >= size_t(b200rt::kMaxSegments);
+			}
+			flight->tickets.push_back({job.scene, std::move(ticket)});
+			if(full) flushCombiner(job.scene);
+			continue;
+		}
 		const unsigned tree_space = job.flags & B200RT_RAYS_TREE_SPACE;
 		Bundle *home = nullptr;
 		for(Bundle &bundle : bundles)
@@ -1304,6 +1473,36 @@ int b200rt_trace_jobs_end(b200rt_flight *flight)
 		}
 		std::lock_guard<std::mutex> lock(f.scene->lane_mutex);
 		f.scene->free_lanes.push_back(std::move(f.lane));
+	}
+	for(auto &t : flight->tickets)
+	{
+		b200rt::CombinedBatch *batch = t.ticket->batch.load(std::memory_order_acquire);
+		if(!batch) flushCombiner(t.scene); // still waiting for company: launch what is there, this job included
+		for(unsigned spins = 0; !(batch = t.ticket->batch.load(std::memory_order_acquire)); ++spins)
+		{
+			// another thread has taken the list and is launching it this moment
+			if(spins < 2000u) {
+#if defined(__x86_64__)
+				__builtin_ia32_pause();
+#endif
+			}
+			else std::this_thread::yield();
+		}
+		if(batch->rc != B200RT_OK)
+		{
+			if(flight->first_error == B200RT_OK) { flight->first_error = batch->rc; flight->error_text = batch->error; }
+		}
+		else
+		{
+			const cudaError_t e = cudaEventSynchronize(batch->event);
+			if(e != cudaSuccess && flight->first_error == B200RT_OK) { flight->first_error = B200RT_E_CUDA; flight->error_text = std::string("b200rt_trace_jobs (combined launch): ") + cudaGetErrorString(e); }
+		}
+		if(batch->users.fetch_sub(1, std::memory_order_acq_rel) == 1)
+		{
+			b200rt::Combiner &c = *t.scene->combiner;
+			std::lock_guard<std::mutex> lock(c.mutex);
+			c.free_batches.push_back(batch);
+		}
 	}
 	const int rc = flight->first_error;
 	if(rc != B200RT_OK) g_last_error = flight->error_text;

@@ -372,6 +372,58 @@ def test_trace_jobs_bundles_match_single_queries(built, split):
     s1.close(); s2.close()
 
 
+def test_flush_combiner_merges_jobs_of_several_threads(built, monkeypatch):
+    """B200RT_COMBINE=1 (off by default): the in-place jobs of several threads' b200rt_trace_jobs calls leave in
+    shared launches of traceSegmentsKernel (kd_segments.cuh).  Eight threads, each tracing its own pinned closest / shadow /
+    transparent-shadow batches in a loop: every answer byte-identical to the single-kind queries, fewer launches than jobs."""
+    import threading
+    monkeypatch.setenv("B200RT_COMBINE", "1")
+    monkeypatch.setenv("B200RT_COMBINE_RAYS", "1500")
+    xyz, idx, _ = scenes.objects(30000, n_spheres=0)
+    flags = helpers.flag_mix(idx.shape[0], seed=4)
+    s = make_scene(xyz, idx, flags)           # the combiner is made by b200rt_build, with the environment as it is now
+    monkeypatch.delenv("B200RT_COMBINE")
+    n_threads, rounds, n = 8, 25, 300
+    fl = rt.RAYS_TREE_SPACE | rt.BUFFERS_PINNED
+    work, expect = [], []
+    for t in range(n_threads):
+        closest, shadow = helpers.ray_zoo(s.bound(), n=n, seed=900 + t)
+        closest, shadow = closest[:n], shadow[:n]
+        bufs = [rt.PinnedBuffer(closest.shape, np.float32), rt.PinnedBuffer((n,), rt.HIT_DTYPE), rt.PinnedBuffer(shadow.shape, np.float32), rt.PinnedBuffer((n,), np.uint32),
+                rt.PinnedBuffer(shadow.shape, np.float32), rt.PinnedBuffer((n,), rt.TSHADOW_DTYPE)]
+        bufs[0].array[:] = closest; bufs[2].array[:] = shadow; bufs[4].array[:] = shadow
+        work.append(bufs)
+    failures = []
+    launches0 = rt.launch_count()
+    def worker(t):
+        b = work[t]
+        try:
+            for _ in range(rounds):
+                b[1].array[:] = 0; b[3].array[:] = 0
+                rt.trace_jobs([(s, rt.QUERY_CLOSEST, fl, b[0].array, b[1].array, 0), (s, rt.QUERY_SHADOW, fl, b[2].array, b[3].array, 0),
+                               (s, rt.QUERY_TSHADOW, fl, b[4].array, b[5].array, 2)], split=True)
+        except Exception as e:  # noqa: BLE001
+            failures.append(repr(e))
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+    for th in threads: th.start()
+    for th in threads: th.join()
+    launches = rt.launch_count() - launches0
+    assert not failures, failures
+    for t in range(n_threads):
+        b = work[t]
+        assert b[1].array.tobytes() == s.trace(rt.QUERY_CLOSEST, b[0].array, flags=rt.RAYS_TREE_SPACE).tobytes()
+        assert b[3].array.tobytes() == s.trace(rt.QUERY_SHADOW, b[2].array, flags=rt.RAYS_TREE_SPACE).tobytes()
+        ref = s.trace(rt.QUERY_TSHADOW, b[4].array, flags=rt.RAYS_TREE_SPACE, max_depth=2)
+        assert np.array_equal(b[5].array["shadowed"], ref["shadowed"]) and np.array_equal(b[5].array["n_transparent"], ref["n_transparent"])
+    n_jobs = n_threads * rounds * 3
+    helpers.report("flush_combiner", jobs=n_jobs, launches=int(launches), rays_per_launch=float(n_jobs * n / max(1, launches)))
+    assert 0 < launches < n_jobs, (launches, n_jobs)
+    for bufs in work:
+        for b in bufs:
+            b.free()
+    s.close()
+
+
 REF_SCENES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_scenes", "*.bin")))
 
 

@@ -48,6 +48,12 @@ with tempfile.TemporaryDirectory() as d:
         wf = re.search(r"wavefront rays closest=(\d+) shadow=(\d+) transparent-shadow=(\d+) in (\d+) batches / (\d+) libb200rt calls \((\d+) rays per batch\), ([0-9.e+-]+) thread-seconds inside libb200rt of ([0-9.e+-]+) thread-seconds in the render workers; per-ray calls outside fibers: (\d+)", p.stdout)
         if wf:
             rec["wavefront"] = dict(zip(("closest", "shadow", "tshadow", "batches", "calls", "rays_per_batch"), map(int, wf.groups()[:6])), trace_thread_seconds=float(wf.group(7)), worker_thread_seconds=float(wf.group(8)), per_ray_calls=int(wf.group(9)))
+            # all passes of the frame: kernel launches (the flush combiner merges the render threads' flushes) and rays
+            lines = re.findall(r"wavefront rays closest=(\d+) shadow=(\d+) transparent-shadow=(\d+) .*?kernel launches: (\d+)", p.stdout)
+            if lines:
+                rec["wavefront"]["kernel_launches"] = sum(int(x[3]) for x in lines)
+                rec["wavefront"]["rays_all_passes"] = sum(int(x[0]) + int(x[1]) + int(x[2]) for x in lines)
+                rec["wavefront"]["rays_per_launch"] = rec["wavefront"]["rays_all_passes"] // max(1, rec["wavefront"]["kernel_launches"])
         if os.path.exists(out):
             img = read_tga(out)
             if first is None:
