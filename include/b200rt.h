@@ -235,7 +235,10 @@ int b200rt_trace_jobs(const b200rt_job *jobs, size_t n_jobs);
 /* The same in two halves, so that a render thread can shade one group of pixels while the rays of another group are
  * on the GPU: _begin enqueues the in-place jobs and returns (jobs that need staging are traced before it returns);
  * _end waits for them, releases the flight and returns the first error of either half.  The job buffers must stay
- * untouched between the two calls; the job array itself may go away after _begin. */
+ * untouched between the two calls; the job array itself may go away after _begin.
+ * Environment (read by b200rt_build): B200RT_COMBINE=1 lets the in-place jobs of ALL calling threads of a scene leave in shared
+ * launches (up to B200RT_COMBINE_RAYS rays each, default 2048; _end launches what is pending if its own job still waits).
+ * Off by default: fewer, larger launches, but a longer wait for each caller. */
 typedef struct b200rt_flight b200rt_flight;
 int b200rt_trace_jobs_begin(const b200rt_job *jobs, size_t n_jobs, b200rt_flight **flight);
 int b200rt_trace_jobs_end(b200rt_flight *flight);
