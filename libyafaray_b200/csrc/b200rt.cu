@@ -56,6 +56,9 @@ int lanesPerCall()
 	static const int value = [] { const char *e = std::getenv("B200RT_LANES"); const long n = e ? std::atol(e) : 0; return int(n > 0 && n <= 16 ? n : 6); }();
 	return value;
 }
+#ifndef B200RT_L2_PERSIST
+#define B200RT_L2_PERSIST 0
+#endif
 constexpr size_t kSmallBatchRays = 256;           // unpinned batches up to this size go through a pinned lane buffer, one cursor-less launch
 constexpr size_t kDirectRays = size_t(1) << 16;  // pinned batches up to this size are traced in place (no staging copies)
 
@@ -143,7 +146,10 @@ struct b200rt_scene
 	float4 *d_inst = nullptr;
 	b200rt::HostTree tree;
 	std::vector<uint32_t> record_of_ref; // float4 offset of every leaf reference's record (for flag updates)
-	uint2 *d_nodes = nullptr;
+	uint2 *d_nodes = nullptr;               // (points into d_scene)
+	void *d_scene = nullptr;                // nodes and leaf records in ONE allocation: one L2 access-policy window can cover both (B200RT_L2_PERSIST)
+	size_t scene_bytes = 0;
+	cudaAccessPolicyWindow l2_window{};     // valid when l2_window.num_bytes != 0
 	uint4 *d_treelets = nullptr;            // B200RT_TREELET: two-level treelets of polygon-only scenes (kd_kernels.cuh, kEmptyRef)
 	uint2 *d_spill = nullptr;               // ... and the per-thread overflow area of the short stack
 	float4 *d_tris = nullptr;
@@ -167,10 +173,9 @@ struct b200rt_scene
 		cudaSetDevice(device);
 		stopCombiner();
 		free_lanes.clear();
-		if(d_nodes) cudaFree(d_nodes);
+		if(d_scene) cudaFree(d_scene);
 		if(d_treelets) cudaFree(d_treelets);
 		if(d_spill) cudaFree(d_spill);
-		if(d_tris) cudaFree(d_tris);
 		if(d_inst) cudaFree(d_inst);
 		if(d_cursors) cudaFree(d_cursors);
 	}
@@ -528,6 +533,19 @@ int launchTrace(b200rt_scene *s, const b200rt_ray *d_rays, size_t n, typename b2
 				{
 					const unsigned tgrid = std::max(1u, std::min(wanted, unsigned(s->resident_blocks_treelet[Q])));
 					b200rt::traceKernel<Q, false, true, true><<<tgrid, b200rt::kBlock, 0, stream>>>(s->view, as_rays, n_regions, d_out + begin, cursor, max_depth, tree_space, nullptr);
+				}
+#endif
+#if B200RT_L2_PERSIST
+				else if(s->l2_window.num_bytes != 0)
+				{
+					cudaLaunchConfig_t cfg{};
+					cfg.gridDim = dim3(grid); cfg.blockDim = dim3(b200rt::kBlock); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+					cudaLaunchAttribute attr{};
+					attr.id = cudaLaunchAttributeAccessPolicyWindow;
+					attr.val.accessPolicyWindow = s->l2_window;
+					cfg.attrs = &attr; cfg.numAttrs = 1;
+					const float *no_times = nullptr;
+					e = cudaLaunchKernelEx(&cfg, b200rt::traceKernel<Q, false, true>, s->view, as_rays, n_regions, d_out + begin, cursor, max_depth, tree_space, no_times);
 				}
 #endif
 				else b200rt::traceKernel<Q, false, true><<<grid, b200rt::kBlock, 0, stream>>>(s->view, as_rays, n_regions, d_out + begin, cursor, max_depth, tree_space, nullptr);
@@ -1072,10 +1090,33 @@ int b200rt_build(b200rt_scene *s)
 	const auto t1 = std::chrono::steady_clock::now();
 	s->stats.build_seconds = std::chrono::duration<double>(t1 - t0).count();
 
-	if(s->d_nodes) { cudaFree(s->d_nodes); s->d_nodes = nullptr; }
-	if(s->d_tris) { cudaFree(s->d_tris); s->d_tris = nullptr; }
-	CUDA_TRY(cudaMalloc(&s->d_nodes, nodes.size() * sizeof(uint2)));
-	CUDA_TRY(cudaMalloc(&s->d_tris, tris.size() * sizeof(float4)));
+	if(s->d_scene) { cudaFree(s->d_scene); s->d_scene = nullptr; s->d_nodes = nullptr; s->d_tris = nullptr; }
+	{
+		const size_t node_bytes = (nodes.size() * sizeof(uint2) + 255) & ~size_t(255);
+		s->scene_bytes = node_bytes + tris.size() * sizeof(float4);
+		CUDA_TRY(cudaMalloc(&s->d_scene, s->scene_bytes));
+		s->d_nodes = static_cast<uint2 *>(s->d_scene);
+		s->d_tris = reinterpret_cast<float4 *>(static_cast<char *>(s->d_scene) + node_bytes);
+	}
+	s->l2_window = cudaAccessPolicyWindow{};
+#if B200RT_L2_PERSIST
+	{
+		// L2 persistence for the scene: the rays, queue entries and results that stream through L2 (1.5 GB per closest pass) keep
+		// evicting it (ncu: ~1.1 GB of scene re-fetched from HBM per launch although nodes + records are 95 MB of a 126 MB L2)
+		cudaDeviceProp prop{};
+		CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
+		const size_t carve = std::min<size_t>(size_t(prop.persistingL2CacheMaxSize), s->scene_bytes);
+		if(carve > 0 && prop.accessPolicyMaxWindowSize > 0)
+		{
+			CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+			s->l2_window.base_ptr = s->d_scene;
+			s->l2_window.num_bytes = std::min<size_t>(s->scene_bytes, size_t(prop.accessPolicyMaxWindowSize));
+			s->l2_window.hitRatio = float(std::min(1.0, double(carve) / double(s->l2_window.num_bytes)));
+			s->l2_window.hitProp = cudaAccessPropertyPersisting;
+			s->l2_window.missProp = cudaAccessPropertyStreaming;
+		}
+	}
+#endif
 	CUDA_TRY(cudaMemcpy(s->d_nodes, nodes.data(), nodes.size() * sizeof(uint2), cudaMemcpyHostToDevice));
 	CUDA_TRY(cudaMemcpy(s->d_tris, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
 	if(s->d_treelets) { cudaFree(s->d_treelets); s->d_treelets = nullptr; }
