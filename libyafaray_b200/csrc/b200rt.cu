@@ -45,10 +45,12 @@ constexpr uint32_t kTriangle = 0xFFFFFFFFu;
 constexpr uint32_t kSphere = 0xFFFFFFFEu; // idx[2] of a sphere face (kd_build.h)
 constexpr uint32_t kBox = 0xFFFFFFFDu;    // idx[2] of a motion-blur face: the builder only sees its bound (kd_build.h)
 // staging granularity of the host-buffer queries and chunks in flight per call; the environment overrides are tuning aids
-// (tools/gpu_e2e_sweep.sh), read once.  Defaults from the measured sweep (profiles/r1m_e2e_sweep.txt): 16 MiB x 6 in flight.
+// (tools/gpu_e2e_sweep.sh), read once.  Defaults from the measured sweeps (profiles/r1m_e2e_sweep.txt, r5d_e2e_sweep.txt): 24 MiB x 6 in flight
+// (round 1: 16 MiB; with the two-pass kernels 24 MiB is 4 % faster on the bench's 512 MiB batches -- 21.3 chunks, a short last one).
+constexpr size_t kTwoPassRaysForward = size_t(1) << 15; // = kTwoPassRays below: tail pieces stay large enough for the two-pass path
 size_t chunkBytes()
 {
-	static const size_t value = [] { const char *e = std::getenv("B200RT_CHUNK_MB"); const long mb = e ? std::atol(e) : 0; return size_t(mb > 0 ? mb : 16) << 20; }();
+	static const size_t value = [] { const char *e = std::getenv("B200RT_CHUNK_MB"); const long mb = e ? std::atol(e) : 0; return size_t(mb > 0 ? mb : 24) << 20; }();
 	return value;
 }
 int lanesPerCall()
@@ -342,7 +344,17 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, const float *times, si
 	}
 	const size_t per_ray = std::max(sizeof(b200rt_ray), sizeof(Out));
 	const size_t chunk = std::max<size_t>(1024, chunkBytes() / per_ray);
-	const size_t n_chunks = (n + chunk - 1) / chunk;
+	// full chunks, then a tapered tail (half, quarter, quarter of what is left): when the last rays have arrived nothing but the last
+	// piece's kernel and copy-out stands between the call and its return, so that piece should be short
+	std::vector<std::pair<size_t, size_t>> pieces; // (first ray, rays)
+	{
+		size_t begin = 0;
+		for(; n - begin > chunk; begin += chunk) pieces.push_back({begin, chunk});
+		size_t rest = n - begin;
+		for(int k = 0; k < 2 && rest >= 4 * kTwoPassRaysForward; ++k) { const size_t half = rest / 2; pieces.push_back({begin, half}); begin += half; rest -= half; }
+		pieces.push_back({begin, rest});
+	}
+	const size_t n_chunks = pieces.size();
 	const int n_lanes = int(std::min<size_t>(size_t(lanesPerCall()), n_chunks));
 
 	std::vector<std::unique_ptr<Lane>> lanes;
@@ -380,7 +392,7 @@ int tracedStaged(b200rt_scene *s, const b200rt_ray *rays, const float *times, si
 		Lane &l = *lanes[c % size_t(n_lanes)];
 		rc = drain(l);
 		if(rc != B200RT_OK) break;
-		const size_t begin = c * chunk, count = std::min(chunk, n - begin);
+		const size_t begin = pieces[c].first, count = pieces[c].second;
 		const void *src = rays + begin;
 		if(!in_pinned) { stagingCopy(l.h_in, src, count * sizeof(b200rt_ray)); src = l.h_in; }
 		cudaError_t e = cudaMemcpyAsync(l.d_in, src, count * sizeof(b200rt_ray), cudaMemcpyHostToDevice, l.stream);
@@ -479,6 +491,7 @@ void buildOrLoadTree(const b200rt::MeshView &mesh, const b200rt::BuildConfig &co
 constexpr uint32_t kCursorRing = 4096;
 constexpr size_t kMaxRaysPerLaunch = size_t(1) << 30;
 constexpr size_t kTwoPassRays = size_t(1) << 15;        // batches from this size on take the two-pass path (setup pass + queue-fed traversal)
+static_assert(kTwoPassRays == kTwoPassRaysForward, "keep the forward copy in step");
 constexpr size_t kMaxRaysPerTwoPass = size_t(1) << 26;  // 64 Mi rays = 4 GiB of queue scratch at most per launch pair
 
 int checkDeviceCall(const b200rt_scene *s, const void *rays, size_t n, const void *out)
