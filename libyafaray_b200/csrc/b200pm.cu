@@ -1,0 +1,287 @@
+// libyafaray_b200/csrc/b200pm.cu -- the C ABI of the photon-map queries (include/b200pm.h): map ownership, packing of the
+// reference's point kd-tree into the 16-byte node layout the kernels read, host-buffer and device-buffer lookups.
+#include "../../include/b200pm.h"
+#include "../../include/b200rt.h"
+#include "pm_build.h"
+#include "pm_kernels.cuh"
+
+#include <chrono>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace b200 {
+int failWith(int code, const std::string &msg); // b200rt.cu: text for b200rt_last_error()
+void countLaunches(uint64_t n);                  // b200rt.cu: b200rt_launch_count()
+} // namespace b200
+
+namespace {
+
+using b200::failWith;
+
+#define PM_CUDA_TRY(expr)                                                                                                   \
+	do {                                                                                                                    \
+		const cudaError_t e_ = (expr);                                                                                      \
+		if(e_ != cudaSuccess)                                                                                               \
+			return failWith(B200RT_E_CUDA, std::string(#expr) + ": " + cudaGetErrorName(e_) + " (" + cudaGetErrorString(e_) + ")"); \
+	} while(0)
+
+double now()
+{
+	return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// device scratch of the host-buffer calls, grown on demand and kept with the map
+struct Scratch
+{
+	void *ptr = nullptr;
+	size_t cap = 0;
+	int reserve(size_t bytes)
+	{
+		if(bytes <= cap) return B200RT_OK;
+		if(ptr) cudaFree(ptr);
+		ptr = nullptr;
+		cap = 0;
+		PM_CUDA_TRY(cudaMalloc(&ptr, bytes));
+		cap = bytes;
+		return B200RT_OK;
+	}
+	~Scratch() { if(ptr) cudaFree(ptr); }
+};
+
+} // namespace
+
+struct b200pm_map
+{
+	int device = 0;
+	size_t n_photons = 0, n_nodes = 0;
+	bool has_dirs = false;
+	uint4 *d_nodes = nullptr;
+	float4 *d_dirs = nullptr;
+	b200pm_stats stats{};
+	cudaStream_t stream = nullptr; // host-buffer calls
+	std::mutex host_call;          // host-buffer calls on one map take turns (they share the scratch buffers)
+	Scratch in, out;
+	bool smem_opt_in = false;
+
+	~b200pm_map()
+	{
+		cudaSetDevice(device);
+		if(d_nodes) cudaFree(d_nodes);
+		if(d_dirs) cudaFree(d_dirs);
+		if(stream) cudaStreamDestroy(stream);
+	}
+};
+
+namespace {
+
+int launchGather(b200pm_map *map, const float *d_points, size_t n_points, uint32_t k, float sq_radius, const float *d_sq_radii, b200pm_found *d_found,
+                 uint32_t *d_n_found, float *d_sq_radius_out, cudaStream_t stream)
+{
+	if(!n_points) return B200RT_OK;
+	const unsigned blocks = unsigned((n_points + b200pm::kPmThreads - 1) / b200pm::kPmThreads);
+	if(k <= b200pm::kPmSmemK)
+	{
+		const size_t smem = size_t(k) * b200pm::kPmThreads * sizeof(uint2);
+		if(!map->smem_opt_in)
+		{
+			PM_CUDA_TRY(cudaFuncSetAttribute(b200pm::pmLookupKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			                                 int(size_t(b200pm::kPmSmemK) * b200pm::kPmThreads * sizeof(uint2))));
+			map->smem_opt_in = true;
+		}
+		b200pm::pmLookupKernel<0><<<blocks, b200pm::kPmThreads, smem, stream>>>(map->d_nodes, map->d_dirs, d_points, nullptr, uint32_t(n_points), k, sq_radius, d_sq_radii,
+		                                                                    reinterpret_cast<uint2 *>(d_found), d_n_found, d_sq_radius_out, nullptr);
+	}
+	else
+		b200pm::pmLookupKernel<1><<<blocks, b200pm::kPmThreads, 0, stream>>>(map->d_nodes, map->d_dirs, d_points, nullptr, uint32_t(n_points), k, sq_radius, d_sq_radii,
+		                                                                 reinterpret_cast<uint2 *>(d_found), d_n_found, d_sq_radius_out, nullptr);
+	PM_CUDA_TRY(cudaGetLastError());
+	b200::countLaunches(1);
+	return B200RT_OK;
+}
+
+int launchNearest(b200pm_map *map, const float *d_points, const float *d_normals, size_t n_points, float dist, uint32_t *d_out, cudaStream_t stream)
+{
+	if(!n_points) return B200RT_OK;
+	const unsigned blocks = unsigned((n_points + b200pm::kPmThreads - 1) / b200pm::kPmThreads);
+	b200pm::pmLookupKernel<2><<<blocks, b200pm::kPmThreads, 0, stream>>>(map->d_nodes, map->d_dirs, d_points, d_normals, uint32_t(n_points), 1u, dist, nullptr, nullptr,
+	                                                                 nullptr, nullptr, d_out);
+	PM_CUDA_TRY(cudaGetLastError());
+	b200::countLaunches(1);
+	return B200RT_OK;
+}
+
+constexpr size_t kMaxPoints = size_t(1) << 31; // blocks * 64 threads must fit the x grid dimension and uint32 point ids
+
+size_t alignUp(size_t v) { return (v + 255) & ~size_t(255); }
+
+} // namespace
+
+extern "C" {
+
+int b200pm_host_tree_build(const float *pos, size_t n, int build_threads, uint32_t *a, uint32_t *b)
+{
+	if(!pos || !a || !b || !n || n >= (size_t(1) << 29)) return failWith(B200RT_E_INVALID, "b200pm_host_tree_build: need 1 <= n < 2^29 photons and non-null arrays");
+	try
+	{
+		b200pm::HostTree tree;
+		b200pm::buildTree(pos, n, build_threads, tree);
+		std::memcpy(a, tree.a.data(), 4 * tree.a.size());
+		std::memcpy(b, tree.b.data(), 4 * tree.b.size());
+	}
+	catch(const std::bad_alloc &) { return failWith(B200RT_E_MEMORY, "out of host memory"); }
+	catch(const std::exception &e) { return failWith(B200RT_E_INVALID, e.what()); }
+	return B200RT_OK;
+}
+
+int b200pm_create(int device, const float *pos, const float *dir, size_t n, int build_threads, b200pm_map **out)
+{
+	if(!out) return failWith(B200RT_E_INVALID, "null argument");
+	*out = nullptr;
+	if(!pos || !n || n >= (size_t(1) << 29)) return failWith(B200RT_E_INVALID, "b200pm_create: need 1 <= n < 2^29 photons");
+	int count = 0;
+	const int rc = b200rt_device_count(&count);
+	if(rc != B200RT_OK) return rc;
+	if(device < 0 || device >= count) return failWith(B200RT_E_NO_DEVICE, "b200pm_create: no such CUDA device");
+	PM_CUDA_TRY(cudaSetDevice(device));
+	b200pm_map *map = nullptr;
+	try
+	{
+		map = new b200pm_map;
+		map->device = device;
+		map->n_photons = n;
+		map->n_nodes = 2 * n - 1;
+		map->has_dirs = dir != nullptr;
+		const double t0 = now();
+		b200pm::HostTree tree;
+		b200pm::buildTree(pos, n, build_threads, tree);
+		// pack: the leaf carries its photon's position
+		std::vector<uint4> nodes(map->n_nodes);
+		for(size_t i = 0; i < map->n_nodes; ++i)
+		{
+			if((tree.b[i] & 3u) == 3u)
+			{
+				const uint32_t photon = tree.a[i];
+				uint32_t xyz[3];
+				std::memcpy(xyz, pos + 3 * size_t(photon), 12);
+				nodes[i] = make_uint4(xyz[0], xyz[1], xyz[2], (photon << 2) | 3u);
+			}
+			else
+				nodes[i] = make_uint4(tree.a[i], 0u, 0u, tree.b[i]);
+		}
+		const double t1 = now();
+		map->stats.n_photons = n;
+		map->stats.n_nodes = map->n_nodes;
+		map->stats.depth = tree.depth;
+		map->stats.build_seconds = t1 - t0;
+		cudaError_t e = cudaMalloc(&map->d_nodes, sizeof(uint4) * map->n_nodes);
+		if(e == cudaSuccess) e = cudaMemcpy(map->d_nodes, nodes.data(), sizeof(uint4) * map->n_nodes, cudaMemcpyHostToDevice);
+		map->stats.device_bytes = sizeof(uint4) * map->n_nodes;
+		if(e == cudaSuccess && dir)
+		{
+			std::vector<float4> dirs(n);
+			for(size_t i = 0; i < n; ++i) dirs[i] = make_float4(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2], 0.f);
+			e = cudaMalloc(&map->d_dirs, sizeof(float4) * n);
+			if(e == cudaSuccess) e = cudaMemcpy(map->d_dirs, dirs.data(), sizeof(float4) * n, cudaMemcpyHostToDevice);
+			map->stats.device_bytes += sizeof(float4) * n;
+		}
+		if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&map->stream, cudaStreamNonBlocking);
+		if(e != cudaSuccess)
+		{
+			delete map;
+			return failWith(B200RT_E_CUDA, std::string("b200pm_create: ") + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+		}
+		map->stats.upload_seconds = now() - t1;
+	}
+	catch(const std::bad_alloc &) { delete map; return failWith(B200RT_E_MEMORY, "out of host memory"); }
+	catch(const std::exception &e) { delete map; return failWith(B200RT_E_INVALID, e.what()); }
+	*out = map;
+	return B200RT_OK;
+}
+
+void b200pm_destroy(b200pm_map *map) { delete map; }
+
+int b200pm_get_stats(const b200pm_map *map, b200pm_stats *out)
+{
+	if(!map || !out) return failWith(B200RT_E_INVALID, "null argument");
+	*out = map->stats;
+	return B200RT_OK;
+}
+
+int b200pm_gather_device(b200pm_map *map, const float *d_points, size_t n_points, uint32_t k, float sq_radius, const float *d_sq_radii, b200pm_found *d_found,
+                         uint32_t *d_n_found, float *d_sq_radius_out, void *stream)
+{
+	if(!map || (n_points && (!d_points || !d_found || !d_n_found))) return failWith(B200RT_E_INVALID, "b200pm_gather_device: null argument");
+	if(!k) return failWith(B200RT_E_INVALID, "b200pm_gather: k must be at least 1");
+	if(n_points >= kMaxPoints) return failWith(B200RT_E_INVALID, "b200pm_gather: at most 2^31 - 1 points per call");
+	PM_CUDA_TRY(cudaSetDevice(map->device));
+	return launchGather(map, d_points, n_points, k, sq_radius, d_sq_radii, d_found, d_n_found, d_sq_radius_out, static_cast<cudaStream_t>(stream));
+}
+
+int b200pm_gather(b200pm_map *map, const float *points, size_t n_points, uint32_t k, float sq_radius, const float *sq_radii, b200pm_found *found, uint32_t *n_found,
+                  float *sq_radius_out)
+{
+	if(!map || (n_points && (!points || !found || !n_found))) return failWith(B200RT_E_INVALID, "b200pm_gather: null argument");
+	if(!k) return failWith(B200RT_E_INVALID, "b200pm_gather: k must be at least 1");
+	if(n_points >= kMaxPoints) return failWith(B200RT_E_INVALID, "b200pm_gather: at most 2^31 - 1 points per call");
+	if(!n_points) return B200RT_OK;
+	std::lock_guard<std::mutex> lock(map->host_call);
+	PM_CUDA_TRY(cudaSetDevice(map->device));
+	// device scratch: [points | radii] in, [found | n_found | radius_out] out
+	const size_t in_points = alignUp(12 * n_points), in_radii = alignUp(4 * n_points);
+	const size_t out_found = alignUp(sizeof(b200pm_found) * n_points * k), out_count = alignUp(4 * n_points), out_radius = alignUp(4 * n_points);
+	int rc = map->in.reserve(in_points + in_radii);
+	if(rc == B200RT_OK) rc = map->out.reserve(out_found + out_count + out_radius);
+	if(rc != B200RT_OK) return rc;
+	char *d_in = static_cast<char *>(map->in.ptr), *d_out = static_cast<char *>(map->out.ptr);
+	float *d_points = reinterpret_cast<float *>(d_in), *d_radii = reinterpret_cast<float *>(d_in + in_points);
+	b200pm_found *d_found = reinterpret_cast<b200pm_found *>(d_out);
+	uint32_t *d_count = reinterpret_cast<uint32_t *>(d_out + out_found);
+	float *d_radius = reinterpret_cast<float *>(d_out + out_found + out_count);
+	PM_CUDA_TRY(cudaMemcpyAsync(d_points, points, 12 * n_points, cudaMemcpyHostToDevice, map->stream));
+	if(sq_radii) PM_CUDA_TRY(cudaMemcpyAsync(d_radii, sq_radii, 4 * n_points, cudaMemcpyHostToDevice, map->stream));
+	rc = launchGather(map, d_points, n_points, k, sq_radius, sq_radii ? d_radii : nullptr, d_found, d_count, d_radius, map->stream);
+	if(rc != B200RT_OK) return rc;
+	PM_CUDA_TRY(cudaMemcpyAsync(found, d_found, sizeof(b200pm_found) * n_points * k, cudaMemcpyDeviceToHost, map->stream));
+	PM_CUDA_TRY(cudaMemcpyAsync(n_found, d_count, 4 * n_points, cudaMemcpyDeviceToHost, map->stream));
+	if(sq_radius_out) PM_CUDA_TRY(cudaMemcpyAsync(sq_radius_out, d_radius, 4 * n_points, cudaMemcpyDeviceToHost, map->stream));
+	PM_CUDA_TRY(cudaStreamSynchronize(map->stream));
+	return B200RT_OK;
+}
+
+int b200pm_find_nearest_device(b200pm_map *map, const float *d_points, const float *d_normals, size_t n_points, float dist, uint32_t *d_out_photon, void *stream)
+{
+	if(!map || (n_points && (!d_points || !d_normals || !d_out_photon))) return failWith(B200RT_E_INVALID, "b200pm_find_nearest_device: null argument");
+	if(!map->has_dirs) return failWith(B200RT_E_INVALID, "b200pm_find_nearest: the map was created without photon directions");
+	if(n_points >= kMaxPoints) return failWith(B200RT_E_INVALID, "b200pm_find_nearest: at most 2^31 - 1 points per call");
+	PM_CUDA_TRY(cudaSetDevice(map->device));
+	return launchNearest(map, d_points, d_normals, n_points, dist, d_out_photon, static_cast<cudaStream_t>(stream));
+}
+
+int b200pm_find_nearest(b200pm_map *map, const float *points, const float *normals, size_t n_points, float dist, uint32_t *out_photon)
+{
+	if(!map || (n_points && (!points || !normals || !out_photon))) return failWith(B200RT_E_INVALID, "b200pm_find_nearest: null argument");
+	if(!map->has_dirs) return failWith(B200RT_E_INVALID, "b200pm_find_nearest: the map was created without photon directions");
+	if(n_points >= kMaxPoints) return failWith(B200RT_E_INVALID, "b200pm_find_nearest: at most 2^31 - 1 points per call");
+	if(!n_points) return B200RT_OK;
+	std::lock_guard<std::mutex> lock(map->host_call);
+	PM_CUDA_TRY(cudaSetDevice(map->device));
+	const size_t in_points = alignUp(12 * n_points);
+	int rc = map->in.reserve(2 * in_points);
+	if(rc == B200RT_OK) rc = map->out.reserve(alignUp(4 * n_points));
+	if(rc != B200RT_OK) return rc;
+	char *d_in = static_cast<char *>(map->in.ptr);
+	float *d_points = reinterpret_cast<float *>(d_in), *d_normals = reinterpret_cast<float *>(d_in + in_points);
+	uint32_t *d_out = static_cast<uint32_t *>(map->out.ptr);
+	PM_CUDA_TRY(cudaMemcpyAsync(d_points, points, 12 * n_points, cudaMemcpyHostToDevice, map->stream));
+	PM_CUDA_TRY(cudaMemcpyAsync(d_normals, normals, 12 * n_points, cudaMemcpyHostToDevice, map->stream));
+	rc = launchNearest(map, d_points, d_normals, n_points, dist, d_out, map->stream);
+	if(rc != B200RT_OK) return rc;
+	PM_CUDA_TRY(cudaMemcpyAsync(out_photon, d_out, 4 * n_points, cudaMemcpyDeviceToHost, map->stream));
+	PM_CUDA_TRY(cudaStreamSynchronize(map->stream));
+	return B200RT_OK;
+}
+
+} // extern "C"

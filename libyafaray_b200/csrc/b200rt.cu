@@ -711,6 +711,12 @@ void b200rt_scene::stopCombiner()
 	combiner.reset();
 }
 
+// shared with the other translation units of the library (b200pm.cu): one error text per thread, one launch counter
+namespace b200 {
+int failWith(int code, const std::string &msg) { return fail(code, msg); }
+void countLaunches(uint64_t n) { g_launches += n; }
+} // namespace b200
+
 extern "C" {
 
 int b200rt_version(void) { return B200RT_VERSION; }

@@ -1,0 +1,249 @@
+// libyafaray_b200/csrc/pm_kernels.cuh -- photon-map lookups on sm_100a (include/b200pm.h).
+//
+// One thread answers one query point: it walks the reference's point kd-tree in the reference's order
+// (PointKdTree::lookup, include/photon/pkdtree.h:221-279) and feeds the photons it meets to the reference's lookup procedure
+// (PhotonGather src/photon/photon.cc:26-44, NearestPhoton include/photon/photon.h:101-109).  The arithmetic is the reference's,
+// operation for operation (__f*_rn: no FMA contraction), so counts, orders, distances and radii come out bit-identical.
+//
+// Data layout (HBM): one 16-byte node per tree node, read with a single 128-bit load --
+//   interior  x = split (float bits)   w = (right child << 2) | axis         left child = this + 1
+//   leaf      x y z = photon position  w = (photon index << 2) | 3
+// -- the leaf carries the position, so testing a photon costs no second dependent load; dirs (float4 per photon) are read only
+// by findNearest, and only for photons inside the radius.
+//
+// Per-thread state: the traversal stack (far child, split, axis: 8 bytes per level) lives in local memory, interleaved per lane
+// by the hardware (one 128-byte line per warp and level); the k-entry max-heap of a gather lives in shared memory, interleaved
+// per thread ([entry][thread], 8-byte entries), when k * 8 * kPmThreads fits (k <= kPmSmemK), else directly in the caller's
+// `found` array.  Shared-memory heaps are copied out to `found` at the end.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <cuda_runtime.h>
+#include "../../include/b200pm.h"
+
+namespace b200pm {
+
+constexpr int kPmThreads = 64;      // threads per block of the lookup kernels
+constexpr uint32_t kPmSmemK = 256;  // largest k whose heaps live in shared memory (256 * 8 * 64 = 128 KiB per block)
+constexpr int kPmStack = 40;        // tree depth <= 30 for n < 2^29 photons; the lookup pushes one entry per level + sentinel
+constexpr uint32_t kPmEmpty = 0xFFFFFFFFu;
+
+// The lookup itself is __host__ __device__: tests/native/pm_host_model.cu runs the SAME code on the CPU (one "thread" at a time)
+// so that the CPU test-suite checks the kernel's logic against the reference without a GPU.  On the device the arithmetic uses
+// the round-to-nearest intrinsics (never contracted into FMAs); the host build has no FMA target.
+#ifdef __CUDA_ARCH__
+#define PM_HD __host__ __device__ __forceinline__
+__device__ __forceinline__ float pmSub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float pmAdd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float pmMul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float pmBitsToFloat(uint32_t u) { return __uint_as_float(u); }
+__device__ __forceinline__ uint32_t pmFloatToBits(float f) { return __float_as_uint(f); }
+__device__ __forceinline__ uint4 pmLoadNode(const uint4 *p) { return __ldg(p); }
+__device__ __forceinline__ float4 pmLoadDir(const float4 *p) { return __ldg(p); }
+#else
+#define PM_HD __host__ __device__ inline
+inline float pmSub(float a, float b) { return a - b; }
+inline float pmAdd(float a, float b) { return a + b; }
+inline float pmMul(float a, float b) { return a * b; }
+inline float pmBitsToFloat(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+inline uint32_t pmFloatToBits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+inline uint4 pmLoadNode(const uint4 *p) { return *p; }
+inline float4 pmLoadDir(const float4 *p) { return *p; }
+#endif
+
+struct HeapSmem
+{
+	uint2 *base; // &smem[threadIdx.x]; entry j at base[j * kPmThreads]
+	PM_HD uint2 get(int j) const { return base[j * kPmThreads]; }
+	PM_HD void set(int j, uint2 v) const { base[j * kPmThreads] = v; }
+};
+struct HeapGlobal
+{
+	uint2 *base; // &found[point * k]
+	PM_HD uint2 get(int j) const { return base[j]; }
+	PM_HD void set(int j, uint2 v) const { base[j] = v; }
+};
+
+PM_HD float heapKey(uint2 v) { return pmBitsToFloat(v.y); }
+
+// libstdc++ std::__push_heap (bits/stl_heap.h) for FoundPhoton::operator< (dist_square_ <)
+template <typename Heap>
+PM_HD void heapPush(const Heap &h, int hole, int top, uint2 value)
+{
+	int parent = (hole - 1) / 2;
+	while(hole > top)
+	{
+		const uint2 pv = h.get(parent);
+		if(!(heapKey(pv) < heapKey(value))) break;
+		h.set(hole, pv);
+		hole = parent;
+		parent = (hole - 1) / 2;
+	}
+	h.set(hole, value);
+}
+
+// libstdc++ std::__adjust_heap
+template <typename Heap>
+PM_HD void heapAdjust(const Heap &h, int hole, int len, uint2 value)
+{
+	const int top = hole;
+	int second = hole;
+	while(second < (len - 1) / 2)
+	{
+		second = 2 * (second + 1);
+		uint2 sv = h.get(second);
+		const uint2 lv = h.get(second - 1);
+		if(heapKey(sv) < heapKey(lv)) { --second; sv = lv; }
+		h.set(hole, sv);
+		hole = second;
+	}
+	if((len & 1) == 0 && second == (len - 2) / 2)
+	{
+		second = 2 * (second + 1);
+		h.set(hole, h.get(second - 1));
+		hole = second - 1;
+	}
+	heapPush(h, hole, top, value);
+}
+
+// libstdc++ std::__make_heap
+template <typename Heap>
+PM_HD void heapMake(const Heap &h, int len)
+{
+	if(len < 2) return;
+	int parent = (len - 2) / 2;
+	for(;;)
+	{
+		const uint2 value = h.get(parent);
+		heapAdjust(h, parent, len, value);
+		if(parent == 0) return;
+		--parent;
+	}
+}
+
+// PhotonGather::operator() (photon.cc:26-44)
+template <typename Heap>
+PM_HD void gatherProc(const Heap &h, uint32_t n_lookup, uint32_t &n_found, uint32_t photon, float dist_2, float &max_dist_squared)
+{
+	const uint2 entry = make_uint2(photon, pmFloatToBits(dist_2));
+	if(n_found < n_lookup)
+	{
+		h.set(int(n_found++), entry);
+		if(n_found == n_lookup)
+		{
+			heapMake(h, int(n_lookup));
+			max_dist_squared = heapKey(h.get(0));
+		}
+	}
+	else
+	{
+		const int n = int(n_lookup);
+		if(n > 1)
+		{
+			// std::pop_heap: the top moves to [n - 1] (overwritten just below), the old last entry is sifted in from the root
+			const uint2 value = h.get(n - 1);
+			heapAdjust(h, 0, n - 1, value);
+		}
+		// found[n - 1] = {photon, dist_2}; std::push_heap
+		heapPush(h, n - 1, 0, entry);
+		max_dist_squared = heapKey(h.get(0));
+	}
+}
+
+// MODE 0: gather with the heap in shared memory, 1: gather with the heap in `found`, 2: findNearest
+// One query point, start to finish.  heap_s: this thread's shared-memory heap (MODE 0 only).
+template <int MODE>
+PM_HD void pmLookupOne(const uint4 *__restrict__ nodes, const float4 *__restrict__ dirs, const float *__restrict__ points, const float *__restrict__ normals,
+                       uint32_t point, uint32_t k, float sq_radius, const float *__restrict__ sq_radii, uint2 *__restrict__ found, uint32_t *__restrict__ n_found_out,
+                       float *__restrict__ sq_radius_out, uint32_t *__restrict__ nearest_out, const HeapSmem heap_s)
+{
+	const float px = points[3 * size_t(point)], py = points[3 * size_t(point) + 1], pz = points[3 * size_t(point) + 2];
+	float nx = 0.f, ny = 0.f, nz = 0.f;
+	if(MODE == 2)
+	{
+		nx = normals[3 * size_t(point)];
+		ny = normals[3 * size_t(point) + 1];
+		nz = normals[3 * size_t(point) + 2];
+	}
+	float max_dist_squared = sq_radii ? sq_radii[point] : sq_radius;
+	uint32_t n_found = 0, nearest = kPmEmpty;
+	const HeapGlobal heap_g{MODE == 2 ? nullptr : found + size_t(point) * k};
+
+	uint32_t st_node[kPmStack]; // (far child << 2) | axis of the parent's split
+	float st_split[kPmStack];
+	int sp = 1;
+	st_node[1] = kPmEmpty; // "nowhere", the reference's termination flag (pkdtree.h:230)
+	uint32_t curr = 0;
+	for(;;)
+	{
+		uint4 node = pmLoadNode(nodes + curr);
+		while((node.w & 3u) != 3u)
+		{
+			const uint32_t axis = node.w & 3u;
+			const float split = pmBitsToFloat(node.x);
+			const float pa = axis == 0 ? px : (axis == 1 ? py : pz);
+			const uint32_t right = node.w >> 2;
+			uint32_t far_child;
+			if(pa <= split) { far_child = right; curr = curr + 1; }
+			else { far_child = curr + 1; curr = right; }
+			++sp;
+			st_node[sp] = (far_child << 2) | axis;
+			st_split[sp] = split;
+			node = pmLoadNode(nodes + curr);
+		}
+		{
+			const float vx = pmSub(pmBitsToFloat(node.x), px), vy = pmSub(pmBitsToFloat(node.y), py), vz = pmSub(pmBitsToFloat(node.z), pz);
+			const float dist_2 = pmAdd(pmAdd(pmMul(vx, vx), pmMul(vy, vy)), pmMul(vz, vz));
+			if(dist_2 < max_dist_squared)
+			{
+				const uint32_t photon = node.w >> 2;
+				if(MODE == 0) gatherProc(heap_s, k, n_found, photon, dist_2, max_dist_squared);
+				else if(MODE == 1) gatherProc(heap_g, k, n_found, photon, dist_2, max_dist_squared);
+				else
+				{
+					const float4 d = pmLoadDir(dirs + photon);
+					const float dot = pmAdd(pmAdd(pmMul(d.x, nx), pmMul(d.y, ny)), pmMul(d.z, nz));
+					if(dot > 0.f) { nearest = photon; max_dist_squared = dist_2; }
+				}
+			}
+		}
+		if(st_node[sp] == kPmEmpty) break;
+		bool done = false;
+		for(;;)
+		{
+			const uint32_t axis = st_node[sp] & 3u;
+			const float pa = axis == 0 ? px : (axis == 1 ? py : pz);
+			float d = pmSub(pa, st_split[sp]);
+			d = pmMul(d, d);
+			if(!(d > max_dist_squared)) break;
+			--sp;
+			if(st_node[sp] == kPmEmpty) { done = true; break; }
+		}
+		if(done) break;
+		curr = st_node[sp] >> 2;
+		--sp;
+	}
+	if(MODE == 2)
+	{
+		nearest_out[point] = nearest;
+		return;
+	}
+	if(MODE == 0)
+		for(uint32_t j = 0; j < n_found; ++j) heap_g.set(int(j), heap_s.get(int(j)));
+	n_found_out[point] = n_found;
+	if(sq_radius_out) sq_radius_out[point] = max_dist_squared;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kPmThreads) pmLookupKernel(const uint4 *__restrict__ nodes, const float4 *__restrict__ dirs, const float *__restrict__ points,
+                                                             const float *__restrict__ normals, uint32_t n_points, uint32_t k, float sq_radius,
+                                                             const float *__restrict__ sq_radii, uint2 *__restrict__ found, uint32_t *__restrict__ n_found_out,
+                                                             float *__restrict__ sq_radius_out, uint32_t *__restrict__ nearest_out)
+{
+	extern __shared__ uint2 pm_heap_smem[];
+	const uint32_t point = blockIdx.x * uint32_t(kPmThreads) + threadIdx.x;
+	if(point >= n_points) return;
+	pmLookupOne<MODE>(nodes, dirs, points, normals, point, k, sq_radius, sq_radii, found, n_found_out, sq_radius_out, nearest_out, HeapSmem{pm_heap_smem + threadIdx.x});
+}
+
+} // namespace b200pm

@@ -375,3 +375,58 @@ def ray_times(n: int, seed: int = 1):
     special = np.array([0.0, 1.0, 0.1, 0.9, 0.25, 0.75, 0.5, -0.5, 1.5], np.float32)
     t[:: max(1, n // 200)] = special[np.arange(len(t[:: max(1, n // 200)])) % len(special)]
     return t
+
+
+# ---- photon maps: synthetic photon sets and gather points ------------------------------------------
+
+def photon_cloud(kind: str = "surfaces", n: int = 100_000, seed: int = 12345):
+    """Synthetic photons: (pos [n,3] f32, dir [n,3] f32).
+
+    uniform   -- uniform in the unit cube
+    surfaces  -- on the six walls and the floor-parallel shelves of a box (what a diffuse photon map looks like: every photon
+                 shares one coordinate with thousands of others, so the median splits meet exact ties)
+    clusters  -- tight Gaussian blobs on a floor plus a thin uniform background (a caustic map)
+    lattice   -- an integer lattice with every point stored several times (exact duplicates: the build's index tie-break
+                 and the lookup's `<=` decide)
+    """
+    rng = np.random.default_rng(seed)
+    if kind == "uniform":
+        pos = rng.random((n, 3), dtype=np.float32)
+    elif kind == "surfaces":
+        pos = rng.random((n, 3), dtype=np.float32)
+        which = rng.integers(0, 8, n)
+        axis = np.array([0, 0, 1, 1, 2, 2, 2, 2])[which]
+        value = np.array([0.0, 1.0, 0.0, 1.0, 0.0, 1.0, 0.25, 0.625], np.float32)[which]
+        pos[np.arange(n), axis] = value
+    elif kind == "clusters":
+        n_bg = n // 10
+        centres = rng.random((24, 3), dtype=np.float32)
+        centres[:, 2] = 0.0
+        which = rng.integers(0, len(centres), n - n_bg)
+        blob = centres[which] + (rng.standard_normal((n - n_bg, 3)) * np.array([0.01, 0.01, 0.0])).astype(np.float32)
+        pos = np.concatenate([blob.astype(np.float32), rng.random((n_bg, 3), dtype=np.float32)])
+        pos = pos[rng.permutation(n)]
+    elif kind == "lattice":
+        side = max(2, int(round((n / 3) ** (1 / 3))))
+        pts = rng.integers(0, side, (n, 3)).astype(np.float32) / np.float32(side)
+        pos = pts
+    else:
+        raise ValueError(kind)
+    d = rng.standard_normal((n, 3)).astype(np.float32)
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-20).astype(np.float32)
+    return np.ascontiguousarray(pos, np.float32), np.ascontiguousarray(d, np.float32)
+
+
+def gather_points(pos, n: int, seed: int = 777, jitter: float = 0.01, outside: float = 0.05):
+    """Query points of a gather: most of them near photons (a shading point lies on the surface the photons landed on), a few
+    exactly ON a photon, a few outside the map's bound.  Returns (points [n,3] f32, normals [n,3] f32)."""
+    rng = np.random.default_rng(seed)
+    base = pos[rng.integers(0, len(pos), n)]
+    pts = base + (rng.standard_normal((n, 3)) * jitter).astype(np.float32)
+    exact = rng.random(n) < 0.05
+    pts[exact] = base[exact]
+    far = rng.random(n) < outside
+    pts[far] = (rng.random((int(far.sum()), 3)) * 3.0 - 1.0).astype(np.float32)
+    nrm = rng.standard_normal((n, 3)).astype(np.float32)
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-20).astype(np.float32)
+    return np.ascontiguousarray(pts, np.float32), np.ascontiguousarray(nrm, np.float32)
