@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-tshadow", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="skip the photon-map gather leg (key photon_gather)")
     return ap.parse_args()
 
 
@@ -456,6 +457,19 @@ def run_b200(args):
         del d_ts
         ts_scene.close()
 
+    # ---- photon-map gather (include/b200pm.h): own key, outside `value` and `gpu_launches`; tools/pm_bench.py ----
+    photon_gather = None
+    if not args.no_gather and rank == 0 and args.workload == "s1m":
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("pm_bench", os.path.join(ROOT, "tools", "pm_bench.py"))
+            pm_bench = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(pm_bench)
+            photon_gather = pm_bench.run(steps=max(2, min(args.steps, 5)), cpu_seconds=min(5.0, args.cpu_seconds), device=local,
+                                         cpu=(world == 1 and not args.no_cpu_baseline))
+        except Exception as exc:  # this leg must never take the judged line down
+            photon_gather = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ---- max over ranks ----
     t = torch.tensor([total_ms, closest_ms, shadow_ms, (e2e_s or 0.0) * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -531,6 +545,8 @@ def run_b200(args):
         }
         if tshadow:
             line["tshadow"] = tshadow
+        if photon_gather:
+            line["photon_gather"] = photon_gather
         if e2e_s is not None:
             line["e2e"] = {"value": world * 2 * n / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
                            "h2d_bytes_per_step": 2 * n * 32, "d2h_bytes_per_step": n * 16 + n * 4,

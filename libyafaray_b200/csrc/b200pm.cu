@@ -6,6 +6,7 @@
 #include "pm_kernels.cuh"
 
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -82,7 +83,13 @@ int launchGather(b200pm_map *map, const float *d_points, size_t n_points, uint32
 {
 	if(!n_points) return B200RT_OK;
 	const unsigned blocks = unsigned((n_points + b200pm::kPmThreads - 1) / b200pm::kPmThreads);
-	if(k <= b200pm::kPmSmemK)
+	// tuning aid (tools/pm_bench.py): B200PM_SMEM_K lowers the largest k whose heaps live in shared memory (0 = always in `found`)
+	static const uint32_t smem_k = [] {
+		const char *e = std::getenv("B200PM_SMEM_K");
+		const long v = e ? std::atol(e) : -1;
+		return v >= 0 && uint32_t(v) < b200pm::kPmSmemK ? uint32_t(v) : b200pm::kPmSmemK;
+	}();
+	if(k <= smem_k)
 	{
 		const size_t smem = size_t(k) * b200pm::kPmThreads * sizeof(uint2);
 		if(!map->smem_opt_in)
