@@ -85,6 +85,12 @@ int b200pm_find_nearest_device(b200pm_map *map, const float *d_points, const flo
  * split for an interior node, the photon index for a leaf; left child = i + 1.  a / b hold 2 n - 1 entries. */
 int b200pm_host_tree_build(const float *pos, size_t n, int build_threads, uint32_t *a, uint32_t *b);
 
+/* Tuning aid (tools/pm_sweep.py), process-wide, not for production use; a negative argument keeps the current value.
+ * phased: 1 = the phased lookup kernel (default), 0 = the plain per-thread loop; round_steps: node visits per round of the phased
+ * kernel; smem_k: largest k whose heaps live in shared memory (0 = always in `found`, at most 256).  The environment variables
+ * B200PM_KERNEL=plain|phased, B200PM_ROUND, B200PM_SMEM_K set the same at load time.  Results do not depend on any of them. */
+int b200pm_debug_set_tuning(int phased, int round_steps, int smem_k);
+
 #ifdef __cplusplus
 }
 #endif

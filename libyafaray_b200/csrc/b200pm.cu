@@ -5,6 +5,7 @@
 #include "pm_build.h"
 #include "pm_kernels.cuh"
 
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -62,9 +63,13 @@ struct b200pm_map
 	uint4 *d_nodes = nullptr;
 	float4 *d_dirs = nullptr;
 	b200pm_stats stats{};
-	cudaStream_t stream = nullptr; // host-buffer calls
-	std::mutex host_call;          // host-buffer calls on one map take turns (they share the scratch buffers)
-	Scratch in, out;
+	// host-buffer calls: two lanes (stream + device scratch) so that the copies of one chunk overlap the kernel of the next
+	struct HostLane
+	{
+		cudaStream_t stream = nullptr;
+		Scratch in, out;
+	} lanes[2];
+	std::mutex host_call; // host-buffer calls on one map take turns (they share the lanes)
 	bool smem_opt_in = false;
 
 	~b200pm_map()
@@ -72,38 +77,65 @@ struct b200pm_map
 		cudaSetDevice(device);
 		if(d_nodes) cudaFree(d_nodes);
 		if(d_dirs) cudaFree(d_dirs);
-		if(stream) cudaStreamDestroy(stream);
+		for(auto &lane : lanes)
+			if(lane.stream) cudaStreamDestroy(lane.stream);
 	}
 };
 
 namespace {
 
+// Tuning aids, read once (tools/pm_bench.py sweeps them; the defaults are the measured best, profiles/r6*_pm_*.json):
+//   B200PM_KERNEL=plain   the plain per-thread loop (pmLookupKernel) instead of the phased state machine (pmLookupPhasedKernel)
+//   B200PM_ROUND=<n>      steps per round of the phased kernel
+//   B200PM_SMEM_K=<k>     largest k whose heaps live in shared memory (0 = always in `found`)
+struct Tuning
+{
+	bool phased = true;
+	int round_steps = 8;
+	uint32_t smem_k = 16;
+	Tuning()
+	{
+		if(const char *e = std::getenv("B200PM_KERNEL")) phased = std::string(e) != "plain";
+		if(const char *e = std::getenv("B200PM_ROUND")) { const long v = std::atol(e); if(v >= 1 && v <= 4096) round_steps = int(v); }
+		if(const char *e = std::getenv("B200PM_SMEM_K")) { const long v = std::atol(e); if(v >= 0 && uint32_t(v) <= b200pm::kPmSmemK) smem_k = uint32_t(v); }
+	}
+};
+Tuning &tuning()
+{
+	static Tuning t;
+	return t;
+}
+
 int launchGather(b200pm_map *map, const float *d_points, size_t n_points, uint32_t k, float sq_radius, const float *d_sq_radii, b200pm_found *d_found,
                  uint32_t *d_n_found, float *d_sq_radius_out, cudaStream_t stream)
 {
 	if(!n_points) return B200RT_OK;
+	const Tuning t = tuning();
 	const unsigned blocks = unsigned((n_points + b200pm::kPmThreads - 1) / b200pm::kPmThreads);
-	// tuning aid (tools/pm_bench.py): B200PM_SMEM_K lowers the largest k whose heaps live in shared memory (0 = always in `found`)
-	static const uint32_t smem_k = [] {
-		const char *e = std::getenv("B200PM_SMEM_K");
-		const long v = e ? std::atol(e) : -1;
-		return v >= 0 && uint32_t(v) < b200pm::kPmSmemK ? uint32_t(v) : b200pm::kPmSmemK;
-	}();
-	if(k <= smem_k)
+	uint2 *found2 = reinterpret_cast<uint2 *>(d_found);
+	if(k <= t.smem_k)
 	{
 		const size_t smem = size_t(k) * b200pm::kPmThreads * sizeof(uint2);
 		if(!map->smem_opt_in)
 		{
-			PM_CUDA_TRY(cudaFuncSetAttribute(b200pm::pmLookupKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-			                                 int(size_t(b200pm::kPmSmemK) * b200pm::kPmThreads * sizeof(uint2))));
+			const int most = int(size_t(b200pm::kPmSmemK) * b200pm::kPmThreads * sizeof(uint2));
+			PM_CUDA_TRY(cudaFuncSetAttribute(b200pm::pmLookupKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+			PM_CUDA_TRY(cudaFuncSetAttribute(b200pm::pmLookupPhasedKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
 			map->smem_opt_in = true;
 		}
-		b200pm::pmLookupKernel<0><<<blocks, b200pm::kPmThreads, smem, stream>>>(map->d_nodes, map->d_dirs, d_points, nullptr, uint32_t(n_points), k, sq_radius, d_sq_radii,
-		                                                                    reinterpret_cast<uint2 *>(d_found), d_n_found, d_sq_radius_out, nullptr);
+		if(t.phased)
+			b200pm::pmLookupPhasedKernel<0><<<blocks, b200pm::kPmThreads, smem, stream>>>(map->d_nodes, map->d_dirs, d_points, nullptr, uint32_t(n_points), k, sq_radius,
+			                                                                          d_sq_radii, found2, d_n_found, d_sq_radius_out, nullptr, t.round_steps);
+		else
+			b200pm::pmLookupKernel<0><<<blocks, b200pm::kPmThreads, smem, stream>>>(map->d_nodes, map->d_dirs, d_points, nullptr, uint32_t(n_points), k, sq_radius, d_sq_radii,
+			                                                                    found2, d_n_found, d_sq_radius_out, nullptr);
 	}
+	else if(t.phased)
+		b200pm::pmLookupPhasedKernel<1><<<blocks, b200pm::kPmThreads, 0, stream>>>(map->d_nodes, map->d_dirs, d_points, nullptr, uint32_t(n_points), k, sq_radius, d_sq_radii,
+		                                                                       found2, d_n_found, d_sq_radius_out, nullptr, t.round_steps);
 	else
 		b200pm::pmLookupKernel<1><<<blocks, b200pm::kPmThreads, 0, stream>>>(map->d_nodes, map->d_dirs, d_points, nullptr, uint32_t(n_points), k, sq_radius, d_sq_radii,
-		                                                                 reinterpret_cast<uint2 *>(d_found), d_n_found, d_sq_radius_out, nullptr);
+		                                                                 found2, d_n_found, d_sq_radius_out, nullptr);
 	PM_CUDA_TRY(cudaGetLastError());
 	b200::countLaunches(1);
 	return B200RT_OK;
@@ -112,9 +144,14 @@ int launchGather(b200pm_map *map, const float *d_points, size_t n_points, uint32
 int launchNearest(b200pm_map *map, const float *d_points, const float *d_normals, size_t n_points, float dist, uint32_t *d_out, cudaStream_t stream)
 {
 	if(!n_points) return B200RT_OK;
+	const Tuning t = tuning();
 	const unsigned blocks = unsigned((n_points + b200pm::kPmThreads - 1) / b200pm::kPmThreads);
-	b200pm::pmLookupKernel<2><<<blocks, b200pm::kPmThreads, 0, stream>>>(map->d_nodes, map->d_dirs, d_points, d_normals, uint32_t(n_points), 1u, dist, nullptr, nullptr,
-	                                                                 nullptr, nullptr, d_out);
+	if(t.phased)
+		b200pm::pmLookupPhasedKernel<2><<<blocks, b200pm::kPmThreads, 0, stream>>>(map->d_nodes, map->d_dirs, d_points, d_normals, uint32_t(n_points), 1u, dist, nullptr,
+		                                                                       nullptr, nullptr, nullptr, d_out, t.round_steps);
+	else
+		b200pm::pmLookupKernel<2><<<blocks, b200pm::kPmThreads, 0, stream>>>(map->d_nodes, map->d_dirs, d_points, d_normals, uint32_t(n_points), 1u, dist, nullptr, nullptr,
+		                                                                 nullptr, nullptr, d_out);
 	PM_CUDA_TRY(cudaGetLastError());
 	b200::countLaunches(1);
 	return B200RT_OK;
@@ -140,6 +177,15 @@ int b200pm_host_tree_build(const float *pos, size_t n, int build_threads, uint32
 	}
 	catch(const std::bad_alloc &) { return failWith(B200RT_E_MEMORY, "out of host memory"); }
 	catch(const std::exception &e) { return failWith(B200RT_E_INVALID, e.what()); }
+	return B200RT_OK;
+}
+
+int b200pm_debug_set_tuning(int phased, int round_steps, int smem_k)
+{
+	Tuning &t = tuning();
+	if(phased >= 0) t.phased = phased != 0;
+	if(round_steps >= 1) t.round_steps = round_steps;
+	if(smem_k >= 0 && uint32_t(smem_k) <= b200pm::kPmSmemK) t.smem_k = uint32_t(smem_k);
 	return B200RT_OK;
 }
 
@@ -194,7 +240,8 @@ int b200pm_create(int device, const float *pos, const float *dir, size_t n, int 
 			if(e == cudaSuccess) e = cudaMemcpy(map->d_dirs, dirs.data(), sizeof(float4) * n, cudaMemcpyHostToDevice);
 			map->stats.device_bytes += sizeof(float4) * n;
 		}
-		if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&map->stream, cudaStreamNonBlocking);
+		for(auto &lane : map->lanes)
+			if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&lane.stream, cudaStreamNonBlocking);
 		if(e != cudaSuccess)
 		{
 			delete map;
@@ -236,25 +283,40 @@ int b200pm_gather(b200pm_map *map, const float *points, size_t n_points, uint32_
 	if(!n_points) return B200RT_OK;
 	std::lock_guard<std::mutex> lock(map->host_call);
 	PM_CUDA_TRY(cudaSetDevice(map->device));
-	// device scratch: [points | radii] in, [found | n_found | radius_out] out
-	const size_t in_points = alignUp(12 * n_points), in_radii = alignUp(4 * n_points);
-	const size_t out_found = alignUp(sizeof(b200pm_found) * n_points * k), out_count = alignUp(4 * n_points), out_radius = alignUp(4 * n_points);
-	int rc = map->in.reserve(in_points + in_radii);
-	if(rc == B200RT_OK) rc = map->out.reserve(out_found + out_count + out_radius);
-	if(rc != B200RT_OK) return rc;
-	char *d_in = static_cast<char *>(map->in.ptr), *d_out = static_cast<char *>(map->out.ptr);
-	float *d_points = reinterpret_cast<float *>(d_in), *d_radii = reinterpret_cast<float *>(d_in + in_points);
-	b200pm_found *d_found = reinterpret_cast<b200pm_found *>(d_out);
-	uint32_t *d_count = reinterpret_cast<uint32_t *>(d_out + out_found);
-	float *d_radius = reinterpret_cast<float *>(d_out + out_found + out_count);
-	PM_CUDA_TRY(cudaMemcpyAsync(d_points, points, 12 * n_points, cudaMemcpyHostToDevice, map->stream));
-	if(sq_radii) PM_CUDA_TRY(cudaMemcpyAsync(d_radii, sq_radii, 4 * n_points, cudaMemcpyHostToDevice, map->stream));
-	rc = launchGather(map, d_points, n_points, k, sq_radius, sq_radii ? d_radii : nullptr, d_found, d_count, d_radius, map->stream);
-	if(rc != B200RT_OK) return rc;
-	PM_CUDA_TRY(cudaMemcpyAsync(found, d_found, sizeof(b200pm_found) * n_points * k, cudaMemcpyDeviceToHost, map->stream));
-	PM_CUDA_TRY(cudaMemcpyAsync(n_found, d_count, 4 * n_points, cudaMemcpyDeviceToHost, map->stream));
-	if(sq_radius_out) PM_CUDA_TRY(cudaMemcpyAsync(sq_radius_out, d_radius, 4 * n_points, cudaMemcpyDeviceToHost, map->stream));
-	PM_CUDA_TRY(cudaStreamSynchronize(map->stream));
+	// chunks of about 32 MiB of results alternate between the two lanes: with page-locked caller buffers the copy back of one
+	// chunk and the copy in of the next overlap the kernel in between (pageable buffers take the same path, the driver stages them)
+	const size_t per_point = sizeof(b200pm_found) * size_t(k) + 8;
+	size_t chunk = (size_t(32) << 20) / per_point;
+	chunk = std::max<size_t>(4096, std::min<size_t>(chunk, size_t(1) << 20));
+	chunk = std::min(chunk, n_points);
+	const size_t in_points = alignUp(12 * chunk), in_radii = alignUp(4 * chunk);
+	const size_t out_found = alignUp(sizeof(b200pm_found) * chunk * k), out_count = alignUp(4 * chunk), out_radius = alignUp(4 * chunk);
+	for(auto &lane : map->lanes)
+	{
+		int rc = lane.in.reserve(in_points + in_radii);
+		if(rc == B200RT_OK) rc = lane.out.reserve(out_found + out_count + out_radius);
+		if(rc != B200RT_OK) return rc;
+		if(n_points <= chunk) break; // one chunk: one lane
+	}
+	size_t index = 0;
+	for(size_t off = 0; off < n_points; off += chunk, ++index)
+	{
+		auto &lane = map->lanes[index & 1];
+		const size_t m = std::min(chunk, n_points - off);
+		char *d_in = static_cast<char *>(lane.in.ptr), *d_out = static_cast<char *>(lane.out.ptr);
+		float *d_points = reinterpret_cast<float *>(d_in), *d_radii = reinterpret_cast<float *>(d_in + in_points);
+		b200pm_found *d_found = reinterpret_cast<b200pm_found *>(d_out);
+		uint32_t *d_count = reinterpret_cast<uint32_t *>(d_out + out_found);
+		float *d_radius = reinterpret_cast<float *>(d_out + out_found + out_count);
+		PM_CUDA_TRY(cudaMemcpyAsync(d_points, points + 3 * off, 12 * m, cudaMemcpyHostToDevice, lane.stream));
+		if(sq_radii) PM_CUDA_TRY(cudaMemcpyAsync(d_radii, sq_radii + off, 4 * m, cudaMemcpyHostToDevice, lane.stream));
+		const int rc = launchGather(map, d_points, m, k, sq_radius, sq_radii ? d_radii : nullptr, d_found, d_count, d_radius, lane.stream);
+		if(rc != B200RT_OK) return rc;
+		PM_CUDA_TRY(cudaMemcpyAsync(found + off * k, d_found, sizeof(b200pm_found) * m * k, cudaMemcpyDeviceToHost, lane.stream));
+		PM_CUDA_TRY(cudaMemcpyAsync(n_found + off, d_count, 4 * m, cudaMemcpyDeviceToHost, lane.stream));
+		if(sq_radius_out) PM_CUDA_TRY(cudaMemcpyAsync(sq_radius_out + off, d_radius, 4 * m, cudaMemcpyDeviceToHost, lane.stream));
+	}
+	for(auto &lane : map->lanes) PM_CUDA_TRY(cudaStreamSynchronize(lane.stream));
 	return B200RT_OK;
 }
 
@@ -276,18 +338,19 @@ int b200pm_find_nearest(b200pm_map *map, const float *points, const float *norma
 	std::lock_guard<std::mutex> lock(map->host_call);
 	PM_CUDA_TRY(cudaSetDevice(map->device));
 	const size_t in_points = alignUp(12 * n_points);
-	int rc = map->in.reserve(2 * in_points);
-	if(rc == B200RT_OK) rc = map->out.reserve(alignUp(4 * n_points));
+	auto &lane = map->lanes[0];
+	int rc = lane.in.reserve(2 * in_points);
+	if(rc == B200RT_OK) rc = lane.out.reserve(alignUp(4 * n_points));
 	if(rc != B200RT_OK) return rc;
-	char *d_in = static_cast<char *>(map->in.ptr);
+	char *d_in = static_cast<char *>(lane.in.ptr);
 	float *d_points = reinterpret_cast<float *>(d_in), *d_normals = reinterpret_cast<float *>(d_in + in_points);
-	uint32_t *d_out = static_cast<uint32_t *>(map->out.ptr);
-	PM_CUDA_TRY(cudaMemcpyAsync(d_points, points, 12 * n_points, cudaMemcpyHostToDevice, map->stream));
-	PM_CUDA_TRY(cudaMemcpyAsync(d_normals, normals, 12 * n_points, cudaMemcpyHostToDevice, map->stream));
-	rc = launchNearest(map, d_points, d_normals, n_points, dist, d_out, map->stream);
+	uint32_t *d_out = static_cast<uint32_t *>(lane.out.ptr);
+	PM_CUDA_TRY(cudaMemcpyAsync(d_points, points, 12 * n_points, cudaMemcpyHostToDevice, lane.stream));
+	PM_CUDA_TRY(cudaMemcpyAsync(d_normals, normals, 12 * n_points, cudaMemcpyHostToDevice, lane.stream));
+	rc = launchNearest(map, d_points, d_normals, n_points, dist, d_out, lane.stream);
 	if(rc != B200RT_OK) return rc;
-	PM_CUDA_TRY(cudaMemcpyAsync(out_photon, d_out, 4 * n_points, cudaMemcpyDeviceToHost, map->stream));
-	PM_CUDA_TRY(cudaStreamSynchronize(map->stream));
+	PM_CUDA_TRY(cudaMemcpyAsync(out_photon, d_out, 4 * n_points, cudaMemcpyDeviceToHost, lane.stream));
+	PM_CUDA_TRY(cudaStreamSynchronize(lane.stream));
 	return B200RT_OK;
 }
 

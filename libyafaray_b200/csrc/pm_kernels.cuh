@@ -246,4 +246,206 @@ __global__ void __launch_bounds__(kPmThreads) pmLookupKernel(const uint4 *__rest
 	pmLookupOne<MODE>(nodes, dirs, points, normals, point, k, sq_radius, sq_radii, found, n_found_out, sq_radius_out, nearest_out, HeapSmem{pm_heap_smem + threadIdx.x});
 }
 
+// ---- phased lookup (the default) --------------------------------------------------------------------------------------------
+// The ncu source view of pmLookupKernel (profiles/r6a_pm_gather_smem_heap.txt) shows where the plain loop above loses the warp:
+// the descent loop runs at 5.3 of 32 lanes (lanes that reached their leaf wait for the longest descent), the stack pops at 6.2,
+// and the heap replacement -- 40 % of all warp instructions -- at 1.1 lanes, because each lane accepts a photon at a different
+// moment.  The same lookup as a per-lane state machine:
+//   pmStep     one node visit: (pop the stack if the last visit was a leaf) -> load the node -> interior: push the far child and
+//              step down | leaf: test the photon; a cheap accept (append below k - 1, findNearest) happens on the spot, an accept
+//              that needs heap work (the k-th photon: make_heap; later ones: pop_heap / push_heap) is only RECORDED (pending);
+//   pmResolve  the pending heap work.
+// The warp alternates a round of up to `round_steps` pmStep calls (a lane with pending work or without nodes left sits the round
+// out) with one pmResolve in which every pending lane does its heap work at the same time.  Visit order, accept tests and heap
+// calls of a lane are exactly those of the plain loop, so the results stay bit-identical; pmLookupPhasedOne (used by the host
+// model) runs the same two functions for one lane.
+struct PmLane
+{
+	float px, py, pz, nx, ny, nz;
+	float max_dist_squared;
+	uint32_t curr, n_found, nearest;
+	uint32_t cand_photon;
+	float cand_dist_2;
+	int sp;
+	bool alive, need_pop, pending;
+};
+
+template <int MODE, typename Heap>
+PM_HD void pmStep(PmLane &s, uint2 *stack, const uint4 *__restrict__ nodes, const float4 *__restrict__ dirs, uint32_t k, const Heap &heap)
+{
+	if(s.need_pop)
+	{
+		// pkdtree.h:263-278: leave the leaf -- drop far children whose split plane is beyond the search radius
+		for(;;)
+		{
+			const uint2 top = stack[s.sp];
+			if(top.x == kPmEmpty) { s.alive = false; return; }
+			const uint32_t axis = top.x & 3u;
+			const float pa = axis == 0 ? s.px : (axis == 1 ? s.py : s.pz);
+			float d = pmSub(pa, pmBitsToFloat(top.y));
+			d = pmMul(d, d);
+			--s.sp;
+			if(!(d > s.max_dist_squared)) { s.curr = top.x >> 2; break; }
+		}
+		s.need_pop = false;
+	}
+	const uint4 node = pmLoadNode(nodes + s.curr);
+	if((node.w & 3u) != 3u)
+	{
+		// pkdtree.h:234-252
+		const uint32_t axis = node.w & 3u;
+		const float split = pmBitsToFloat(node.x);
+		const float pa = axis == 0 ? s.px : (axis == 1 ? s.py : s.pz);
+		const uint32_t right = node.w >> 2;
+		uint32_t far_child;
+		if(pa <= split) { far_child = right; s.curr = s.curr + 1; }
+		else { far_child = s.curr + 1; s.curr = right; }
+		++s.sp;
+		stack[s.sp] = make_uint2((far_child << 2) | axis, node.x);
+		return;
+	}
+	// pkdtree.h:254-261
+	s.need_pop = true;
+	const float vx = pmSub(pmBitsToFloat(node.x), s.px), vy = pmSub(pmBitsToFloat(node.y), s.py), vz = pmSub(pmBitsToFloat(node.z), s.pz);
+	const float dist_2 = pmAdd(pmAdd(pmMul(vx, vx), pmMul(vy, vy)), pmMul(vz, vz));
+	if(!(dist_2 < s.max_dist_squared)) return;
+	const uint32_t photon = node.w >> 2;
+	if(MODE == 2)
+	{
+		const float4 d = pmLoadDir(dirs + photon);
+		const float dot = pmAdd(pmAdd(pmMul(d.x, s.nx), pmMul(d.y, s.ny)), pmMul(d.z, s.nz));
+		if(dot > 0.f) { s.nearest = photon; s.max_dist_squared = dist_2; }
+	}
+	else if(s.n_found + 1u < k)
+		heap.set(int(s.n_found++), make_uint2(photon, pmFloatToBits(dist_2))); // photon.cc:29-32, below the k-th photon
+	else
+	{
+		s.pending = true;
+		s.cand_photon = photon;
+		s.cand_dist_2 = dist_2;
+	}
+}
+
+template <typename Heap>
+PM_HD void pmResolve(PmLane &s, uint32_t k, const Heap &heap)
+{
+	gatherProc(heap, k, s.n_found, s.cand_photon, s.cand_dist_2, s.max_dist_squared);
+	s.pending = false;
+}
+
+PM_HD void pmLaneInit(PmLane &s, uint2 *stack, const float *__restrict__ points, const float *__restrict__ normals, bool with_normal, uint32_t point, float sq_radius,
+                      const float *__restrict__ sq_radii)
+{
+	s.px = points[3 * size_t(point)];
+	s.py = points[3 * size_t(point) + 1];
+	s.pz = points[3 * size_t(point) + 2];
+	s.nx = s.ny = s.nz = 0.f;
+	if(with_normal)
+	{
+		s.nx = normals[3 * size_t(point)];
+		s.ny = normals[3 * size_t(point) + 1];
+		s.nz = normals[3 * size_t(point) + 2];
+	}
+	s.max_dist_squared = sq_radii ? sq_radii[point] : sq_radius;
+	s.curr = 0;
+	s.n_found = 0;
+	s.nearest = kPmEmpty;
+	s.cand_photon = 0;
+	s.cand_dist_2 = 0.f;
+	s.sp = 1;
+	stack[1] = make_uint2(kPmEmpty, 0u); // "nowhere", the reference's termination flag (pkdtree.h:230)
+	s.alive = true;
+	s.need_pop = false;
+	s.pending = false;
+}
+
+template <int MODE>
+PM_HD void pmLaneFinish(const PmLane &s, uint32_t point, uint32_t k, uint2 *__restrict__ found, uint32_t *__restrict__ n_found_out, float *__restrict__ sq_radius_out,
+                        uint32_t *__restrict__ nearest_out, const HeapSmem heap_s)
+{
+	if(MODE == 2)
+	{
+		nearest_out[point] = s.nearest;
+		return;
+	}
+	if(MODE == 0)
+	{
+		const HeapGlobal heap_g{found + size_t(point) * k};
+		for(uint32_t j = 0; j < s.n_found; ++j) heap_g.set(int(j), heap_s.get(int(j)));
+	}
+	n_found_out[point] = s.n_found;
+	if(sq_radius_out) sq_radius_out[point] = s.max_dist_squared;
+}
+
+// one lane, start to finish, through the same state machine (host model; also what a warp of one lane would do)
+template <int MODE>
+PM_HD void pmLookupPhasedOne(const uint4 *__restrict__ nodes, const float4 *__restrict__ dirs, const float *__restrict__ points, const float *__restrict__ normals,
+                             uint32_t point, uint32_t k, float sq_radius, const float *__restrict__ sq_radii, uint2 *__restrict__ found,
+                             uint32_t *__restrict__ n_found_out, float *__restrict__ sq_radius_out, uint32_t *__restrict__ nearest_out, const HeapSmem heap_s, int round_steps)
+{
+	PmLane s;
+	uint2 stack[kPmStack];
+	pmLaneInit(s, stack, points, normals, MODE == 2, point, sq_radius, sq_radii);
+	const HeapGlobal heap_g{MODE == 2 ? nullptr : found + size_t(point) * k};
+	while(s.alive)
+	{
+		for(int step = 0; step < round_steps && s.alive && !s.pending; ++step)
+		{
+			if(MODE == 0) pmStep<MODE>(s, stack, nodes, dirs, k, heap_s);
+			else pmStep<MODE>(s, stack, nodes, dirs, k, heap_g);
+		}
+		if(s.pending)
+		{
+			if(MODE == 0) pmResolve(s, k, heap_s);
+			else pmResolve(s, k, heap_g);
+		}
+	}
+	pmLaneFinish<MODE>(s, point, k, found, n_found_out, sq_radius_out, nearest_out, heap_s);
+}
+
+#ifdef __CUDACC__
+template <int MODE>
+__global__ void __launch_bounds__(kPmThreads) pmLookupPhasedKernel(const uint4 *__restrict__ nodes, const float4 *__restrict__ dirs, const float *__restrict__ points,
+                                                                   const float *__restrict__ normals, uint32_t n_points, uint32_t k, float sq_radius,
+                                                                   const float *__restrict__ sq_radii, uint2 *__restrict__ found, uint32_t *__restrict__ n_found_out,
+                                                                   float *__restrict__ sq_radius_out, uint32_t *__restrict__ nearest_out, int round_steps)
+{
+	extern __shared__ uint2 pm_heap_smem[];
+	const uint32_t point = blockIdx.x * uint32_t(kPmThreads) + threadIdx.x;
+	const bool in_range = point < n_points;
+	PmLane s;
+	uint2 stack[kPmStack];
+	pmLaneInit(s, stack, points, normals, MODE == 2, in_range ? point : 0u, sq_radius, sq_radii);
+	s.alive = in_range;
+	const HeapSmem heap_s{pm_heap_smem + threadIdx.x};
+	const HeapGlobal heap_g{MODE == 2 ? nullptr : found + size_t(in_range ? point : 0u) * k};
+	// all 32 lanes stay in the loop until the whole warp is done, so that the votes and __syncwarp below are always complete
+	while(__any_sync(0xFFFFFFFFu, s.alive))
+	{
+#pragma unroll 1
+		for(int step = 0; step < round_steps; ++step)
+		{
+			if(s.alive && !s.pending)
+			{
+				if(MODE == 0) pmStep<MODE>(s, stack, nodes, dirs, k, heap_s);
+				else pmStep<MODE>(s, stack, nodes, dirs, k, heap_g);
+			}
+			// no lane left that could use another step of this round
+			if(!__any_sync(0xFFFFFFFFu, s.alive && !s.pending)) break;
+		}
+		if(MODE != 2)
+		{
+			__syncwarp();
+			if(s.pending)
+			{
+				if(MODE == 0) pmResolve(s, k, heap_s);
+				else pmResolve(s, k, heap_g);
+			}
+			__syncwarp();
+		}
+	}
+	if(in_range) pmLaneFinish<MODE>(s, point, k, found, n_found_out, sq_radius_out, nearest_out, heap_s);
+}
+#endif
+
 } // namespace b200pm

@@ -19,7 +19,7 @@ assert FOUND_DTYPE.itemsize == 8
 
 #: every symbol include/b200pm.h declares (tests check that the library exports all of them)
 SYMBOLS = ["b200pm_create", "b200pm_destroy", "b200pm_get_stats", "b200pm_gather", "b200pm_gather_device", "b200pm_find_nearest",
-           "b200pm_find_nearest_device", "b200pm_host_tree_build"]
+           "b200pm_find_nearest_device", "b200pm_host_tree_build", "b200pm_debug_set_tuning"]
 
 
 class Stats(C.Structure):
@@ -47,6 +47,7 @@ def lib():
         L.b200pm_find_nearest.argtypes = [P, P, P, Z, F, P]
         L.b200pm_find_nearest_device.argtypes = [P, P, P, Z, F, P, P]
         L.b200pm_host_tree_build.argtypes = [P, Z, C.c_int, P, P]
+        L.b200pm_debug_set_tuning.argtypes = [C.c_int, C.c_int, C.c_int]
         _ready = True
     return L
 
@@ -56,6 +57,11 @@ def _f32(a, cols=3):
     if a.ndim != 2 or a.shape[1] != cols:
         raise ValueError(f"expected an [n, {cols}] array, got {a.shape}")
     return a
+
+
+def set_tuning(phased: int = -1, round_steps: int = -1, smem_k: int = -1):
+    """b200pm_debug_set_tuning: kernel variant / round length / shared-memory heap threshold (tuning aid; results do not change)."""
+    rt._check(lib().b200pm_debug_set_tuning(phased, round_steps, smem_k))
 
 
 def host_tree(pos, build_threads: int = 0):
@@ -118,23 +124,29 @@ class PhotonMap:
         rt._check(lib().b200pm_get_stats(self._h, C.byref(s)))
         return s.as_dict()
 
-    def gather(self, points, k: int, sq_radius: float = 0.0, sq_radii=None):
+    def gather(self, points, k: int, sq_radius: float = 0.0, sq_radii=None, out=None):
         """PhotonMap::gather (src/photon/photon.cc:58-64) for every row of `points`.
 
         Returns (found [n, k] FOUND_DTYPE, n_found [n] u32, sq_radius_out [n] f32); entries of `found` past n_found are
-        photon = NONE, dist_square = 0."""
+        photon = NONE, dist_square = 0.  out = the three result arrays to fill (e.g. page-locked ones from rt.PinnedBuffer); with
+        `out` the entries past n_found are left as the library wrote them (unspecified)."""
         points = _f32(points)
         n = len(points)
-        found = np.zeros((n, k), FOUND_DTYPE)
-        n_found = np.zeros(n, np.uint32)
-        radius_out = np.zeros(n, np.float32)
+        if out is not None:
+            found, n_found, radius_out = out
+            assert found.dtype == FOUND_DTYPE and found.shape == (n, k) and found.flags.c_contiguous
+            assert n_found.dtype == np.uint32 and n_found.shape == (n,) and radius_out.dtype == np.float32 and radius_out.shape == (n,)
+        else:
+            found = np.zeros((n, k), FOUND_DTYPE)
+            n_found = np.zeros(n, np.uint32)
+            radius_out = np.zeros(n, np.float32)
         radii = None
         if sq_radii is not None:
             radii = np.ascontiguousarray(sq_radii, np.float32)
             if radii.shape != (n,):
                 raise ValueError("one squared radius per point")
         rt._check(lib().b200pm_gather(self._h, rt._p(points), n, k, float(sq_radius), rt._p(radii), rt._p(found), rt._p(n_found), rt._p(radius_out)))
-        if n:
+        if n and out is None:
             past = np.arange(k)[None, :] >= n_found[:, None]
             found["photon"][past] = NONE
             found["dist_square"][past] = 0.0

@@ -137,16 +137,16 @@ def host_model(built):
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared", "-o", out, src])
     L = C.CDLL(out)
-    L.pm_model_lookup.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_uint32, C.c_uint32, C.c_float] + [C.c_void_p] * 5
+    L.pm_model_lookup.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_uint32, C.c_uint32, C.c_float] + [C.c_void_p] * 5 + [C.c_int]
     return L
 
 
-def run_model(L, mode, nodes, dirs4, points, normals, k, r2, radii=None):
+def run_model(L, mode, nodes, dirs4, points, normals, k, r2, radii=None, round_steps=0):
     n = len(points)
     found = np.zeros((n, k, 2), np.uint32)
     n_found, radius_out, nearest = np.zeros(n, np.uint32), np.zeros(n, np.float32), np.zeros(n, np.uint32)
     rc = L.pm_model_lookup(mode, rt._p(nodes), rt._p(dirs4), rt._p(points), rt._p(normals), n, k, C.c_float(r2), rt._p(radii), rt._p(found), rt._p(n_found), rt._p(radius_out),
-                           rt._p(nearest))
+                           rt._p(nearest), round_steps)
     assert rc == 0
     return (found[:, :, 0], found[:, :, 1].view(np.float32), n_found, radius_out), nearest
 
@@ -163,15 +163,18 @@ def test_kernel_lookup_code_on_the_host_matches_oracle(built, host_model, kind):
         dirs4[:, :3] = dirs
         for k, r2 in ((1, 1e-3), (2, 1e-2), (7, 1e-2), (64, 0.05), (33, 1e30)):
             want = o.gather(points, k, r2)
-            for mode in (0, 1):
-                got, _ = run_model(host_model, mode, nodes, dirs4, points, normals, k, r2)
-                assert_gather_equal(got, want, f"{kind} n={n} k={k} r2={r2} mode={mode}")
+            # round_steps 0: the plain loop (pmLookupOne); otherwise the phased state machine (pmStep / pmResolve)
+            for mode, round_steps in ((0, 0), (1, 0), (0, 1), (1, 1), (0, 8), (1, 8), (1, 1000)):
+                got, _ = run_model(host_model, mode, nodes, dirs4, points, normals, k, r2, round_steps=round_steps)
+                assert_gather_equal(got, want, f"{kind} n={n} k={k} r2={r2} mode={mode} round_steps={round_steps}")
         radii = (np.random.default_rng(n).random(len(points)).astype(np.float32) * 0.05) ** 2
-        got, _ = run_model(host_model, 0, nodes, dirs4, points, normals, 10, 0.0, radii)
-        assert_gather_equal(got, o.gather(points, 10, 0.0, radii), "per-point radii")
+        for round_steps in (0, 8):
+            got, _ = run_model(host_model, 0, nodes, dirs4, points, normals, 10, 0.0, radii, round_steps=round_steps)
+            assert_gather_equal(got, o.gather(points, 10, 0.0, radii), "per-point radii")
         for dist in (1e-4, 1e-2, 1.0):
-            _, nearest = run_model(host_model, 2, nodes, dirs4, points, normals, 1, dist)
-            assert np.array_equal(nearest, o.nearest(points, normals, dist)), (kind, n, dist)
+            for round_steps in (0, 8):
+                _, nearest = run_model(host_model, 2, nodes, dirs4, points, normals, 1, dist, round_steps=round_steps)
+                assert np.array_equal(nearest, o.nearest(points, normals, dist)), (kind, n, dist, round_steps)
 
 
 # -------------------------------------------------------------------------------------------------------------------- GPU

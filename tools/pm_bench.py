@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-KERNEL = "b200pm::pmLookupKernel<0> (heaps in shared memory)"
+KERNEL = "b200pm::pmLookupPhasedKernel<1> (k > 16: heaps in the result array; B200PM_KERNEL=plain: pmLookupKernel)"
 
 
 def run(photons=1_000_000, points=1_000_000, k=100, sq_radius=2.5e-4, steps=5, cpu_seconds=5.0, device=0, kind="surfaces", cpu=True):
@@ -62,11 +62,22 @@ def run(photons=1_000_000, points=1_000_000, k=100, sq_radius=2.5e-4, steps=5, c
     ev[1].record()
     torch.cuda.synchronize(dev)
     near_ms = ev[0].elapsed_time(ev[1]) / steps
-    # end to end: host buffers in, host buffers out
-    m.gather(pts[:4096], k, sq_radius)
+    # end to end: host buffers in, host buffers out -- page-locked (b200rt_host_alloc) and, for comparison, pageable
+    pin = [rt.PinnedBuffer((points, 3), np.float32), rt.PinnedBuffer((points, k), pm.FOUND_DTYPE), rt.PinnedBuffer(points, np.uint32), rt.PinnedBuffer(points, np.float32)]
+    pin[0].array[:] = pts
+    outs = (pin[1].array, pin[2].array, pin[3].array)
+    m.gather(pin[0].array, k, sq_radius, out=outs)
+    e2e_steps = max(2, min(steps, 3))
     t0 = time.perf_counter()
-    found, n_found, radius_out = m.gather(pts, k, sq_radius)
-    e2e_s = time.perf_counter() - t0
+    for _ in range(e2e_steps):
+        m.gather(pin[0].array, k, sq_radius, out=outs)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    found, n_found, radius_out = outs[0].copy(), outs[1].copy(), outs[2].copy()
+    for b in pin:
+        b.free()
+    t0 = time.perf_counter()
+    found_p, n_found_p, _ = m.gather(pts, k, sq_radius)
+    pageable_s = time.perf_counter() - t0
     valid = np.arange(k)[None, :] < n_found[:, None]
     same = bool(np.array_equal(n_found, n_found_dev) and np.array_equal(found["photon"][valid], found_dev[:, :, 0][valid]))
     line = {
@@ -74,9 +85,11 @@ def run(photons=1_000_000, points=1_000_000, k=100, sq_radius=2.5e-4, steps=5, c
         "kernel": KERNEL, "gpu_launches": int(launches), "dtype": "f32",
         "config": {"workload": f"{photons} photons ({kind}), {points} gather points, k={k}, sq_radius={sq_radius}", "inputs": "points and results resident in HBM"},
         "mean_found": float(n_found.mean()), "full_fraction": float((n_found == k).mean()),
-        "find_nearest": {"value": points / (near_ms * 1e-3) / 1e6, "unit": "Mpoints/s", "ms": near_ms, "kernel": "b200pm::pmLookupKernel<2>"},
+        "find_nearest": {"value": points / (near_ms * 1e-3) / 1e6, "unit": "Mpoints/s", "ms": near_ms, "kernel": "b200pm::pmLookupPhasedKernel<2>"},
         "e2e": {"value": points / e2e_s / 1e6, "unit": "Mpoints/s", "h2d_bytes": int(pts.nbytes), "d2h_bytes": int(found.nbytes + n_found.nbytes + radius_out.nbytes),
-                "path": "b200pm_gather on pageable host buffers", "same_as_device_resident": same},
+                "path": "b200pm_gather on page-locked host buffers (chunks over two streams: H2D, kernel, D2H overlap)", "same_as_device_resident": same,
+                "pageable_value": points / pageable_s / 1e6, "pageable_same": bool(np.array_equal(n_found_p, n_found))},
+        "tuning": {key: os.environ.get(key) for key in ("B200PM_KERNEL", "B200PM_ROUND", "B200PM_SMEM_K") if os.environ.get(key) is not None},
         "tree": stats,
     }
     if cpu:
