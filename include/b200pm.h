@@ -86,10 +86,12 @@ int b200pm_find_nearest_device(b200pm_map *map, const float *d_points, const flo
 int b200pm_host_tree_build(const float *pos, size_t n, int build_threads, uint32_t *a, uint32_t *b);
 
 /* Tuning aid (tools/pm_sweep.py), process-wide, not for production use; a negative argument keeps the current value.
- * phased: 1 = the phased lookup kernel (default), 0 = the plain per-thread loop; round_steps: node visits per round of the phased
- * kernel; smem_k: largest k whose heaps live in shared memory (0 = always in `found`, at most 256).  The environment variables
- * B200PM_KERNEL=plain|phased, B200PM_ROUND, B200PM_SMEM_K set the same at load time.  Results do not depend on any of them. */
-int b200pm_debug_set_tuning(int phased, int round_steps, int smem_k);
+ * kernel: gather kernel -- 0 = the plain per-thread loop, 1 = the phased state machine, 2 = phased with one stack pop per step;
+ * round_steps: node visits per round of the phased kernels; smem_k: largest k whose heaps live in shared memory (0 = always in
+ * `found`, at most 256); patience: lanes of a warp that must have a make_heap pending before it is done (1 = no waiting).  The
+ * environment variables B200PM_KERNEL=plain|phased1|phased, B200PM_ROUND, B200PM_SMEM_K, B200PM_PATIENCE set the same at load
+ * time.  Results do not depend on any of them. */
+int b200pm_debug_set_tuning(int kernel, int round_steps, int smem_k, int patience);
 
 #ifdef __cplusplus
 }

@@ -84,19 +84,24 @@ struct b200pm_map
 
 namespace {
 
-// Tuning aids, read once (tools/pm_bench.py sweeps them; the defaults are the measured best, profiles/r6*_pm_*.json):
-//   B200PM_KERNEL=plain   the plain per-thread loop (pmLookupKernel) instead of the phased state machine (pmLookupPhasedKernel)
-//   B200PM_ROUND=<n>      steps per round of the phased kernel
+// Tuning aids (tools/pm_sweep.py sweeps them through b200pm_debug_set_tuning; the defaults are the measured best,
+// profiles/r6*_pm_*): environment, read once --
+//   B200PM_KERNEL=plain|phased|phased1   gather above smem_k: the plain per-thread loop (pmLookupKernel), the phased state machine
+//                         with one stack pop per step (pmLookupPhasedKernel<.,true>), or with the pop loop inside a step
+//   B200PM_ROUND=<n>      node visits per round of the phased kernel
+//   B200PM_PATIENCE=<n>   lanes that must have a make_heap pending before the warp does it (1 = no waiting)
 //   B200PM_SMEM_K=<k>     largest k whose heaps live in shared memory (0 = always in `found`)
 struct Tuning
 {
-	bool phased = true;
+	int kernel = 0; // 0 plain, 1 phased, 2 phased + single pop
 	int round_steps = 8;
+	int patience = 8;
 	uint32_t smem_k = 16;
 	Tuning()
 	{
-		if(const char *e = std::getenv("B200PM_KERNEL")) phased = std::string(e) != "plain";
+		if(const char *e = std::getenv("B200PM_KERNEL")) kernel = std::string(e) == "plain" ? 0 : (std::string(e) == "phased1" ? 1 : 2);
 		if(const char *e = std::getenv("B200PM_ROUND")) { const long v = std::atol(e); if(v >= 1 && v <= 4096) round_steps = int(v); }
+		if(const char *e = std::getenv("B200PM_PATIENCE")) { const long v = std::atol(e); if(v >= 1 && v <= 32) patience = int(v); }
 		if(const char *e = std::getenv("B200PM_SMEM_K")) { const long v = std::atol(e); if(v >= 0 && uint32_t(v) <= b200pm::kPmSmemK) smem_k = uint32_t(v); }
 	}
 };
@@ -113,29 +118,33 @@ int launchGather(b200pm_map *map, const float *d_points, size_t n_points, uint32
 	const Tuning t = tuning();
 	const unsigned blocks = unsigned((n_points + b200pm::kPmThreads - 1) / b200pm::kPmThreads);
 	uint2 *found2 = reinterpret_cast<uint2 *>(d_found);
-	if(k <= t.smem_k)
+	const bool in_smem = k <= t.smem_k;
+	const size_t smem = in_smem ? size_t(k) * b200pm::kPmThreads * sizeof(uint2) : 0;
+	if(in_smem && !map->smem_opt_in)
 	{
-		const size_t smem = size_t(k) * b200pm::kPmThreads * sizeof(uint2);
-		if(!map->smem_opt_in)
-		{
-			const int most = int(size_t(b200pm::kPmSmemK) * b200pm::kPmThreads * sizeof(uint2));
-			PM_CUDA_TRY(cudaFuncSetAttribute(b200pm::pmLookupKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
-			PM_CUDA_TRY(cudaFuncSetAttribute(b200pm::pmLookupPhasedKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
-			map->smem_opt_in = true;
-		}
-		if(t.phased)
-			b200pm::pmLookupPhasedKernel<0><<<blocks, b200pm::kPmThreads, smem, stream>>>(map->d_nodes, map->d_dirs, d_points, nullptr, uint32_t(n_points), k, sq_radius,
-			                                                                          d_sq_radii, found2, d_n_found, d_sq_radius_out, nullptr, t.round_steps);
-		else
-			b200pm::pmLookupKernel<0><<<blocks, b200pm::kPmThreads, smem, stream>>>(map->d_nodes, map->d_dirs, d_points, nullptr, uint32_t(n_points), k, sq_radius, d_sq_radii,
-			                                                                    found2, d_n_found, d_sq_radius_out, nullptr);
+		const int most = int(size_t(b200pm::kPmSmemK) * b200pm::kPmThreads * sizeof(uint2));
+		PM_CUDA_TRY(cudaFuncSetAttribute(b200pm::pmLookupKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+		PM_CUDA_TRY(cudaFuncSetAttribute(b200pm::pmLookupPhasedKernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+		PM_CUDA_TRY(cudaFuncSetAttribute(b200pm::pmLookupPhasedKernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+		map->smem_opt_in = true;
 	}
-	else if(t.phased)
-		b200pm::pmLookupPhasedKernel<1><<<blocks, b200pm::kPmThreads, 0, stream>>>(map->d_nodes, map->d_dirs, d_points, nullptr, uint32_t(n_points), k, sq_radius, d_sq_radii,
-		                                                                       found2, d_n_found, d_sq_radius_out, nullptr, t.round_steps);
+#define PM_ARGS map->d_nodes, map->d_dirs, d_points, nullptr, uint32_t(n_points), k, sq_radius, d_sq_radii, found2, d_n_found, d_sq_radius_out, nullptr
+	if(t.kernel == 0)
+	{
+		if(in_smem) b200pm::pmLookupKernel<0><<<blocks, b200pm::kPmThreads, smem, stream>>>(PM_ARGS);
+		else b200pm::pmLookupKernel<1><<<blocks, b200pm::kPmThreads, 0, stream>>>(PM_ARGS);
+	}
+	else if(t.kernel == 1)
+	{
+		if(in_smem) b200pm::pmLookupPhasedKernel<0, false><<<blocks, b200pm::kPmThreads, smem, stream>>>(PM_ARGS, t.round_steps, t.patience);
+		else b200pm::pmLookupPhasedKernel<1, false><<<blocks, b200pm::kPmThreads, 0, stream>>>(PM_ARGS, t.round_steps, t.patience);
+	}
 	else
-		b200pm::pmLookupKernel<1><<<blocks, b200pm::kPmThreads, 0, stream>>>(map->d_nodes, map->d_dirs, d_points, nullptr, uint32_t(n_points), k, sq_radius, d_sq_radii,
-		                                                                 found2, d_n_found, d_sq_radius_out, nullptr);
+	{
+		if(in_smem) b200pm::pmLookupPhasedKernel<0, true><<<blocks, b200pm::kPmThreads, smem, stream>>>(PM_ARGS, t.round_steps, t.patience);
+		else b200pm::pmLookupPhasedKernel<1, true><<<blocks, b200pm::kPmThreads, 0, stream>>>(PM_ARGS, t.round_steps, t.patience);
+	}
+#undef PM_ARGS
 	PM_CUDA_TRY(cudaGetLastError());
 	b200::countLaunches(1);
 	return B200RT_OK;
@@ -146,12 +155,12 @@ int launchNearest(b200pm_map *map, const float *d_points, const float *d_normals
 	if(!n_points) return B200RT_OK;
 	const Tuning t = tuning();
 	const unsigned blocks = unsigned((n_points + b200pm::kPmThreads - 1) / b200pm::kPmThreads);
-	if(t.phased)
-		b200pm::pmLookupPhasedKernel<2><<<blocks, b200pm::kPmThreads, 0, stream>>>(map->d_nodes, map->d_dirs, d_points, d_normals, uint32_t(n_points), 1u, dist, nullptr,
-		                                                                       nullptr, nullptr, nullptr, d_out, t.round_steps);
-	else
-		b200pm::pmLookupKernel<2><<<blocks, b200pm::kPmThreads, 0, stream>>>(map->d_nodes, map->d_dirs, d_points, d_normals, uint32_t(n_points), 1u, dist, nullptr, nullptr,
-		                                                                 nullptr, nullptr, d_out);
+#define PM_ARGS map->d_nodes, map->d_dirs, d_points, d_normals, uint32_t(n_points), 1u, dist, nullptr, nullptr, nullptr, nullptr, d_out
+	// findNearest has no heap work to gather: the plain loop is the fastest (profiles/r6b_pm_sweep.jsonl); the phased kernels only on request
+	if(t.kernel == 0 || !std::getenv("B200PM_NEAREST_PHASED")) b200pm::pmLookupKernel<2><<<blocks, b200pm::kPmThreads, 0, stream>>>(PM_ARGS);
+	else if(t.kernel == 1) b200pm::pmLookupPhasedKernel<2, false><<<blocks, b200pm::kPmThreads, 0, stream>>>(PM_ARGS, t.round_steps, t.patience);
+	else b200pm::pmLookupPhasedKernel<2, true><<<blocks, b200pm::kPmThreads, 0, stream>>>(PM_ARGS, t.round_steps, t.patience);
+#undef PM_ARGS
 	PM_CUDA_TRY(cudaGetLastError());
 	b200::countLaunches(1);
 	return B200RT_OK;
@@ -180,12 +189,13 @@ int b200pm_host_tree_build(const float *pos, size_t n, int build_threads, uint32
 	return B200RT_OK;
 }
 
-int b200pm_debug_set_tuning(int phased, int round_steps, int smem_k)
+int b200pm_debug_set_tuning(int kernel, int round_steps, int smem_k, int patience)
 {
 	Tuning &t = tuning();
-	if(phased >= 0) t.phased = phased != 0;
+	if(kernel >= 0 && kernel <= 2) t.kernel = kernel;
 	if(round_steps >= 1) t.round_steps = round_steps;
 	if(smem_k >= 0 && uint32_t(smem_k) <= b200pm::kPmSmemK) t.smem_k = uint32_t(smem_k);
+	if(patience >= 1 && patience <= 32) t.patience = patience;
 	return B200RT_OK;
 }
 

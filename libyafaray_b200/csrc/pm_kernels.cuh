@@ -270,7 +270,10 @@ struct PmLane
 	bool alive, need_pop, pending;
 };
 
-template <int MODE, typename Heap>
+// SINGLE_POP: a step pops ONE stack entry; a lane whose entry was beyond the radius pops the next one in its next step instead of
+// looping here while the rest of the warp waits (the pop loop ran at 4.6 of 32 lanes and was 36 % of all warp instructions,
+// profiles/r6b_pm_gather_phased.txt).
+template <int MODE, bool SINGLE_POP, typename Heap>
 PM_HD void pmStep(PmLane &s, uint2 *stack, const uint4 *__restrict__ nodes, const float4 *__restrict__ dirs, uint32_t k, const Heap &heap)
 {
 	if(s.need_pop)
@@ -286,6 +289,7 @@ PM_HD void pmStep(PmLane &s, uint2 *stack, const uint4 *__restrict__ nodes, cons
 			d = pmMul(d, d);
 			--s.sp;
 			if(!(d > s.max_dist_squared)) { s.curr = top.x >> 2; break; }
+			if(SINGLE_POP) return;
 		}
 		s.need_pop = false;
 	}
@@ -378,7 +382,7 @@ PM_HD void pmLaneFinish(const PmLane &s, uint32_t point, uint32_t k, uint2 *__re
 }
 
 // one lane, start to finish, through the same state machine (host model; also what a warp of one lane would do)
-template <int MODE>
+template <int MODE, bool SINGLE_POP>
 PM_HD void pmLookupPhasedOne(const uint4 *__restrict__ nodes, const float4 *__restrict__ dirs, const float *__restrict__ points, const float *__restrict__ normals,
                              uint32_t point, uint32_t k, float sq_radius, const float *__restrict__ sq_radii, uint2 *__restrict__ found,
                              uint32_t *__restrict__ n_found_out, float *__restrict__ sq_radius_out, uint32_t *__restrict__ nearest_out, const HeapSmem heap_s, int round_steps)
@@ -391,8 +395,8 @@ PM_HD void pmLookupPhasedOne(const uint4 *__restrict__ nodes, const float4 *__re
 	{
 		for(int step = 0; step < round_steps && s.alive && !s.pending; ++step)
 		{
-			if(MODE == 0) pmStep<MODE>(s, stack, nodes, dirs, k, heap_s);
-			else pmStep<MODE>(s, stack, nodes, dirs, k, heap_g);
+			if(MODE == 0) pmStep<MODE, SINGLE_POP>(s, stack, nodes, dirs, k, heap_s);
+			else pmStep<MODE, SINGLE_POP>(s, stack, nodes, dirs, k, heap_g);
 		}
 		if(s.pending)
 		{
@@ -404,11 +408,15 @@ PM_HD void pmLookupPhasedOne(const uint4 *__restrict__ nodes, const float4 *__re
 }
 
 #ifdef __CUDACC__
-template <int MODE>
+// patience: a lane whose pending work is the expensive one -- the k-th photon, i.e. std::make_heap over k entries, ~3000
+// instructions for k = 100, which ran at 1.2 lanes when every lane did it on its own -- waits until `patience` lanes of the warp
+// have the same work pending, or no lane of the warp can take another step; replacements (pop_heap / push_heap) are resolved at
+// the end of every round.  1 = no waiting.
+template <int MODE, bool SINGLE_POP>
 __global__ void __launch_bounds__(kPmThreads) pmLookupPhasedKernel(const uint4 *__restrict__ nodes, const float4 *__restrict__ dirs, const float *__restrict__ points,
                                                                    const float *__restrict__ normals, uint32_t n_points, uint32_t k, float sq_radius,
                                                                    const float *__restrict__ sq_radii, uint2 *__restrict__ found, uint32_t *__restrict__ n_found_out,
-                                                                   float *__restrict__ sq_radius_out, uint32_t *__restrict__ nearest_out, int round_steps)
+                                                                   float *__restrict__ sq_radius_out, uint32_t *__restrict__ nearest_out, int round_steps, int patience)
 {
 	extern __shared__ uint2 pm_heap_smem[];
 	const uint32_t point = blockIdx.x * uint32_t(kPmThreads) + threadIdx.x;
@@ -427,16 +435,19 @@ __global__ void __launch_bounds__(kPmThreads) pmLookupPhasedKernel(const uint4 *
 		{
 			if(s.alive && !s.pending)
 			{
-				if(MODE == 0) pmStep<MODE>(s, stack, nodes, dirs, k, heap_s);
-				else pmStep<MODE>(s, stack, nodes, dirs, k, heap_g);
+				if(MODE == 0) pmStep<MODE, SINGLE_POP>(s, stack, nodes, dirs, k, heap_s);
+				else pmStep<MODE, SINGLE_POP>(s, stack, nodes, dirs, k, heap_g);
 			}
 			// no lane left that could use another step of this round
 			if(!__any_sync(0xFFFFFFFFu, s.alive && !s.pending)) break;
 		}
 		if(MODE != 2)
 		{
-			__syncwarp();
-			if(s.pending)
+			const bool heavy = s.pending && s.n_found + 1u == k && k > 2u;
+			const int n_heavy = __popc(__ballot_sync(0xFFFFFFFFu, heavy));
+			const bool someone_can_step = __any_sync(0xFFFFFFFFu, s.alive && !s.pending);
+			const bool heavy_now = n_heavy >= patience || !someone_can_step;
+			if(s.pending && (!heavy || heavy_now))
 			{
 				if(MODE == 0) pmResolve(s, k, heap_s);
 				else pmResolve(s, k, heap_g);

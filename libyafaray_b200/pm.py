@@ -47,7 +47,7 @@ def lib():
         L.b200pm_find_nearest.argtypes = [P, P, P, Z, F, P]
         L.b200pm_find_nearest_device.argtypes = [P, P, P, Z, F, P, P]
         L.b200pm_host_tree_build.argtypes = [P, Z, C.c_int, P, P]
-        L.b200pm_debug_set_tuning.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.b200pm_debug_set_tuning.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
         _ready = True
     return L
 
@@ -59,9 +59,10 @@ def _f32(a, cols=3):
     return a
 
 
-def set_tuning(phased: int = -1, round_steps: int = -1, smem_k: int = -1):
-    """b200pm_debug_set_tuning: kernel variant / round length / shared-memory heap threshold (tuning aid; results do not change)."""
-    rt._check(lib().b200pm_debug_set_tuning(phased, round_steps, smem_k))
+def set_tuning(kernel: int = -1, round_steps: int = -1, smem_k: int = -1, patience: int = -1):
+    """b200pm_debug_set_tuning: gather kernel (0 plain, 1 phased, 2 phased + single pop) / round length / shared-memory heap
+    threshold / make_heap patience (tuning aid; results do not change)."""
+    rt._check(lib().b200pm_debug_set_tuning(kernel, round_steps, smem_k, patience))
 
 
 def host_tree(pos, build_threads: int = 0):

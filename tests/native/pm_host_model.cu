@@ -7,7 +7,7 @@
 #include <vector>
 
 extern "C" int pm_model_lookup(int mode, const uint32_t *nodes4, const float *dirs4, const float *points, const float *normals, uint32_t n_points, uint32_t k,
-                               float sq_radius, const float *sq_radii, uint32_t *found2, uint32_t *n_found, float *sq_radius_out, uint32_t *nearest, int round_steps)
+                               float sq_radius, const float *sq_radii, uint32_t *found2, uint32_t *n_found, float *sq_radius_out, uint32_t *nearest, int round_steps, int single_pop)
 {
 	using namespace b200pm;
 	const uint4 *nodes = reinterpret_cast<const uint4 *>(nodes4);
@@ -20,9 +20,12 @@ extern "C" int pm_model_lookup(int mode, const uint32_t *nodes4, const float *di
 		if(round_steps > 0)
 		{
 			// the phased state machine (pmStep / pmResolve), one lane
-			if(mode == 0) pmLookupPhasedOne<0>(nodes, dirs, points, normals, point, k, sq_radius, sq_radii, found, n_found, sq_radius_out, nearest, heap_s, round_steps);
-			else if(mode == 1) pmLookupPhasedOne<1>(nodes, dirs, points, normals, point, k, sq_radius, sq_radii, found, n_found, sq_radius_out, nearest, heap_s, round_steps);
-			else if(mode == 2) pmLookupPhasedOne<2>(nodes, dirs, points, normals, point, k, sq_radius, sq_radii, found, n_found, sq_radius_out, nearest, heap_s, round_steps);
+			if(mode == 0 && single_pop) pmLookupPhasedOne<0, true>(nodes, dirs, points, normals, point, k, sq_radius, sq_radii, found, n_found, sq_radius_out, nearest, heap_s, round_steps);
+			else if(mode == 1 && single_pop) pmLookupPhasedOne<1, true>(nodes, dirs, points, normals, point, k, sq_radius, sq_radii, found, n_found, sq_radius_out, nearest, heap_s, round_steps);
+			else if(mode == 2 && single_pop) pmLookupPhasedOne<2, true>(nodes, dirs, points, normals, point, k, sq_radius, sq_radii, found, n_found, sq_radius_out, nearest, heap_s, round_steps);
+			else if(mode == 0) pmLookupPhasedOne<0, false>(nodes, dirs, points, normals, point, k, sq_radius, sq_radii, found, n_found, sq_radius_out, nearest, heap_s, round_steps);
+			else if(mode == 1) pmLookupPhasedOne<1, false>(nodes, dirs, points, normals, point, k, sq_radius, sq_radii, found, n_found, sq_radius_out, nearest, heap_s, round_steps);
+			else if(mode == 2) pmLookupPhasedOne<2, false>(nodes, dirs, points, normals, point, k, sq_radius, sq_radii, found, n_found, sq_radius_out, nearest, heap_s, round_steps);
 			else return -1;
 			continue;
 		}

@@ -21,6 +21,7 @@ from oracle import pmo
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "pm_*.npz")))
 KINDS = ["uniform", "surfaces", "clusters", "lattice"]
+DEFAULT_TUNING = (0, 8, 16, 8)  # b200pm.cu Tuning: kernel, round_steps, smem_k, patience
 
 
 def bits(a):
@@ -137,16 +138,16 @@ def host_model(built):
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared", "-o", out, src])
     L = C.CDLL(out)
-    L.pm_model_lookup.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_uint32, C.c_uint32, C.c_float] + [C.c_void_p] * 5 + [C.c_int]
+    L.pm_model_lookup.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_uint32, C.c_uint32, C.c_float] + [C.c_void_p] * 5 + [C.c_int, C.c_int]
     return L
 
 
-def run_model(L, mode, nodes, dirs4, points, normals, k, r2, radii=None, round_steps=0):
+def run_model(L, mode, nodes, dirs4, points, normals, k, r2, radii=None, round_steps=0, single_pop=0):
     n = len(points)
     found = np.zeros((n, k, 2), np.uint32)
     n_found, radius_out, nearest = np.zeros(n, np.uint32), np.zeros(n, np.float32), np.zeros(n, np.uint32)
     rc = L.pm_model_lookup(mode, rt._p(nodes), rt._p(dirs4), rt._p(points), rt._p(normals), n, k, C.c_float(r2), rt._p(radii), rt._p(found), rt._p(n_found), rt._p(radius_out),
-                           rt._p(nearest), round_steps)
+                           rt._p(nearest), round_steps, single_pop)
     assert rc == 0
     return (found[:, :, 0], found[:, :, 1].view(np.float32), n_found, radius_out), nearest
 
@@ -164,16 +165,16 @@ def test_kernel_lookup_code_on_the_host_matches_oracle(built, host_model, kind):
         for k, r2 in ((1, 1e-3), (2, 1e-2), (7, 1e-2), (64, 0.05), (33, 1e30)):
             want = o.gather(points, k, r2)
             # round_steps 0: the plain loop (pmLookupOne); otherwise the phased state machine (pmStep / pmResolve)
-            for mode, round_steps in ((0, 0), (1, 0), (0, 1), (1, 1), (0, 8), (1, 8), (1, 1000)):
-                got, _ = run_model(host_model, mode, nodes, dirs4, points, normals, k, r2, round_steps=round_steps)
-                assert_gather_equal(got, want, f"{kind} n={n} k={k} r2={r2} mode={mode} round_steps={round_steps}")
+            for mode, round_steps, single_pop in ((0, 0, 0), (1, 0, 0), (0, 1, 0), (1, 1, 1), (0, 8, 1), (1, 8, 0), (1, 8, 1), (1, 1000, 1)):
+                got, _ = run_model(host_model, mode, nodes, dirs4, points, normals, k, r2, round_steps=round_steps, single_pop=single_pop)
+                assert_gather_equal(got, want, f"{kind} n={n} k={k} r2={r2} mode={mode} round_steps={round_steps} single_pop={single_pop}")
         radii = (np.random.default_rng(n).random(len(points)).astype(np.float32) * 0.05) ** 2
         for round_steps in (0, 8):
-            got, _ = run_model(host_model, 0, nodes, dirs4, points, normals, 10, 0.0, radii, round_steps=round_steps)
+            got, _ = run_model(host_model, 0, nodes, dirs4, points, normals, 10, 0.0, radii, round_steps=round_steps, single_pop=1)
             assert_gather_equal(got, o.gather(points, 10, 0.0, radii), "per-point radii")
         for dist in (1e-4, 1e-2, 1.0):
             for round_steps in (0, 8):
-                _, nearest = run_model(host_model, 2, nodes, dirs4, points, normals, 1, dist, round_steps=round_steps)
+                _, nearest = run_model(host_model, 2, nodes, dirs4, points, normals, 1, dist, round_steps=round_steps, single_pop=round_steps // 8)
                 assert np.array_equal(nearest, o.nearest(points, normals, dist)), (kind, n, dist, round_steps)
 
 
@@ -211,6 +212,24 @@ def test_gpu_matches_oracle(built, kind):
             for dist in (1e-4, 1e-2, 1.0):
                 assert np.array_equal(m.find_nearest(points, normals, dist), o.nearest(points, normals, dist)), (kind, n, dist)
     assert rt.launch_count() > launches, "no kernel of libb200rt.so was launched"
+
+
+@pytest.mark.gpu
+def test_gpu_kernel_variants_agree(built):
+    """Every kernel variant behind b200pm_debug_set_tuning (plain loop, phased, phased + one pop per step; round length; heaps
+    in shared memory or in the result array; make_heap patience) gives the reference's results, bit for bit."""
+    pos, dirs = scenes.photon_cloud("surfaces", 150_000, seed=31)
+    points, normals = scenes.gather_points(pos, 20_000, seed=32, jitter=0.004)
+    o = pmo.OracleMap(pos, dirs)
+    wants = {(k, r2): o.gather(points, k, r2) for k, r2 in ((1, 1e-3), (2, 1e-3), (3, 1e-3), (16, 2e-3), (60, 2e-3))}
+    try:
+        with pm.PhotonMap(pos, dirs) as m:
+            for kernel, steps, smem_k, patience in ((0, 8, 0, 1), (0, 8, 256, 1), (1, 1, 0, 1), (1, 8, 16, 8), (2, 1, 0, 1), (2, 8, 0, 8), (2, 8, 256, 32), (2, 64, 16, 4), (2, 3, 0, 2)):
+                pm.set_tuning(kernel, steps, smem_k, patience)
+                for (k, r2), want in wants.items():
+                    assert_gather_equal(product_result(*m.gather(points, k, r2)), want, f"kernel={kernel} steps={steps} smem_k={smem_k} patience={patience} k={k}")
+    finally:
+        pm.set_tuning(*DEFAULT_TUNING)
 
 
 @pytest.mark.gpu

@@ -35,13 +35,15 @@ def main():
         torch.cuda.synchronize()
         return ev[0].elapsed_time(ev[1]) / reps
 
-    variants = [(0, 8, 0), (0, 8, 256), (1, 1, 0), (1, 2, 0), (1, 4, 0), (1, 8, 0), (1, 16, 0), (1, 32, 0), (1, 64, 0), (1, 8, 16), (1, 8, 256), (1, 16, 256)]
-    cases = [("gather", 100, 2.5e-4), ("gather", 8, 1e-4), ("gather", 50, 1e-3), ("nearest", 1, 2.5e-4)]
+    # (kernel, round_steps, smem_k, patience); kernel 0 = plain loop, 1 = phased, 2 = phased + one pop per step
+    variants = [(0, 8, 0, 1), (0, 8, 256, 1), (1, 8, 0, 1), (1, 8, 0, 8), (2, 8, 0, 1), (2, 8, 0, 4), (2, 8, 0, 8), (2, 8, 0, 16), (2, 8, 0, 32), (2, 4, 0, 8), (2, 16, 0, 8),
+                (2, 32, 0, 8), (2, 16, 0, 16), (2, 8, 256, 8)]
+    cases = [("gather", 100, 2.5e-4), ("gather", 8, 1e-4), ("gather", 50, 1e-3), ("gather", 200, 1e-3)]
     for what, k, r2 in cases:
-        for phased, steps, smem_k in variants:
-            if what == "nearest" and smem_k != 0:
+        for kernel, steps, smem_k, patience in variants:
+            if smem_k and k > smem_k:
                 continue
-            pm.set_tuning(phased, steps, smem_k)
+            pm.set_tuning(kernel, steps, smem_k, patience)
             if what == "gather":
                 out = m.gather_device(d_pts, k, r2)
                 ms = timed(lambda: m.gather_device(d_pts, k, r2, out=out))
@@ -55,7 +57,7 @@ def main():
                 sig = (int(out.long().sum()),)
             key = (what, k, r2)
             same = reference.setdefault(key, sig) == sig
-            print(json.dumps({"what": what, "k": k, "sq_radius": r2, "phased": phased, "round_steps": steps, "smem_k": smem_k, "ms": ms,
+            print(json.dumps({"what": what, "k": k, "sq_radius": r2, "kernel": kernel, "round_steps": steps, "smem_k": smem_k, "patience": patience, "ms": ms,
                               "mpoints_per_s": len(pts) / ms / 1e3, "same_results_as_first_variant": same}), flush=True)
     m.close()
 
