@@ -86,7 +86,8 @@ int b200pm_find_nearest_device(b200pm_map *map, const float *d_points, const flo
 int b200pm_host_tree_build(const float *pos, size_t n, int build_threads, uint32_t *a, uint32_t *b);
 
 /* Tuning aid (tools/pm_sweep.py), process-wide, not for production use; a negative argument keeps the current value.
- * kernel: gather kernel -- 0 = the plain per-thread loop, 1 = the phased state machine, 2 = phased with one stack pop per step;
+ * kernel: gather kernel -- 0 = the plain per-thread loop, 1 = the phased state machine, 2 = phased with one stack pop per step,
+ * 3 = the default again (2 above smem_k, 0 with shared-memory heaps up to smem_k);
  * round_steps: node visits per round of the phased kernels; smem_k: largest k whose heaps live in shared memory (0 = always in
  * `found`, at most 256); patience: lanes of a warp that must have a make_heap pending before it is done (1 = no waiting).  The
  * environment variables B200PM_KERNEL=plain|phased1|phased, B200PM_ROUND, B200PM_SMEM_K, B200PM_PATIENCE set the same at load

@@ -33,6 +33,7 @@ class AcceleratorB200 final : public Accelerator
 		AcceleratorB200(Logger &logger, ParamResult &param_result, const RenderControl *render_control, const std::vector<const Primitive *> &primitives, const ParamMap &param_map);
 		~AcceleratorB200() override;
 		bool ok() const { return scene_ != nullptr; }
+		int device() const { return params_.device_; } //!< CUDA device of the scene (photon/photon_gather_b200.h puts its photon map there)
 
 		/* The batched entry of north-star (c) is the wavefront ray queue below: every Accelerator::intersect / isShadowed /
 		 * isShadowedTransparentShadow call an integrator makes on a fiber joins the batch its render thread flushes through

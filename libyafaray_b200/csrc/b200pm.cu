@@ -93,13 +93,20 @@ namespace {
 //   B200PM_SMEM_K=<k>     largest k whose heaps live in shared memory (0 = always in `found`)
 struct Tuning
 {
-	int kernel = 0; // 0 plain, 1 phased, 2 phased + single pop
+	// defaults from profiles/r6c_pm_sweep.jsonl (1 M photons, 1 M points): k = 100 plain 10.1 ms, phased 9.7, phased + single pop 8.9,
+	// + patience 16 7.0; k = 8 with heaps in shared memory: plain 2.4 ms, phased 2.9 -- small k keeps the plain loop
+	int kernel = 2; // 0 plain, 1 phased, 2 phased + single pop
+	bool small_k_plain = true; // k <= smem_k: the plain loop with shared-memory heaps, unless a kernel was asked for explicitly
 	int round_steps = 8;
-	int patience = 8;
+	int patience = 16;
 	uint32_t smem_k = 16;
 	Tuning()
 	{
-		if(const char *e = std::getenv("B200PM_KERNEL")) kernel = std::string(e) == "plain" ? 0 : (std::string(e) == "phased1" ? 1 : 2);
+		if(const char *e = std::getenv("B200PM_KERNEL"))
+		{
+			kernel = std::string(e) == "plain" ? 0 : (std::string(e) == "phased1" ? 1 : 2);
+			small_k_plain = false;
+		}
 		if(const char *e = std::getenv("B200PM_ROUND")) { const long v = std::atol(e); if(v >= 1 && v <= 4096) round_steps = int(v); }
 		if(const char *e = std::getenv("B200PM_PATIENCE")) { const long v = std::atol(e); if(v >= 1 && v <= 32) patience = int(v); }
 		if(const char *e = std::getenv("B200PM_SMEM_K")) { const long v = std::atol(e); if(v >= 0 && uint32_t(v) <= b200pm::kPmSmemK) smem_k = uint32_t(v); }
@@ -129,7 +136,7 @@ int launchGather(b200pm_map *map, const float *d_points, size_t n_points, uint32
 		map->smem_opt_in = true;
 	}
 #define PM_ARGS map->d_nodes, map->d_dirs, d_points, nullptr, uint32_t(n_points), k, sq_radius, d_sq_radii, found2, d_n_found, d_sq_radius_out, nullptr
-	if(t.kernel == 0)
+	if(t.kernel == 0 || (in_smem && t.small_k_plain))
 	{
 		if(in_smem) b200pm::pmLookupKernel<0><<<blocks, b200pm::kPmThreads, smem, stream>>>(PM_ARGS);
 		else b200pm::pmLookupKernel<1><<<blocks, b200pm::kPmThreads, 0, stream>>>(PM_ARGS);
@@ -192,7 +199,8 @@ int b200pm_host_tree_build(const float *pos, size_t n, int build_threads, uint32
 int b200pm_debug_set_tuning(int kernel, int round_steps, int smem_k, int patience)
 {
 	Tuning &t = tuning();
-	if(kernel >= 0 && kernel <= 2) t.kernel = kernel;
+	if(kernel >= 0 && kernel <= 2) { t.kernel = kernel; t.small_k_plain = false; }
+	if(kernel == 3) { t.kernel = 2; t.small_k_plain = true; } // the library default: phased + single pop above smem_k, plain below
 	if(round_steps >= 1) t.round_steps = round_steps;
 	if(smem_k >= 0 && uint32_t(smem_k) <= b200pm::kPmSmemK) t.smem_k = uint32_t(smem_k);
 	if(patience >= 1 && patience <= 32) t.patience = patience;

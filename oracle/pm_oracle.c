@@ -12,8 +12,8 @@
  *
  * PARITY STATUS: PINNED -- tests/test_pm_oracle.py compares the node array, every gather result (photon ids in the
  * reference's own `found` order, squared distances bit for bit, counts, final radii) and every findNearest result with the
- * UNMODIFIED reference (oracle/_ref/libyafref.so through ref_pm_driver.cc) and with tests/golden/pm_*.npz, which
- * tests/golden/make_pm_golden.py generated from that same unmodified reference.
+ * UNMODIFIED reference (oracle/_ref/libyafref.so through ref_pm_driver.cc) and with tests/golden/pm/pm_*.npz, which
+ * tests/golden/pm/make_pm_golden.py generated from that same unmodified reference.
  *
  * std::make_heap / pop_heap / push_heap are not in the reference tree: they come from libstdc++ (GCC 13 here,
  * bits/stl_heap.h __push_heap / __adjust_heap / __make_heap / __pop_heap); the three functions heap_* below restate that

@@ -1,6 +1,6 @@
-"""Generates tests/golden/pm_*.npz from the UNMODIFIED reference (oracle/_ref/libyafref.so, built by `make -C oracle ref`
+"""Generates tests/golden/pm/pm_*.npz from the UNMODIFIED reference (oracle/_ref/libyafref.so, built by `make -C oracle ref`
 from /root/reference): the reference's own point kd-tree node array, PhotonMap::gather and PhotonMap::findNearest results
-for small photon sets.  Run from the repo root:  python tests/golden/make_pm_golden.py
+for small photon sets.  Run from the repo root:  python tests/golden/pm/make_pm_golden.py
 The fixtures travel to the GPU box; /root/reference does not.
 """
 import os
@@ -8,7 +8,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, ROOT)
 from libyafaray_b200 import scenes  # noqa: E402
 from oracle import pmo  # noqa: E402
@@ -35,7 +35,7 @@ def main():
         out.update(radii=radii, gr_idx=idx, gr_d2=d2, gr_n=cnt, gr_r=rad)
         for i, dist in enumerate(NEAREST):
             out[f"n{i}"] = ref.nearest(points, normals, dist)
-        path = os.path.join(ROOT, "tests", "golden", f"pm_{kind}.npz")
+        path = os.path.join(ROOT, "tests", "golden", "pm", f"pm_{kind}.npz")
         np.savez_compressed(path, **out)
         print(path, os.path.getsize(path), "bytes; mean found", [float(out[f"g{i}_n"].mean()) for i in range(len(GATHERS))])
 

@@ -283,6 +283,29 @@ def test_photon_passes_run_on_fibers(tmp_path, integrator, extra):
     assert value > min(floor - 3.0, 40.0)
 
 
+@pytest.mark.gpu
+@needs_render_bench
+def test_radiance_pre_gather_runs_on_the_device(tmp_path):
+    """SURVEY.md 8f row N4 (photon-map gather): with final gathering on, PhotonIntegrator's radiance-map precompute
+    (src/integrator/surface/integrator_photon_mapping.cc:98-147,505-514: one PhotonMap::gather per radiance point) is one batched
+    b200pm_gather call (integration/include/photon/photon_gather_b200.h); the gathers are bit-identical to the reference's
+    (tests/test_pm.py), so the frame agrees with the stock render as well as two stock renders agree with each other."""
+    extra = ("i:diffuse_photons=100000", "i:caustic_photons=10000", "b:finalGather=1", "i:fg_samples=4")
+    stock = _render_film(tmp_path, "stock", "photonmapping", "0/1", size=(160, 100), aa=1, threads=4, extra=extra)
+    again = _render_film(tmp_path, "again", "photonmapping", "0/1", size=(160, 100), aa=1, threads=4, extra=extra)
+    prefix = str(tmp_path / "b200")
+    cmd = [RENDER_BENCH, "b200-kdtree", "photonmapping", "48", "160", "100", "1", prefix + ".tga", "4", "film_save=" + prefix, *extra]
+    p = subprocess.run(cmd, cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, errors="replace", timeout=600)
+    assert p.returncode == 0 and "no usable accelerator" not in p.stdout, p.stdout[-2000:]
+    assert "b200pm: radiance pre-gather on the device" in p.stdout, p.stdout[-3000:]
+    assert "gathering on the host" not in p.stdout
+    b200 = film.read_film(film.film_path(prefix))
+    floor = film.psnr(film.normalized(again), film.normalized(stock))
+    value = film.psnr(film.normalized(b200), film.normalized(stock))
+    print(f"photonmapping with final gather: b200 vs stock {value:.1f} dB, stock vs stock {floor:.1f} dB")
+    assert value > min(floor - 3.0, 40.0)
+
+
 @needs_render_bench
 @pytest.mark.parametrize("integrator,extra", [("photonmapping", ("i:diffuse_photons=20000", "i:caustic_photons=4000")), ("SPPM", ("i:photons=20000", "i:passNums=2"))])
 def test_patched_photon_launch_sites_keep_the_reference_behaviour_on_cpu(tmp_path, integrator, extra):

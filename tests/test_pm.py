@@ -2,7 +2,7 @@
 (src/photon/photon.cc:46-72, include/photon/pkdtree.h) on B200.
 
 CPU (`-m "not gpu"`): the C restatement (oracle/pm_oracle.c) against the committed golden vectors (made from the unmodified
-reference by tests/golden/make_pm_golden.py) and against the live reference when oracle/_ref is there; the product's host-side
+reference by tests/golden/pm/make_pm_golden.py) and against the live reference when oracle/_ref is there; the product's host-side
 tree builder against both; the kernel's lookup code itself, compiled for the host (tests/native/pm_host_model.cu), against the
 oracle; the C ABI's symbols and argument checks.
 GPU (`-m gpu`): b200pm_* through the C ABI against the oracle and the golden vectors, bit for bit; properties at full size.
@@ -19,9 +19,9 @@ from libyafaray_b200 import pm, rt, scenes
 from oracle import pmo
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "pm_*.npz")))
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "pm", "pm_*.npz")))
 KINDS = ["uniform", "surfaces", "clusters", "lattice"]
-DEFAULT_TUNING = (0, 8, 16, 8)  # b200pm.cu Tuning: kernel, round_steps, smem_k, patience
+DEFAULT_TUNING = (3, 8, 16, 16)  # b200pm.cu Tuning: kernel (3 = default mix), round_steps, smem_k, patience
 
 
 def bits(a):

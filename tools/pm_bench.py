@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-KERNEL = "b200pm::pmLookupPhasedKernel<1> (k > 16: heaps in the result array; B200PM_KERNEL=plain: pmLookupKernel)"
+KERNEL = "b200pm::pmLookupPhasedKernel<1,true> (k > 16: phased lookup, one pop per step, heaps in the result array; k <= 16: pmLookupKernel<0>, heaps in shared memory)"
 
 
 def run(photons=1_000_000, points=1_000_000, k=100, sq_radius=2.5e-4, steps=5, cpu_seconds=5.0, device=0, kind="surfaces", cpu=True):
@@ -85,11 +85,11 @@ def run(photons=1_000_000, points=1_000_000, k=100, sq_radius=2.5e-4, steps=5, c
         "kernel": KERNEL, "gpu_launches": int(launches), "dtype": "f32",
         "config": {"workload": f"{photons} photons ({kind}), {points} gather points, k={k}, sq_radius={sq_radius}", "inputs": "points and results resident in HBM"},
         "mean_found": float(n_found.mean()), "full_fraction": float((n_found == k).mean()),
-        "find_nearest": {"value": points / (near_ms * 1e-3) / 1e6, "unit": "Mpoints/s", "ms": near_ms, "kernel": "b200pm::pmLookupPhasedKernel<2>"},
+        "find_nearest": {"value": points / (near_ms * 1e-3) / 1e6, "unit": "Mpoints/s", "ms": near_ms, "kernel": "b200pm::pmLookupKernel<2>"},
         "e2e": {"value": points / e2e_s / 1e6, "unit": "Mpoints/s", "h2d_bytes": int(pts.nbytes), "d2h_bytes": int(found.nbytes + n_found.nbytes + radius_out.nbytes),
                 "path": "b200pm_gather on page-locked host buffers (chunks over two streams: H2D, kernel, D2H overlap)", "same_as_device_resident": same,
                 "pageable_value": points / pageable_s / 1e6, "pageable_same": bool(np.array_equal(n_found_p, n_found))},
-        "tuning": {key: os.environ.get(key) for key in ("B200PM_KERNEL", "B200PM_ROUND", "B200PM_SMEM_K") if os.environ.get(key) is not None},
+        "tuning": {key: os.environ.get(key) for key in ("B200PM_KERNEL", "B200PM_ROUND", "B200PM_SMEM_K", "B200PM_PATIENCE") if os.environ.get(key) is not None},
         "tree": stats,
     }
     if cpu:
