@@ -317,6 +317,31 @@ static void lookup(const pmo_map *m, const float p[3], proc_t *proc, float *max_
 	}
 }
 
+/* The lookup WITHOUT the split-plane pruning: every leaf, near child first -- the order PointKdTree::lookup visits the leaves it
+ * does visit.  Not a restatement of anything in the reference: a cross-check of the argument DESIGN.md 11 rests on (pruning only
+ * skips photons the distance test would reject anyway, so any traversal that keeps the leaf order gives the same results). */
+static void lookup_unpruned(const pmo_map *m, const float p[3], proc_t *proc, float *max_dist_squared, int64_t node)
+{
+	if((m->node_b[node] & 3u) == 3u)
+	{
+		const uint32_t photon = m->node_a[node];
+		const float *q = &m->pos[3 * (size_t) photon];
+		const float vx = q[0] - p[0], vy = q[1] - p[1], vz = q[2] - p[2];
+		const float dist_2 = vx * vx + vy * vy + vz * vz;
+		if(dist_2 < *max_dist_squared) proc_call(m, proc, photon, dist_2, max_dist_squared);
+		return;
+	}
+	const int axis = (int) (m->node_b[node] & 3u);
+	float split_val;
+	memcpy(&split_val, &m->node_a[node], 4);
+	const int64_t left = node + 1, right = (int64_t) (m->node_b[node] >> 2);
+	if(p[axis] <= split_val) { lookup_unpruned(m, p, proc, max_dist_squared, left); lookup_unpruned(m, p, proc, max_dist_squared, right); }
+	else { lookup_unpruned(m, p, proc, max_dist_squared, right); lookup_unpruned(m, p, proc, max_dist_squared, left); }
+}
+
+static int g_unpruned = 0;
+void pmo_set_unpruned(int on) { g_unpruned = on; }
+
 /* PhotonMap::gather for n points; same argument meaning as yref_pm_gather (ref_pm_driver.cc) */
 void pmo_gather(const pmo_map *m, const float *points, size_t n, uint32_t k, float sq_radius, const float *sq_radii,
                 uint32_t *found_idx, float *found_d2, uint32_t *n_found, float *sq_radius_out)
@@ -330,7 +355,8 @@ void pmo_gather(const pmo_map *m, const float *points, size_t n, uint32_t k, flo
 		proc.found = found;
 		proc.n_lookup = k;
 		float radius = sq_radii ? sq_radii[i] : sq_radius;
-		lookup(m, &points[3 * i], &proc, &radius);
+		if(g_unpruned) lookup_unpruned(m, &points[3 * i], &proc, &radius, 0);
+		else lookup(m, &points[3 * i], &proc, &radius);
 		if(n_found) n_found[i] = proc.n_found;
 		if(sq_radius_out) sq_radius_out[i] = radius;
 		for(uint32_t j = 0; j < proc.n_found; ++j)
@@ -353,7 +379,8 @@ void pmo_nearest(const pmo_map *m, const float *points, const float *normals, si
 		proc.normal = &normals[3 * i];
 		proc.nearest = 0xFFFFFFFFu;
 		float radius = dist;
-		lookup(m, &points[3 * i], &proc, &radius);
+		if(g_unpruned) lookup_unpruned(m, &points[3 * i], &proc, &radius, 0);
+		else lookup(m, &points[3 * i], &proc, &radius);
 		out_idx[i] = proc.nearest;
 	}
 }

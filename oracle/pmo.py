@@ -49,8 +49,14 @@ def _oracle_lib():
         L.pmo_tree_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.pmo_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_float, C.c_void_p] + [C.c_void_p] * 4
         L.pmo_nearest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_void_p]
+        L.pmo_set_unpruned.argtypes = [C.c_int]
         _olib = L
     return _olib
+
+
+def set_unpruned(on: bool):
+    """Cross-check mode of pm_oracle.c: visit every leaf in the lookup's order, no split-plane pruning."""
+    _oracle_lib().pmo_set_unpruned(1 if on else 0)
 
 
 class OracleMap(_Base):

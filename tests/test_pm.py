@@ -78,6 +78,31 @@ def test_oracle_matches_live_reference(built, kind):
             assert np.array_equal(o.nearest(points, normals, dist), ref.nearest(points, normals, dist))
 
 
+@pytest.mark.parametrize("kind", KINDS)
+def test_pruning_never_changes_a_result(built, kind):
+    """the split-plane test only skips photons the distance test would reject, so the results are a function
+    of the leaf ORDER alone -- the lookup with the pruning switched off gives the same bits."""
+    pos, dirs = scenes.photon_cloud(kind, 3000, seed=77)
+    points, normals = scenes.gather_points(pos, 400, seed=78, jitter=0.02)
+    o = pmo.OracleMap(pos, dirs)
+    for k, r2 in ((1, 1e-3), (7, 5e-3), (40, 2e-2), (25, 1e30)):
+        want = o.gather(points, k, r2)
+        pmo.set_unpruned(True)
+        try:
+            got = o.gather(points, k, r2)
+        finally:
+            pmo.set_unpruned(False)
+        assert_gather_equal(got, want, f"{kind} k={k} r2={r2}")
+    for dist in (1e-3, 1.0):
+        want = o.nearest(points, normals, dist)
+        pmo.set_unpruned(True)
+        try:
+            got = o.nearest(points, normals, dist)
+        finally:
+            pmo.set_unpruned(False)
+        assert np.array_equal(got, want)
+
+
 # ------------------------------------------------------------------------------------------------ host side of the product
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
