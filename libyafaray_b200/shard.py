@@ -47,6 +47,25 @@ def trace_sharded(trace_fn, rays, rank: int, world: int, gather: bool = True, gr
     return np.concatenate(out)
 
 
+def gather_sharded(gather_fn, points, k: int, rank: int, world: int, gather: bool = True, group=None):
+    """The photon-map gather over the GPUs of one box: the photon map is replicated like the scene, every rank
+    gathers a contiguous slice of the points, no exchange step.  gather_fn(points_slice) -> (found [m, k] (photon, dist_square),
+    n_found [m], sq_radius_out [m]) -- `pm.PhotonMap.gather` with k and the radius bound, in production.  Returns the same three
+    arrays for the whole batch (with `gather`) or for this rank's slice."""
+    found_dtype = np.dtype([("photon", np.uint32), ("dist_square", np.float32)])
+    row = np.dtype([("found", found_dtype, (k,)), ("n_found", np.uint32), ("radius", np.float32)])
+
+    def packed(slice_points):
+        found, n_found, radius = gather_fn(slice_points)
+        out = np.zeros(len(slice_points), row)
+        out["found"]["photon"], out["found"]["dist_square"] = found["photon"], found["dist_square"]
+        out["n_found"], out["radius"] = n_found, radius
+        return out
+
+    whole = trace_sharded(packed, points, rank, world, gather=gather, group=group)
+    return whole["found"], whole["n_found"], whole["radius"]
+
+
 def max_over_ranks(value: float, world: int, device=None, group=None) -> float:
     if world == 1:
         return float(value)

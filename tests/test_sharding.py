@@ -66,3 +66,41 @@ def test_two_rank_gloo_sharded_trace_equals_unsharded(built, tmp_path):
         assert got.shape[0] == 10001
         assert np.array_equal(got["t"], ref["t"]) and np.array_equal(got["prim"].astype(np.int64), ref["prim"].astype(np.int64) & 0xFFFFFFFF)
         assert float(open(os.path.join(tmp_path, f"max{rank}.txt")).read()) == float(world)
+
+
+def _gather_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from oracle import pmo
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pos, dirs = scenes.photon_cloud("surfaces", 4000, seed=2)
+    points, _ = scenes.gather_points(pos, 1501, seed=3)  # odd size: ragged shards
+    o = pmo.OracleMap(pos, dirs)
+    k, r2 = 12, 4e-3
+
+    def gather(p):
+        idx, d2, n_found, radius = o.gather(p, k, r2)
+        found = np.zeros((len(p), k), dtype=[("photon", np.uint32), ("dist_square", np.float32)])
+        found["photon"], found["dist_square"] = idx, d2
+        return found, n_found, radius
+
+    found, n_found, radius = shard.gather_sharded(gather, points, k, rank, world)
+    np.savez(os.path.join(out_dir, f"gather{rank}.npz"), photon=found["photon"], d2=found["dist_square"], n_found=n_found, radius=radius)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharded_photon_gather_equals_unsharded(built, tmp_path):
+    """Photon-map gather sharded by points over two ranks: the concatenated results are the unsharded ones."""
+    from oracle import pmo
+    world = 2
+    mp.spawn(_gather_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    pos, dirs = scenes.photon_cloud("surfaces", 4000, seed=2)
+    points, _ = scenes.gather_points(pos, 1501, seed=3)
+    idx, d2, n_found, radius = pmo.OracleMap(pos, dirs).gather(points, 12, 4e-3)
+    for rank in range(world):
+        got = np.load(os.path.join(tmp_path, f"gather{rank}.npz"))
+        assert np.array_equal(got["n_found"], n_found) and np.array_equal(got["radius"].view(np.uint32), radius.view(np.uint32))
+        valid = np.arange(12)[None, :] < n_found[:, None]
+        assert np.array_equal(got["photon"][valid], idx[valid]) and np.array_equal(got["d2"].view(np.uint32)[valid], d2.view(np.uint32)[valid])
