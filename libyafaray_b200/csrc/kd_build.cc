@@ -122,13 +122,26 @@ Split findSplitBinned(const Context &c, const std::vector<Ref> &refs, const Box 
 	return best;
 }
 
-struct Edge
+// An edge of the exact sweep as ONE integer: the float position mapped to an unsigned integer of the same order (sign bit flipped for
+// positive values, all bits for negative ones) in the high bits, the kind (0 = end, 1 = planar, 2 = start) in the low two.  Sorting
+// the integers is the (position, kind) order the sweep needs, with one compare per pair instead of two float compares and a branch;
+// equal keys are indistinguishable, so any sorting algorithm gives the same sweep.
+inline uint64_t edgeKey(float pos, uint32_t kind)
 {
-	float pos;
-	uint32_t kind; // 0 = end, 1 = planar, 2 = start
-};
+	uint32_t u = floatBits(pos);
+	u ^= (u & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u;
+	return (uint64_t(u) << 2) | kind;
+}
+inline float edgePos(uint64_t key)
+{
+	uint32_t u = uint32_t(key >> 2);
+	u ^= (u & 0x80000000u) ? 0x80000000u : 0xFFFFFFFFu;
+	float f;
+	std::memcpy(&f, &u, 4);
+	return f;
+}
 
-Split findSplitExact(const Context &c, const std::vector<Ref> &refs, const Box &box, std::vector<Edge> &edges)
+Split findSplitExact(const Context &c, const std::vector<Ref> &refs, const Box &box, std::vector<uint64_t> &edges)
 {
 	Split best;
 	const double ext[3] = {double(box.hi[0]) - box.lo[0], double(box.hi[1]) - box.lo[1], double(box.hi[2]) - box.lo[2]};
@@ -136,25 +149,28 @@ Split findSplitExact(const Context &c, const std::vector<Ref> &refs, const Box &
 	if(!(area > 0.0)) return best;
 	const double inv_area = 1.0 / area;
 	const size_t n = refs.size();
+	edges.resize(2 * n);
 	for(int axis = 0; axis < 3; ++axis)
 	{
 		if(!(ext[axis] > 0.0)) continue;
-		edges.clear();
+		size_t n_edges = 0;
 		for(const Ref &r : refs)
 		{
-			if(r.lo[axis] == r.hi[axis]) edges.push_back({r.lo[axis], 1u});
-			else { edges.push_back({r.lo[axis], 2u}); edges.push_back({r.hi[axis], 0u}); }
+			if(r.lo[axis] == r.hi[axis]) edges[n_edges++] = edgeKey(r.lo[axis], 1u);
+			else { edges[n_edges++] = edgeKey(r.lo[axis], 2u); edges[n_edges++] = edgeKey(r.hi[axis], 0u); }
 		}
-		std::sort(edges.begin(), edges.end(), [](const Edge &x, const Edge &y) { return x.pos < y.pos || (x.pos == y.pos && x.kind < y.kind); });
+		std::sort(edges.begin(), edges.begin() + n_edges);
 		size_t started = 0, ended = 0; // references with lo < p / hi < p
-		for(size_t i = 0; i < edges.size();)
+		for(size_t i = 0; i < n_edges;)
 		{
-			const float p = edges[i].pos;
+			const float p = edgePos(edges[i]);
 			size_t n_end = 0, n_planar = 0, n_start = 0;
-			for(; i < edges.size() && edges[i].pos == p; ++i)
+			// one plane = one float value: -0 and +0 are different keys but the same plane
+			for(; i < n_edges && edgePos(edges[i]) == p; ++i)
 			{
-				if(edges[i].kind == 0u) ++n_end;
-				else if(edges[i].kind == 1u) ++n_planar;
+				const uint32_t kind = uint32_t(edges[i] & 3u);
+				if(kind == 0u) ++n_end;
+				else if(kind == 1u) ++n_planar;
 				else ++n_start;
 			}
 			if(p > box.lo[axis] && p < box.hi[axis])
@@ -310,8 +326,7 @@ void buildNode(const Context &c, Subtree &st, std::vector<Ref> &refs, const Box 
 	if(n > kExactThreshold) split = findSplitBinned(c, refs, box);
 	else
 	{
-		std::vector<Edge> edges;
-		edges.reserve(2 * n);
+		static thread_local std::vector<uint64_t> edges; // scratch of the exact sweep, one per build thread
 		split = findSplitExact(c, refs, box, edges);
 	}
 	const double leaf_cost = double(n);
