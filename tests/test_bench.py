@@ -75,3 +75,17 @@ def test_product_arm_line_on_the_gpu(built):
     assert e2e["h2d_bytes_per_step"] == 2 * (1 << 20) * 32 and e2e["d2h_bytes_per_step"] == (1 << 20) * 20 and 0 < e2e["value"] < rec["value"]
     assert rec["cpu_baseline"]["value"] > 0 and rec["cpu_baseline"]["kind"] in ("reference", "port")
     assert rec["clocks"]["sm_mhz"] and not set(rec["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_photon_gather_roofline_block():
+    """tools/pm_bench.py: the roofline of the gather kernel is attached to the default workload only, names the tighter bound and is
+    arithmetic on the committed counters and the live duration."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pm_bench", os.path.join(ROOT, "tools", "pm_bench.py"))
+    pm_bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pm_bench)
+    roof = pm_bench.gather_roofline(7.0, 1_000_000, 1_000_000, 100, "surfaces", 2.5e-4, {})
+    assert roof["bound"] == "issue" and 0.4 < roof["frac"] < 0.7 and roof["issue"]["frac"] == roof["frac"]
+    assert abs(roof["hbm"]["achieved"] - 1_000_000 * 820 / 7.0e-3 / 1e9) < 1e-6 and roof["traffic"] > 8 * 1_000_000 * 820
+    assert pm_bench.gather_roofline(7.0, 1_000_000, 1_000_000, 8, "surfaces", 2.5e-4, {}) is None
+    assert pm_bench.gather_roofline(7.0, 1_000_000, 1_000_000, 100, "surfaces", 2.5e-4, {"B200PM_KERNEL": "plain"}) is None

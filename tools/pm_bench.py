@@ -26,6 +26,35 @@ if ROOT not in sys.path:
 KERNEL = "b200pm::pmLookupPhasedKernel<1,true> (k > 16: phased lookup, one pop per step, heaps in the result array; k <= 16: pmLookupKernel<0>, heaps in shared memory)"
 
 
+def gather_roofline(ms, photons, points, k, kind, sq_radius, tuning):
+    """Roofline of the gather kernel on the DEFAULT workload: both bounds, the tighter one named; None for any
+    other workload or tuning.  The counters are those of the committed ncu capture of this kernel
+    (profiles/r6c_pm_gather_phased_single_pop.txt: one launch, patience 8; the default patience 16 is 3 % faster); `ms` is the
+    duration measured live by the caller."""
+    if (photons, points, k, kind) != (1_000_000, 1_000_000, 100, "surfaces") or abs(sq_radius - 2.5e-4) > 1e-12 or tuning:
+        return None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+    warp_inst, dram_bytes = 4_538_847_914, 4_170_942_000 + 2_924_250_000
+    algo_bytes = points * (12 + 8 * k + 8)
+    issue = {"achieved": warp_inst / (ms * 1e-3) / 1e9, "peak": 148 * 4 * sm_mhz * 1e6 / 1e9, "unit": "G warp-inst/s", "warp_inst_per_point": warp_inst / points,
+             "lanes_per_inst": 11.36, "peak_source": f"148 SMs x 4 schedulers x {sm_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz)"}
+    issue["frac"] = issue["achieved"] / issue["peak"]
+    hbm = {"achieved": algo_bytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "algorithmic_bytes_per_point": 12 + 8 * k + 8, "traffic": dram_bytes,
+           "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"}
+    hbm["frac"] = hbm["achieved"] / hbm["peak"]
+    tighter = issue if issue["frac"] >= hbm["frac"] else hbm
+    return {"bound": "issue" if tighter is issue else "hbm", "kernel": "b200pm::pmLookupPhasedKernel<1,true>", "launch_ms": ms, "achieved": tighter["achieved"],
+            "peak": tighter["peak"], "unit": tighter["unit"], "frac": tighter["frac"], "traffic": dram_bytes, "issue": issue, "hbm": hbm,
+            "counters_source": "profiles/r6c_pm_gather_phased_single_pop.txt (ncu --set full, one launch of this kernel on this workload)",
+            "note": "tree (48 MB) and live heaps are L2 / L1 traffic; DRAM traffic is 8.6x the algorithmic bytes because the heaps of all resident warps do not fit L2 (DESIGN.md 11)"}
+
+
 def run(photons=1_000_000, points=1_000_000, k=100, sq_radius=2.5e-4, steps=5, cpu_seconds=5.0, device=0, kind="surfaces", cpu=True):
     import torch
 
@@ -92,6 +121,9 @@ def run(photons=1_000_000, points=1_000_000, k=100, sq_radius=2.5e-4, steps=5, c
         "tuning": {key: os.environ.get(key) for key in ("B200PM_KERNEL", "B200PM_ROUND", "B200PM_SMEM_K", "B200PM_PATIENCE") if os.environ.get(key) is not None},
         "tree": stats,
     }
+    roof = gather_roofline(ms, photons, points, k, kind, sq_radius, line["tuning"])
+    if roof:
+        line["roofline"] = roof
     if cpu:
         from oracle import pmo
 
