@@ -12,9 +12,9 @@
 // by findNearest, and only for photons inside the radius.
 //
 // Per-thread state: the traversal stack (far child, split, axis: 8 bytes per level) lives in local memory, interleaved per lane
-// by the hardware (one 128-byte line per warp and level); the k-entry max-heap of a gather lives in shared memory, interleaved
-// per thread ([entry][thread], 8-byte entries), when k * 8 * kPmThreads fits (k <= kPmSmemK), else directly in the caller's
-// `found` array.  Shared-memory heaps are copied out to `found` at the end.
+// by the hardware (one 128-byte line per warp and level); the k-entry max-heap of a gather lives directly in the caller's `found`
+// array, or -- for small k (<= 16 by default, b200pm.cu Tuning; at most kPmSmemK) -- in shared memory, interleaved per thread
+// ([entry][thread], 8-byte entries) and copied out to `found` at the end: at k = 100 shared-memory heaps cost 3.7x in occupancy.
 #pragma once
 #include <cstdint>
 #include <cstring>
