@@ -53,7 +53,7 @@ typedef struct b200pm_stats
 
 typedef struct b200pm_map b200pm_map;
 
-/* Build the reference's point kd-tree over n photons (1 <= n < 2^29) and upload it to CUDA device `device`.
+/* Build the reference's point kd-tree over n photons (1 <= n < 2^29, finite positions) and upload it to CUDA device `device`.
  * pos: 3 floats per photon (Photon::pos_).  dir: 3 floats per photon (Photon::dir_), needed by b200pm_find_nearest only; may be
  * NULL.  build_threads: host threads for the build (0 = all); the tree does not depend on it, as in the reference. */
 int b200pm_create(int device, const float *pos, const float *dir, size_t n, int build_threads, b200pm_map **out);

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -177,6 +178,14 @@ constexpr size_t kMaxPoints = size_t(1) << 31; // blocks * 64 threads must fit t
 
 size_t alignUp(size_t v) { return (v + 255) & ~size_t(255); }
 
+// the median splits order photons by coordinate: a NaN has no place in that order (std::nth_element would be undefined)
+bool allFinite(const float *pos, size_t n)
+{
+	for(size_t i = 0; i < 3 * n; ++i)
+		if(!std::isfinite(pos[i])) return false;
+	return true;
+}
+
 } // namespace
 
 extern "C" {
@@ -184,6 +193,7 @@ extern "C" {
 int b200pm_host_tree_build(const float *pos, size_t n, int build_threads, uint32_t *a, uint32_t *b)
 {
 	if(!pos || !a || !b || !n || n >= (size_t(1) << 29)) return failWith(B200RT_E_INVALID, "b200pm_host_tree_build: need 1 <= n < 2^29 photons and non-null arrays");
+	if(!allFinite(pos, n)) return failWith(B200RT_E_INVALID, "b200pm_host_tree_build: photon positions must be finite");
 	try
 	{
 		b200pm::HostTree tree;
@@ -212,6 +222,7 @@ int b200pm_create(int device, const float *pos, const float *dir, size_t n, int 
 	if(!out) return failWith(B200RT_E_INVALID, "null argument");
 	*out = nullptr;
 	if(!pos || !n || n >= (size_t(1) << 29)) return failWith(B200RT_E_INVALID, "b200pm_create: need 1 <= n < 2^29 photons");
+	if(!allFinite(pos, n)) return failWith(B200RT_E_INVALID, "b200pm_create: photon positions must be finite");
 	int count = 0;
 	const int rc = b200rt_device_count(&count);
 	if(rc != B200RT_OK) return rc;

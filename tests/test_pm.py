@@ -142,6 +142,8 @@ def test_argument_checks_without_a_device(built):
     assert L.b200pm_host_tree_build(rt._p(pos), 0, 1, rt._p(a), rt._p(b)) == -1       # empty map: the reference logs an error and builds nothing
     assert L.b200pm_host_tree_build(None, 4, 1, rt._p(a), rt._p(b)) == -1
     assert b"photons" in L.b200rt_last_error()
+    bad = np.array([[0, 0, 0], [1, np.nan, 0], [2, 2, 2], [3, 3, 3]], np.float32)
+    assert L.b200pm_host_tree_build(rt._p(bad), 4, 1, rt._p(a), rt._p(b)) == -1 and b"finite" in L.b200rt_last_error()
     h = C.c_void_p(0)
     assert L.b200pm_create(0, None, None, 4, 1, C.byref(h)) == -1 and not h.value
     assert L.b200pm_gather(None, None, 0, 1, C.c_float(1.0), None, None, None, None) == -1
