@@ -135,6 +135,25 @@ def test_library_exports_every_photon_map_symbol(built):
     assert declared == set(pm.SYMBOLS), declared ^ set(pm.SYMBOLS)
 
 
+def test_lookup_kernels_contain_no_fused_multiply_add(built):
+    """Bit parity of the squared distances rests on separate multiplies and adds (the reference is compiled without FMA
+    contraction): the SASS of every photon-map kernel in the shipped library must not contain a single FFMA."""
+    import shutil
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", rt.LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    kernels, current = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            current = line.split("Function :")[1].strip()
+            kernels[current] = 0
+        elif current and "FFMA" in line:
+            kernels[current] += 1
+    pm_kernels = {name: n for name, n in kernels.items() if "pmLookup" in name}
+    assert len(pm_kernels) >= 9, sorted(kernels)  # plain <0,1,2> + phased <0,1,2> x <single pop>
+    assert all(n == 0 for n in pm_kernels.values()), pm_kernels
+
+
 def test_argument_checks_without_a_device(built):
     pos = np.zeros((4, 3), np.float32)
     a, b = np.zeros(8, np.uint32), np.zeros(8, np.uint32)
